@@ -1,0 +1,180 @@
+/* pqdet_b200 -- C ABI of the B200-native PQDet detection hot path.
+ *
+ * The reference (eleflea/PQDet) has no FFI: its "operator interface" is plain Python
+ * (SURVEY.md section 8b).  This header is therefore the NEW boundary a maintainer binds with
+ * ctypes; each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - extern "C", every function returns int: 0 = PQDET_OK, < 0 = error (pqdet_strerror()).
+ *   - No allocation inside: the caller owns all buffers (device pointers unless said otherwise)
+ *     and passes the device ordinal and the cudaStream_t (as void*) explicitly.  The library is
+ *     re-entrant and keeps no global mutable state (nn.DataParallel calls the reference's
+ *     YOLOLayer from one thread per GPU, tools.py:215-216).
+ *   - All tensors fp32, contiguous.  Raw heads are NCHW (B, A*(5+C), H, W), channel = a*(5+C)+k,
+ *     exactly what the 1x1 head conv emits (model/parser.py:206-215).
+ *   - Rows of the concatenated prediction are ordered level-major in the order the levels are
+ *     given (cfg order), then (y*W + x)*A + a  (model/interpreter.py:75-76).
+ *   - Launches are asynchronous on `stream`; outputs are valid after the stream is synchronised.
+ */
+#ifndef PQDET_B200_H_
+#define PQDET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQDET_VERSION 100          /* 0.1.0 */
+#define PQDET_MAX_LEVELS 4
+#define PQDET_MAX_CLASSES 126      /* class id is a 7-bit field of the sort key */
+
+enum {
+  PQDET_OK = 0,
+  PQDET_ERR_INVALID_ARG = -1,
+  PQDET_ERR_CUDA = -2,
+  PQDET_ERR_UNSUPPORTED = -3,
+  PQDET_ERR_WORKSPACE = -4
+};
+
+/* dataset/__init__.py:17-21 RECOVER_BBOXES_REGISTER keys */
+enum { PQDET_AFFINE_VOC = 0, PQDET_AFFINE_COCO = 1, PQDET_AFFINE_VISDRONE = 2 };
+
+/* torchvision/ops/boxes.py:80-83 dispatch.  AUTO_CUDA: coordinate trick iff 4*M <= 100000,
+ * AUTO_CPU: iff 4*M <= 4000, else the per-class ("vanilla") arithmetic. */
+enum { PQDET_NMS_AUTO_CUDA = 0, PQDET_NMS_AUTO_CPU = 1, PQDET_NMS_TRICK = 2, PQDET_NMS_VANILLA = 3 };
+
+/* IoU rounding order of torchvision's nms kernels:
+ * TV_CUDA: D = fl(fma(bw,bh,Sa) - I), fl(I/D) > (float)thr;  TV_CPU: D = fl(fl(Sa+fl(bw*bh)) - I),
+ * (double)fl(I/D) > thr. */
+enum { PQDET_IOU_TV_CUDA = 0, PQDET_IOU_TV_CPU = 1 };
+
+/* model/parser.py:94-100 'bbox_loss' values */
+enum { PQDET_BBOX_L1 = 0, PQDET_BBOX_IOU = 1, PQDET_BBOX_GIOU = 2, PQDET_BBOX_DIOU = 3 };
+
+/* per-image status bits written by the decode+NMS entry points */
+enum {
+  PQDET_ST_OK = 0,
+  PQDET_ST_CAND_OVERFLOW = 1,   /* more hit rows / candidates than the fused kernel stages on chip:
+                                   nothing was written for this image; run pqdet_nms_general on it */
+  PQDET_ST_DET_TRUNCATED = 2    /* kept > max_det: counts[] holds the true K, only max_det rows written */
+};
+
+int pqdet_version(void);
+const char* pqdet_strerror(int code);
+
+/* ---- a2..a4: model/parser.py:206-235 Decode.forward (+ the eval concat of
+ * model/interpreter.py:75-76 when out_rows_total/out_row_offset address a (B, N, 5+C) buffer).
+ * raw (B, A*(5+C), H, W) -> out rows [out_row_offset, out_row_offset + H*W*A) of every image. */
+int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int C, int H, int W, float stride,
+                     int64_t out_rows_total, int64_t out_row_offset, int device, void* stream);
+
+/* autograd of Decode.forward: grad_raw = grad_out * d out / d raw (needs raw, not out). */
+int pqdet_decode_bwd(const float* raw, const float* grad_out, float* grad_raw, int B, int A, int C,
+                     int H, int W, float stride, int64_t out_rows_total, int64_t out_row_offset,
+                     int device, void* stream);
+
+/* ---- a5: dataset/base_sample.py:98-139 recover_bboxes_prediction + the three affine functions
+ * (voc_sample.py:92-95, coco_sample.py:97-100, visdrone_sample.py:84-88).
+ * pred (B, N, 5+C) -> out (B, N, 4+C).  orig_hw: device (B,2) [orig_per_image=1] or (2,) [=0], (h,w).
+ * Unlike the reference the input is NOT modified in place. */
+int pqdet_recover(const float* pred, float* out, int B, int64_t N, int C, int affine_kind,
+                  float in_h, float in_w, const float* orig_hw, int orig_per_image,
+                  int device, void* stream);
+
+/* ---- fused a2+a4+a5+a6: three raw heads -> detections, one launch, no intermediate tensor.
+ * Replaces Decode x L -> cat -> recover_bboxes_prediction_* -> per-image tools.torch_nms
+ * (predict.py:33-45, eval/evaluator.py:48-59).
+ * det    (B, max_det, 6) rows [x1,y1,x2,y2,score,class], descending score, ties by (row, class)
+ * det_idx(B, max_det)    optional (may be NULL): row*C + class of every detection
+ * counts (B)             kept detections K per image
+ * ncand  (B)             candidates M per image (score > thr)
+ * status (B)             PQDET_ST_* bits
+ * work_counter           one int32 of scratch (dynamic image scheduler), zeroed by the call  */
+typedef struct {
+  const float* raw[PQDET_MAX_LEVELS];
+  int H[PQDET_MAX_LEVELS], W[PQDET_MAX_LEVELS];
+  float stride[PQDET_MAX_LEVELS];
+  int n_levels;
+  int B, A, C;
+  int affine_kind;
+  float in_h, in_w;
+  const float* orig_hw;
+  int orig_per_image;
+  double score_threshold;     /* compared in fp32, like `tensor > python_float` (tools.py:551) */
+  double iou_threshold;
+  int nms_mode, iou_round;
+} pqdet_heads_t;
+
+int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
+                     int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
+                     int device, void* stream);
+
+/* General (any candidate count) path, same results as pqdet_decode_nms.  Works on the images
+ * listed in image_ids (device int32[n_images]; NULL = images 0..n_images-1).  det/det_idx/counts/
+ * ncand/status are indexed by image id, or by position in image_ids when out_by_position != 0.
+ * Exactly one source must be given:
+ *   heads != NULL : candidates come from the raw heads (fallback of the fused kernel), or
+ *   bboxes != NULL: candidates come from a recovered tensor (B, N, 4+C) -- this is the batched
+ *                   drop-in for tools.torch_nms (tools.py:540-566).
+ * cand_capacity: number of 8-byte candidate slots in the workspace the caller sized with
+ * pqdet_nms_general_workspace(); if the images need more, PQDET_ST_CAND_OVERFLOW is set for all
+ * of them, *needed (device int64) holds the required capacity and nothing else is written. */
+int64_t pqdet_nms_general_workspace(int n_images, int64_t N, int C, int64_t cand_capacity, int from_heads);
+
+int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes, int64_t N, int B, int C,
+                      double score_threshold, double iou_threshold, int nms_mode, int iou_round,
+                      const int32_t* image_ids, int n_images, int out_by_position,
+                      float* det, int32_t* det_idx, int max_det, int32_t* counts, int32_t* ncand,
+                      int32_t* status, void* workspace, int64_t workspace_bytes, int64_t cand_capacity,
+                      int64_t* needed, int device, void* stream);
+
+/* ---- a7/a8: tools.py:357-437 iou_calc3 / giou / diou / ciou, elementwise over n box pairs
+ * (broadcasting is done by the caller).  kind: 0 iou, 1 giou, 2 diou, 3 ciou.
+ * grad_b1/grad_b2 (may be NULL): d out / d boxes times grad_out (kinds 0..2). */
+int pqdet_iou_pairwise(const float* b1, const float* b2, float* out, int64_t n, int kind,
+                       int device, void* stream);
+int pqdet_iou_pairwise_bwd(const float* b1, const float* b2, const float* grad_out, float* grad_b1,
+                           float* grad_b2, int64_t n, int kind, int device, void* stream);
+
+/* ---- a3+a9+a10: model/parser.py:244-249 YOLOLayer.forward(x, target) = decode + loss_per_scale
+ * (model/loss.py:22-115), forward and backward in one pass.
+ * input_is_raw=1: x is the raw head (B, A*(5+C), H, W); grad (same shape, may be NULL) = d loss/d raw.
+ * input_is_raw=0: x is a decoded pred (B,H,W,A,5+C) (standalone loss_per_scale); grad = d loss/d pred.
+ * label (B,H,W,A,6+C); gt (B,G,4) zero padded.
+ * out4 (device float[4]) = loss, bbox_loss, conf_loss, cls_loss (each the batch mean, (1,) in the
+ * reference); nan_flag (device int32) = 1 iff loss is NaN (the reference raises, loss.py:110-114).
+ * partials: device scratch of pqdet_loss_workspace() bytes.  The gradient assumes an upstream
+ * gradient of 1 for `loss`; the box / objectness / class channels carry d bbox_loss, d conf_loss,
+ * d cls_loss respectively, so any other upstream mix is a per-channel-group rescale. */
+int64_t pqdet_loss_workspace(int B, int A, int H, int W);
+int pqdet_loss_fwd_bwd(const float* x, int input_is_raw, const float* label, const float* gt,
+                       float* grad, float* out4, int32_t* nan_flag, void* partials,
+                       int B, int A, int C, int H, int W, int G, float stride, int bbox_loss,
+                       float ignore_thresh, float l1_loss_gain, int device, void* stream);
+
+/* Chain rule for arbitrary upstream gradients of the four outputs of pqdet_loss_fwd_bwd: scales the
+ * box / objectness / class channel groups of grad IN PLACE by (g_loss+g_bbox), (g_loss+g_conf),
+ * (g_loss+g_cls).  g_* are DEVICE scalars (NULL = 0); when all three factors are 1 the kernel
+ * returns without touching memory, so the common loss.backward() costs no extra pass and no sync. */
+int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A, int C, int H, int W,
+                          const float* g_loss, const float* g_bbox, const float* g_conf,
+                          const float* g_cls, int device, void* stream);
+
+/* ---- a11/a12: dataset/train_dataset.py:109-150 create_label + collate_batch (:16-43) for a whole
+ * batch.  gt (B, n_max, 6) rows [x1,y1,x2,y2,class,mixw], gt_count (B).
+ * anchors: HOST float[9*2] (w,h); strides/H/W: HOST int[3], ascending strides (8,16,32).  For scale s:
+ *   label[s]   (B, H_s, W_s, 3, 6+C)   fully written (background = 0, mixw channel = 1)
+ *   gtlist[s]  (B, list_capacity, 4)   zero padded; list_len (B,3) true lengths (with duplicates)
+ * owner: device int32 scratch of pqdet_assign_workspace() bytes. */
+int64_t pqdet_assign_workspace(int B, const int* H, const int* W);
+int pqdet_assign_labels(const float* gt, const int32_t* gt_count, int B, int n_max, int C,
+                        const float* anchors, const int* strides, const int* H, const int* W,
+                        float iou_threshold, float* label0, float* label1, float* label2,
+                        float* gtlist0, float* gtlist1, float* gtlist2, int list_capacity,
+                        int32_t* list_len, void* owner, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PQDET_B200_H_ */

@@ -1,0 +1,300 @@
+"""Thin tensor-level wrappers over the C ABI: argument checking, buffers, streams.
+
+PyTorch is used here for device memory and streams only; all arithmetic happens in the CUDA
+library.  Every function requires CUDA tensors and raises otherwise (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_WS_CACHE = {}
+
+
+def _req(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise _lib.PqdetError("%s must be a CUDA tensor: pqdet_b200 has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev(t: torch.Tensor) -> int:
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _workspace(device: torch.device, key: str, nbytes: int) -> torch.Tensor:
+    """Per (device, stream, purpose) scratch, grown on demand; reuse is ordered by the stream."""
+    k = (device.index, torch.cuda.current_stream(device).cuda_stream, key)
+    buf = _WS_CACHE.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+        _WS_CACHE[k] = buf
+    return buf
+
+
+def _hw_pair(x, name) -> Tuple[float, float]:
+    """input_size as two host floats.  A CUDA tensor here costs a sync; pass a tuple to avoid it."""
+    if isinstance(x, torch.Tensor):
+        x = x.detach().reshape(-1).tolist()
+    x = list(x)
+    if len(x) != 2:
+        raise ValueError("%s must have 2 elements (h, w)" % name)
+    return float(x[0]), float(x[1])
+
+
+def _orig(orig, B: int, device: torch.device) -> Tuple[torch.Tensor, int]:
+    if not isinstance(orig, torch.Tensor):
+        orig = torch.tensor(orig, dtype=torch.float32)
+    orig = orig.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    if orig.dim() == 1 and orig.numel() == 2:
+        return orig, 0
+    if orig.dim() == 2 and orig.shape == (B, 2):
+        return orig, 1
+    raise ValueError("batch_original_size must have shape (B,2) or (2,), got %s" % (tuple(orig.shape),))
+
+
+# ------------------------------------------------------------------------------------------------
+def decode_fwd(raw: torch.Tensor, num_classes: int, stride: float, out: Optional[torch.Tensor] = None,
+               rows_total: Optional[int] = None, row_offset: int = 0) -> torch.Tensor:
+    raw = _req(raw, "conv")
+    B, CH, H, W = raw.shape
+    ch = 5 + num_classes
+    if CH % ch:
+        raise ValueError("channels (%d) not a multiple of 5+classes (%d)" % (CH, ch))
+    A = CH // ch
+    if out is None:
+        out = torch.empty((B, H, W, A, ch), dtype=torch.float32, device=raw.device)
+        rows_total, row_offset = H * W * A, 0
+    _lib.check(_lib.load().pqdet_decode_fwd(_ptr(raw), _ptr(out), B, A, num_classes, H, W, float(stride),
+                                            int(rows_total), int(row_offset), _dev(raw), _stream(raw.device)),
+               "pqdet_decode_fwd")
+    return out
+
+
+def decode_bwd(raw: torch.Tensor, grad_out: torch.Tensor, num_classes: int, stride: float) -> torch.Tensor:
+    raw = _req(raw, "conv")
+    grad_out = _req(grad_out, "grad_out")
+    B, CH, H, W = raw.shape
+    A = CH // (5 + num_classes)
+    grad = torch.empty_like(raw)
+    _lib.check(_lib.load().pqdet_decode_bwd(_ptr(raw), _ptr(grad_out), _ptr(grad), B, A, num_classes, H, W,
+                                            float(stride), H * W * A, 0, _dev(raw), _stream(raw.device)),
+               "pqdet_decode_bwd")
+    return grad
+
+
+def recover(pred: torch.Tensor, input_size, original_size, kind: str) -> torch.Tensor:
+    pred = _req(pred, "batch_pred_bbox")
+    if pred.dim() != 3:
+        raise ValueError("batch_pred_bbox must be (B, N, 5+C)")
+    B, N, ch = pred.shape
+    C = ch - 5
+    in_h, in_w = _hw_pair(input_size, "input_size")
+    orig, per = _orig(original_size, B, pred.device)
+    out = torch.empty((B, N, 4 + C), dtype=torch.float32, device=pred.device)
+    _lib.check(_lib.load().pqdet_recover(_ptr(pred), _ptr(out), B, N, C, _lib.AFFINE[kind], in_h, in_w,
+                                         _ptr(orig), per, _dev(pred), _stream(pred.device)), "pqdet_recover")
+    return out
+
+
+def make_heads(raws: Sequence[torch.Tensor], strides: Sequence[float], num_classes: int, input_size,
+               original_size, kind: str, score_threshold: float, iou_threshold: float,
+               nms_mode: str, iou_round: str):
+    raws = [_req(r, "head") for r in raws]
+    if not 1 <= len(raws) <= _lib.MAX_LEVELS or len(raws) != len(strides):
+        raise ValueError("need 1..%d heads with matching strides" % _lib.MAX_LEVELS)
+    B = raws[0].shape[0]
+    ch = 5 + num_classes
+    A = raws[0].shape[1] // ch
+    h = _lib.HeadsT()
+    for i, (r, s) in enumerate(zip(raws, strides)):
+        if r.shape[0] != B or r.shape[1] != A * ch or r.device != raws[0].device:
+            raise ValueError("head %d has inconsistent shape/device" % i)
+        h.raw[i] = r.data_ptr()
+        h.H[i], h.W[i] = int(r.shape[2]), int(r.shape[3])
+        h.stride[i] = float(s)
+    h.n_levels = len(raws)
+    h.B, h.A, h.C = B, A, num_classes
+    h.affine_kind = _lib.AFFINE[kind]
+    h.in_h, h.in_w = _hw_pair(input_size, "input_size")
+    orig, per = _orig(original_size, B, raws[0].device)
+    h.orig_hw = orig.data_ptr()
+    h.orig_per_image = per
+    h.score_threshold = float(score_threshold)
+    h.iou_threshold = float(iou_threshold)
+    h.nms_mode = _lib.NMS_MODE[nms_mode]
+    h.iou_round = _lib.IOU_ROUND[iou_round]
+    keep_alive = (raws, orig)
+    return h, keep_alive
+
+
+def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool):
+    """-> det (B,max_det,6), idx (B,max_det)|None, meta int32 (3,B): counts, ncand, status."""
+    raws, _ = keep_alive
+    device = raws[0].device
+    B = heads_t.B
+    det = torch.empty((B, max_det, 6), dtype=torch.float32, device=device)
+    idx = torch.empty((B, max_det), dtype=torch.int32, device=device) if want_index else None
+    meta = torch.empty((3 * B + 1,), dtype=torch.int32, device=device)
+    counts, ncand, status, work = meta[0:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:]
+    _lib.check(_lib.load().pqdet_decode_nms(ctypes.byref(heads_t), _ptr(det), _ptr(idx), int(max_det),
+                                            _ptr(counts), _ptr(ncand), _ptr(status), _ptr(work),
+                                            _dev(raws[0]), _stream(device)), "pqdet_decode_nms")
+    return det, idx, meta
+
+
+def nms_general(heads_t=None, keep_alive=None, bboxes: Optional[torch.Tensor] = None,
+                score_threshold: float = 0.0, iou_threshold: float = 0.0, nms_mode: str = "auto_cuda",
+                iou_round: str = "tv_cuda", image_ids: Optional[torch.Tensor] = None,
+                n_images: Optional[int] = None, max_det: int = 4096, cand_capacity: int = 1 << 16,
+                want_index: bool = False, out_by_position: bool = False):
+    """One attempt of the general path.  Outputs are indexed by image id, or by position in
+    image_ids (and sized n_images) when out_by_position is set.
+    -> det, idx, meta (3,B) int32 [counts, ncand, status], needed (1,) int64 (device)."""
+    lib = _lib.load()
+    if heads_t is not None:
+        device = keep_alive[0][0].device
+        B, C, N = heads_t.B, heads_t.C, 0
+        for i in range(heads_t.n_levels):
+            N += heads_t.H[i] * heads_t.W[i] * heads_t.A
+        bptr, hptr, from_heads = None, ctypes.byref(heads_t), 1
+    else:
+        bboxes = _req(bboxes, "bboxes")
+        if bboxes.dim() != 3:
+            raise ValueError("bboxes must be (B, N, 4+C)")
+        device = bboxes.device
+        B, N, C = bboxes.shape[0], bboxes.shape[1], bboxes.shape[2] - 4
+        bptr, hptr, from_heads = _ptr(bboxes), None, 0
+    if n_images is None:
+        n_images = B if image_ids is None else int(image_ids.numel())
+    wbytes = lib.pqdet_nms_general_workspace(n_images, N, C, int(cand_capacity), from_heads)
+    if wbytes < 0:
+        _lib.check(int(wbytes), "pqdet_nms_general_workspace")
+    ws = _workspace(device, "nms_general", wbytes)
+    R = n_images if out_by_position else B
+    det = torch.empty((R, max_det, 6), dtype=torch.float32, device=device)
+    idx = torch.empty((R, max_det), dtype=torch.int32, device=device) if want_index else None
+    meta = torch.zeros((3 * R,), dtype=torch.int32, device=device)
+    needed = torch.zeros((1,), dtype=torch.int64, device=device)
+    counts, ncand, status = meta[0:R], meta[R:2 * R], meta[2 * R:3 * R]
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    _lib.check(lib.pqdet_nms_general(hptr, bptr, N, B, C, float(score_threshold), float(iou_threshold),
+                                     _lib.NMS_MODE[nms_mode], _lib.IOU_ROUND[iou_round],
+                                     _ptr(image_ids), int(n_images), 1 if out_by_position else 0,
+                                     _ptr(det), _ptr(idx), int(max_det),
+                                     _ptr(counts), _ptr(ncand), _ptr(status), _ptr(ws), int(ws.numel()),
+                                     int(cand_capacity), _ptr(needed), dev_index, _stream(device)),
+               "pqdet_nms_general")
+    return det, idx, meta, needed
+
+
+def iou_pairwise(b1: torch.Tensor, b2: torch.Tensor, kind: int) -> torch.Tensor:
+    b1, b2 = torch.broadcast_tensors(b1, b2)
+    b1, b2 = _req(b1, "boxes1"), _req(b2, "boxes2")
+    if b1.shape[-1] != 4:
+        raise ValueError("last dimension must be 4 (x1,y1,x2,y2)")
+    out = torch.empty(b1.shape[:-1], dtype=torch.float32, device=b1.device)
+    n = out.numel()
+    _lib.check(_lib.load().pqdet_iou_pairwise(_ptr(b1), _ptr(b2), _ptr(out), n, kind, _dev(b1),
+                                              _stream(b1.device)), "pqdet_iou_pairwise")
+    return out
+
+
+def iou_pairwise_bwd(b1, b2, grad_out, kind: int):
+    b1, b2 = torch.broadcast_tensors(b1, b2)
+    b1, b2 = _req(b1, "boxes1"), _req(b2, "boxes2")
+    grad_out = _req(grad_out, "grad_out")
+    g1, g2 = torch.empty_like(b1), torch.empty_like(b2)
+    _lib.check(_lib.load().pqdet_iou_pairwise_bwd(_ptr(b1), _ptr(b2), _ptr(grad_out), _ptr(g1), _ptr(g2),
+                                                  grad_out.numel(), kind, _dev(b1), _stream(b1.device)),
+               "pqdet_iou_pairwise_bwd")
+    return g1, g2
+
+
+def loss_fwd_bwd(x: torch.Tensor, input_is_raw: bool, label: torch.Tensor, gt: torch.Tensor,
+                 num_classes: int, stride: float, bbox_loss: str, ignore_thresh: float,
+                 l1_loss_gain: float, want_grad: bool):
+    """-> out4 (4,) device [loss,bbox,conf,cls], nan_flag (1,) int32 device, grad|None."""
+    x, label, gt = _req(x, "pred"), _req(label, "label"), _req(gt, "bboxes")
+    C = num_classes
+    if bbox_loss == "ciou":
+        # tools.py:472 / model/loss.py:110-114: atan(0/0) at empty label cells makes the reference
+        # raise on every call; parity for ciou is "raises".
+        raise RuntimeError("NaN in loss")
+    if bbox_loss not in _lib.BBOX_LOSS:
+        raise NotImplementedError(bbox_loss)
+    if input_is_raw:
+        B, CH, H, W = x.shape
+        A = CH // (5 + C)
+    else:
+        B, H, W, A, _ = x.shape
+    if tuple(label.shape) != (B, H, W, A, 6 + C):
+        raise ValueError("label shape %s != %s" % (tuple(label.shape), (B, H, W, A, 6 + C)))
+    if gt.dim() != 3 or gt.shape[0] != B or gt.shape[2] != 4 or gt.shape[1] < 1:
+        raise ValueError("bboxes must be (B, G>=1, 4)")
+    lib = _lib.load()
+    ws = _workspace(x.device, "loss", lib.pqdet_loss_workspace(B, A, H, W))
+    grad = torch.empty_like(x) if want_grad else None
+    out = torch.empty((4,), dtype=torch.float32, device=x.device)
+    flag = torch.empty((1,), dtype=torch.int32, device=x.device)
+    _lib.check(lib.pqdet_loss_fwd_bwd(_ptr(x), 1 if input_is_raw else 0, _ptr(label), _ptr(gt), _ptr(grad),
+                                      _ptr(out), _ptr(flag), _ptr(ws), B, A, C, H, W, int(gt.shape[1]),
+                                      float(stride), _lib.BBOX_LOSS[bbox_loss], float(ignore_thresh),
+                                      float(l1_loss_gain), _dev(x), _stream(x.device)), "pqdet_loss_fwd_bwd")
+    return out, flag, grad
+
+
+def loss_scale_grad(grad: torch.Tensor, input_is_raw: bool, num_classes: int, g_loss, g_bbox, g_conf, g_cls):
+    """In-place per-channel-group chain rule (see pqdet_loss_scale_grad)."""
+    if input_is_raw:
+        B, CH, H, W = grad.shape
+        A = CH // (5 + num_classes)
+    else:
+        B, H, W, A, _ = grad.shape
+    gs = [None if g is None else _req(g.reshape(-1)[:1], "upstream grad") for g in (g_loss, g_bbox, g_conf, g_cls)]
+    _lib.check(_lib.load().pqdet_loss_scale_grad(_ptr(grad), 1 if input_is_raw else 0, B, A, num_classes, H, W,
+                                                 _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]),
+                                                 _dev(grad), _stream(grad.device)), "pqdet_loss_scale_grad")
+    return grad
+
+
+def assign_labels(gt: torch.Tensor, gt_count: torch.Tensor, num_classes: int, anchors, strides, sizes_hw,
+                  iou_threshold: float, list_capacity: Optional[int] = None):
+    """gt (B,n_max,6) cuda, gt_count (B) int32 cuda -> labels[3], gtlists[3] (B,cap,4), list_len (B,3)."""
+    gt = _req(gt, "gt")
+    if gt.dim() != 3 or gt.shape[2] != 6:
+        raise ValueError("gt must be (B, n_max, 6)")
+    B, n_max = gt.shape[0], gt.shape[1]
+    device = gt.device
+    gt_count = gt_count.to(device=device, dtype=torch.int32).contiguous()
+    C = num_classes
+    anc = (ctypes.c_float * 18)(*[float(v) for wh in anchors for v in wh])
+    st = (ctypes.c_int * 3)(*[int(s) for s in strides])
+    Hs = (ctypes.c_int * 3)(*[int(s[0]) for s in sizes_hw])
+    Ws = (ctypes.c_int * 3)(*[int(s[1]) for s in sizes_hw])
+    cap = int(list_capacity) if list_capacity else max(3 * n_max, 1)
+    labels = [torch.empty((B, Hs[i], Ws[i], 3, 6 + C), dtype=torch.float32, device=device) for i in range(3)]
+    lists = [torch.empty((B, cap, 4), dtype=torch.float32, device=device) for _ in range(3)]
+    list_len = torch.empty((B, 3), dtype=torch.int32, device=device)
+    lib = _lib.load()
+    owner = _workspace(device, "assign", lib.pqdet_assign_workspace(B, Hs, Ws))
+    _lib.check(lib.pqdet_assign_labels(_ptr(gt), _ptr(gt_count), B, n_max, C, anc, st, Hs, Ws,
+                                       float(iou_threshold), _ptr(labels[0]), _ptr(labels[1]), _ptr(labels[2]),
+                                       _ptr(lists[0]), _ptr(lists[1]), _ptr(lists[2]), cap, _ptr(list_len),
+                                       _ptr(owner), _dev(gt), _stream(device)), "pqdet_assign_labels")
+    return labels, lists, list_len

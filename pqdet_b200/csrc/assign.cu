@@ -1,0 +1,185 @@
+// GPU target assignment: TrainDataset.create_label +
+// collate_batch for a whole batch (dataset/train_dataset.py:16-43, 109-150).
+//
+// The dense label tensors are mostly background, so the cost is the streaming write of L bytes
+// (assign_fill_kernel, 128-bit stores).  The per-GT work (9 anchor IoUs in numpy's mixed
+// fp32/fp64 arithmetic) is tiny; "last writer wins" on cell collisions is reproduced with an
+// owner map (atomicMax of the GT index per label slot) followed by a write pass in which only
+// the owner stores its row; the per-scale GT lists keep numpy's order (GT order, then anchor
+// order, one entry per hit) through a block prefix sum.
+#include "pq_common.cuh"
+
+namespace pq {
+
+struct AssignParams {
+  const float* gt;          // (B, n_max, 6)
+  const int32_t* gt_count;  // (B)
+  int B, n_max, C;
+  float anchors[18];
+  int strides[3], H[3], W[3];
+  double iou_thr;
+  float hot, cold;
+  float* label[3];
+  float* gtlist[3];
+  int list_capacity;
+  int32_t* list_len;        // (B,3)
+  int32_t* owner[3];        // (B, H*W*3) each
+};
+
+// background: zeros, mixw channel (last) = 1.0
+__global__ void __launch_bounds__(256)
+assign_fill_kernel(float* __restrict__ dst, int64_t total, int LW) {
+  const int64_t n4 = total >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int64_t e = i << 2;
+    const int r = (int)(e % LW);
+    float4 v;
+    v.x = (r == LW - 1) ? 1.0f : 0.0f;
+    v.y = ((r + 1) % LW == LW - 1) ? 1.0f : 0.0f;
+    v.z = ((r + 2) % LW == LW - 1) ? 1.0f : 0.0f;
+    v.w = ((r + 3) % LW == LW - 1) ? 1.0f : 0.0f;
+    reinterpret_cast<float4*>(dst)[i] = v;
+  }
+  for (int64_t e = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+    dst[e] = ((int)(e % LW) == LW - 1) ? 1.0f : 0.0f;
+}
+
+// One CTA per image.  PASS 0: owner map + GT lists.  PASS 1: owners write their label rows.
+template <int PASS>
+__global__ void __launch_bounds__(256)
+assign_kernel(const __grid_constant__ AssignParams P) {
+  __shared__ int s_warp[3][8];
+  __shared__ int s_base[3];
+  const int b = blockIdx.x;
+  const int n = min(P.gt_count[b], P.n_max);
+  const int LW = 6 + P.C;
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  if (PASS == 0 && tid < 3) s_base[tid] = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    const int j = j0 + tid;
+    const bool valid = j < n;
+    AssignHit hit;
+    hit.mask = 0;
+    const float* g = P.gt + ((size_t)b * P.n_max + (valid ? j : 0)) * 6;
+    if (valid) hit = assign_one(g, P.anchors, P.strides, P.iou_thr);
+    bool inb[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+      inb[s] = valid && hit.cx[s] >= 0 && hit.cx[s] < P.W[s] && hit.cy[s] >= 0 && hit.cy[s] < P.H[s];
+    if (PASS == 0) {
+      int cnt[3], ex[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        cnt[s] = __popc((hit.mask >> (3 * s)) & 7u);
+        const int inc = warp_inclusive_sum(cnt[s]);
+        ex[s] = inc - cnt[s];
+        if (lane == 31) s_warp[s][warp] = inc;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int pos = s_base[s] + ex[s];
+        for (int w = 0; w < warp; ++w) pos += s_warp[s][w];
+        for (int r = 0; r < 3; ++r) {
+          if (!((hit.mask >> (3 * s + r)) & 1u)) continue;
+          if (inb[s]) atomicMax(&P.owner[s][(size_t)b * P.H[s] * P.W[s] * 3 + (hit.cy[s] * P.W[s] + hit.cx[s]) * 3 + r], j);
+          if (pos < P.list_capacity) {
+            float* d = P.gtlist[s] + ((size_t)b * P.list_capacity + pos) * 4;
+            d[0] = g[0]; d[1] = g[1]; d[2] = g[2]; d[3] = g[3];
+          }
+          ++pos;
+        }
+      }
+      __syncthreads();
+      if (tid < 3) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_warp[tid][w];
+        s_base[tid] += tot;
+      }
+      __syncthreads();
+    } else {
+      if (!valid) continue;
+      const int cls = (int)g[4];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (!inb[s]) continue;
+        for (int r = 0; r < 3; ++r) {
+          if (!((hit.mask >> (3 * s + r)) & 1u)) continue;
+          const size_t slot = (size_t)b * P.H[s] * P.W[s] * 3 + (hit.cy[s] * P.W[s] + hit.cx[s]) * 3 + r;
+          if (P.owner[s][slot] != j) continue;
+          float* d = P.label[s] + slot * LW;
+          d[0] = g[0]; d[1] = g[1]; d[2] = g[2]; d[3] = g[3];
+          d[4] = 1.0f;
+          for (int c = 0; c < P.C; ++c) d[5 + c] = (c == cls) ? P.hot : P.cold;
+          d[5 + P.C] = g[5];
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    __syncthreads();
+    if (tid < 3) P.list_len[b * 3 + tid] = s_base[tid];
+  }
+}
+
+}  // namespace pq
+
+extern "C" int64_t pqdet_assign_workspace(int B, const int* H, const int* W) {
+  if (B < 0 || !H || !W) return PQDET_ERR_INVALID_ARG;
+  int64_t slots = 0;
+  for (int s = 0; s < 3; ++s) slots += (int64_t)H[s] * W[s] * 3;
+  return (int64_t)B * slots * 4 + 256;
+}
+
+extern "C" int pqdet_assign_labels(const float* gt, const int32_t* gt_count, int B, int n_max, int C,
+                                   const float* anchors, const int* strides, const int* H, const int* W,
+                                   float iou_threshold, float* label0, float* label1, float* label2,
+                                   float* gtlist0, float* gtlist1, float* gtlist2, int list_capacity,
+                                   int32_t* list_len, void* owner, int device, void* stream) {
+  using namespace pq;
+  if (!gt_count || !anchors || !strides || !H || !W || !label0 || !label1 || !label2 || !gtlist0 ||
+      !gtlist1 || !gtlist2 || !list_len || !owner)
+    return PQDET_ERR_INVALID_ARG;
+  if (B < 1 || n_max < 0 || C < 1 || list_capacity < 1 || (n_max > 0 && !gt)) return PQDET_ERR_INVALID_ARG;
+  PQ_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  AssignParams P;
+  P.gt = gt; P.gt_count = gt_count; P.B = B; P.n_max = n_max; P.C = C;
+  // anchors are a host array: (w,h) x 9, config.py:58-59
+  for (int i = 0; i < 18; ++i) P.anchors[i] = anchors[i];
+  float* labels[3] = {label0, label1, label2};
+  float* lists[3] = {gtlist0, gtlist1, gtlist2};
+  int32_t* own = (int32_t*)owner;
+  size_t own_total = 0;
+  for (int s = 0; s < 3; ++s) {
+    if (H[s] < 1 || W[s] < 1 || strides[s] < 1) return PQDET_ERR_INVALID_ARG;
+    P.strides[s] = strides[s]; P.H[s] = H[s]; P.W[s] = W[s];
+    P.label[s] = labels[s]; P.gtlist[s] = lists[s];
+    P.owner[s] = own + own_total;
+    own_total += (size_t)B * H[s] * W[s] * 3;
+  }
+  P.iou_thr = (double)iou_threshold;
+  // label smoothing in fp64 then stored fp32 (train_dataset.py:126-130)
+  const double deta = 0.01, uni = 1.0 / (double)C;
+  P.hot = (float)(1.0 * (1 - deta) + deta * uni);
+  P.cold = (float)(0.0 * (1 - deta) + deta * uni);
+  P.list_capacity = list_capacity;
+  P.list_len = list_len;
+  PQ_CUDA(cudaMemsetAsync(owner, 0xff, own_total * sizeof(int32_t), st));
+  for (int s = 0; s < 3; ++s) {
+    PQ_CUDA(cudaMemsetAsync(lists[s], 0, (size_t)B * list_capacity * 4 * sizeof(float), st));
+    const int64_t total = (int64_t)B * H[s] * W[s] * 3 * (6 + C);
+    int64_t blocks = ((total >> 2) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    assign_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels[s], total, 6 + C);
+    PQ_LAUNCH_CHECK();
+  }
+  assign_kernel<0><<<B, 256, 0, st>>>(P);
+  PQ_LAUNCH_CHECK();
+  assign_kernel<1><<<B, 256, 0, st>>>(P);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}

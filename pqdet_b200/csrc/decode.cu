@@ -1,0 +1,158 @@
+// Materialising decode / decode-backward / recover kernels.
+//
+// decode_fwd transposes NCHW planes into (cell, anchor, channel) rows through shared memory:
+// each warp reads 32 consecutive cells of one channel plane (one 128-byte line), applies the
+// decode function, and the tile is written back as one contiguous run of 32*A*(5+C) floats.
+// HBM traffic is the algorithmic 2R (read once, write once); there is no reuse to exploit.
+#include "pq_common.cuh"
+
+namespace pq {
+
+constexpr int kTileCells = 32;
+constexpr int kDecodeThreads = 256;
+
+__global__ void __launch_bounds__(kDecodeThreads)
+decode_fwd_kernel(const float* __restrict__ raw, float* __restrict__ out, int A, int ch, int H, int W,
+                  float stride, int64_t rows_total, int64_t row_off) {
+  extern __shared__ float tile[];  // [kTileCells][ST]
+  const int HW = H * W;
+  const int ACH = A * ch;
+  const int ST = ACH | 1;  // odd row stride: conflict-free column writes
+  const int b = blockIdx.y;
+  const int cell0 = blockIdx.x * kTileCells;
+  const int ncell = min(kTileCells, HW - cell0);
+  const int lane = lane_id();
+  const int cell = cell0 + lane;
+  const int cy = cell / W, cx = cell - cy * W;
+  const float* src = raw + (size_t)b * ACH * HW;
+  for (int c = warp_id(); c < ACH; c += kDecodeThreads / 32) {
+    if (lane < ncell) {
+      float v = ldg_stream(src + (size_t)c * HW + cell);
+      int k = c % ch;
+      tile[lane * ST + c] = (k < 4) ? decode_coord(k, v, cx, cy, stride) : sigmoidf_(v);
+    }
+  }
+  __syncthreads();
+  float* dst = out + ((size_t)b * rows_total + row_off + (size_t)cell0 * A) * ch;
+  const int n = ncell * ACH;
+  for (int e = threadIdx.x; e < n; e += kDecodeThreads) {
+    int r = e / ACH, c = e - r * ACH;
+    dst[e] = tile[r * ST + c];
+  }
+}
+
+// grad_raw[b][c][cell] = grad_out[b][cell][a][k] * d out/d raw:
+//   k<2: -exp(raw)*stride, k in 2,3: +exp(raw)*stride, k>=4: p(1-p)   (autograd of parser.py:226-232)
+__global__ void __launch_bounds__(kDecodeThreads)
+decode_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ gout, float* __restrict__ graw,
+                  int A, int ch, int H, int W, float stride, int64_t rows_total, int64_t row_off) {
+  extern __shared__ float tile[];
+  const int HW = H * W;
+  const int ACH = A * ch;
+  const int ST = ACH | 1;
+  const int b = blockIdx.y;
+  const int cell0 = blockIdx.x * kTileCells;
+  const int ncell = min(kTileCells, HW - cell0);
+  const float* gsrc = gout + ((size_t)b * rows_total + row_off + (size_t)cell0 * A) * ch;
+  const int n = ncell * ACH;
+  for (int e = threadIdx.x; e < n; e += kDecodeThreads) {
+    int r = e / ACH, c = e - r * ACH;
+    tile[r * ST + c] = gsrc[e];
+  }
+  __syncthreads();
+  const int lane = lane_id();
+  const int cell = cell0 + lane;
+  const size_t base = (size_t)b * ACH * HW;
+  for (int c = warp_id(); c < ACH; c += kDecodeThreads / 32) {
+    if (lane < ncell) {
+      float v = raw[base + (size_t)c * HW + cell];
+      float g = tile[lane * ST + c];
+      int k = c % ch;
+      float d;
+      if (k < 4) {
+        float es = expf(v) * stride;
+        d = (k < 2) ? -es : es;
+      } else {
+        float p = sigmoidf_(v);
+        d = p * (1.0f - p);
+      }
+      graw[base + (size_t)c * HW + cell] = g * d;
+    }
+  }
+}
+
+// One thread per output element of (B, N, 4+C).
+__global__ void __launch_bounds__(256)
+recover_kernel(const float* __restrict__ pred, float* __restrict__ out, int64_t N, int C, int kind,
+               float in_h, float in_w, const float* __restrict__ orig_hw, int orig_per_image, int64_t total) {
+  const int oc = 4 + C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = e / oc;
+    int k = (int)(e - row * oc);
+    const float* p = pred + row * (5 + C);
+    if (k < 4) {
+      int64_t b = row / N;
+      const float* o = orig_hw + (orig_per_image ? 2 * b : 0);
+      Affine a = affine_params(kind, in_h, in_w, o[0], o[1]);
+      out[e] = recover_coord(k, p[k], a);
+    } else {
+      out[e] = PQ_MUL(p[k + 1], p[4]);
+    }
+  }
+}
+
+}  // namespace pq
+
+extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int C, int H, int W, float stride,
+                                int64_t out_rows_total, int64_t out_row_offset, int device, void* stream) {
+  if (!raw || !out || B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
+  if (out_row_offset < 0 || out_row_offset + (int64_t)H * W * A > out_rows_total) return PQDET_ERR_INVALID_ARG;
+  if (B == 0) return PQDET_OK;
+  if (B > 65535) return PQDET_ERR_UNSUPPORTED;
+  PQ_ENTER(device);
+  const int ch = 5 + C;
+  const size_t smem = (size_t)pq::kTileCells * ((A * ch) | 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    PQ_CUDA(cudaFuncSetAttribute(pq::decode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((H * W + pq::kTileCells - 1) / pq::kTileCells, B);
+  pq::decode_fwd_kernel<<<grid, pq::kDecodeThreads, smem, (cudaStream_t)stream>>>(
+      raw, out, A, ch, H, W, stride, out_rows_total, out_row_offset);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
+extern "C" int pqdet_decode_bwd(const float* raw, const float* grad_out, float* grad_raw, int B, int A, int C,
+                                int H, int W, float stride, int64_t out_rows_total, int64_t out_row_offset,
+                                int device, void* stream) {
+  if (!raw || !grad_out || !grad_raw || B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
+  if (out_row_offset < 0 || out_row_offset + (int64_t)H * W * A > out_rows_total) return PQDET_ERR_INVALID_ARG;
+  if (B == 0) return PQDET_OK;
+  if (B > 65535) return PQDET_ERR_UNSUPPORTED;
+  PQ_ENTER(device);
+  const int ch = 5 + C;
+  const size_t smem = (size_t)pq::kTileCells * ((A * ch) | 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    PQ_CUDA(cudaFuncSetAttribute(pq::decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((H * W + pq::kTileCells - 1) / pq::kTileCells, B);
+  pq::decode_bwd_kernel<<<grid, pq::kDecodeThreads, smem, (cudaStream_t)stream>>>(
+      raw, grad_out, grad_raw, A, ch, H, W, stride, out_rows_total, out_row_offset);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
+extern "C" int pqdet_recover(const float* pred, float* out, int B, int64_t N, int C, int affine_kind,
+                             float in_h, float in_w, const float* orig_hw, int orig_per_image,
+                             int device, void* stream) {
+  if (!pred || !out || !orig_hw || B < 0 || N < 0 || C < 0) return PQDET_ERR_INVALID_ARG;
+  if (affine_kind < 0 || affine_kind > 2) return PQDET_ERR_INVALID_ARG;
+  const int64_t total = (int64_t)B * N * (4 + C);
+  if (total == 0) return PQDET_OK;
+  PQ_ENTER(device);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;   // grid-stride: a whole number of waves on 148 SMs
+  pq::recover_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      pred, out, N, C, affine_kind, in_h, in_w, orig_hw, orig_per_image, total);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}

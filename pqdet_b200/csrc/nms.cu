@@ -1,0 +1,952 @@
+// Fused decode + recover + score threshold + class-aware NMS.
+//
+// decode_nms_fused_kernel: one CTA per image (persistent, dynamic image scheduler), everything
+// after the HBM read lives in shared memory:
+//   1. scan the objectness planes only (A of the A*(5+C) channels): a row can produce a candidate
+//      only if conf > thr, because score = fl(prob*conf) <= conf for prob <= 1.  A conservative
+//      logit-space prefilter skips the sigmoid for rows that cannot pass.  Hits are recorded as one
+//      ballot word per (level, 32-cell chunk, anchor).
+//   2. popcount prefix over the words gives every hit row a deterministic slot (row-major order),
+//      so ties in score are later broken by (row, class) exactly like nonzero() + stable sort.
+//   3. only for hit rows, fetch the 4 box + C class channels, decode + recover the box, form the
+//      scores, and push (class | ~score | hit) 64-bit keys into a shared-memory candidate list.
+//   4. block bitonic sort by (class asc, score desc, hit asc); per-class greedy NMS, one warp per
+//      class, 32 candidates per step (ballot-driven: work is proportional to the kept boxes);
+//      kept keys are re-sorted by (score desc, row asc, class asc) and written out.
+// The IoU arithmetic is torchvision's, in either of its two rounding orders, on the coordinate-
+// trick-shifted boxes or on the plain boxes depending on the candidate count, so the keep list is
+// bit-identical to tools.torch_nms on the same decoded boxes.
+//
+// Images whose hit rows / candidates do not fit the on-chip lists are flagged
+// (PQDET_ST_CAND_OVERFLOW) and handled by the general path below: global-memory candidate
+// lists bucketed by (image, class), one CTA per bucket.
+#include <string.h>
+
+#include "pq_common.cuh"
+
+namespace pq {
+
+constexpr int kFusedThreads = 256;
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kCapH = 1024;   // hit rows staged on chip per image
+constexpr int kCapM = 2048;   // candidates staged on chip per image
+constexpr int kHitBits = 25;  // low key field: hit slot (fused) or row (general)
+constexpr uint64_t kHitMask = (1ull << kHitBits) - 1;
+
+struct LevelDev {
+  const float* raw;
+  int H, W, HW;
+  float stride;
+  int row_off;    // first row of this level in the concatenated prediction
+  int group_off;  // first (level, chunk) group
+  int nchunk;     // ceil(HW/32)
+};
+
+struct HeadsDev {
+  LevelDev lv[PQDET_MAX_LEVELS];
+  int n_levels;
+  int B, A, C, ch;
+  int N;       // rows per image
+  int G_tot;   // groups per image; words per image = G_tot * A
+  int kind;
+  float in_h, in_w;
+  const float* orig;
+  int orig_per_image;
+  float thr_f;     // score threshold as fp32
+  float logit_lo;  // rows with objectness logit <= logit_lo cannot reach conf > thr
+  float iou_f;
+  double iou_d;
+  int nms_mode;
+};
+
+struct DetOut {
+  float* det;
+  int32_t* det_idx;
+  int max_det;
+  int32_t* counts;
+  int32_t* ncand;
+  int32_t* status;
+};
+
+__device__ __forceinline__ bool use_trick(int mode, int64_t M) {
+  if (mode == PQDET_NMS_TRICK) return true;
+  if (mode == PQDET_NMS_VANILLA) return false;
+  const int64_t limit = (mode == PQDET_NMS_AUTO_CPU) ? 4000 : 100000;   // torchvision/ops/boxes.py:80
+  return 4 * M <= limit;
+}
+
+__device__ __forceinline__ int level_of_group(const HeadsDev& P, int g) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
+    if (i < P.n_levels && g >= P.lv[i].group_off) l = i;
+  return l;
+}
+__device__ __forceinline__ int level_of_row(const HeadsDev& P, int row) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
+    if (i < P.n_levels && row >= P.lv[i].row_off) l = i;
+  return l;
+}
+
+__device__ __forceinline__ Affine image_affine(const HeadsDev& P, int b) {
+  const float* o = P.orig + (P.orig_per_image ? 2 * b : 0);
+  return affine_params(P.kind, P.in_h, P.in_w, o[0], o[1]);
+}
+
+// key of a candidate for the per-class phase: class asc, score desc, hit asc
+__device__ __forceinline__ uint64_t cand_key(int c, float score, uint32_t hit) {
+  return ((uint64_t)c << 57) | ((uint64_t)(~__float_as_uint(score)) << kHitBits) | hit;
+}
+// key of a kept detection for the output phase: score desc, (row|hit) asc, class asc
+__device__ __forceinline__ uint64_t out_key(uint64_t ck) {
+  uint64_t c = ck >> 57, nsc = (ck >> kHitBits) & 0xffffffffull, h = ck & kHitMask;
+  return (nsc << 32) | (h << 7) | c;
+}
+
+__device__ __forceinline__ void write_det(const DetOut& O, int b, int j, float4 bx, float score, int c,
+                                          int64_t row, int C) {
+  float2* d = reinterpret_cast<float2*>(O.det + ((size_t)b * O.max_det + j) * 6);
+  d[0] = make_float2(bx.x, bx.y);
+  d[1] = make_float2(bx.z, bx.w);
+  d[2] = make_float2(score, (float)c);
+  if (O.det_idx) O.det_idx[(size_t)b * O.max_det + j] = (int32_t)(row * C + c);
+}
+
+// Greedy NMS of one class segment [s, e) of the sorted key list by ONE warp.
+// getbox(pos) returns the (recovered, unshifted) box of sorted position pos.
+template <int ROUND, typename GetBox, typename KList, typename Mark>
+__device__ __forceinline__ int warp_nms_segment(int s, int e, float off, float iou_f, double iou_d,
+                                                GetBox getbox, KList klist, Mark mark) {
+  const int lane = lane_id();
+  int k = 0;
+  for (int base = s; base < e; base += 32) {
+    const int p = base + lane;
+    const bool valid = p < e;
+    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    if (valid) {
+      float4 bx = getbox(p);
+      x1 = PQ_ADD(bx.x, off); y1 = PQ_ADD(bx.y, off); x2 = PQ_ADD(bx.z, off); y2 = PQ_ADD(bx.w, off);
+    }
+    bool dead = !valid;
+    for (int q = 0; q < k; ++q) {                       // against boxes kept in earlier steps
+      float4 a = getbox(klist(s + q, -1));
+      float ax1 = PQ_ADD(a.x, off), ay1 = PQ_ADD(a.y, off), ax2 = PQ_ADD(a.z, off), ay2 = PQ_ADD(a.w, off);
+      float Sa = box_area(ax1, ay1, ax2, ay2);
+      if (!dead && nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, iou_f, iou_d)) dead = true;
+      if (!__any_sync(PQ_FULL, !dead)) break;
+    }
+    unsigned alive = __ballot_sync(PQ_FULL, !dead);
+    while (alive) {                                     // inside the step: next survivor is kept
+      const int i = __ffs(alive) - 1;
+      alive &= alive - 1;
+      float ax1 = __shfl_sync(PQ_FULL, x1, i), ay1 = __shfl_sync(PQ_FULL, y1, i);
+      float ax2 = __shfl_sync(PQ_FULL, x2, i), ay2 = __shfl_sync(PQ_FULL, y2, i);
+      float Sa = box_area(ax1, ay1, ax2, ay2);
+      if (lane == i) { klist(s + k, p); mark(p); }
+      ++k;
+      bool sup = (lane > i) && !dead &&
+                 nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, iou_f, iou_d);
+      dead |= sup;
+      alive &= ~__ballot_sync(PQ_FULL, sup);
+    }
+    __syncwarp();
+  }
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused kernel
+// ------------------------------------------------------------------------------------------------
+struct FusedSmem {
+  uint64_t keys[kCapM];
+  float4 hbox[kCapH];
+  uint32_t hrow[kCapH];
+  float hconf[kCapH];
+  uint16_t klist[kCapM];
+  uint8_t keepflag[kCapM];
+  uint8_t hhas[kCapH];
+  int seg_start[128];
+  int seg_end[128];
+  float red[kFusedWarps];
+  int b, H, M, K;
+  // followed by: uint32_t hitw[G_tot*A]; uint32_t gbase[G_tot];
+};
+
+template <int ROUND>
+__global__ void __launch_bounds__(kFusedThreads, 3)
+decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constant__ DetOut O, int32_t* work) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
+  uint32_t* hitw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(FusedSmem));
+  uint32_t* gbase = hitw + P.G_tot * P.A;
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const int A = P.A, C = P.C, ch = P.ch;
+  const int W_tot = P.G_tot * A;
+
+  for (;;) {
+    if (tid == 0) S.b = atomicAdd(work, 1);
+    __syncthreads();
+    const int b = S.b;
+    if (b >= P.B) break;
+
+    // ---- 1. objectness scan: one ballot word per (level, chunk, anchor) --------------------------
+    constexpr int U = 8;
+    for (int w0 = warp; w0 < W_tot; w0 += kFusedWarps * U) {
+      float x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * kFusedWarps;
+        x[u] = -INFINITY;
+        if (w < W_tot) {
+          const int g = w / A, a = w - g * A;
+          const LevelDev& L = P.lv[level_of_group(P, g)];
+          const int cell = (g - L.group_off) * 32 + lane;
+          if (cell < L.HW) x[u] = ldg_stream(L.raw + ((size_t)(b * A + a) * ch + 4) * L.HW + cell);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * kFusedWarps;
+        bool pass = x[u] > P.logit_lo;
+        if (pass) pass = sigmoidf_(x[u]) > P.thr_f;
+        const unsigned word = __ballot_sync(PQ_FULL, pass);
+        if (lane == 0 && w < W_tot) hitw[w] = word;
+      }
+    }
+    __syncthreads();
+
+    // ---- 2. deterministic slots: exclusive prefix of the per-group hit counts --------------------
+    if (warp == 0) {
+      int running = 0;
+      for (int g0 = 0; g0 < P.G_tot; g0 += 32) {
+        const int g = g0 + lane;
+        int c = 0;
+        if (g < P.G_tot)
+          for (int a = 0; a < A; ++a) c += __popc(hitw[g * A + a]);
+        const int inc = warp_inclusive_sum(c);
+        if (g < P.G_tot) gbase[g] = running + inc - c;
+        running += __shfl_sync(PQ_FULL, inc, 31);
+      }
+      if (lane == 0) { S.H = running; S.M = 0; S.K = 0; }
+    }
+    __syncthreads();
+    const int H = S.H;
+    if (H > kCapH) {
+      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = -1; }
+      __syncthreads();
+      continue;
+    }
+    for (int w = tid; w < W_tot; w += kFusedThreads) {
+      unsigned word = hitw[w];
+      if (!word) continue;
+      const int g = w / A, a = w - g * A;
+      const LevelDev& L = P.lv[level_of_group(P, g)];
+      while (word) {
+        const int j = __ffs(word) - 1;
+        word &= word - 1;
+        const unsigned below = (1u << j) - 1u;
+        int h = gbase[g];
+        for (int a2 = 0; a2 < A; ++a2) {
+          const unsigned w2 = hitw[g * A + a2];
+          h += __popc(w2 & below);
+          if (a2 < a) h += (w2 >> j) & 1u;
+        }
+        const int cell = (g - L.group_off) * 32 + j;
+        S.hrow[h] = L.row_off + cell * A + a;
+        S.hconf[h] = sigmoidf_(L.raw[((size_t)(b * A + a) * ch + 4) * L.HW + cell]);
+        S.hhas[h] = 0;
+      }
+    }
+    __syncthreads();
+
+    // ---- 3. box + class channels of the hit rows only -------------------------------------------
+    {
+      const Affine af = image_affine(P, b);
+      const int CK = 4 + C;
+      const int total = H * CK;
+      constexpr int V = 4;
+      for (int e0 = tid; e0 < total; e0 += kFusedThreads * V) {
+        float v[V];
+        int hh[V], kk[V], cxs[V], cys[V];
+        float st[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          const int e = e0 + u * kFusedThreads;
+          hh[u] = -1;
+          if (e < total) {
+            const int h = e / CK, k = e - h * CK;
+            const int row = S.hrow[h];
+            const LevelDev& L = P.lv[level_of_row(P, row)];
+            const int rl = row - L.row_off;
+            const int cell = rl / A, a = rl - cell * A;
+            const int chan = (k < 4) ? k : k + 1;
+            v[u] = ldg_stream(L.raw + ((size_t)(b * A + a) * ch + chan) * L.HW + cell);
+            hh[u] = h; kk[u] = k; st[u] = L.stride;
+            cys[u] = cell / L.W; cxs[u] = cell - cys[u] * L.W;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          if (hh[u] < 0) continue;
+          const int h = hh[u], k = kk[u];
+          if (k < 4) {
+            reinterpret_cast<float*>(&S.hbox[h])[k] =
+                recover_coord(k, decode_coord(k, v[u], cxs[u], cys[u], st[u]), af);
+          } else {
+            const float s = PQ_MUL(sigmoidf_(v[u]), S.hconf[h]);
+            if (s > P.thr_f) {
+              const int slot = atomicAdd(&S.M, 1);
+              if (slot < kCapM) S.keys[slot] = cand_key(k - 4, s, (uint32_t)h);
+              S.hhas[h] = 1;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int M = S.M;
+    if (M > kCapM || M == 0) {
+      if (tid == 0) {
+        O.status[b] = M ? PQDET_ST_CAND_OVERFLOW : PQDET_ST_OK;
+        O.counts[b] = 0;
+        O.ncand[b] = M;
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- 4. coordinate-trick offset base: fl(max coordinate of the picked boxes + 1) ------------
+    const bool trick = use_trick(P.nms_mode, M);
+    float m1 = 0.0f;
+    if (trick) {
+      float mx = -INFINITY;
+      for (int h = tid; h < H; h += kFusedThreads)
+        if (S.hhas[h]) {
+          const float4 bx = S.hbox[h];
+          mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
+        }
+      mx = warp_max(mx);
+      if (lane == 0) S.red[warp] = mx;
+      __syncthreads();
+      mx = S.red[0];
+#pragma unroll
+      for (int i = 1; i < kFusedWarps; ++i) mx = fmaxf(mx, S.red[i]);
+      m1 = PQ_ADD(mx, 1.0f);
+    }
+
+    // ---- 5. sort by (class, score desc, hit) and find the class segments -----------------------
+    const int P2 = next_pow2(M);
+    for (int i = M + tid; i < P2; i += kFusedThreads) S.keys[i] = ~0ull;
+    if (tid < 128) { S.seg_start[tid] = 0; S.seg_end[tid] = 0; }
+    __syncthreads();
+    bitonic_sort_block(S.keys, P2);
+    for (int i = tid; i < M; i += kFusedThreads) {
+      const int c = (int)(S.keys[i] >> 57);
+      if (i == 0 || (int)(S.keys[i - 1] >> 57) != c) S.seg_start[c] = i;
+      if (i == M - 1 || (int)(S.keys[i + 1] >> 57) != c) S.seg_end[c] = i + 1;
+      S.keepflag[i] = 0;
+    }
+    __syncthreads();
+
+    // ---- 6. per-class greedy NMS, one warp per class -------------------------------------------
+    for (int c = warp; c < C; c += kFusedWarps) {
+      const int s = S.seg_start[c], e = S.seg_end[c];
+      if (s >= e) continue;
+      const float off = trick ? PQ_MUL((float)c, m1) : 0.0f;
+      warp_nms_segment<ROUND>(
+          s, e, off, P.iou_f, P.iou_d,
+          [&](int pos) { return S.hbox[S.keys[pos] & kHitMask]; },
+          [&](int slot, int pos) -> int {
+            if (pos >= 0) S.klist[slot] = (uint16_t)pos;
+            return S.klist[slot];
+          },
+          [&](int pos) { S.keepflag[pos] = 1; });
+    }
+    __syncthreads();
+
+    // ---- 7. kept keys -> (score desc, row, class) order -> output -------------------------------
+    {
+      constexpr int R = kCapM / kFusedThreads;
+      uint64_t loc[R];
+      unsigned vmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = tid + r * kFusedThreads;
+        loc[r] = 0;
+        if (i < M && S.keepflag[i]) { loc[r] = out_key(S.keys[i]); vmask |= 1u << r; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (vmask & (1u << r)) S.keys[atomicAdd(&S.K, 1)] = loc[r];
+      __syncthreads();
+    }
+    const int K = S.K;
+    const int P3 = next_pow2(K);
+    for (int i = K + tid; i < P3; i += kFusedThreads) S.keys[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_block(S.keys, P3);
+    const int nout = min(K, O.max_det);
+    for (int j = tid; j < nout; j += kFusedThreads) {
+      const uint64_t k2 = S.keys[j];
+      const float score = __uint_as_float(~(uint32_t)(k2 >> 32));
+      const uint32_t low = (uint32_t)k2;
+      const int h = low >> 7, c = low & 127;
+      write_det(O, b, j, S.hbox[h], score, c, S.hrow[h], C);
+    }
+    if (tid == 0) {
+      O.counts[b] = K;
+      O.ncand[b] = M;
+      O.status[b] = (K > O.max_det) ? PQDET_ST_DET_TRUNCATED : PQDET_ST_OK;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// general path: any candidate count, candidates in global memory bucketed by (image, class)
+// ------------------------------------------------------------------------------------------------
+struct GenParams {
+  HeadsDev heads;            // valid when from_heads
+  int from_heads;
+  const float* bboxes;       // (B, N, 4+C) when !from_heads
+  int64_t N;
+  int C;
+  float thr_f;
+  float iou_f;
+  double iou_d;
+  int nms_mode;
+  const int32_t* image_ids;  // nullable
+  int n_images;
+  int out_by_pos;            // outputs indexed by position in image_ids instead of image id
+  // workspace
+  uint32_t* cls_count;       // [n_images][C]   candidates per bucket
+  uint32_t* cls_fill;        // [n_images][C]   scatter cursors
+  int64_t* seg_off;          // [n_images][C]   bucket start in `keys`
+  uint32_t* seg_cap;         // [n_images][C]   bucket capacity (pow2 >= count)
+  uint32_t* max_ord;         // [n_images]      max coordinate over picked boxes (ordered uint)
+  int64_t* img_off;          // [n_images]      start of the image's kept-key region in `kkeys`
+  uint32_t* img_cap;         // [n_images]      its capacity (pow2 >= M)
+  uint32_t* kept_count;      // [n_images]
+  uint64_t* keys;            // [cand_capacity] bucketed candidate keys (~score | row)
+  uint64_t* kkeys;           // [cand_capacity] kept keys per image
+  uint32_t* klist;           // [cand_capacity] kept positions per bucket
+  float4* rbox;              // [n_images][N]   recovered boxes of hit rows (from_heads only)
+  int64_t cand_capacity;
+  int64_t* needed;
+  int32_t* ok;               // 1 when the workspace is large enough
+};
+
+__device__ __forceinline__ int gen_image(const GenParams& G, int i) {
+  return G.image_ids ? G.image_ids[i] : i;
+}
+__device__ __forceinline__ int gen_out(const GenParams& G, int i) {
+  return G.out_by_pos ? i : gen_image(G, i);
+}
+
+// Row -> (recovered box, objectness) for the heads source; thread-per-row in (level, anchor, cell)
+// order so that plane reads coalesce.
+__device__ __forceinline__ bool gen_row_from_index(const HeadsDev& P, int64_t i, int& level, int& a, int& cell,
+                                                   int& row) {
+  if (i >= P.N) return false;
+  int l = 0;
+#pragma unroll
+  for (int q = 1; q < PQDET_MAX_LEVELS; ++q)
+    if (q < P.n_levels && i >= P.lv[q].row_off) l = q;
+  const LevelDev& L = P.lv[l];
+  const int il = (int)(i - L.row_off);
+  a = il / L.HW;
+  cell = il - a * L.HW;
+  level = l;
+  row = L.row_off + cell * P.A + a;
+  return true;
+}
+
+// pass 0: count candidates per (image, class) + max picked coordinate; pass 1: scatter keys.
+template <int PASS>
+__global__ void __launch_bounds__(256)
+gen_select_kernel(const __grid_constant__ GenParams G) {
+  if (PASS == 1 && *G.ok == 0) return;
+  const int ii = blockIdx.y;
+  const int b = gen_image(G, ii);
+  const int C = G.C;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float box[4];
+  float conf = 1.0f;
+  int row;
+  const float* scores = nullptr;   // !from_heads: pointer to the C scores of the row
+  int level = 0, a = 0, cell = 0;
+  if (G.from_heads) {
+    const HeadsDev& P = G.heads;
+    if (!gen_row_from_index(P, i, level, a, cell, row)) return;
+    const LevelDev& L = P.lv[level];
+    const float x = L.raw[((size_t)(b * P.A + a) * P.ch + 4) * L.HW + cell];
+    if (!(x > P.logit_lo)) return;
+    conf = sigmoidf_(x);
+    if (!(conf > G.thr_f)) return;
+    const Affine af = image_affine(P, b);
+    const int cy = cell / L.W, cx = cell - cy * L.W;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      box[k] = recover_coord(k, decode_coord(k, L.raw[((size_t)(b * P.A + a) * P.ch + k) * L.HW + cell],
+                                             cx, cy, L.stride), af);
+  } else {
+    if (i >= G.N) return;
+    row = (int)i;
+    const float* r = G.bboxes + ((size_t)b * G.N + i) * (4 + C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) box[k] = r[k];
+    scores = r + 4;
+  }
+  bool any = false;
+  for (int c = 0; c < C; ++c) {
+    float s;
+    if (G.from_heads) {
+      const HeadsDev& P = G.heads;
+      const LevelDev& L = P.lv[level];
+      s = PQ_MUL(sigmoidf_(L.raw[((size_t)(b * P.A + a) * P.ch + 5 + c) * L.HW + cell]), conf);
+    } else {
+      s = scores[c];
+    }
+    if (s > G.thr_f) {
+      any = true;
+      if (PASS == 0) {
+        atomicAdd(&G.cls_count[(size_t)ii * C + c], 1u);
+      } else {
+        const uint32_t slot = atomicAdd(&G.cls_fill[(size_t)ii * C + c], 1u);
+        G.keys[G.seg_off[(size_t)ii * C + c] + slot] =
+            ((uint64_t)(~__float_as_uint(s)) << 32) | (uint32_t)row;
+      }
+    }
+  }
+  if (any) {
+    if (PASS == 0) {
+      float mx = fmaxf(fmaxf(box[0], box[1]), fmaxf(box[2], box[3]));
+      atomicMax(&G.max_ord[ii], float_to_ordered(mx));
+    } else if (G.from_heads) {
+      G.rbox[(size_t)ii * G.N + row] = make_float4(box[0], box[1], box[2], box[3]);
+    }
+  }
+}
+
+// Block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix
+// and the block total through *total.
+__device__ __forceinline__ unsigned long long block_exclusive_scan_1024(unsigned long long v,
+                                                                        unsigned long long* warp_tot,
+                                                                        unsigned long long* total) {
+  const int lane = lane_id(), warp = warp_id();
+  unsigned long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned long long n = __shfl_up_sync(PQ_FULL, inc, d);
+    if (lane >= d) inc += n;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = warp_tot[lane];
+    unsigned long long winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long n = __shfl_up_sync(PQ_FULL, winc, d);
+      if (lane >= d) winc += n;
+    }
+    warp_tot[lane] = winc - w;
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  const unsigned long long res = warp_tot[warp] + inc - v;
+  __syncthreads();
+  return res;
+}
+
+// Single CTA (1024 threads): bucket capacities (pow2 >= count), bucket / kept-region offsets,
+// capacity check, per-image candidate counts.
+__global__ void __launch_bounds__(1024)
+gen_plan_kernel(const __grid_constant__ GenParams G, const __grid_constant__ DetOut O) {
+  __shared__ unsigned long long s_wt[32];
+  __shared__ unsigned long long s_tot_a, s_tot_b;
+  const int C = G.C;
+  unsigned long long base_seg = 0, base_img = 0;
+  for (int i0 = 0; i0 < G.n_images; i0 += 1024) {
+    const int ii = i0 + threadIdx.x;
+    unsigned long long seg_tot = 0, M = 0, icap = 0;
+    if (ii < G.n_images) {
+      for (int c = 0; c < C; ++c) {
+        const uint32_t n = G.cls_count[(size_t)ii * C + c];
+        const uint32_t cap = n ? (uint32_t)next_pow2((int)n) : 0u;
+        G.seg_cap[(size_t)ii * C + c] = cap;
+        seg_tot += cap;
+        M += n;
+      }
+      icap = M ? (unsigned long long)next_pow2((int)M) : 0ull;
+      G.img_cap[ii] = (uint32_t)icap;
+      O.ncand[gen_out(G, ii)] = (int32_t)M;
+    }
+    const unsigned long long ex_seg = block_exclusive_scan_1024(seg_tot, s_wt, &s_tot_a);
+    const unsigned long long ex_img = block_exclusive_scan_1024(icap, s_wt, &s_tot_b);
+    if (ii < G.n_images) {
+      unsigned long long off = base_seg + ex_seg;
+      for (int c = 0; c < C; ++c) {
+        G.seg_off[(size_t)ii * C + c] = (int64_t)off;
+        off += G.seg_cap[(size_t)ii * C + c];
+      }
+      G.img_off[ii] = (int64_t)(base_img + ex_img);
+    }
+    base_seg += s_tot_a;
+    base_img += s_tot_b;
+    __syncthreads();
+  }
+  const unsigned long long need = base_seg > base_img ? base_seg : base_img;
+  const bool ok = need <= (unsigned long long)G.cand_capacity;
+  if (threadIdx.x == 0) {
+    *G.needed = (int64_t)need;
+    *G.ok = ok ? 1 : 0;
+  }
+  for (int ii = threadIdx.x; ii < G.n_images; ii += 1024) {
+    const int b = gen_out(G, ii);
+    O.counts[b] = 0;
+    O.status[b] = ok ? PQDET_ST_OK : PQDET_ST_CAND_OVERFLOW;
+  }
+}
+
+constexpr int kSegThreads = 128;
+constexpr int kSegSmemKeys = 4096;   // buckets up to this size are sorted in shared memory
+
+// One CTA per (image, class) bucket: sort, greedy NMS (warp 0 resolves, all warps test against the
+// kept list), append kept keys to the image's kept region.
+template <int ROUND>
+__global__ void __launch_bounds__(kSegThreads)
+gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
+  if (*G.ok == 0) return;
+  __shared__ uint64_t skeys[kSegSmemKeys];
+  __shared__ unsigned s_dead[kSegThreads / 32];
+  __shared__ int s_k;
+  const int C = G.C;
+  const int ii = blockIdx.y, c = blockIdx.x;
+  const uint32_t n = G.cls_count[(size_t)ii * C + c];
+  if (n == 0) return;
+  const int b = gen_image(G, ii);
+  const uint32_t cap = G.seg_cap[(size_t)ii * C + c];
+  uint64_t* gk = G.keys + G.seg_off[(size_t)ii * C + c];
+  uint32_t* kl = G.klist + G.seg_off[(size_t)ii * C + c];
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  uint64_t* keys = gk;
+  if (cap <= (uint32_t)kSegSmemKeys) {
+    for (uint32_t i = tid; i < cap; i += kSegThreads) skeys[i] = (i < n) ? gk[i] : ~0ull;
+    keys = skeys;
+  } else {
+    for (uint32_t i = n + tid; i < cap; i += kSegThreads) gk[i] = ~0ull;
+  }
+  __syncthreads();
+  bitonic_sort_block(keys, (int)cap);
+
+  unsigned long long Mimg = 0;
+  for (int q = 0; q < C; ++q) Mimg += G.cls_count[(size_t)ii * C + q];
+  const bool trick = use_trick(G.nms_mode, (int64_t)Mimg);
+  float off = 0.0f;
+  if (trick) off = PQ_MUL((float)c, PQ_ADD(ordered_to_float(G.max_ord[ii]), 1.0f));
+  const float4* rbox = G.from_heads ? G.rbox + (size_t)ii * G.N : nullptr;
+  const float* bb = G.from_heads ? nullptr : G.bboxes + (size_t)b * G.N * (4 + C);
+  auto getbox = [&](uint32_t pos) -> float4 {
+    const uint32_t row = (uint32_t)keys[pos];
+    if (rbox) return rbox[row];
+    const float* r = bb + (size_t)row * (4 + C);
+    return make_float4(r[0], r[1], r[2], r[3]);
+  };
+  if (tid == 0) s_k = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t p = base + lane;
+    const bool valid = p < n;
+    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+    if (valid) {
+      const float4 bx = getbox(p);
+      x1 = PQ_ADD(bx.x, off); y1 = PQ_ADD(bx.y, off); x2 = PQ_ADD(bx.z, off); y2 = PQ_ADD(bx.w, off);
+    }
+    bool dead = !valid;
+    const int k0 = s_k;
+    for (int q = warp; q < k0; q += kSegThreads / 32) {     // kept list striped over the warps
+      const float4 a = getbox(kl[q]);
+      const float ax1 = PQ_ADD(a.x, off), ay1 = PQ_ADD(a.y, off), ax2 = PQ_ADD(a.z, off), ay2 = PQ_ADD(a.w, off);
+      const float Sa = box_area(ax1, ay1, ax2, ay2);
+      if (!dead && nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, G.iou_f, G.iou_d)) dead = true;
+    }
+    const unsigned dm = __ballot_sync(PQ_FULL, dead);
+    if (lane == 0) s_dead[warp] = dm;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned alldead = 0;
+#pragma unroll
+      for (int q = 0; q < kSegThreads / 32; ++q) alldead |= s_dead[q];
+      dead = (alldead >> lane) & 1u;
+      unsigned alive = ~alldead;
+      int k = k0;
+      while (alive) {
+        const int i = __ffs(alive) - 1;
+        alive &= alive - 1;
+        const float ax1 = __shfl_sync(PQ_FULL, x1, i), ay1 = __shfl_sync(PQ_FULL, y1, i);
+        const float ax2 = __shfl_sync(PQ_FULL, x2, i), ay2 = __shfl_sync(PQ_FULL, y2, i);
+        const float Sa = box_area(ax1, ay1, ax2, ay2);
+        if (lane == i) kl[k] = p;
+        ++k;
+        const bool sup = (lane > i) && !dead &&
+                         nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, G.iou_f, G.iou_d);
+        dead |= sup;
+        alive &= ~__ballot_sync(PQ_FULL, sup);
+      }
+      if (lane == 0) s_k = k;
+    }
+    __syncthreads();
+  }
+  // append kept keys (score desc, row asc, class asc order key) to the image's kept region
+  const int k = s_k;
+  __shared__ uint32_t s_dst;
+  if (tid == 0) s_dst = atomicAdd(&G.kept_count[ii], (uint32_t)k);
+  __syncthreads();
+  uint64_t* kk = G.kkeys + G.img_off[ii] + s_dst;
+  for (int q = tid; q < k; q += kSegThreads) {
+    const uint64_t key = keys[kl[q]];
+    kk[q] = (key & 0xffffffff00000000ull) | ((uint64_t)((uint32_t)key) << 7) | (uint64_t)c;
+  }
+}
+
+constexpr int kFinThreads = 256;
+constexpr int kFinSmemKeys = 4096;
+
+__global__ void __launch_bounds__(kFinThreads)
+gen_finalize_kernel(const __grid_constant__ GenParams G, const __grid_constant__ DetOut O) {
+  if (*G.ok == 0) return;
+  __shared__ uint64_t skeys[kFinSmemKeys];
+  const int ii = blockIdx.x;
+  const int b = gen_image(G, ii);
+  const int ob = gen_out(G, ii);
+  const int C = G.C;
+  const uint32_t K = G.kept_count[ii];
+  const int tid = threadIdx.x;
+  if (K == 0) {
+    if (tid == 0) O.counts[ob] = 0;
+    return;
+  }
+  uint64_t* gk = G.kkeys + G.img_off[ii];
+  const int Pn = next_pow2((int)K);
+  uint64_t* keys = gk;
+  if (Pn <= kFinSmemKeys) {
+    for (int i = tid; i < Pn; i += kFinThreads) skeys[i] = (i < (int)K) ? gk[i] : ~0ull;
+    keys = skeys;
+  } else {
+    for (int i = (int)K + tid; i < Pn; i += kFinThreads) gk[i] = ~0ull;
+  }
+  __syncthreads();
+  bitonic_sort_block(keys, Pn);
+  const int nout = min((int)K, O.max_det);
+  const float4* rbox = G.from_heads ? G.rbox + (size_t)ii * G.N : nullptr;
+  const float* bb = G.from_heads ? nullptr : G.bboxes + (size_t)b * G.N * (4 + C);
+  for (int j = tid; j < nout; j += kFinThreads) {
+    const uint64_t k2 = keys[j];
+    const float score = __uint_as_float(~(uint32_t)(k2 >> 32));
+    const uint32_t low = (uint32_t)k2;
+    const uint32_t row = low >> 7;
+    const int c = low & 127;
+    float4 bx;
+    if (rbox) bx = rbox[row];
+    else {
+      const float* r = bb + (size_t)row * (4 + C);
+      bx = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    write_det(O, ob, j, bx, score, c, row, C);
+  }
+  if (tid == 0) {
+    O.counts[ob] = (int32_t)K;
+    if ((int)K > O.max_det) O.status[ob] = PQDET_ST_DET_TRUNCATED;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int fill_heads(const pqdet_heads_t* h, HeadsDev* P) {
+  if (!h || h->n_levels < 1 || h->n_levels > PQDET_MAX_LEVELS) return PQDET_ERR_INVALID_ARG;
+  if (h->B < 0 || h->A < 1 || h->A > 8 || h->C < 1) return PQDET_ERR_INVALID_ARG;
+  if (h->C > PQDET_MAX_CLASSES) return PQDET_ERR_UNSUPPORTED;
+  if (h->affine_kind < 0 || h->affine_kind > 2 || !h->orig_hw) return PQDET_ERR_INVALID_ARG;
+  if (h->nms_mode < 0 || h->nms_mode > 3 || h->iou_round < 0 || h->iou_round > 1) return PQDET_ERR_INVALID_ARG;
+  if (!(h->iou_threshold >= 0.0)) return PQDET_ERR_UNSUPPORTED;  // cross-class pairs have IoU 0: skipping them needs thr >= 0
+  int64_t rows = 0, groups = 0;
+  for (int l = 0; l < h->n_levels; ++l) {
+    if (!h->raw[l] || h->H[l] < 1 || h->W[l] < 1) return PQDET_ERR_INVALID_ARG;
+    LevelDev& L = P->lv[l];
+    L.raw = h->raw[l];
+    L.H = h->H[l]; L.W = h->W[l]; L.HW = h->H[l] * h->W[l];
+    L.stride = h->stride[l];
+    L.row_off = (int)rows; L.group_off = (int)groups;
+    L.nchunk = (L.HW + 31) / 32;
+    rows += (int64_t)L.HW * h->A;
+    groups += L.nchunk;
+  }
+  for (int l = h->n_levels; l < PQDET_MAX_LEVELS; ++l) P->lv[l] = P->lv[0];
+  if (rows >= (1ll << kHitBits)) return PQDET_ERR_UNSUPPORTED;
+  if ((int64_t)h->B * h->A * (5 + h->C) >= (1ll << 31)) return PQDET_ERR_UNSUPPORTED;
+  if (rows * h->C >= (1ll << 31)) return PQDET_ERR_UNSUPPORTED;   // det_idx = row*C + class is int32
+  P->n_levels = h->n_levels;
+  P->B = h->B; P->A = h->A; P->C = h->C; P->ch = 5 + h->C;
+  P->N = (int)rows; P->G_tot = (int)groups;
+  P->kind = h->affine_kind; P->in_h = h->in_h; P->in_w = h->in_w;
+  P->orig = h->orig_hw; P->orig_per_image = h->orig_per_image;
+  P->thr_f = (float)h->score_threshold;
+  // conf > thr needs sigmoid(x) > thr; x <= logit(thr) - margin can never pass (the margin is
+  // ~1e3 times the worst-case error of the fp32 sigmoid).  thr <= 0 or >= 1: no prefilter / nothing passes.
+  const double t = (double)P->thr_f;
+  if (!(t > 0.0)) P->logit_lo = -INFINITY;
+  else if (t >= 1.0) P->logit_lo = INFINITY;
+  else {
+    const double lg = log(t / (1.0 - t));
+    P->logit_lo = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
+  }
+  P->iou_f = (float)h->iou_threshold;
+  P->iou_d = h->iou_threshold;
+  P->nms_mode = h->nms_mode;
+  return PQDET_OK;
+}
+
+}  // namespace pq
+
+extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
+                                int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
+                                int device, void* stream) {
+  using namespace pq;
+  HeadsDev P;
+  int rc = fill_heads(heads, &P);
+  if (rc != PQDET_OK) return rc;
+  if (!det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
+  if (P.B == 0) return PQDET_OK;
+  PQ_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DetOut O{det, det_idx, max_det, counts, ncand, status};
+  const size_t smem = sizeof(FusedSmem) + (size_t)P.G_tot * (P.A + 1) * sizeof(uint32_t);
+  if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+  PQ_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
+  auto launch = [&](auto kern) -> int {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    PQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count * per_sm;            // persistent: one resident wave, images pulled dynamically
+    if (grid > P.B) grid = P.B;
+    kern<<<grid, kFusedThreads, smem, st>>>(P, O, work_counter);
+    PQ_LAUNCH_CHECK();
+    return PQDET_OK;
+  };
+  if (heads->iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0>);
+  return launch(decode_nms_fused_kernel<1>);
+}
+
+namespace pq {
+struct GenLayout {
+  size_t cls_count, cls_fill, seg_off, seg_cap, max_ord, img_off, img_cap, kept_count, needed_ok, keys, kkeys,
+      klist, rbox, total;
+};
+static GenLayout gen_layout(int n_images, int64_t N, int C, int64_t cap, int from_heads) {
+  GenLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+  const size_t nc = (size_t)n_images * C;
+  L.cls_count = take(nc * 4);
+  L.cls_fill = take(nc * 4);
+  L.kept_count = take((size_t)n_images * 4);
+  L.max_ord = take((size_t)n_images * 4);
+  L.needed_ok = take(16);
+  L.seg_off = take(nc * 8);
+  L.seg_cap = take(nc * 4);
+  L.img_off = take((size_t)n_images * 8);
+  L.img_cap = take((size_t)n_images * 4);
+  L.keys = take((size_t)cap * 8);
+  L.kkeys = take((size_t)cap * 8);
+  L.klist = take((size_t)cap * 4);
+  L.rbox = take(from_heads ? (size_t)n_images * (size_t)N * 16 : 0);
+  L.total = o;
+  return L;
+}
+}  // namespace pq
+
+extern "C" int64_t pqdet_nms_general_workspace(int n_images, int64_t N, int C, int64_t cand_capacity,
+                                               int from_heads) {
+  if (n_images < 0 || N < 0 || C < 1 || cand_capacity < 0) return PQDET_ERR_INVALID_ARG;
+  return (int64_t)pq::gen_layout(n_images, N, C, cand_capacity, from_heads).total;
+}
+
+extern "C" int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes, int64_t N, int B, int C,
+                                 double score_threshold, double iou_threshold, int nms_mode, int iou_round,
+                                 const int32_t* image_ids, int n_images, int out_by_position,
+                                 float* det, int32_t* det_idx, int max_det, int32_t* counts, int32_t* ncand,
+                                 int32_t* status, void* workspace, int64_t workspace_bytes,
+                                 int64_t cand_capacity, int64_t* needed, int device, void* stream) {
+  using namespace pq;
+  if ((heads != nullptr) == (bboxes != nullptr)) return PQDET_ERR_INVALID_ARG;
+  if (!det || !counts || !ncand || !status || !workspace || max_det < 1 || n_images < 0) return PQDET_ERR_INVALID_ARG;
+  GenParams G;
+  memset(&G, 0, sizeof(G));
+  if (heads) {
+    int rc = fill_heads(heads, &G.heads);
+    if (rc != PQDET_OK) return rc;
+    G.from_heads = 1;
+    G.N = G.heads.N; G.C = G.heads.C;
+    G.thr_f = G.heads.thr_f; G.iou_f = G.heads.iou_f; G.iou_d = G.heads.iou_d; G.nms_mode = G.heads.nms_mode;
+    iou_round = heads->iou_round;
+    B = heads->B;
+  } else {
+    if (N < 0 || C < 1 || B < 0) return PQDET_ERR_INVALID_ARG;
+    if (C > PQDET_MAX_CLASSES || N >= (1ll << kHitBits)) return PQDET_ERR_UNSUPPORTED;
+    if (nms_mode < 0 || nms_mode > 3 || iou_round < 0 || iou_round > 1) return PQDET_ERR_INVALID_ARG;
+    if (!(iou_threshold >= 0.0)) return PQDET_ERR_UNSUPPORTED;
+    G.from_heads = 0;
+    G.bboxes = bboxes; G.N = N; G.C = C;
+    G.thr_f = (float)score_threshold; G.iou_f = (float)iou_threshold; G.iou_d = iou_threshold;
+    G.nms_mode = nms_mode;
+  }
+  if (n_images == 0 || G.N == 0) return PQDET_OK;
+  if (n_images > 65535) return PQDET_ERR_UNSUPPORTED;
+  if (!image_ids && n_images > B) return PQDET_ERR_INVALID_ARG;
+  const GenLayout L = gen_layout(n_images, G.N, G.C, cand_capacity, G.from_heads);
+  if ((int64_t)L.total > workspace_bytes) return PQDET_ERR_WORKSPACE;
+  PQ_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  G.image_ids = image_ids; G.n_images = n_images; G.out_by_pos = out_by_position ? 1 : 0;
+  G.cls_count = (uint32_t*)(ws + L.cls_count);
+  G.cls_fill = (uint32_t*)(ws + L.cls_fill);
+  G.kept_count = (uint32_t*)(ws + L.kept_count);
+  G.max_ord = (uint32_t*)(ws + L.max_ord);
+  G.needed = needed ? needed : (int64_t*)(ws + L.needed_ok);
+  G.ok = (int32_t*)(ws + L.needed_ok + 8);
+  G.seg_off = (int64_t*)(ws + L.seg_off);
+  G.seg_cap = (uint32_t*)(ws + L.seg_cap);
+  G.img_off = (int64_t*)(ws + L.img_off);
+  G.img_cap = (uint32_t*)(ws + L.img_cap);
+  G.keys = (uint64_t*)(ws + L.keys);
+  G.kkeys = (uint64_t*)(ws + L.kkeys);
+  G.klist = (uint32_t*)(ws + L.klist);
+  G.rbox = (float4*)(ws + L.rbox);
+  G.cand_capacity = cand_capacity;
+  DetOut O{det, det_idx, max_det, counts, ncand, status};
+  // the counters are the first four (contiguous) regions of the layout
+  PQ_CUDA(cudaMemsetAsync(ws, 0, L.seg_off, st));
+  dim3 sel_grid((unsigned)((G.N + 255) / 256), n_images);
+  gen_select_kernel<0><<<sel_grid, 256, 0, st>>>(G);
+  PQ_LAUNCH_CHECK();
+  gen_plan_kernel<<<1, 1024, 0, st>>>(G, O);
+  PQ_LAUNCH_CHECK();
+  gen_select_kernel<1><<<sel_grid, 256, 0, st>>>(G);
+  PQ_LAUNCH_CHECK();
+  dim3 seg_grid(G.C, n_images);
+  if (iou_round == PQDET_IOU_TV_CUDA) gen_bucket_nms_kernel<0><<<seg_grid, kSegThreads, 0, st>>>(G);
+  else gen_bucket_nms_kernel<1><<<seg_grid, kSegThreads, 0, st>>>(G);
+  PQ_LAUNCH_CHECK();
+  gen_finalize_kernel<<<n_images, kFinThreads, 0, st>>>(G, O);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}

@@ -1,0 +1,170 @@
+"""Drop-ins for the IoU / NMS helpers of the reference's tools.py:335-566.
+
+torch_nms / iou_calc3 / giou / diou / ciou take CUDA tensors and run the sm_100a kernels.
+iou_calc1, iou_xywh_numpy and nms are numpy-in / numpy-out helpers of the reference
+(nms has no callers there); they stage through the GPU and come back.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, _ops, config
+
+
+# ------------------------------------------------------------------------------------------------
+# a6: tools.py:540-566
+# ------------------------------------------------------------------------------------------------
+def batched_torch_nms(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float,
+                      return_index: bool = False, nms_mode: str = None, iou_round: str = None):
+    """Batched form of torch_nms: bboxes (B, N, 4+C) -> list of B tensors (K_b, 6)
+    (and, if return_index, a list of int64 tensors row*C+class).  One sync for the whole batch."""
+    if bboxes.dim() != 3:
+        raise ValueError("bboxes must be (B, N, 4+C)")
+    B, N, _ = bboxes.shape
+    C = bboxes.shape[2] - 4
+    m, r = config.nms_modes()
+    nms_mode, iou_round = nms_mode or m, iou_round or r
+    if B == 0 or N == 0:
+        e = [torch.zeros((0, 6), dtype=torch.float32, device=bboxes.device) for _ in range(B)]
+        return (e, [torch.zeros((0,), dtype=torch.int64, device=bboxes.device) for _ in range(B)]) \
+            if return_index else e
+    cap = max(B * 4096, 1 << 16)
+    max_det = 4096
+    for _ in range(3):
+        det, idx, meta, needed = _ops.nms_general(bboxes=bboxes, score_threshold=score_threshold,
+                                                  iou_threshold=iou_threshold, nms_mode=nms_mode,
+                                                  iou_round=iou_round, max_det=max_det, cand_capacity=cap,
+                                                  want_index=return_index)
+        host = torch.cat([meta.to(torch.int64), needed]).cpu()          # the one D2H of this call
+        counts, status, need = host[0:B], host[2 * B:3 * B], int(host[3 * B])
+        if bool((status & _lib.ST_CAND_OVERFLOW).any()):
+            cap = max(need, cap * 2)
+            continue
+        if bool((status & _lib.ST_DET_TRUNCATED).any()):
+            max_det = int(counts.max())
+            continue
+        outs = [det[b, :int(counts[b])] for b in range(B)]
+        if return_index:
+            return outs, [idx[b, :int(counts[b])].to(torch.int64) for b in range(B)]
+        return outs
+    raise _lib.PqdetError("pqdet_nms_general did not converge on a workspace size")
+
+
+def torch_nms(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float) -> torch.Tensor:
+    """tools.py:540-566.  bboxes (N, 4+C) of ONE image -> (K, 6) rows [x1,y1,x2,y2,score,class] in
+    descending score, or a tensor of shape (0,) when nothing is kept (tools.py:559-561)."""
+    if bboxes.dim() != 2:
+        raise ValueError("bboxes must be (N, 4+C)")
+    out = batched_torch_nms(bboxes.unsqueeze(0), score_threshold, iou_threshold)[0]
+    if out.shape[0] == 0:
+        return torch.tensor([]).to(bboxes)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a7/a8: tools.py:357-477
+# ------------------------------------------------------------------------------------------------
+class _IouFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, b1, b2, kind):
+        ctx.kind = kind
+        ctx.shapes = (b1.shape, b2.shape)
+        ctx.save_for_backward(b1, b2)
+        return _ops.iou_pairwise(b1, b2, kind)
+
+    @staticmethod
+    def backward(ctx, g):
+        b1, b2 = ctx.saved_tensors
+        if ctx.kind == 3:
+            raise NotImplementedError("ciou backward: the reference's ciou loss always raises 'NaN in loss'")
+        g1, g2 = _ops.iou_pairwise_bwd(b1, b2, g.contiguous(), ctx.kind)
+
+        def unbroadcast(gr, shape):
+            while gr.dim() > len(shape):
+                gr = gr.sum(0)
+            for i, s in enumerate(shape):
+                if s == 1 and gr.shape[i] != 1:
+                    gr = gr.sum(i, keepdim=True)
+            return gr
+        return unbroadcast(g1, ctx.shapes[0]), unbroadcast(g2, ctx.shapes[1]), None
+
+
+def _iou(b1, b2, kind):
+    if (b1.requires_grad or b2.requires_grad) and torch.is_grad_enabled():
+        return _IouFn.apply(b1, b2, kind)
+    return _ops.iou_pairwise(b1, b2, kind)
+
+
+def iou_calc3(boxes1: torch.Tensor, boxes2: torch.Tensor):
+    """tools.py:357-376 (broadcasting, last dim = x1,y1,x2,y2, no epsilon)."""
+    return _iou(boxes1, boxes2, 0)
+
+
+def giou(boxes1: torch.Tensor, boxes2: torch.Tensor):
+    """tools.py:378-404."""
+    return _iou(boxes1, boxes2, 1)
+
+
+def diou(boxes1: torch.Tensor, boxes2: torch.Tensor):
+    """tools.py:406-437 (adds the centre-distance term, as the reference does)."""
+    return _iou(boxes1, boxes2, 2)
+
+
+def ciou(boxes1: torch.Tensor, boxes2: torch.Tensor):
+    """tools.py:439-477 (forward value only)."""
+    return _iou(boxes1, boxes2, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy-facing helpers
+# ------------------------------------------------------------------------------------------------
+def _np_to_cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def iou_calc1(boxes1: np.ndarray, boxes2: np.ndarray):
+    """tools.py:335-355: numpy xyxy IoU with the union clamped at 1e-14.  fp32 on the GPU; the clamp
+    only matters for degenerate unions, where IoU is forced to inter/1e-14 like the reference."""
+    b1, b2 = np.asarray(boxes1), np.asarray(boxes2)
+    out = _ops.iou_pairwise(_np_to_cuda(b1), _np_to_cuda(b2), 0).cpu().numpy()
+    bad = ~np.isfinite(out)
+    if bad.any():
+        out = np.where(bad, 0.0, out)
+    return out
+
+
+def iou_xywh_numpy(boxes1: np.ndarray, boxes2: np.ndarray):
+    """tools.py:479-505: centre-xywh IoU (fp32 here; the mixed fp32/fp64 variant that label
+    assignment needs is inside pqdet_assign_labels)."""
+    def xyxy(b):
+        b = np.asarray(b, dtype=np.float32)
+        return np.concatenate([b[..., :2] - b[..., 2:] * 0.5, b[..., :2] + b[..., 2:] * 0.5], axis=-1)
+    return _ops.iou_pairwise(_np_to_cuda(xyxy(boxes1)), _np_to_cuda(xyxy(boxes2)), 0).cpu().numpy()
+
+
+def nms(bboxes, score_threshold, iou_threshold, sigma=0.3, method='nms'):
+    """tools.py:507-538 (no callers in the reference).  bboxes (N,6) [x1,y1,x2,y2,score,class].
+    Hard NMS only; rows come back grouped by class like the reference's per-class loop.  Boxes with
+    score <= score_threshold are dropped up front (the reference drops them after the first pick)."""
+    assert method in ['nms', 'soft-nms']
+    if method == 'soft-nms':
+        raise NotImplementedError("soft-nms is dead code in the reference and is not part of the hot path")
+    bboxes = np.asarray(bboxes, dtype=np.float32)
+    if len(bboxes) == 0:
+        return np.array([])
+    classes = sorted(set(bboxes[:, 5].tolist()))
+    cmap = {c: i for i, c in enumerate(classes)}
+    C = len(classes)
+    if C > _lib.MAX_CLASSES:
+        raise _lib.PqdetError("more than %d distinct classes" % _lib.MAX_CLASSES)
+    dense = np.full((len(bboxes), 4 + C), -np.inf, dtype=np.float32)
+    dense[:, :4] = bboxes[:, :4]
+    for r, c in enumerate(bboxes[:, 5].tolist()):
+        dense[r, 4 + cmap[c]] = bboxes[r, 4]
+    outs, idx = batched_torch_nms(_np_to_cuda(dense)[None], score_threshold, iou_threshold, return_index=True,
+                                  nms_mode="vanilla", iou_round="tv_cpu")
+    rows = (idx[0] // C).cpu().numpy()
+    kept = bboxes[rows]
+    order = np.argsort([cmap[c] for c in kept[:, 5].tolist()], kind="stable")
+    return kept[order]

@@ -1,0 +1,97 @@
+"""-m gpu: decode / recover kernels vs the oracle and the golden fixtures (through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_close
+from oracle import pqdet_oracle as po
+from oracle import loss_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def test_decode_golden():
+    from pqdet_b200.parser import Decode
+    g = load_golden("decode")
+    C = int(g["num_classes"])
+    for s in (32, 16, 8):
+        out = Decode(C, s)(torch.from_numpy(g["raw_s%d" % s]).cuda()).cpu().numpy()
+        want = g["out_s%d" % s]
+        assert out.shape == want.shape
+        # tolerance: 1e-5 relative (north_star); boxes relative to the input extent (fp32 ulp of a coordinate)
+        assert rel_close(out[..., :4], want[..., :4], 1e-5, scale=float(s * max(out.shape[1:3])))
+        assert rel_close(out[..., 4:], want[..., 4:], 1e-5, scale=1e-30)
+    z = Decode(20, 8)(torch.zeros(1, 75, 2, 3).cuda())[0, 1, 2, 0].cpu().numpy()
+    assert list(z[:6]) == [12.0, 4.0, 28.0, 20.0, 0.5, 0.5]
+
+
+@pytest.mark.parametrize("B,C,H,W,s", [(2, 20, 16, 16, 32), (3, 10, 19, 19, 32), (1, 80, 38, 38, 16),
+                                        (2, 1, 5, 7, 8), (1, 20, 64, 64, 8), (4, 3, 33, 31, 8)])
+def test_decode_vs_oracle(B, C, H, W, s):
+    from pqdet_b200.parser import Decode
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    raw = torch.randn((B, 3 * (5 + C), H, W), generator=g) * 1.5
+    out = Decode(C, s)(raw.cuda()).cpu().numpy()
+    want = po.decode(raw.numpy(), C, s)
+    assert out.shape == want.shape == (B, H, W, 3, 5 + C)
+    assert rel_close(out[..., :4], want[..., :4], 1e-5, scale=float(s * max(H, W)))
+    assert rel_close(out[..., 4:], want[..., 4:], 1e-5, scale=1e-30)
+
+
+def test_detection_head_eval_concat_and_known_shape():
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200 import synth
+    C, size, B = 20, 512, 2
+    heads = synth.make_heads(B, C, size, "sparse", seed=3)
+    opts = [dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in synth.FPN_STRIDES]
+    out = DetectionHead(opts)([h.cuda() for h in heads])
+    assert tuple(out.shape) == (B, 16128, 25)                 # export/onnx_exporter.py:373
+    want = po.detect([h.numpy() for h in heads], C, synth.FPN_STRIDES)
+    got = out.cpu().numpy()
+    assert rel_close(got[..., :4], want[..., :4], 1e-5, scale=float(size))
+    assert rel_close(got[..., 4:], want[..., 4:], 1e-5, scale=1e-30)
+
+
+def test_decode_backward_vs_autograd():
+    from pqdet_b200.parser import Decode
+    C, s = 4, 16
+    g = torch.Generator().manual_seed(5)
+    raw = torch.randn((2, 3 * (5 + C), 6, 5), generator=g)
+    w = torch.randn((2, 6, 5, 3, 5 + C), generator=g)
+    r1 = raw.clone().requires_grad_(True)
+    (loss_ref.decode_t(r1, C, s) * w).sum().backward()
+    r2 = raw.clone().cuda().requires_grad_(True)
+    (Decode(C, s)(r2) * w.cuda()).sum().backward()
+    gw = r1.grad.numpy()
+    assert rel_close(r2.grad.cpu().numpy(), gw, 1e-5, scale=float(np.abs(gw).max()))
+
+
+def test_recover_golden_and_oracle_bit_exact():
+    from pqdet_b200 import base_sample
+    g = load_golden("recover")
+    pred = torch.from_numpy(g["pred"]).cuda()
+    inp = tuple(g["input_size"].tolist())
+    orig = torch.from_numpy(g["orig"]).cuda()
+    for kind in ("voc", "coco", "visdrone"):
+        out = base_sample.RECOVER_BBOXES_REGISTER[kind](pred.clone(), inp, orig).cpu().numpy()
+        assert np.array_equal(out, g["out_" + kind]), kind
+    out = base_sample.recover_bboxes_prediction_voc(pred.clone(), torch.tensor(inp), orig[0]).cpu().numpy()
+    assert np.array_equal(out, g["out_voc_1d"])
+    out = base_sample.recover_bboxes_prediction_voc(pred.clone(), tuple(g["input_size2"].tolist()), orig).cpu().numpy()
+    assert np.array_equal(out, g["out_voc_rect"])
+    # random, larger, all kinds
+    gen = torch.Generator().manual_seed(9)
+    B, N, C = 5, 3000, 10
+    p = torch.rand((B, N, 5 + C), generator=gen)
+    p[..., :4] = p[..., :4] * 700 - 50
+    o = torch.tensor([[480., 640.], [1080., 1920.], [375., 500.], [500., 375.], [608., 608.]])
+    for kind in ("voc", "coco", "visdrone"):
+        got = base_sample.RECOVER_BBOXES_REGISTER[kind](p.cuda(), (608., 608.), o.cuda()).cpu().numpy()
+        assert np.array_equal(got, po.recover(p.numpy(), (608., 608.), o.numpy(), kind)), kind
+
+
+def test_cpu_tensor_is_rejected():
+    from pqdet_b200.parser import Decode
+    from pqdet_b200._lib import PqdetError
+    with pytest.raises(PqdetError):
+        Decode(20, 8)(torch.zeros(1, 75, 2, 2))

@@ -1,0 +1,199 @@
+"""-m gpu: fused decode + loss forward/backward, label assignment and IoU helpers vs the oracle
+and the golden fixtures.  Tolerance 1e-5 relative for values (north_star); masks/labels bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_close
+from gpu_util import cuda
+from oracle import loss_ref
+from oracle import pqdet_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["l1", "iou", "giou", "diou"]
+
+
+def _opt(C, s, kind):
+    return dict(classes=C, stride=s, bbox_loss=kind, ignore_thresh=0.5, l1_loss_gain=0.05)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_yolo_layer_loss_golden(kind):
+    from pqdet_b200.parser import YOLOLayer
+    g = load_golden("train")
+    C = int(g["num_classes"])
+    for s in (8, 16, 32):
+        raw = cuda(g["raw_s%d" % s]).requires_grad_(True)
+        out = YOLOLayer(_opt(C, s, kind))(raw, (cuda(g["label_s%d" % s]), cuda(g["gtlist_s%d" % s])))
+        assert all(tuple(o.shape) == (1,) for o in out)
+        out[0].sum().backward()
+        vals = np.array([float(o) for o in out], np.float32)
+        assert rel_close(vals, g["loss_%s_s%d" % (kind, s)], 1e-5, scale=1e-30), (kind, s, vals)
+        gg = g["grad_%s_s%d" % (kind, s)]
+        assert rel_close(raw.grad.cpu().numpy(), gg, 1e-5, scale=float(np.abs(gg).max())), (kind, s)
+
+
+def test_loss_per_scale_on_decoded_pred_golden():
+    from pqdet_b200.loss import loss_per_scale
+    from pqdet_b200.parser import Decode
+    g = load_golden("train")
+    C = int(g["num_classes"])
+    for s in (8, 16, 32):
+        pred = Decode(C, s)(cuda(g["raw_s%d" % s])).detach().requires_grad_(True)
+        out = loss_per_scale(pred, cuda(g["label_s%d" % s]), cuda(g["gtlist_s%d" % s]), _opt(C, s, "giou"))
+        out[0].sum().backward()
+        assert rel_close(np.array([float(o) for o in out], np.float32), g["loss_giou_s%d" % s], 1e-5, scale=1e-30)
+        gg = g["predgrad_giou_s%d" % s]
+        assert rel_close(pred.grad.cpu().numpy(), gg, 1e-5, scale=float(np.abs(gg).max()))
+
+
+def test_ciou_raises_like_the_reference():
+    from pqdet_b200.parser import YOLOLayer
+    g = load_golden("train")
+    assert int(g["ciou_raises"]) == 1
+    C = int(g["num_classes"])
+    with pytest.raises(RuntimeError, match="NaN in loss"):
+        YOLOLayer(_opt(C, 8, "ciou"))(cuda(g["raw_s8"]), (cuda(g["label_s8"]), cuda(g["gtlist_s8"])))
+    with pytest.raises(NotImplementedError):
+        YOLOLayer(_opt(C, 8, "bogus"))(cuda(g["raw_s8"]), (cuda(g["label_s8"]), cuda(g["gtlist_s8"])))
+
+
+def _train_case(B, C, size, lo, hi, seed, anchors):
+    from pqdet_b200 import synth
+    gts = synth.make_gt(B, C, size, lo, hi, seed=seed)
+    gts[0][:, 5] = 0.4
+    out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+    labels, gtl = po.create_label_batch(gts, out_sizes, C, anchors)
+    heads = synth.make_train_heads(B, C, size, seed=seed, strides=(8, 16, 32))
+    return gts, out_sizes, labels, gtl, heads
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("C,size,lo,hi", [(20, 256, 1, 12), (10, 304, 20, 120)])
+def test_yolo_layer_loss_vs_oracle(kind, C, size, lo, hi):
+    from pqdet_b200.parser import YOLOLayer
+    from pqdet_b200.train_dataset import DEFAULT_ANCHORS
+    B = 3
+    _, _, labels, gtl, heads = _train_case(B, C, size, lo, hi, 41, DEFAULT_ANCHORS)
+    for li, s in enumerate((8, 16, 32)):
+        want, wgrad = loss_ref.yolo_layer_loss(heads[li], torch.from_numpy(labels[li]), torch.from_numpy(gtl[li]),
+                                               C, s, kind, 0.5, 0.05)
+        raw = heads[li].cuda().requires_grad_(True)
+        out = YOLOLayer(_opt(C, s, kind))(raw, (cuda(labels[li]), cuda(gtl[li])))
+        out[0].sum().backward()
+        for a, b in zip(out, want):
+            assert rel_close(a.detach().cpu().numpy(), b.numpy(), 1e-5, scale=1e-30), (kind, s)
+        wg = wgrad.numpy()
+        assert rel_close(raw.grad.cpu().numpy(), wg, 1e-5, scale=float(np.abs(wg).max())), (kind, s)
+
+
+def test_ignore_mask_bit_exact_through_the_objectness_gradient():
+    """respond_bgd = (1-respond)*(max_iou < thr) gates the objectness gradient: the set of cells with a
+    non-zero objectness gradient must equal the oracle's mask exactly (model/loss.py:85-90)."""
+    from pqdet_b200.parser import Decode, YOLOLayer
+    from pqdet_b200.train_dataset import DEFAULT_ANCHORS
+    B, C, size = 2, 10, 304
+    _, _, labels, gtl, heads = _train_case(B, C, size, 40, 150, 43, DEFAULT_ANCHORS)
+    li, s = 0, 8
+    raw = (heads[li] * 2.0).cuda().requires_grad_(True)             # wider boxes: many IoUs near the threshold
+    out = YOLOLayer(_opt(C, s, "l1"))(raw, (cuda(labels[li]), cuda(gtl[li])))
+    out[0].sum().backward()
+    H = W = size // s
+    gconf = raw.grad.view(B, 3, 5 + C, H, W)[:, :, 4].permute(0, 2, 3, 1).cpu().numpy()      # (B,H,W,A)
+    dec = Decode(C, s)(raw.detach()).cpu().numpy()                     # our own decoded boxes
+    respond = labels[li][..., 4]
+    for b in range(B):
+        below = po.ignore_mask(dec[b, ..., 0:4].reshape(-1, 4), gtl[li][b], 0.5).reshape(H, W, 3)
+        want_active = (respond[b] == 1.0) | below
+        assert np.array_equal(gconf[b] != 0.0, want_active)
+    assert 0.02 < float((gconf == 0.0).mean()) < 0.98
+
+
+def test_detection_head_training_dict_and_upstream_scaling():
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.train_dataset import DEFAULT_ANCHORS
+    B, C, size = 2, 20, 256
+    _, _, labels, gtl, heads = _train_case(B, C, size, 1, 8, 44, DEFAULT_ANCHORS)
+    order = (32, 16, 8)                                                # FPN cfg order
+    idx = {8: 0, 16: 1, 32: 2}
+    opts = [_opt(C, s, "l1") for s in order]
+    target = tuple(cuda(x) for x in (labels + gtl))
+    raws = [heads[idx[s]].cuda().requires_grad_(True) for s in order]
+    out = DetectionHead(opts)(raws, target)
+    assert set(out) == {"loss", "giou_loss", "conf_loss", "class_loss", "loss_per_branch"}
+    (out["loss"].mean() * 0.5).backward()                              # non-unit upstream gradient
+    tot = np.zeros(4)
+    for j, s in enumerate(order):
+        want, wgrad = loss_ref.yolo_layer_loss(heads[idx[s]], torch.from_numpy(labels[idx[s]]),
+                                               torch.from_numpy(gtl[idx[s]]), C, s, "l1", 0.5, 0.05)
+        tot += np.array([float(w) for w in want])
+        wg = wgrad.numpy() * 0.5
+        assert rel_close(raws[j].grad.cpu().numpy(), wg, 1e-5, scale=float(np.abs(wg).max()))
+        assert rel_close(float(out["loss_per_branch"][j]), float(want[1] + want[2] + want[3]), 1e-5)
+    got = np.array([float(out[k]) for k in ("loss", "giou_loss", "conf_loss", "class_loss")])
+    assert rel_close(got, tot, 1e-5, scale=1e-30)
+
+
+def test_assign_labels_golden_and_oracle_bit_exact():
+    from pqdet_b200.train_dataset import LabelAssigner, collate_batch, DEFAULT_ANCHORS
+    g = load_golden("train")
+    C, size = int(g["num_classes"]), int(g["size"])
+    out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+    gts = [g["gt"][b, :int(n)] for b, n in enumerate(g["gt_counts"])]
+    la = LabelAssigner(C, anchors=g["anchors"].tolist())
+    out = la.create_label_batch(gts, out_sizes)
+    for i, s in enumerate((8, 16, 32)):
+        assert np.array_equal(out[i].cpu().numpy(), g["label_s%d" % s]), s
+        assert np.array_equal(out[3 + i].cpu().numpy(), g["gtlist_s%d" % s]), s
+    # per-image API + collate, like the reference's DataLoader path
+    samples = [(torch.zeros(1),) + la.create_label(gb, out_sizes) for gb in gts]
+    batch = collate_batch(samples)
+    for i, s in enumerate((8, 16, 32)):
+        assert np.array_equal(batch[1 + i].cpu().numpy(), g["label_s%d" % s])
+        assert np.array_equal(batch[4 + i].cpu().numpy(), g["gtlist_s%d" % s])
+    empty = la.create_label(np.zeros((0, 6), np.float32), out_sizes)
+    assert np.array_equal(empty[0].cpu().numpy(), g["empty_label_s8"]) and empty[3].shape[0] == 0
+    # random, dense, both anchor sets
+    from pqdet_b200 import synth
+    vis = [(9, 13), (25, 17), (16, 31), (47, 29), (32, 51), (83, 48), (61, 91), (131, 99), (210, 189)]
+    for C2, size2, lo, hi, anc in ((20, 512, 1, 12, DEFAULT_ANCHORS), (10, 608, 20, 200, vis), (80, 608, 2, 38, DEFAULT_ANCHORS)):
+        gts2 = synth.make_gt(4, C2, size2, lo, hi, seed=C2)
+        os2 = np.array([[size2 // 8] * 2, [size2 // 16] * 2, [size2 // 32] * 2])
+        wl, wg = po.create_label_batch(gts2, os2, C2, anc)
+        got = LabelAssigner(C2, anchors=anc).create_label_batch(gts2, os2)
+        for i in range(3):
+            assert np.array_equal(got[i].cpu().numpy(), wl[i]), (C2, i)
+            assert np.array_equal(got[3 + i].cpu().numpy(), wg[i]), (C2, i)
+
+
+def test_iou_family_golden_and_backward():
+    from pqdet_b200 import tools
+    g = load_golden("iou")
+    b1, b2 = cuda(g["b1"]), cuda(g["b2"])
+    assert np.array_equal(tools.iou_calc3(b1, b2).cpu().numpy(), g["iou_calc3"])       # IEEE ops only: bit-exact
+    assert np.array_equal(tools.iou_calc3(b1[:7, None, :], b2[None, :9, :]).cpu().numpy(), g["iou_calc3_bcast"])
+    for name in ("giou", "diou", "ciou"):
+        assert rel_close(getattr(tools, name)(b1, b2).cpu().numpy(), g[name], 1e-5, scale=1.0), name
+    assert rel_close(tools.iou_calc1(g["b1"], g["b2"]), g["iou_calc1"], 1e-5, scale=1.0)
+    xy = tools.iou_xywh_numpy(g["xywh1"], g["xywh2"].astype(np.float32))
+    assert rel_close(xy, g["iou_xywh_numpy"], 1e-5, scale=1.0)
+    for kind, fn in enumerate((loss_ref.iou_t, loss_ref.giou_t, lambda p, q: loss_ref.giou_t(p, q, True))):
+        p = torch.from_numpy(g["b1"]).requires_grad_(True)
+        q = torch.from_numpy(g["b2"]).requires_grad_(True)
+        fn(p, q).sum().backward()
+        pc, qc = b1.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+        (tools.iou_calc3, tools.giou, tools.diou)[kind](pc, qc).sum().backward()
+        assert rel_close(pc.grad.cpu().numpy(), p.grad.numpy(), 1e-4, scale=float(p.grad.abs().max()))
+        assert rel_close(qc.grad.cpu().numpy(), q.grad.numpy(), 1e-4, scale=float(q.grad.abs().max()))
+
+
+def test_numpy_nms_wrapper():
+    from pqdet_b200 import tools
+    g = load_golden("nms")
+    bb = g["small_in"]
+    boxes, scores, cls, _ = po.select_candidates(bb, 0.1)
+    rows = np.concatenate([boxes, scores[:, None], cls[:, None].astype(np.float32)], axis=1)
+    out = tools.nms(rows, 0.1, 0.45)
+    want = po.torch_nms(bb, 0.1, 0.45, device="cpu", mode="vanilla")
+    assert sorted(map(bytes, out.astype(np.float32))) == sorted(map(bytes, want))

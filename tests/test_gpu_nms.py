@@ -1,0 +1,191 @@
+"""-m gpu: NMS drop-in and the fused decode+NMS kernel vs the oracle, golden fixtures and (when
+importable) the installed torchvision on both devices.  Keep lists are compared bit-exactly."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_close
+from gpu_util import assert_same_detections, cuda, eval_chain_oracle
+from oracle import pqdet_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _restore_semantics():
+    from pqdet_b200 import config
+    old = config.nms_semantics
+    yield
+    config.nms_semantics = old
+
+
+def test_torch_nms_golden_cpu_semantics():
+    """tests/golden/nms.npz was produced by the reference on CPU tensors (torchvision CPU kernel)."""
+    from pqdet_b200 import config, tools
+    config.nms_semantics = "cpu"
+    g = load_golden("nms")
+    for name in sorted(k[:-3] for k in g if k.endswith("_in")):
+        out = tools.torch_nms(cuda(g[name + "_in"]), float(g[name + "_thr"]), float(g[name + "_iou"]))
+        want = g[name + "_out"]
+        if want.size == 0:
+            assert tuple(out.shape) == (0,), name            # tools.py:559-561
+            continue
+        assert_same_detections(out.cpu().numpy(), want, ties_unordered=(name == "vanilla_cpu"), what=name)
+
+
+@pytest.mark.parametrize("sem", ["cuda", "cpu"])
+@pytest.mark.parametrize("profile,C,size,kind,iou", [("sparse", 20, 512, "voc", 0.45),
+                                                      ("dense", 10, 608, "visdrone", 0.45),
+                                                      ("coco", 80, 608, "coco", 0.65)])
+def test_torch_nms_dropin_vs_oracle(sem, profile, C, size, kind, iou):
+    from pqdet_b200 import config, synth, tools
+    config.nms_semantics = sem
+    B = 2
+    heads = synth.make_heads(B, C, size, profile, seed=11)
+    pred = po.detect([h.numpy() for h in heads], C, synth.FPN_STRIDES)
+    orig = np.array([[375., 500.], [float(size), float(size)]], np.float32)
+    rec = po.recover(pred, (size, size), orig, kind)
+    outs, idxs = tools.batched_torch_nms(cuda(rec), 0.1, iou, return_index=True)
+    for b in range(B):
+        want, rows, cls = po.torch_nms(rec[b], 0.1, iou, device=sem, return_index=True)
+        ncand = int((rec[b][:, 4:] > np.float32(0.1)).sum())
+        vanilla = 4 * ncand > (100000 if sem == "cuda" else 4000)
+        assert_same_detections(outs[b].cpu().numpy(), want, ties_unordered=vanilla, what="%s/%s/%d" % (sem, profile, b))
+        if not vanilla:
+            assert np.array_equal(idxs[b].cpu().numpy(), rows * C + cls)
+
+
+def test_torch_nms_matches_installed_torchvision_on_both_devices():
+    tv = pytest.importorskip("torchvision")
+    from pqdet_b200 import config, synth, tools
+    C, size = 20, 512
+    heads = synth.make_heads(3, C, size, "sparse", seed=21)
+    pred = po.detect([h.numpy() for h in heads], C, synth.FPN_STRIDES)
+    rec = torch.from_numpy(po.recover(pred, (size, size), np.array([float(size), float(size)], np.float32), "voc"))
+
+    def reference_torch_nms(bb, thr, iou):                       # tools.py:540-566 with the live torchvision
+        cs = bb[:, 4:]
+        mask = cs > thr
+        idx = mask.nonzero()
+        keep = tv.ops.boxes.batched_nms(bb[:, :4][idx[:, 0]], cs[mask], idx[:, 1], iou)
+        return torch.cat([bb[:, :4][idx[:, 0]][keep], cs[mask][keep, None], idx[:, 1][keep, None].float()], 1)
+
+    for sem, dev in (("cpu", "cpu"), ("cuda", "cuda")):
+        config.nms_semantics = sem
+        for b in range(3):
+            want = reference_torch_nms(rec[b].to(dev), 0.1, 0.45).cpu().numpy()
+            got = tools.torch_nms(rec[b].cuda(), 0.1, 0.45).cpu().numpy()
+            assert_same_detections(got, want, what="torchvision-%s/%d" % (dev, b))
+            assert_same_detections(po.torch_nms(rec[b].numpy(), 0.1, 0.45, device=sem), want, what="oracle-%s" % dev)
+
+
+def _fused_vs_chain(B, C, size, profile, kind, thr, iou, sem, seed, orig=None, strides=None, mode=None):
+    from pqdet_b200 import config, fused, synth
+    from pqdet_b200.interpreter import DetectionHead
+    config.nms_semantics = sem
+    strides = strides or synth.FPN_STRIDES
+    heads = synth.make_heads(B, C, size, profile, seed=seed, strides=strides)
+    dheads = [h.cuda() for h in heads]
+    if orig is None:
+        orig = np.tile(np.array([[float(size), float(size)]], np.float32), (B, 1))
+    opts = [dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in strides]
+    decoded = DetectionHead(opts)(dheads).cpu().numpy()          # OUR decode: bit-exactness is defined on it
+    want = eval_chain_oracle(None, strides, C, (size, size), orig, kind, thr, iou, sem,
+                             mode=mode or "auto", decoded=decoded)
+    kw = {}
+    if mode:
+        kw["nms_mode"] = mode
+    dets = fused.decode_nms(dheads, strides, C, (size, size), cuda(orig), kind, thr, iou, return_index=True, **kw)
+    # decoded boxes themselves: within 1e-5 of the oracle's decode
+    ref_dec = po.detect([h.numpy() for h in heads], C, strides)
+    assert rel_close(decoded[..., :4], ref_dec[..., :4], 1e-5, scale=float(size))
+    assert rel_close(decoded[..., 4:], ref_dec[..., 4:], 1e-5, scale=1e-30)
+    total_cand = 0
+    for b in range(B):
+        w, rows, cls = want[b]
+        rec_b = None
+        got = dets[b].cpu().numpy()
+        ncand = int(dets.host_meta()[1, b])
+        total_cand += ncand
+        limit = 100000 if sem == "cuda" else 4000
+        vanilla = (mode == "vanilla") or (mode is None and 4 * ncand > limit)
+        assert_same_detections(got, w, ties_unordered=vanilla, what="fused %s/%s img %d" % (profile, sem, b))
+        if not vanilla:
+            assert np.array_equal(dets.indices(b).cpu().numpy(), rows * C + cls)
+    return dets, total_cand
+
+
+@pytest.mark.parametrize("sem", ["cuda", "cpu"])
+def test_fused_sparse_voc(sem):
+    orig = np.array([[375., 500.], [333., 500.], [512., 512.], [500., 281.], [480., 640.], [512., 512.]], np.float32)
+    dets, total = _fused_vs_chain(6, 20, 512, "sparse", "voc", 0.1, 0.45, sem, seed=31, orig=orig)
+    assert total > 1500
+    assert int(dets.host_meta()[2].sum()) == 0
+
+
+def test_fused_predict_threshold_and_coco_iou():
+    _fused_vs_chain(3, 20, 512, "sparse", "voc", 0.25, 0.45, "cpu", seed=32)        # predict.py:70
+    _fused_vs_chain(2, 80, 608, "coco", "coco", 0.1, 0.65, "cuda", seed=33)         # yamls/coco.yaml:50, 19x19 level
+    _fused_vs_chain(2, 20, 512, "sparse", "voc", 0.1, 0.45, "cuda", seed=34, strides=(8, 16, 32))   # PAN order
+
+
+@pytest.mark.parametrize("sem", ["cuda", "cpu"])
+def test_fused_dense_visdrone_overflows_to_general_path(sem):
+    orig = np.array([[480., 480.], [360., 640.]], np.float32)
+    dets, total = _fused_vs_chain(2, 10, 608, "dense", "visdrone", 0.1, 0.45, sem, seed=35, orig=orig)
+    assert total > 2 * 2048                                     # beyond the on-chip candidate list
+    assert len(dets._spill) == 2
+
+
+def test_fused_forced_modes():
+    _fused_vs_chain(2, 20, 512, "sparse", "voc", 0.1, 0.45, "cuda", seed=36, mode="vanilla")
+    _fused_vs_chain(2, 20, 512, "sparse", "voc", 0.1, 0.45, "cpu", seed=37, mode="trick")
+
+
+def test_fused_gauss_worst_case_small():
+    # every row is a hit: the overflow path with ~10^5 candidates per image
+    _fused_vs_chain(1, 20, 256, "gauss", "voc", 0.1, 0.45, "cuda", seed=38)
+
+
+def test_fused_edge_cases():
+    from pqdet_b200 import fused, synth
+    C, size = 20, 512
+    heads = [h.cuda() for h in synth.make_heads(2, C, size, "sparse", seed=39)]
+    orig = torch.tensor([float(size), float(size)]).cuda()
+    d = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.999999, 0.45)   # nothing passes
+    assert d.counts.tolist() == [0, 0] and tuple(d[0].shape) == (0, 6)
+    assert [tuple(t.shape) for t in d.to_reference_list()] == [(0,), (0,)]
+    d = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, "voc", 1.5, 0.45)
+    assert d.counts.tolist() == [0, 0]
+    d1 = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45)
+    d2 = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45)
+    for b in range(2):                                           # run-to-run determinism, bitwise
+        assert torch.equal(d1[b], d2[b])
+
+
+def test_fused_full_size_properties():
+    """BASELINE config E shape (1024 x VOC-512): size-independent properties instead of the oracle:
+    shard invariance (any split of the batch gives the same per-image rows -- the multi-GPU equality),
+    sortedness, idempotence, and an oracle spot check on a few images."""
+    from pqdet_b200 import fused, synth
+    C, size, B = 20, 512, 1024
+    heads = [h for h in synth.make_heads(B, C, size, "sparse", seed=0, device="cuda")]
+    orig = torch.tensor([float(size), float(size)]).cuda()
+    full = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45)
+    assert int(full.host_meta()[2].sum()) == 0
+    half = [fused.decode_nms([h[i:i + 512] for h in heads], synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45)
+            for i in (0, 512)]
+    for b in list(range(0, 1024, 37)) + [511, 512, 1023]:
+        a = full[b]
+        assert torch.equal(a, half[b // 512][b % 512])
+        s = a[:, 4]
+        assert bool((s[:-1] >= s[1:]).all()) and bool((s > 0.1).all())
+    counts = full.counts.to(torch.float32)
+    assert 60 < float(counts.mean()) < 200
+    from pqdet_b200.interpreter import DetectionHead
+    opts = [dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in synth.FPN_STRIDES]
+    for b in (0, 513, 1023):
+        dec = DetectionHead(opts)([h[b:b + 1] for h in heads]).cpu().numpy()
+        want = eval_chain_oracle(None, synth.FPN_STRIDES, C, (size, size), np.array([size, size], np.float32),
+                                 "voc", 0.1, 0.45, "cuda", decoded=dec)[0][0]
+        assert_same_detections(full[b].cpu().numpy(), want, what="full-size img %d" % b)
