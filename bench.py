@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the PQDet detection hot path on B200 (driver contract: one JSON line on rank 0).
+
+  python bench.py --gpus N --steps K --warmup W              # our arm (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path on the host cores
+
+Headline workload = BASELINE.json config E: VOC-shaped heads (C=20, 512x512, FPN strides 32/16/8),
+PQ-SYNTH-v1 "sparse" profile, score thr 0.1, NMS IoU 0.45, 1024 images per GPU (weak scaling: every
+rank owns its own 1024 images end to end, no data-path collective).  A step = one pass of the fused
+decode + recover + threshold + class-aware NMS kernel over the rank's batch.  The head tensors of one
+step are 1.65 GB (> the 126 MB L2), so every step reads HBM.
+
+Also reported in the same line: `e2e` (host buffers in, detections out, copies inside the timed region),
+`roofline` (algorithmic bytes R*B + 24*K over the kernel time vs the measured HBM copy peak),
+`cpu_baseline` (the reference's CPU sequence on the host cores, bounded sample), and `loss`
+(BASELINE config B: decode + loss forward/backward, VOC-512 bs=16) with its own roofline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+C_VOC, SIZE, B_PER_GPU = 20, 512, 1024
+THR, IOU = 0.1, 0.45
+STRIDES = (32, 16, 8)
+
+
+def cells(size):
+    return sum((size // s) ** 2 for s in STRIDES)
+
+
+def raw_bytes(C, size):            # R: raw heads of one image, read once
+    return 4 * 3 * (5 + C) * cells(size)
+
+
+def label_bytes(C, size):          # L: dense labels of one image
+    return 4 * 3 * (6 + C) * cells(size)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def cpu_eval_rate(n_images: int, repeats: int = 1, seed: int = 1234):
+    """images/s of the reference's CPU sequence on `n_images` of the headline workload, all host cores."""
+    from oracle import cpu_path
+    from pqdet_b200 import synth
+    cores = cpu_path.host_cores()
+    heads = synth.make_heads(n_images, C_VOC, SIZE, "sparse", seed=seed, device="cpu")
+    orig = torch.tensor([[float(SIZE), float(SIZE)]])
+    torch.set_num_threads(cores)
+    cpu_path.eval_chain_image_parallel([h[:min(8, n_images)] for h in heads], STRIDES, C_VOC, (SIZE, SIZE), orig,
+                                       "voc", THR, IOU, cores)                       # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        out = cpu_path.eval_chain_image_parallel(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, cores)
+    dt_par = (time.perf_counter() - t0) / repeats
+    n_seq = min(n_images, 32)
+    t0 = time.perf_counter()
+    cpu_path.eval_chain([h[:n_seq] for h in heads], STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU)
+    dt_seq = time.perf_counter() - t0
+    kept = float(np.mean([o.shape[0] for o in out]))
+    return {"par": n_images / dt_par, "seq": n_seq / dt_seq, "cores": cores, "kept_per_image": kept,
+            "n": n_images, "n_seq": n_seq}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sample = 64
+    from oracle import cpu_path
+    from pqdet_b200 import synth
+    cores = cpu_path.host_cores()
+    heads = synth.make_heads(sample, C_VOC, SIZE, "sparse", seed=1234, device="cpu")
+    orig = torch.tensor([[float(SIZE), float(SIZE)]])
+    torch.set_num_threads(cores)
+
+    def step():
+        return cpu_path.eval_chain_image_parallel(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, cores)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "images/sec decode+NMS", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(sample_note="CPU arm: each step = %d images of the same workload" % sample),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+                         "sample": "%d images/step, image-parallel thread pool (1 intra-op thread each), torch CPU "
+                                   "ops + torchvision.ops.batched_nms = the reference's own CPU stack; the "
+                                   "reference's Python cannot travel to the GPU box" % sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(sample_note=None):
+    cfg = {"workload": "BASELINE config E: eval sweep, VOC-shaped heads C=20 512x512 FPN(32,16,8), PQ-SYNTH-v1 sparse, "
+                       "fused decode+recover+threshold+class-aware NMS",
+           "images_per_gpu": B_PER_GPU, "score_threshold": THR, "nms_iou": IOU,
+           "nms_semantics": "torchvision-CUDA (trick <= 25000 candidates, FMA IoU order)",
+           "l2_policy": "inputs (1.65 GB/step/GPU) larger than L2 (126 MB)"}
+    if sample_note:
+        cfg["note"] = sample_note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def time_steps(fn, steps, stream_sync=True):
+    """CUDA-event time of every step on the current stream -> list of ms."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s, e in evs:
+        s.record()
+        fn()
+        e.record()
+    torch.cuda.synchronize()
+    return [s.elapsed_time(e) for s, e in evs]
+
+
+def bench_loss(device, steps, warmup, peak):
+    """BASELINE config B: regnetx-600m-fpn VOC 512x512 bs=16, bbox_loss=l1 (cfg default), decode + loss
+    forward + backward over the 3 levels.  L2 is flushed between timed iterations (26 MB working set)."""
+    from pqdet_b200 import synth
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.train_dataset import LabelAssigner
+    B, C, size = 16, C_VOC, SIZE
+    gts = synth.make_gt(B, C, size, 1, 12, seed=0)
+    out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+    target = LabelAssigner(C, device=device).create_label_batch(gts, out_sizes)
+    raws = [t.requires_grad_(True) for t in synth.make_train_heads(B, C, size, seed=0, device=device)]
+    res = {}
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=device)
+    from pqdet_b200 import config as pqcfg
+    old = pqcfg.nan_check
+    pqcfg.nan_check = "off"                  # the NaN flag is still computed on the device; no per-step host read
+    try:
+        for kind in ("l1", "giou", "iou"):
+            opts = [dict(classes=C, stride=s, bbox_loss=kind, ignore_thresh=0.5, l1_loss_gain=0.05) for s in STRIDES]
+            head = DetectionHead(opts)
+
+            def step():
+                for r in raws:
+                    r.grad = None
+                out = head(raws, target)
+                out["loss"].mean().backward()
+            for _ in range(warmup):
+                step()
+            ts = []
+            for _ in range(steps):
+                flush.zero_()
+                ts += time_steps(step, 1)
+            ms = float(np.median(ts))
+            alg = 2 * raw_bytes(C, size) + label_bytes(C, size)
+            res[kind] = {"images_per_s": B / (ms * 1e-3), "ms_per_step": ms,
+                         "roofline_frac": (alg * B / (ms * 1e-3)) / (peak * 1e9),
+                         "achieved_gbs": alg * B / (ms * 1e-3) / 1e9}
+    finally:
+        pqcfg.nan_check = old
+    return {"workload": "BASELINE config B: VOC C=20 512x512 bs=16 decode+loss fwd+bwd, 3 levels, GT 1-12/img",
+            "algorithmic_bytes_per_image": 2 * raw_bytes(C, size) + label_bytes(C, size),
+            "timing": "median of per-step CUDA events incl. autograd glue, L2 flushed between steps",
+            "kernels_per_step": 9, "by_bbox_loss": res}
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from pqdet_b200 import _ops, synth
+    import pqdet_b200
+    pqdet_b200.load_library()
+    B = B_PER_GPU
+    heads = synth.make_heads(B, C_VOC, SIZE, "sparse", seed=rank, device=device)
+    orig = torch.tensor([float(SIZE), float(SIZE)], device=device)
+    h, keep = _ops.make_heads(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, "auto_cuda", "tv_cuda")
+    MAXDET = 2048
+    out = _ops.alloc_fused_outputs(B, MAXDET, False, device)
+
+    def step():
+        _ops.decode_nms_fused(h, keep, MAXDET, False, out=out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    per_step = time_steps(step, args.steps)
+    t_stop.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([t_start.elapsed_time(t_stop)], device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    meta = out[2][:3 * B].view(3, B).cpu()
+    counts, ncand, status = meta[0], meta[1], meta[2]
+    overflow = int((status != 0).sum())
+
+    # ---- end to end: pinned host heads -> H2D -> kernel -> D2H of the detections, every step ----
+    host_heads = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in heads]
+    for hh, t in zip(host_heads, heads):
+        hh.copy_(t)
+    dev_in = [torch.empty_like(t) for t in heads]
+    h2, keep2 = _ops.make_heads(dev_in, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, "auto_cuda", "tv_cuda")
+    host_meta = torch.empty((3 * B,), dtype=torch.int32, pin_memory=True)
+    d2h_bytes = [0]
+
+    def e2e_step():
+        for d, s in zip(dev_in, host_heads):
+            d.copy_(s, non_blocking=True)
+        det, _, m = _ops.decode_nms_fused(h2, keep2, MAXDET, False, out=out)
+        host_meta.copy_(m[:3 * B], non_blocking=True)
+        torch.cuda.synchronize()
+        kmax = int(host_meta[:B].max())
+        rows = det[:, :kmax].contiguous().cpu()              # the detections a caller consumes
+        d2h_bytes[0] = host_meta.numel() * 4 + rows.numel() * 4
+        return rows
+    e2e_steps = max(3, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ee.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([max(es.elapsed_time(ee), (time.perf_counter() - t0) * 1e3)], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / (float(e2e_ms) * 1e-3)
+    h2d = sum(t.numel() * 4 for t in heads)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    ms_step = total_ms / args.steps
+    k_mean = float(counts.float().mean())
+    alg_bytes = raw_bytes(C_VOC, SIZE) * B + 24.0 * float(counts.sum())
+    kern_ms = float(np.mean(per_step))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = ncu_traffic("decode_nms_fused_kernel")
+    line = {
+        "metric": "images/sec decode+NMS", "value": world * B * args.steps / (total_ms * 1e-3), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "roofline": {"bound": "hbm", "kernel": "pq::decode_nms_fused_kernel<0>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src,
+                     "achieved_dram": (traffic / (kern_ms * 1e-3) / 1e9) if traffic else None,
+                     "note": "achieved = algorithmic bytes (R*B + 24*K, SURVEY 8d) / mean kernel time; the kernel "
+                             "reads only the objectness planes plus the box/class channels of rows with conf > thr "
+                             "(exact early-out), so DRAM traffic is far below the algorithmic bytes and frac can "
+                             "exceed 1; achieved_dram = measured ncu DRAM bytes / time"},
+        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes[0],
+                "steps": e2e_steps, "note": "pinned host heads -> H2D -> fused kernel -> D2H counts + detection rows"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "stats": {"kept_per_image": k_mean, "candidates_per_image": float(ncand.float().mean()),
+                  "max_candidates": int(ncand.max()), "overflow_images": overflow,
+                  "kernel_ms_mean": kern_ms, "kernel_ms_min": float(np.min(per_step))},
+    }
+    if world == 1 and args.cpu_sample > 0:
+        try:
+            r = cpu_eval_rate(args.cpu_sample)
+            line["cpu_baseline"] = {
+                "value": r["par"], "unit": "images/s", "cores": r["cores"], "kind": "port", "cpu": cpu_model(),
+                "sequential_as_is": r["seq"],
+                "sample": "%d images of the same workload, image-parallel thread pool over all host cores; "
+                          "sequential_as_is = the reference's per-image loop on %d images with intra-op threads; "
+                          "torch CPU ops + torchvision.ops.batched_nms (oracle/cpu_path.py)" % (r["n"], r["n_seq"])}
+        except Exception as e:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    if world == 1 and not args.no_loss:
+        line["loss"] = bench_loss(device, max(args.steps, 10), 3, peak)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=512)
+    ap.add_argument("--no-loss", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

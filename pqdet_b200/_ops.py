@@ -143,14 +143,20 @@ def make_heads(raws: Sequence[torch.Tensor], strides: Sequence[float], num_class
     return h, keep_alive
 
 
-def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool):
-    """-> det (B,max_det,6), idx (B,max_det)|None, meta int32 (3,B): counts, ncand, status."""
-    raws, _ = keep_alive
-    device = raws[0].device
-    B = heads_t.B
+def alloc_fused_outputs(B: int, max_det: int, want_index: bool, device):
     det = torch.empty((B, max_det, 6), dtype=torch.float32, device=device)
     idx = torch.empty((B, max_det), dtype=torch.int32, device=device) if want_index else None
     meta = torch.empty((3 * B + 1,), dtype=torch.int32, device=device)
+    return det, idx, meta
+
+
+def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool, out=None):
+    """-> det (B,max_det,6), idx (B,max_det)|None, meta int32 (3B+1): counts, ncand, status, scheduler word.
+    `out` = buffers from alloc_fused_outputs to reuse across calls (no allocation in the hot loop)."""
+    raws, _ = keep_alive
+    device = raws[0].device
+    B = heads_t.B
+    det, idx, meta = out if out is not None else alloc_fused_outputs(B, max_det, want_index, device)
     counts, ncand, status, work = meta[0:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:]
     _lib.check(_lib.load().pqdet_decode_nms(ctypes.byref(heads_t), _ptr(det), _ptr(idx), int(max_det),
                                             _ptr(counts), _ptr(ncand), _ptr(status), _ptr(work),
