@@ -161,6 +161,26 @@ int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A, int C, in
                           const float* g_loss, const float* g_bbox, const float* g_conf,
                           const float* g_cls, int device, void* stream);
 
+/* ---- a4 (training branch): all FPN levels of DetectionModel.forward(x, target)
+ * (model/interpreter.py:51-54, 77-85) in ONE launch: per-level decode + loss_per_scale forward+backward,
+ * the Python-order sums over levels and loss_per_branch.  Host arrays of n_levels device pointers / ints.
+ * out (device float[4 + 5*n_levels]):
+ *   [0..3]          loss, bbox(giou_loss), conf_loss, class_loss summed over levels, ((0+h0)+h1)+h2
+ *   [4+4l..7+4l]    the four per-level losses YOLOLayer returns
+ *   [4+4L+l]        loss_per_branch[l] = bbox+conf+cls of level l
+ * workspace: pqdet_loss_levels_workspace() bytes; pass workspace_initialised=0 the first time a buffer is
+ * used (its scheduler word is then zeroed by the call), 1 afterwards (the kernel re-arms it itself). */
+int64_t pqdet_loss_levels_workspace(int n_levels, int B, int A, const int* H, const int* W);
+int pqdet_loss_levels(int n_levels, const float* const* raw, const float* const* label,
+                      const float* const* gt, float* const* grad, const int* H, const int* W,
+                      const int* G, const float* stride, int B, int A, int C, int bbox_loss,
+                      float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
+                      void* workspace, int workspace_initialised, int device, void* stream);
+/* Chain rule for pqdet_loss_levels: upstream = d L / d out (device float[4 + 5*n_levels]); scales every
+ * level's grad in place; returns without memory traffic when all factors are 1 (loss.backward()). */
+int pqdet_loss_levels_scale_grad(int n_levels, float* const* grad, const int* H, const int* W,
+                                 int B, int A, int C, const float* upstream, int device, void* stream);
+
 /* ---- a11/a12: dataset/train_dataset.py:109-150 create_label + collate_batch (:16-43) for a whole
  * batch.  gt (B, n_max, 6) rows [x1,y1,x2,y2,class,mixw], gt_count (B).
  * anchors: HOST float[9*2] (w,h); strides/H/W: HOST int[3], ascending strides (8,16,32).  For scale s:

@@ -67,6 +67,13 @@ SIGNATURES = {
                                    c_float, c_float, c_int, c_void_p]),
     "pqdet_loss_scale_grad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_void_p]),
+    "pqdet_loss_levels_workspace": (c_int64, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "pqdet_loss_levels": (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                  POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                  POINTER(c_float), c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
+                                  c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "pqdet_loss_levels_scale_grad": (c_int, [c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int,
+                                             c_int, c_int, c_void_p, c_int, c_void_p]),
     "pqdet_assign_workspace": (c_int64, [c_int, POINTER(c_int), POINTER(c_int)]),
     "pqdet_assign_labels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float),
                                     POINTER(c_int), POINTER(c_int), POINTER(c_int), c_float,

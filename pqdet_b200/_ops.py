@@ -279,6 +279,62 @@ def loss_scale_grad(grad: torch.Tensor, input_is_raw: bool, num_classes: int, g_
     return grad
 
 
+_WS_ARMED = set()
+
+
+def loss_levels(raws, labels, gts, num_classes: int, strides, bbox_loss: str, ignore_thresh: float,
+                l1_loss_gain: float, want_grad: bool):
+    """All levels in one launch.  -> out (4+5L,) device, nan_flag (1,) int32, grads list|None."""
+    if bbox_loss == "ciou":
+        raise RuntimeError("NaN in loss")          # the reference always raises for ciou (SURVEY.md item 6)
+    if bbox_loss not in _lib.BBOX_LOSS:
+        raise NotImplementedError(bbox_loss)
+    raws = [_req(r, "head") for r in raws]
+    labels = [_req(x, "label") for x in labels]
+    gts = [_req(x, "bboxes") for x in gts]
+    L = len(raws)
+    C = num_classes
+    B = raws[0].shape[0]
+    A = raws[0].shape[1] // (5 + C)
+    device = raws[0].device
+    for r, lab, g in zip(raws, labels, gts):
+        _, CH, H, W = r.shape
+        if r.shape[0] != B or CH != A * (5 + C) or tuple(lab.shape) != (B, H, W, A, 6 + C):
+            raise ValueError("head/label shapes do not match: %s vs %s" % (tuple(r.shape), tuple(lab.shape)))
+        if g.dim() != 3 or g.shape[0] != B or g.shape[2] != 4 or g.shape[1] < 1:
+            raise ValueError("bboxes must be (B, G>=1, 4)")
+    grads = [torch.empty_like(r) for r in raws] if want_grad else None
+    VP = ctypes.c_void_p * L
+    IP = ctypes.c_int * L
+    Hs, Ws = IP(*[r.shape[2] for r in raws]), IP(*[r.shape[3] for r in raws])
+    lib = _lib.load()
+    ws = _workspace(device, "loss_levels", lib.pqdet_loss_levels_workspace(L, B, A, Hs, Ws))
+    armed = (ws.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+    out = torch.empty((4 + 5 * L,), dtype=torch.float32, device=device)
+    flag = torch.empty((1,), dtype=torch.int32, device=device)
+    _lib.check(lib.pqdet_loss_levels(
+        L, VP(*[r.data_ptr() for r in raws]), VP(*[x.data_ptr() for x in labels]), VP(*[x.data_ptr() for x in gts]),
+        VP(*[g.data_ptr() for g in grads]) if want_grad else None, Hs, Ws, IP(*[g.shape[1] for g in gts]),
+        (ctypes.c_float * L)(*[float(s) for s in strides]), B, A, C, _lib.BBOX_LOSS[bbox_loss],
+        float(ignore_thresh), float(l1_loss_gain), _ptr(out), _ptr(flag), _ptr(ws),
+        1 if armed in _WS_ARMED else 0, _dev(raws[0]), _stream(device)), "pqdet_loss_levels")
+    _WS_ARMED.add(armed)
+    return out, flag, grads
+
+
+def loss_levels_scale_grad(grads, num_classes: int, upstream: torch.Tensor):
+    L = len(grads)
+    B, CH = grads[0].shape[0], grads[0].shape[1]
+    A = CH // (5 + num_classes)
+    upstream = _req(upstream, "upstream grad")
+    VP = ctypes.c_void_p * L
+    IP = ctypes.c_int * L
+    _lib.check(_lib.load().pqdet_loss_levels_scale_grad(
+        L, VP(*[g.data_ptr() for g in grads]), IP(*[g.shape[2] for g in grads]), IP(*[g.shape[3] for g in grads]),
+        B, A, num_classes, _ptr(upstream), _dev(grads[0]), _stream(grads[0].device)), "pqdet_loss_levels_scale_grad")
+    return grads
+
+
 def assign_labels(gt: torch.Tensor, gt_count: torch.Tensor, num_classes: int, anchors, strides, sizes_hw,
                   iou_threshold: float, list_capacity: Optional[int] = None):
     """gt (B,n_max,6) cuda, gt_count (B) int32 cuda -> labels[3], gtlists[3] (B,cap,4), list_len (B,3)."""

@@ -11,6 +11,8 @@
 //
 // HBM traffic: label tile L + 5/(5+C) of the raw head + the class channels of responsible cells,
 // plus the full gradient write R.  Algorithmic figure used for the roofline: 2R + L.
+#include <string.h>
+
 #include "pq_common.cuh"
 
 namespace pq {
@@ -30,16 +32,14 @@ struct LossParams {
 };
 
 template <bool RAW>
-__global__ void __launch_bounds__(256)
-loss_fwd_bwd_kernel(const __grid_constant__ LossParams P) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, const int ntiles, const int b,
+                                          float* smem) {
   const int A = P.A, C = P.C, ch = 5 + C, LW = 6 + C, LWp = LW | 1;
   const int HW = P.H * P.W;
   float* slab = smem;                                   // [32*A][LWp]
   float* sgt = smem + kLossTile * A * LWp;              // [kGtChunk][5]
   __shared__ double sred[8][3];
-  const int b = blockIdx.y;
-  const int cell0 = blockIdx.x * kLossTile;
+  const int cell0 = tile * kLossTile;
   const int ncell = min(kLossTile, HW - cell0);
   const int lane = lane_id(), a = warp_id();
   const int cell = cell0 + lane;
@@ -158,7 +158,110 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossParams P) {
   if (threadIdx.x < 3) {
     double s = 0.0;
     for (int w = 0; w < A; ++w) s += sred[w][threadIdx.x];
-    P.partials[((size_t)b * gridDim.x + blockIdx.x) * 3 + threadIdx.x] = s;
+    P.partials[((size_t)b * ntiles + tile) * 3 + threadIdx.x] = s;
+  }
+}
+
+template <bool RAW>
+__global__ void __launch_bounds__(256)
+loss_fwd_bwd_kernel(const __grid_constant__ LossParams P) {
+  extern __shared__ __align__(16) float smem[];
+  loss_tile<RAW>(P, blockIdx.x, gridDim.x, blockIdx.y, smem);
+}
+
+// ---- all FPN levels in ONE launch (DetectionModel.forward training branch, model/interpreter.py:77-85)
+// grid.x enumerates the tiles of every level back to back, grid.y = image.  The last CTA to finish
+// (atomic ticket) reduces every level's partial sums in index order - deterministic regardless of which
+// CTA happens to be last - and writes
+//   out[0..3]            loss, bbox, conf, cls summed over levels in Python-sum order ((0+h0)+h1)+h2
+//   out[4+4l .. 7+4l]    the four (1,) losses of level l (what YOLOLayer.forward returns)
+//   out[4+4L+l]          loss_per_branch[l] = (bbox+conf)+cls of level l
+struct MultiLossParams {
+  LossParams lv[PQDET_MAX_LEVELS];
+  int tile_off[PQDET_MAX_LEVELS + 1];
+  int n_levels;
+  unsigned total_blocks;
+  unsigned* ticket;
+  float* out;
+  int32_t* nan_flag;
+};
+
+__global__ void __launch_bounds__(256)
+loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ bool s_last;
+  __shared__ double s_fin[256][3];
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
+    if (i < M.n_levels && (int)blockIdx.x >= M.tile_off[i]) l = i;
+  const int ntiles = M.tile_off[l + 1] - M.tile_off[l];
+  loss_tile<true>(M.lv[l], blockIdx.x - M.tile_off[l], ntiles, blockIdx.y, smem);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(M.ticket, 1u) == M.total_blocks - 1u);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float tot[4] = {0.f, 0.f, 0.f, 0.f};
+  bool nan = false;
+  for (int q = 0; q < M.n_levels; ++q) {
+    const LossParams& P = M.lv[q];
+    const int64_t n = (int64_t)P.B * (M.tile_off[q + 1] - M.tile_off[q]);
+    double acc[3] = {0.0, 0.0, 0.0};
+    const volatile double* part = P.partials;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      acc[0] += part[i * 3 + 0]; acc[1] += part[i * 3 + 1]; acc[2] += part[i * 3 + 2];
+    }
+    for (int j = 0; j < 3; ++j) s_fin[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sum[3] = {0.0, 0.0, 0.0};
+      for (unsigned t = 0; t < blockDim.x; ++t)
+        for (int j = 0; j < 3; ++j) sum[j] += s_fin[t][j];
+      const double invB = 1.0 / (double)P.B;
+      const float lb = (float)(sum[0] * invB), lc = (float)(sum[1] * invB), lp = (float)(sum[2] * invB);
+      const float loss = PQ_ADD(PQ_ADD(lb, lc), lp);
+      float* o = M.out + 4 + 4 * q;
+      o[0] = loss; o[1] = lb; o[2] = lc; o[3] = lp;
+      M.out[4 + 4 * M.n_levels + q] = PQ_ADD(PQ_ADD(lb, lc), lp);
+      tot[0] = q ? PQ_ADD(tot[0], loss) : loss; tot[1] = q ? PQ_ADD(tot[1], lb) : lb;
+      tot[2] = q ? PQ_ADD(tot[2], lc) : lc;     tot[3] = q ? PQ_ADD(tot[3], lp) : lp;
+      nan |= (loss != loss);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < 4; ++j) M.out[j] = tot[j];
+    *M.nan_flag = nan ? 1 : 0;
+    *M.ticket = 0u;                                  // re-arm for the next launch (stream ordered)
+  }
+}
+
+// Chain rule for the multi-level outputs.  g = upstream gradient of out (device, 4+5L floats).  Level l's
+// box/objectness/class groups are scaled by g[0] + g[1+j] + g[4+4l] + g[5+4l+j] + g[4+4L+l], j = 0,1,2.
+struct MultiScaleParams {
+  float* grad[PQDET_MAX_LEVELS];
+  int64_t total[PQDET_MAX_LEVELS];
+  int HW[PQDET_MAX_LEVELS];
+  int n_levels, ch;
+  const float* g;
+};
+
+__global__ void __launch_bounds__(256)
+scale_levels_kernel(const __grid_constant__ MultiScaleParams S) {
+  const int l = blockIdx.y;
+  const int L = S.n_levels;
+  const float base = S.g[0] + S.g[4 + 4 * l] + S.g[4 + 4 * L + l];
+  const float cb = base + S.g[1] + S.g[5 + 4 * l];
+  const float cc = base + S.g[2] + S.g[6 + 4 * l];
+  const float cp = base + S.g[3] + S.g[7 + 4 * l];
+  if (cb == 1.0f && cc == 1.0f && cp == 1.0f) return;
+  float* grad = S.grad[l];
+  const int HW = S.HW[l], ch = S.ch;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < S.total[l]; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)((e / HW) % ch);
+    grad[e] *= (k < 4) ? cb : (k == 4 ? cc : cp);
   }
 }
 
@@ -262,6 +365,89 @@ extern "C" int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A
   if (blocks > 148 * 16) blocks = 148 * 16;
   pq::scale_groups_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       grad, total, input_is_raw, 5 + C, H * W, g_loss, g_bbox, g_conf, g_cls);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
+extern "C" int64_t pqdet_loss_levels_workspace(int n_levels, int B, int A, const int* H, const int* W) {
+  if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || B < 0 || A < 1 || !H || !W) return PQDET_ERR_INVALID_ARG;
+  int64_t bytes = 256;   // ticket
+  for (int l = 0; l < n_levels; ++l) {
+    const int64_t tiles = ((int64_t)H[l] * W[l] + pq::kLossTile - 1) / pq::kLossTile;
+    bytes += ((int64_t)B * tiles * 3 * (int64_t)sizeof(double) + 255) / 256 * 256;
+  }
+  return bytes;
+}
+
+extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const float* const* label,
+                                 const float* const* gt, float* const* grad, const int* H, const int* W,
+                                 const int* G, const float* stride, int B, int A, int C, int bbox_loss,
+                                 float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
+                                 void* workspace, int workspace_initialised, int device, void* stream) {
+  using namespace pq;
+  if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || !raw || !label || !gt || !H || !W || !G || !stride ||
+      !out || !nan_flag || !workspace)
+    return PQDET_ERR_INVALID_ARG;
+  if (B < 1 || B > 65535 || A < 1 || A > 8 || C < 1) return PQDET_ERR_INVALID_ARG;
+  if (bbox_loss < 0 || bbox_loss > 3) return PQDET_ERR_UNSUPPORTED;
+  PQ_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MultiLossParams M;
+  memset(&M, 0, sizeof(M));
+  unsigned char* ws = (unsigned char*)workspace;
+  M.ticket = (unsigned*)ws;
+  size_t off = 256;
+  int tiles_total = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!raw[l] || !label[l] || !gt[l] || H[l] < 1 || W[l] < 1 || G[l] < 1) return PQDET_ERR_INVALID_ARG;
+    LossParams& P = M.lv[l];
+    P.x = raw[l]; P.label = label[l]; P.gt = gt[l]; P.grad = grad ? grad[l] : nullptr;
+    P.partials = (double*)(ws + off);
+    const int tiles = (H[l] * W[l] + kLossTile - 1) / kLossTile;
+    off += ((size_t)B * tiles * 3 * sizeof(double) + 255) / 256 * 256;
+    P.B = B; P.A = A; P.C = C; P.H = H[l]; P.W = W[l]; P.G = G[l];
+    P.stride = stride[l];
+    P.in_area = (float)((double)(stride[l] * H[l]) * (double)(stride[l] * W[l]));
+    P.ignore_thresh = ignore_thresh; P.l1_gain = l1_loss_gain; P.inv_B = 1.0f / (float)B;
+    P.bbox_loss = bbox_loss;
+    M.tile_off[l] = tiles_total;
+    tiles_total += tiles;
+  }
+  for (int l = n_levels; l <= PQDET_MAX_LEVELS; ++l) M.tile_off[l] = tiles_total;
+  M.n_levels = n_levels;
+  M.total_blocks = (unsigned)tiles_total * (unsigned)B;
+  M.out = out; M.nan_flag = nan_flag;
+  if (!workspace_initialised) PQ_CUDA(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned), st));
+  const size_t smem = ((size_t)kLossTile * A * ((6 + C) | 1) + kGtChunk * 5) * sizeof(float);
+  if (smem > 48 * 1024)
+    PQ_CUDA(cudaFuncSetAttribute(loss_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(tiles_total, B);
+  loss_levels_kernel<<<grid, 32 * A, smem, st>>>(M);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
+extern "C" int pqdet_loss_levels_scale_grad(int n_levels, float* const* grad, const int* H, const int* W,
+                                            int B, int A, int C, const float* upstream, int device, void* stream) {
+  using namespace pq;
+  if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || !grad || !H || !W || !upstream) return PQDET_ERR_INVALID_ARG;
+  if (B < 1 || A < 1 || C < 1) return PQDET_ERR_INVALID_ARG;
+  PQ_ENTER(device);
+  MultiScaleParams S;
+  memset(&S, 0, sizeof(S));
+  int64_t mx = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!grad[l]) return PQDET_ERR_INVALID_ARG;
+    S.grad[l] = grad[l];
+    S.HW[l] = H[l] * W[l];
+    S.total[l] = (int64_t)B * A * (5 + C) * H[l] * W[l];
+    if (S.total[l] > mx) mx = S.total[l];
+  }
+  S.n_levels = n_levels; S.ch = 5 + C; S.g = upstream;
+  int64_t blocks = (mx + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 grid((unsigned)blocks, n_levels);
+  scale_levels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }

@@ -159,23 +159,73 @@ __device__ __forceinline__ int warp_nms_segment(int s, int e, float off, float i
 // ------------------------------------------------------------------------------------------------
 // fused kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kWarpSortMax = 256;   // classes up to this many candidates are rank-sorted by one warp
+constexpr int kRankOutMax = 256;    // kept lists up to this size are ordered by rank counting
+
 struct FusedSmem {
-  uint64_t keys[kCapM];
-  float4 hbox[kCapH];
-  uint32_t hrow[kCapH];
+  uint64_t keys[kCapM];     // candidate keys in emission order; reused for the output keys
+  float4 hbox[kCapH];       // recovered box of every hit row
+  uint32_t hmeta[kCapH];    // level << 30 | anchor << 27 | cell
   float hconf[kCapH];
-  uint16_t klist[kCapM];
-  uint8_t keepflag[kCapM];
+  uint16_t order[kCapM];    // per-class member lists (candidate slots), score-sorted in place
+  uint16_t klist[kCapM];    // per-class kept positions (also scratch of the multi-tile rank sort)
+  uint8_t keepflag[kCapM];  // by candidate slot
   uint8_t hhas[kCapH];
+  int cls_cnt[128];
+  int cls_fill[128];
   int seg_start[128];
-  int seg_end[128];
+  const float* pbase[PQDET_MAX_LEVELS * 8];   // objectness plane of (level, anchor) for this image
   float red[kFusedWarps];
-  int b, H, M, K;
+  int b, H, M, K, maxcnt;
   // followed by: uint32_t hitw[G_tot*A]; uint32_t gbase[G_tot];
 };
 
+__device__ __forceinline__ uint32_t pack_meta(int level, int a, int cell) {
+  return ((uint32_t)level << 30) | ((uint32_t)a << 27) | (uint32_t)cell;
+}
+
+// Rank sort of one class' member list by ONE warp: order[s..s+n) holds candidate slots in arbitrary
+// order; afterwards it holds them sorted by key (score desc, hit asc).  Keys are unique, so the rank
+// (number of smaller keys) is the final position.  n <= 32: pure register/shuffle; larger: tiles.
+__device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* order, uint16_t* scratch,
+                                               int s, int n) {
+  const int lane = lane_id();
+  if (n <= 32) {
+    const int slot = (lane < n) ? order[s + lane] : 0;
+    const uint64_t mine = (lane < n) ? keys[slot] : ~0ull;
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const uint64_t o = __shfl_sync(PQ_FULL, mine, j);
+      rank += (o < mine) ? 1 : 0;
+    }
+    __syncwarp();
+    if (lane < n) order[s + rank] = (uint16_t)slot;
+    __syncwarp();
+    return;
+  }
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    const bool va = t0 + lane < n;
+    const int slot = va ? order[s + t0 + lane] : 0;
+    const uint64_t mine = va ? keys[slot] : ~0ull;
+    int rank = 0;
+    for (int t1 = 0; t1 < n; t1 += 32) {
+      const uint64_t other = (t1 + lane < n) ? keys[order[s + t1 + lane]] : ~0ull;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const uint64_t o = __shfl_sync(PQ_FULL, other, j);
+        rank += (o < mine) ? 1 : 0;
+      }
+    }
+    if (va) scratch[s + rank] = (uint16_t)slot;
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) order[s + i] = scratch[s + i];
+  __syncwarp();
+}
+
 template <int ROUND>
-__global__ void __launch_bounds__(kFusedThreads, 3)
+__global__ void __launch_bounds__(kFusedThreads, 4)
 decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constant__ DetOut O, int32_t* work) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
@@ -190,29 +240,40 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     __syncthreads();
     const int b = S.b;
     if (b >= P.B) break;
+    if (tid < P.n_levels * A) {
+      const int l = tid / A, a = tid - l * A;
+      S.pbase[tid] = P.lv[l].raw + ((size_t)(b * A + a) * ch + 4) * P.lv[l].HW;
+    }
+    if (tid < 128) { S.cls_cnt[tid] = 0; S.cls_fill[tid] = 0; }
+    __syncthreads();
 
-    // ---- 1. objectness scan: one ballot word per (level, chunk, anchor) --------------------------
-    constexpr int U = 8;
-    for (int w0 = warp; w0 < W_tot; w0 += kFusedWarps * U) {
-      float x[U];
+    // ---- 1. objectness scan: one ballot word per (level, chunk, anchor); no divisions -----------
+    {
+      constexpr int U = 8;
+      // word index w = warp + 8*i  <->  (group g, anchor a), advanced incrementally
+      int g = warp / A, a = warp - g * A;
+      const int dg = kFusedWarps / A, da = kFusedWarps - dg * A;
+      for (int w0 = warp; w0 < W_tot; w0 += kFusedWarps * U) {
+        float x[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int w = w0 + u * kFusedWarps;
-        x[u] = -INFINITY;
-        if (w < W_tot) {
-          const int g = w / A, a = w - g * A;
-          const LevelDev& L = P.lv[level_of_group(P, g)];
-          const int cell = (g - L.group_off) * 32 + lane;
-          if (cell < L.HW) x[u] = ldg_stream(L.raw + ((size_t)(b * A + a) * ch + 4) * L.HW + cell);
+        for (int u = 0; u < U; ++u) {
+          x[u] = -INFINITY;
+          if (w0 + u * kFusedWarps < W_tot) {
+            const int l = level_of_group(P, g);
+            const int cell = (g - P.lv[l].group_off) * 32 + lane;
+            if (cell < P.lv[l].HW) x[u] = ldg_stream(S.pbase[l * A + a] + cell);
+          }
+          g += dg; a += da;
+          if (a >= A) { a -= A; ++g; }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int w = w0 + u * kFusedWarps;
-        bool pass = x[u] > P.logit_lo;
-        if (pass) pass = sigmoidf_(x[u]) > P.thr_f;
-        const unsigned word = __ballot_sync(PQ_FULL, pass);
-        if (lane == 0 && w < W_tot) hitw[w] = word;
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * kFusedWarps;
+          bool pass = x[u] > P.logit_lo;
+          if (pass) pass = sigmoidf_(x[u]) > P.thr_f;
+          const unsigned word = __ballot_sync(PQ_FULL, pass);
+          if (lane == 0 && w < W_tot) hitw[w] = word;
+        }
       }
     }
     __syncthreads();
@@ -229,7 +290,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         if (g < P.G_tot) gbase[g] = running + inc - c;
         running += __shfl_sync(PQ_FULL, inc, 31);
       }
-      if (lane == 0) { S.H = running; S.M = 0; S.K = 0; }
+      if (lane == 0) { S.H = running; S.M = 0; S.K = 0; S.maxcnt = 0; }
     }
     __syncthreads();
     const int H = S.H;
@@ -242,7 +303,8 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       unsigned word = hitw[w];
       if (!word) continue;
       const int g = w / A, a = w - g * A;
-      const LevelDev& L = P.lv[level_of_group(P, g)];
+      const int l = level_of_group(P, g);
+      const LevelDev& L = P.lv[l];
       while (word) {
         const int j = __ffs(word) - 1;
         word &= word - 1;
@@ -254,52 +316,47 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
           if (a2 < a) h += (w2 >> j) & 1u;
         }
         const int cell = (g - L.group_off) * 32 + j;
-        S.hrow[h] = L.row_off + cell * A + a;
-        S.hconf[h] = sigmoidf_(L.raw[((size_t)(b * A + a) * ch + 4) * L.HW + cell]);
+        S.hmeta[h] = pack_meta(l, a, cell);
+        S.hconf[h] = sigmoidf_(S.pbase[l * A + a][cell]);
         S.hhas[h] = 0;
       }
     }
     __syncthreads();
 
-    // ---- 3. box + class channels of the hit rows only -------------------------------------------
+    // ---- 3. box + class channels of the hit rows only: 8 lanes per row, 4 rows per warp step ------
     {
       const Affine af = image_affine(P, b);
       const int CK = 4 + C;
-      const int total = H * CK;
-      constexpr int V = 4;
-      for (int e0 = tid; e0 < total; e0 += kFusedThreads * V) {
-        float v[V];
-        int hh[V], kk[V], cxs[V], cys[V];
-        float st[V];
+      const int sub = lane >> 3, k0 = lane & 7;
+      constexpr int V = 3;                                   // channel rounds in flight per row
+      for (int h = warp * 4 + sub; h < H; h += kFusedWarps * 4) {
+        const uint32_t meta = S.hmeta[h];
+        const int l = meta >> 30, a = (meta >> 27) & 7, cell = meta & 0x7ffffff;
+        const LevelDev& L = P.lv[l];
+        const float* base = S.pbase[l * A + a] + cell - (size_t)4 * L.HW;   // channel 0 of this row
+        const float conf = S.hconf[h];
+        for (int kb = k0; kb < CK; kb += 8 * V) {
+          float v[V];
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-          const int e = e0 + u * kFusedThreads;
-          hh[u] = -1;
-          if (e < total) {
-            const int h = e / CK, k = e - h * CK;
-            const int row = S.hrow[h];
-            const LevelDev& L = P.lv[level_of_row(P, row)];
-            const int rl = row - L.row_off;
-            const int cell = rl / A, a = rl - cell * A;
-            const int chan = (k < 4) ? k : k + 1;
-            v[u] = ldg_stream(L.raw + ((size_t)(b * A + a) * ch + chan) * L.HW + cell);
-            hh[u] = h; kk[u] = k; st[u] = L.stride;
-            cys[u] = cell / L.W; cxs[u] = cell - cys[u] * L.W;
+          for (int u = 0; u < V; ++u) {
+            const int k = kb + 8 * u;
+            if (k < CK) v[u] = ldg_stream(base + (size_t)((k < 4) ? k : k + 1) * L.HW);
           }
-        }
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-          if (hh[u] < 0) continue;
-          const int h = hh[u], k = kk[u];
-          if (k < 4) {
-            reinterpret_cast<float*>(&S.hbox[h])[k] =
-                recover_coord(k, decode_coord(k, v[u], cxs[u], cys[u], st[u]), af);
-          } else {
-            const float s = PQ_MUL(sigmoidf_(v[u]), S.hconf[h]);
-            if (s > P.thr_f) {
-              const int slot = atomicAdd(&S.M, 1);
-              if (slot < kCapM) S.keys[slot] = cand_key(k - 4, s, (uint32_t)h);
-              S.hhas[h] = 1;
+          for (int u = 0; u < V; ++u) {
+            const int k = kb + 8 * u;
+            if (k >= CK) continue;
+            if (k < 4) {
+              const int cy = cell / L.W, cx = cell - cy * L.W;
+              reinterpret_cast<float*>(&S.hbox[h])[k] = recover_coord(k, decode_coord(k, v[u], cx, cy, L.stride), af);
+            } else {
+              const float sc = PQ_MUL(sigmoidf_(v[u]), conf);
+              if (sc > P.thr_f) {
+                const int slot = atomicAdd(&S.M, 1);
+                if (slot < kCapM) S.keys[slot] = cand_key(k - 4, sc, (uint32_t)h);
+                atomicAdd(&S.cls_cnt[k - 4], 1);
+                S.hhas[h] = 1;
+              }
             }
           }
         }
@@ -317,18 +374,33 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       continue;
     }
 
-    // ---- 4. coordinate-trick offset base: fl(max coordinate of the picked boxes + 1) ------------
+    // ---- 4. coordinate-trick offset base + class segment starts ---------------------------------
     const bool trick = use_trick(P.nms_mode, M);
     float m1 = 0.0f;
-    if (trick) {
+    {
       float mx = -INFINITY;
-      for (int h = tid; h < H; h += kFusedThreads)
-        if (S.hhas[h]) {
-          const float4 bx = S.hbox[h];
-          mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
-        }
+      if (trick)
+        for (int h = tid; h < H; h += kFusedThreads)
+          if (S.hhas[h]) {
+            const float4 bx = S.hbox[h];
+            mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
+          }
       mx = warp_max(mx);
       if (lane == 0) S.red[warp] = mx;
+      if (warp == 1) {                                     // exclusive prefix of the class counts
+        int running = 0, mc = 0;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          const int c = c0 + lane;
+          const int n = (c < C) ? S.cls_cnt[c] : 0;
+          const int inc = warp_inclusive_sum(n);
+          if (c < C) S.seg_start[c] = running + inc - n;
+          running += __shfl_sync(PQ_FULL, inc, 31);
+          mc = max(mc, n);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mc = max(mc, __shfl_xor_sync(PQ_FULL, mc, d));
+        if (lane == 0) S.maxcnt = mc;
+      }
       __syncthreads();
       mx = S.red[0];
 #pragma unroll
@@ -336,33 +408,38 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       m1 = PQ_ADD(mx, 1.0f);
     }
 
-    // ---- 5. sort by (class, score desc, hit) and find the class segments -----------------------
-    const int P2 = next_pow2(M);
-    for (int i = M + tid; i < P2; i += kFusedThreads) S.keys[i] = ~0ull;
-    if (tid < 128) { S.seg_start[tid] = 0; S.seg_end[tid] = 0; }
-    __syncthreads();
-    bitonic_sort_block(S.keys, P2);
-    for (int i = tid; i < M; i += kFusedThreads) {
-      const int c = (int)(S.keys[i] >> 57);
-      if (i == 0 || (int)(S.keys[i - 1] >> 57) != c) S.seg_start[c] = i;
-      if (i == M - 1 || (int)(S.keys[i + 1] >> 57) != c) S.seg_end[c] = i + 1;
-      S.keepflag[i] = 0;
+    // ---- 5. per-class member lists, score-sorted ------------------------------------------------
+    const bool warp_sort = S.maxcnt <= kWarpSortMax;
+    if (warp_sort) {
+      for (int i = tid; i < M; i += kFusedThreads) {
+        const int c = (int)(S.keys[i] >> 57);
+        S.order[S.seg_start[c] + atomicAdd(&S.cls_fill[c], 1)] = (uint16_t)i;
+        S.keepflag[i] = 0;
+      }
+    } else {                                               // one huge class: block bitonic sort instead
+      const int P2 = next_pow2(M);
+      for (int i = M + tid; i < P2; i += kFusedThreads) S.keys[i] = ~0ull;
+      __syncthreads();
+      bitonic_sort_block(S.keys, P2);                      // class-major keys: segments are contiguous
+      for (int i = tid; i < M; i += kFusedThreads) { S.order[i] = (uint16_t)i; S.keepflag[i] = 0; }
     }
     __syncthreads();
 
-    // ---- 6. per-class greedy NMS, one warp per class -------------------------------------------
+    // ---- 6. per-class sort + greedy NMS, one warp per class -------------------------------------
     for (int c = warp; c < C; c += kFusedWarps) {
-      const int s = S.seg_start[c], e = S.seg_end[c];
-      if (s >= e) continue;
+      const int n = S.cls_cnt[c];
+      if (n == 0) continue;
+      const int s = S.seg_start[c];
+      if (warp_sort) warp_rank_sort(S.keys, S.order, S.klist, s, n);
       const float off = trick ? PQ_MUL((float)c, m1) : 0.0f;
       warp_nms_segment<ROUND>(
-          s, e, off, P.iou_f, P.iou_d,
-          [&](int pos) { return S.hbox[S.keys[pos] & kHitMask]; },
+          s, s + n, off, P.iou_f, P.iou_d,
+          [&](int pos) { return S.hbox[S.keys[S.order[pos]] & kHitMask]; },
           [&](int slot, int pos) -> int {
             if (pos >= 0) S.klist[slot] = (uint16_t)pos;
             return S.klist[slot];
           },
-          [&](int pos) { S.keepflag[pos] = 1; });
+          [&](int pos) { S.keepflag[S.order[pos]] = 1; });
     }
     __syncthreads();
 
@@ -384,17 +461,29 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       __syncthreads();
     }
     const int K = S.K;
-    const int P3 = next_pow2(K);
-    for (int i = K + tid; i < P3; i += kFusedThreads) S.keys[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort_block(S.keys, P3);
-    const int nout = min(K, O.max_det);
-    for (int j = tid; j < nout; j += kFusedThreads) {
-      const uint64_t k2 = S.keys[j];
+    auto emit = [&](int j, uint64_t k2) {
       const float score = __uint_as_float(~(uint32_t)(k2 >> 32));
       const uint32_t low = (uint32_t)k2;
       const int h = low >> 7, c = low & 127;
-      write_det(O, b, j, S.hbox[h], score, c, S.hrow[h], C);
+      const uint32_t meta = S.hmeta[h];
+      const LevelDev& L = P.lv[meta >> 30];
+      const int64_t row = L.row_off + (int64_t)(meta & 0x7ffffff) * A + ((meta >> 27) & 7);
+      write_det(O, b, j, S.hbox[h], score, c, row, C);
+    };
+    if (K <= kRankOutMax) {                                // position = number of smaller keys
+      if (tid < K) {
+        const uint64_t mine = S.keys[tid];
+        int rank = 0;
+        for (int j = 0; j < K; ++j) rank += (S.keys[j] < mine) ? 1 : 0;
+        if (rank < O.max_det) emit(rank, mine);
+      }
+    } else {
+      const int P3 = next_pow2(K);
+      for (int i = K + tid; i < P3; i += kFusedThreads) S.keys[i] = ~0ull;
+      __syncthreads();
+      bitonic_sort_block(S.keys, P3);
+      const int nout = min(K, O.max_det);
+      for (int j = tid; j < nout; j += kFusedThreads) emit(j, S.keys[j]);
     }
     if (tid == 0) {
       O.counts[b] = K;

@@ -32,6 +32,30 @@ _TARGET_MAP = {
 }
 
 
+class _MultiLossFn(torch.autograd.Function):
+    """All levels' decode + loss forward/backward in one kernel launch (csrc/loss.cu loss_levels_kernel).
+    Inputs: L raw heads, then L labels, then L GT lists.  Output: one (4+5L,) tensor (see the header)."""
+
+    @staticmethod
+    def forward(ctx, L, num_classes, strides, bbox_loss, ignore_thresh, l1_gain, *tensors):
+        raws, labels, gts = tensors[:L], tensors[L:2 * L], tensors[2 * L:3 * L]
+        want_grad = any(r.requires_grad for r in raws)
+        out, flag, grads = _ops.loss_levels([r.detach() for r in raws], labels, gts, num_classes, strides,
+                                            bbox_loss, ignore_thresh, l1_gain, want_grad)
+        ctx.pq = (L, num_classes, grads)
+        ctx.mark_non_differentiable(flag)
+        return out, flag
+
+    @staticmethod
+    def backward(ctx, g_out, _g_flag):
+        L, num_classes, grads = ctx.pq
+        if grads is None:
+            raise RuntimeError("pqdet loss: backward called twice (the fused gradient is consumed in place)")
+        ctx.pq = (L, num_classes, None)
+        _ops.loss_levels_scale_grad(grads, num_classes, g_out.contiguous())
+        return (None,) * 6 + tuple(grads) + (None,) * (2 * L)
+
+
 class DetectionHead(nn.Module):
     def __init__(self, opts: Sequence[dict], onnx: bool = False):
         """opts: one [yolo] option dict per level, in cfg order (FPN: strides 32, 16, 8)."""
@@ -57,6 +81,36 @@ class DetectionHead(nn.Module):
                 _ops.decode_fwd(h, C, l.opt['stride'], out=out, rows_total=N, row_offset=off)
                 off += r
             return out
+        L = len(self.layers)
+        opt0 = self.layers[0].opt
+        same = all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
+                   and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in self.layers)
+        if not same or opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
+            return self._forward_per_level(heads, target)
+        pairs = [_TARGET_MAP[l.opt['stride']](target) for l in self.layers]
+        C = pairs[0][0].shape[-1] - 6
+        out, flag = _MultiLossFn.apply(L, C, [l.opt['stride'] for l in self.layers], opt0['bbox_loss'],
+                                       opt0['ignore_thresh'], opt0.get('l1_loss_gain', 0.1),
+                                       *heads, *[p[0] for p in pairs], *[p[1] for p in pairs])
+        if config.nan_check == "sync" and int(flag.item()) != 0:
+            for l in range(L):                                        # model/loss.py:110-114
+                lo = out[4 + 4 * l:8 + 4 * l]
+                if bool(torch.isnan(lo[0])):
+                    print('xy: {}, conf: {}, cls: {}'.format(lo[1].item(), lo[2].item(), lo[3].item()))
+            raise RuntimeError('NaN in loss')
+        res = {
+            'loss': out[0:1],
+            'giou_loss': out[1:2],
+            'conf_loss': out[2:3],
+            'class_loss': out[3:4],
+            'loss_per_branch': [out[4 + 4 * L + l:5 + 4 * L + l] for l in range(L)],
+        }
+        if config.nan_check == "lazy":
+            res['loss'].pq_nan_flag = flag
+        return res
+
+    def _forward_per_level(self, heads, target):
+        """One launch per level (levels with different loss options)."""
         mode = config.nan_check
         if mode == "sync":
             config.nan_check = "lazy"            # one host sync per step instead of one per level
