@@ -247,16 +247,29 @@ def bench_loss(device, steps, warmup, peak):
                 flush.zero_()
                 ts += time_steps(step, 1)
             ms = float(np.median(ts))
+            # the same step captured into a CUDA graph (pqdet_b200.graphs): host glue out of the loop
+            from pqdet_b200.graphs import GraphedLossStep
+            gstep = GraphedLossStep(head, raws, target)
+            for _ in range(warmup):
+                gstep.replay()
+            tg = []
+            for _ in range(steps):
+                flush.zero_()
+                tg += time_steps(gstep.replay, 1)
+            msg = float(np.median(tg))
             alg = 2 * raw_bytes(C, size) + label_bytes(C, size)
-            res[kind] = {"images_per_s": B / (ms * 1e-3), "ms_per_step": ms,
-                         "roofline_frac": (alg * B / (ms * 1e-3)) / (peak * 1e9),
-                         "achieved_gbs": alg * B / (ms * 1e-3) / 1e9}
+            res[kind] = {"images_per_s": B / (msg * 1e-3), "ms_per_step": msg,
+                         "roofline_frac": (alg * B / (msg * 1e-3)) / (peak * 1e9),
+                         "achieved_gbs": alg * B / (msg * 1e-3) / 1e9,
+                         "eager_images_per_s": B / (ms * 1e-3), "eager_ms_per_step": ms}
     finally:
         pqcfg.nan_check = old
     return {"workload": "BASELINE config B: VOC C=20 512x512 bs=16 decode+loss fwd+bwd, 3 levels, GT 1-12/img",
             "algorithmic_bytes_per_image": 2 * raw_bytes(C, size) + label_bytes(C, size),
-            "timing": "median of per-step CUDA events incl. autograd glue, L2 flushed between steps",
-            "kernels_per_step": 9, "by_bbox_loss": res}
+            "timing": "median of per-step CUDA events, L2 flushed between steps; headline = CUDA-graph replay of "
+                      "forward+backward (pqdet_b200.graphs.GraphedLossStep), eager_* = the same step driven from "
+                      "Python/autograd",
+            "kernels_per_step": 2, "by_bbox_loss": res}
 
 
 def run_ours(args):

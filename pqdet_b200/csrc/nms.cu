@@ -176,7 +176,7 @@ struct FusedSmem {
   int seg_start[128];
   const float* pbase[PQDET_MAX_LEVELS * 8];   // objectness plane of (level, anchor) for this image
   float red[kFusedWarps];
-  int b, H, M, K, maxcnt;
+  int b, H, M, K, maxcnt, next_class;
   // followed by: uint32_t hitw[G_tot*A]; uint32_t gbase[G_tot];
 };
 
@@ -193,11 +193,23 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
   if (n <= 32) {
     const int slot = (lane < n) ? order[s + lane] : 0;
     const uint64_t mine = (lane < n) ? keys[slot] : ~0ull;
+    // same class => the order is decided by bits [56:25] (~score) and, only on exact score ties, by the
+    // hit index: count with one 32-bit shuffle per peer and redo in 64 bits in the (rare) tie case.
+    const uint32_t ms = (uint32_t)(mine >> kHitBits);
     int rank = 0;
+    bool tie = false;
 #pragma unroll 8
     for (int j = 0; j < 32; ++j) {
-      const uint64_t o = __shfl_sync(PQ_FULL, mine, j);
-      rank += (o < mine) ? 1 : 0;
+      const uint32_t o = __shfl_sync(PQ_FULL, ms, j);
+      rank += (o < ms) ? 1 : 0;
+      tie |= (o == ms) && (j != lane);
+    }
+    if (__any_sync(PQ_FULL, tie && lane < n)) {
+      rank = 0;
+      for (int j = 0; j < 32; ++j) {
+        const uint64_t o = __shfl_sync(PQ_FULL, mine, j);
+        rank += (o < mine) ? 1 : 0;
+      }
     }
     __syncwarp();
     if (lane < n) order[s + rank] = (uint16_t)slot;
@@ -248,23 +260,24 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     __syncthreads();
 
     // ---- 1. objectness scan: one ballot word per (level, chunk, anchor); no divisions -----------
-    {
+    for (int l = 0; l < P.n_levels; ++l) {
       constexpr int U = 8;
-      // word index w = warp + 8*i  <->  (group g, anchor a), advanced incrementally
-      int g = warp / A, a = warp - g * A;
-      const int dg = kFusedWarps / A, da = kFusedWarps - dg * A;
-      for (int w0 = warp; w0 < W_tot; w0 += kFusedWarps * U) {
+      const LevelDev& L = P.lv[l];
+      const int HW = L.HW, nw = L.nchunk * A;
+      const size_t astride = (size_t)ch * HW;                       // anchor a -> a + 1
+      const float* p0 = L.raw + ((size_t)b * A * ch + 4) * HW + lane;  // objectness plane of anchor 0
+      uint32_t* hw = hitw + L.group_off * A;
+      // word index w = warp + 8*i  <->  (chunk c, anchor a), advanced incrementally
+      int c = warp / A, a = warp - c * A;
+      const int dc = kFusedWarps / A, da = kFusedWarps - dc * A;
+      for (int w0 = warp; w0 < nw; w0 += kFusedWarps * U) {
         float x[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           x[u] = -INFINITY;
-          if (w0 + u * kFusedWarps < W_tot) {
-            const int l = level_of_group(P, g);
-            const int cell = (g - P.lv[l].group_off) * 32 + lane;
-            if (cell < P.lv[l].HW) x[u] = ldg_stream(S.pbase[l * A + a] + cell);
-          }
-          g += dg; a += da;
-          if (a >= A) { a -= A; ++g; }
+          if (w0 + u * kFusedWarps < nw && c * 32 + lane < HW) x[u] = ldg_stream(p0 + a * astride + c * 32);
+          c += dc; a += da;
+          if (a >= A) { a -= A; ++c; }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -272,7 +285,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
           bool pass = x[u] > P.logit_lo;
           if (pass) pass = sigmoidf_(x[u]) > P.thr_f;
           const unsigned word = __ballot_sync(PQ_FULL, pass);
-          if (lane == 0 && w < W_tot) hitw[w] = word;
+          if (lane == 0 && w < nw) hw[w] = word;
         }
       }
     }
@@ -290,7 +303,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         if (g < P.G_tot) gbase[g] = running + inc - c;
         running += __shfl_sync(PQ_FULL, inc, 31);
       }
-      if (lane == 0) { S.H = running; S.M = 0; S.K = 0; S.maxcnt = 0; }
+      if (lane == 0) { S.H = running; S.M = 0; S.K = 0; S.maxcnt = 0; S.next_class = 0; }
     }
     __syncthreads();
     const int H = S.H;
@@ -352,7 +365,13 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
             } else {
               const float sc = PQ_MUL(sigmoidf_(v[u]), conf);
               if (sc > P.thr_f) {
-                const int slot = atomicAdd(&S.M, 1);
+                // one shared-memory atomic per warp instead of one per candidate
+                const unsigned peers = __activemask();
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&S.M, __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                const int slot = base + __popc(peers & ((1u << lane) - 1u));
                 if (slot < kCapM) S.keys[slot] = cand_key(k - 4, sc, (uint32_t)h);
                 atomicAdd(&S.cls_cnt[k - 4], 1);
                 S.hhas[h] = 1;
@@ -426,7 +445,11 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     __syncthreads();
 
     // ---- 6. per-class sort + greedy NMS, one warp per class -------------------------------------
-    for (int c = warp; c < C; c += kFusedWarps) {
+    for (;;) {                                             // warps pull classes dynamically (uneven sizes)
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&S.next_class, 1);
+      c = __shfl_sync(PQ_FULL, c, 0);
+      if (c >= C) break;
       const int n = S.cls_cnt[c];
       if (n == 0) continue;
       const int s = S.seg_start[c];
