@@ -142,6 +142,50 @@ def cpu_eval_rate(n_images: int, repeats: int = 1, seed: int = 1234):
             "n": n_images, "n_seq": n_seq}
 
 
+def gpu_stock_rate(device, n_images: int = 64, seed: int = 4321):
+    """The bar on the same box: the reference's own sequence on CUDA tensors, i.e. the
+    stock ATen elementwise kernels + torchvision's sm_100 nms kernels driven by the per-image Python loop
+    (oracle/cpu_path.py restates the reference's glue; /root/reference cannot travel).  Bounded sample."""
+    from oracle import cpu_path
+    from pqdet_b200 import synth
+    heads = synth.make_heads(n_images, C_VOC, SIZE, "sparse", seed=seed, device=device)
+    orig = torch.tensor([[float(SIZE), float(SIZE)]], device=device)
+
+    def run():
+        with torch.no_grad():
+            outs = []
+            for h, s in zip(heads, STRIDES):
+                B, CH, H, W = h.shape
+                ch = 5 + C_VOC
+                x = h.permute(0, 2, 3, 1).reshape(B, H, W, CH // ch, ch)
+                gx = (torch.arange(W, dtype=torch.float32, device=device) + 0.5).view(1, 1, W, 1, 1)
+                gy = (torch.arange(H, dtype=torch.float32, device=device) + 0.5).view(1, H, 1, 1, 1)
+                grid = torch.cat([gx.expand(1, H, W, 1, 1), gy.expand(1, H, W, 1, 1)], dim=-1)
+                xymin = (grid - torch.exp(x[..., 0:2])) * s
+                xymax = (grid + torch.exp(x[..., 2:4])) * s
+                outs.append(torch.cat([xymin, xymax, torch.sigmoid(x[..., 4:])], dim=-1).reshape(B, -1, ch))
+            pred = torch.cat(outs, dim=1)
+            inp = torch.tensor([float(SIZE), float(SIZE)], device=device)
+            ratio = (inp / orig).min(dim=-1, keepdim=True)[0]
+            delta = ((inp - (ratio * orig).round()) / 2).floor()
+            coor = (pred[..., 0:4] - delta[:, [1, 0, 1, 0]].unsqueeze(1)) / ratio.unsqueeze(1)
+            edge = (orig - 1)[:, [1, 0]].unsqueeze(1)
+            coor = torch.cat([coor[..., :2].clamp_min(0), torch.min(coor[..., 2:], edge)], dim=-1)
+            rec = torch.cat([coor, pred[..., 5:] * pred[..., 4:5]], dim=-1)
+            return [cpu_path.torch_nms_t(rec[b], THR, IOU).cpu() for b in range(rec.shape[0])]   # .cpu(): evaluator.py:59
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        out = run()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n_images / dt, "unit": "images/s", "sample": "%d images, stock torch %s CUDA elementwise kernels + "
+            "torchvision batched_nms (CUDA) in the reference's per-image loop with .cpu() per image" % (n_images, torch.__version__),
+            "kept_per_image": float(np.mean([o.shape[0] for o in out]))}
+
+
 def cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
@@ -399,6 +443,11 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     if world == 1 and not args.no_loss:
         line["loss"] = bench_loss(device, max(args.steps, 10), 3, peak)
+    if world == 1 and args.cpu_sample > 0:
+        try:
+            line["gpu_stock_baseline"] = gpu_stock_rate(device)
+        except Exception as e:
+            line["gpu_stock_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

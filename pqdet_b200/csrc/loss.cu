@@ -34,10 +34,9 @@ struct LossParams {
 template <bool RAW>
 __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, const int ntiles, const int b,
                                           float* smem) {
-  const int A = P.A, C = P.C, ch = 5 + C, LW = 6 + C, LWp = LW | 1;
+  const int A = P.A, C = P.C, ch = 5 + C, LW = 6 + C;
   const int HW = P.H * P.W;
-  float* slab = smem;                                   // [32*A][LWp]
-  float* sgt = smem + kLossTile * A * LWp;              // [kGtChunk][5]
+  float* sgt = smem;                                    // [kGtChunk][5]
   __shared__ double sred[8][3];
   const int cell0 = tile * kLossTile;
   const int ncell = min(kLossTile, HW - cell0);
@@ -45,14 +44,22 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   const int cell = cell0 + lane;
   const bool active = lane < ncell;
 
-  // ---- stage the label tile (contiguous in global memory) ----
-  {
-    const float* src = P.label + ((size_t)b * HW + cell0) * A * LW;
-    const int n = ncell * A * LW;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      const int r = e / LW, k = e - r * LW;
-      slab[r * LWp + k] = ldg_stream(src + e);
+  // ---- label row: only [box(4), respond] and the trailing mixw are needed for every row; the class
+  // targets are read at responsible cells only.  Rows are 4*(6+C) bytes apart (8-byte aligned for even C),
+  // the three anchors of a cell are adjacent, so the three warps of the CTA share L1 lines.
+  const float* lab = P.label + (((size_t)b * HW + cell) * A + a) * LW;
+  float tb[4] = {0.f, 0.f, 0.f, 0.f}, respond = 0.f, mixw = 0.f;
+  if (active) {
+    if ((LW & 1) == 0) {
+      const float2 t01 = __ldg(reinterpret_cast<const float2*>(lab));
+      const float2 t23 = __ldg(reinterpret_cast<const float2*>(lab) + 1);
+      tb[0] = t01.x; tb[1] = t01.y; tb[2] = t23.x; tb[3] = t23.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tb[k] = __ldg(lab + k);
     }
+    respond = __ldg(lab + 4);
+    mixw = __ldg(lab + 5 + C);
   }
   // ---- prediction: box + objectness ----
   float pb[4] = {0.f, 0.f, 1.f, 1.f}, es[4] = {0.f, 0.f, 0.f, 0.f}, pconf = 0.5f;
@@ -61,28 +68,21 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   if (active) {
     if (RAW) {
       const int cy = cell / P.W, cx = cell - cy * P.W;
+      float v[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[k] = ldg_stream(P.x + plane0 + (size_t)k * HW + cell);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float v = ldg_stream(P.x + plane0 + (size_t)k * HW + cell);
-        pb[k] = decode_coord(k, v, cx, cy, P.stride);
-        const float e = expf(v) * P.stride;
+        pb[k] = decode_coord(k, v[k], cx, cy, P.stride);
+        const float e = expf(v[k]) * P.stride;
         es[k] = (k < 2) ? -e : e;                                  // d pb[k] / d raw[k]
       }
-      pconf = sigmoidf_(ldg_stream(P.x + plane0 + (size_t)4 * HW + cell));
+      pconf = sigmoidf_(v[4]);
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) pb[k] = P.x[prow + k];
       pconf = P.x[prow + 4];
     }
-  }
-  __syncthreads();
-  const float* lab = slab + (lane * A + a) * LWp;
-  float tb[4] = {0.f, 0.f, 0.f, 0.f}, respond = 0.f, mixw = 0.f;
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tb[k] = lab[k];
-    respond = lab[4];
-    mixw = lab[5 + C];
   }
   // ---- box term ----
   float dbox[4] = {0.f, 0.f, 0.f, 0.f};
@@ -126,7 +126,7 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   for (int c = 0; c < C; ++c) {
     float g = 0.f;
     if (active && respond != 0.0f) {
-      const float t = lab[5 + c];
+      const float t = __ldg(lab + 5 + c);
       float p, dp;
       if (RAW) p = sigmoidf_(P.x[plane0 + (size_t)(5 + c) * HW + cell]);
       else p = P.x[prow + 5 + c];
@@ -338,7 +338,7 @@ extern "C" int pqdet_loss_fwd_bwd(const float* x, int input_is_raw, const float*
   P.ignore_thresh = ignore_thresh; P.l1_gain = l1_loss_gain; P.inv_B = 1.0f / (float)B;
   P.bbox_loss = bbox_loss;
   const int tiles = (H * W + kLossTile - 1) / kLossTile;
-  const size_t smem = ((size_t)kLossTile * A * ((6 + C) | 1) + kGtChunk * 5) * sizeof(float);
+  const size_t smem = (size_t)kGtChunk * 5 * sizeof(float);
   dim3 grid(tiles, B);
   if (input_is_raw) {
     if (smem > 48 * 1024)
@@ -362,7 +362,7 @@ extern "C" int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A
   PQ_ENTER(device);
   const int64_t total = (int64_t)B * A * (5 + C) * H * W;
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   pq::scale_groups_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       grad, total, input_is_raw, 5 + C, H * W, g_loss, g_bbox, g_conf, g_cls);
   PQ_LAUNCH_CHECK();
@@ -418,7 +418,7 @@ extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const fl
   M.total_blocks = (unsigned)tiles_total * (unsigned)B;
   M.out = out; M.nan_flag = nan_flag;
   if (!workspace_initialised) PQ_CUDA(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned), st));
-  const size_t smem = ((size_t)kLossTile * A * ((6 + C) | 1) + kGtChunk * 5) * sizeof(float);
+  const size_t smem = (size_t)kGtChunk * 5 * sizeof(float);
   if (smem > 48 * 1024)
     PQ_CUDA(cudaFuncSetAttribute(loss_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tiles_total, B);
@@ -445,7 +445,7 @@ extern "C" int pqdet_loss_levels_scale_grad(int n_levels, float* const* grad, co
   }
   S.n_levels = n_levels; S.ch = 5 + C; S.g = upstream;
   int64_t blocks = (mx + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148) blocks = 148;            // usually a no-op (all factors 1): keep the launch tiny
   dim3 grid((unsigned)blocks, n_levels);
   scale_levels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S);
   PQ_LAUNCH_CHECK();

@@ -1,0 +1,41 @@
+"""The monkey-patch hooks of pqdet_b200/install.py against the real reference tree (CPU only, in a
+subprocess so the patched modules do not leak into the other tests).  Skipped where /root/reference is absent."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+from conftest import ROOT
+from oracle import ref_harness as rh
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="/root/reference not present")
+
+
+def test_install_patches_the_reference_hook_points():
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r)
+        from oracle import ref_harness as rh
+        ref = rh.load()
+        import pqdet_b200.install as inst
+        from pqdet_b200 import parser as pqp, tools as pqt, base_sample as pqb, loss as pql
+        done = inst.install(strict=True)
+        assert all(done.values()), done
+        import tools, model.parser, model.loss, dataset, dataset.base_sample
+        assert model.parser.YOLOLayer is pqp.YOLOLayer and model.parser.Decode is pqp.Decode
+        assert model.loss.loss_per_scale is pql.loss_per_scale
+        assert tools.torch_nms is pqt.torch_nms and tools.giou is pqt.giou
+        assert dataset.RECOVER_BBOXES_REGISTER['voc'] is pqb.recover_bboxes_prediction_voc
+        # the cfg parser now builds OUR layer for every [yolo] block, with the reference's opt dict
+        from model.interpreter import DetectionModel
+        m = DetectionModel(%r)
+        yolo = [l for l in m.module_list if l._type == 'yolo']
+        assert len(yolo) == 3 and all(isinstance(l, pqp.YOLOLayer) for l in yolo)
+        assert [l.opt['stride'] for l in yolo] == [32, 16, 8]
+        assert yolo[0].opt['classes'] == 20 and yolo[0].opt['bbox_loss'] == 'l1'
+        print('ok')
+    """) % (ROOT, os.path.join(rh.REFERENCE_ROOT, "model", "cfg", "regnetx-600m-fpn.cfg"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=rh.REFERENCE_ROOT, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
