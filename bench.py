@@ -316,6 +316,81 @@ def bench_loss(device, steps, warmup, peak):
             "kernels_per_step": 2, "by_bbox_loss": res}
 
 
+def bench_other_configs(device, peak):
+    """The other named BASELINE configs, one line each (bounded: a few launches per config).
+    C: regnetx-600m-fpn-visdrone 10-class 608x608 bs=64, dense profile (decode+NMS through the fused kernel with
+       the general path for images that overflow its on-chip lists; and decode+loss fwd+bwd with 20-200 GT/img).
+    D: COCO 80-class 608x608, 16 images per GPU (the bs=128 / 8-GPU shard): GPU label assignment + GIoU loss."""
+    from pqdet_b200 import fused, synth
+    from pqdet_b200.graphs import GraphedLossStep
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.train_dataset import LabelAssigner
+    from pqdet_b200 import config as pqcfg
+    out = {}
+    vis = [(9, 13), (25, 17), (16, 31), (47, 29), (32, 51), (83, 48), (61, 91), (131, 99), (210, 189)]
+
+    def wall(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    # ---- C: dense decode + NMS
+    B, C, size = 64, 10, 608
+    heads = synth.make_heads(B, C, size, "dense", seed=0, device=device)
+    orig = torch.tensor([480.0, 480.0], device=device)
+    res = {}
+    def run_c():
+        res["d"] = fused.decode_nms(heads, STRIDES, C, (size, size), orig, "visdrone", THR, IOU)
+    dt = wall(run_c, 3)
+    hm = res["d"].host_meta()
+    out["C_decode_nms"] = {"workload": "VisDrone-shaped C=10 608x608 bs=64 dense profile, fused + general path incl. host "
+                                       "round trips", "images_per_s": B / dt, "ms": dt * 1e3,
+                           "candidates_per_image": float(hm[1].float().mean()), "kept_per_image": float(hm[0].float().mean()),
+                           "images_via_general_path": len(res["d"]._spill),
+                           "roofline_frac": raw_bytes(C, size) * B / dt / (peak * 1e9)}
+    del heads
+    old = pqcfg.nan_check
+    pqcfg.nan_check = "off"
+    try:
+        for name, (B, C, size, lo, hi, kind, anchors) in {
+                "C_loss": (64, 10, 608, 20, 200, "l1", vis),
+                "D_assign_loss": (16, 80, 608, 2, 38, "giou", None)}.items():
+            gts = synth.make_gt(B, C, size, lo, hi, seed=0)
+            out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+            la = LabelAssigner(C, device=device) if anchors is None else LabelAssigner(C, anchors=anchors, device=device)
+            from pqdet_b200.train_dataset import pack_gt, assign_labels
+            gt_dev, cnt_dev = pack_gt(gts, device)
+            tgt = {}
+            def run_assign():
+                tgt["t"] = assign_labels(gt_dev, cnt_dev, out_sizes, C, la._anchors.tolist(), la._strides.tolist(), 0.3)
+            dt_a = wall(run_assign, 5)
+            target = tgt["t"]
+            raws = [t.requires_grad_(True) for t in synth.make_train_heads(B, C, size, seed=0, device=device)]
+            opts = [dict(classes=C, stride=s, bbox_loss=kind, ignore_thresh=0.5, l1_loss_gain=0.05) for s in STRIDES]
+            g = GraphedLossStep(DetectionHead(opts), raws, target)
+            ts = []
+            flush = torch.empty((256 << 20,), dtype=torch.uint8, device=device)
+            for _ in range(10):
+                flush.zero_()
+                ts += time_steps(g.replay, 1)
+            ms = float(np.median(ts))
+            alg = 2 * raw_bytes(C, size) + label_bytes(C, size)
+            out[name] = {"workload": "C=%d %dx%d bs=%d bbox_loss=%s GT %d-%d/img" % (C, size, size, B, kind, lo, hi),
+                         "loss_images_per_s": B / (ms * 1e-3), "loss_ms_per_step": ms,
+                         "loss_roofline_frac": alg * B / (ms * 1e-3) / (peak * 1e9),
+                         "gt_list_len": [int(t.shape[1]) for t in target[3:]],
+                         "assign_images_per_s": B / dt_a, "assign_ms": dt_a * 1e3,
+                         "assign_roofline_frac": label_bytes(C, size) * B / dt_a / (peak * 1e9)}
+            del raws, g, target, tgt
+    finally:
+        pqcfg.nan_check = old
+    return out
+
+
 def run_ours(args):
     rank, local_rank, world = dist_env()
     import torch.distributed as dist
@@ -443,6 +518,11 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     if world == 1 and not args.no_loss:
         line["loss"] = bench_loss(device, max(args.steps, 10), 3, peak)
+    if world == 1 and not args.no_loss:
+        try:
+            line["other_configs"] = bench_other_configs(device, peak)
+        except Exception as e:
+            line["other_configs"] = {"error": repr(e)}
     if world == 1 and args.cpu_sample > 0:
         try:
             line["gpu_stock_baseline"] = gpu_stock_rate(device)

@@ -90,21 +90,52 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   if (active) lb = bbox_loss_row(P.bbox_loss, pb, tb, respond, P.in_area, P.l1_gain, dbox);
 
   // ---- ignore mask: every GT has iou < thr (NaN -> false), only needed where respond != 1 ----
+  // Exact culling: a GT that does not strictly overlap the union bounding box of this CTA's predictions
+  // has inter == 0 with every one of them, i.e. iou == +0 < thr, and cannot change the mask - provided
+  // thr > 0, the prediction areas are positive finite numbers and the GT area is a finite number >= 0
+  // (otherwise 0/0 or NaN could appear, so culling is switched off for the CTA / that GT).
   bool below = true;
   const bool need = active && (respond != 1.0f);
   const float a1 = box_area(pb[0], pb[1], pb[2], pb[3]);
+  __shared__ float s_u[8][4];
+  __shared__ int s_ng;
+  float ux1 = INFINITY, uy1 = INFINITY, ux2 = -INFINITY, uy2 = -INFINITY;
+  if (need) {
+    const bool sane = (a1 > 0.0f) && (a1 < INFINITY) && (P.ignore_thresh > 0.0f);
+    ux1 = sane ? pb[0] : -INFINITY; uy1 = sane ? pb[1] : -INFINITY;
+    ux2 = sane ? pb[2] : INFINITY;  uy2 = sane ? pb[3] : INFINITY;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    ux1 = fminf(ux1, __shfl_xor_sync(PQ_FULL, ux1, d)); uy1 = fminf(uy1, __shfl_xor_sync(PQ_FULL, uy1, d));
+    ux2 = fmaxf(ux2, __shfl_xor_sync(PQ_FULL, ux2, d)); uy2 = fmaxf(uy2, __shfl_xor_sync(PQ_FULL, uy2, d));
+  }
+  if (lane == 0) { s_u[a][0] = ux1; s_u[a][1] = uy1; s_u[a][2] = ux2; s_u[a][3] = uy2; }
+  __syncthreads();
+  for (int w = 0; w < A; ++w) {
+    ux1 = fminf(ux1, s_u[w][0]); uy1 = fminf(uy1, s_u[w][1]);
+    ux2 = fmaxf(ux2, s_u[w][2]); uy2 = fmaxf(uy2, s_u[w][3]);
+  }
   for (int g0 = 0; g0 < P.G; g0 += kGtChunk) {
     const int ng = min(kGtChunk, P.G - g0);
     __syncthreads();
+    if (threadIdx.x == 0) s_ng = 0;
+    __syncthreads();
     for (int e = threadIdx.x; e < ng; e += blockDim.x) {
-      const float* q = P.gt + ((size_t)b * P.G + g0 + e) * 4;
-      const float x1 = q[0], y1 = q[1], x2 = q[2], y2 = q[3];
-      sgt[e * 5 + 0] = x1; sgt[e * 5 + 1] = y1; sgt[e * 5 + 2] = x2; sgt[e * 5 + 3] = y2;
-      sgt[e * 5 + 4] = box_area(x1, y1, x2, y2);
+      const float4 q = __ldg(reinterpret_cast<const float4*>(P.gt + ((size_t)b * P.G + g0 + e) * 4));
+      const float a2 = box_area(q.x, q.y, q.z, q.w);
+      const bool cullable = (a2 >= 0.0f) && (a2 < INFINITY);
+      const bool overlaps = (q.z > ux1) && (q.x < ux2) && (q.w > uy1) && (q.y < uy2);
+      if (!cullable || overlaps) {
+        const int pos = atomicAdd(&s_ng, 1);
+        sgt[pos * 5 + 0] = q.x; sgt[pos * 5 + 1] = q.y; sgt[pos * 5 + 2] = q.z; sgt[pos * 5 + 3] = q.w;
+        sgt[pos * 5 + 4] = a2;
+      }
     }
     __syncthreads();
+    const int nk = s_ng;
     if (need && below) {
-      for (int g = 0; g < ng; ++g) {
+      for (int g = 0; g < nk; ++g) {
         const float* q = sgt + g * 5;
         if (!iou_below(pb[0], pb[1], pb[2], pb[3], a1, q[0], q[1], q[2], q[3], q[4], P.ignore_thresh)) {
           below = false;

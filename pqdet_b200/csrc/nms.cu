@@ -267,17 +267,26 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       const size_t astride = (size_t)ch * HW;                       // anchor a -> a + 1
       const float* p0 = L.raw + ((size_t)b * A * ch + 4) * HW + lane;  // objectness plane of anchor 0
       uint32_t* hw = hitw + L.group_off * A;
-      // word index w = warp + 8*i  <->  (chunk c, anchor a), advanced incrementally
-      int c = warp / A, a = warp - c * A;
+      // word index w = warp + 8*i  <->  (chunk c, anchor a); pointer and cell advance incrementally with
+      // two loop-invariant strides (anchor wraps or not), so the inner loop has no multiplies.
+      const int c0 = warp / A;
+      int a = warp - c0 * A;
       const int dc = kFusedWarps / A, da = kFusedWarps - dc * A;
+      const float* p = p0 + (size_t)a * astride + c0 * 32;
+      int cell = c0 * 32 + lane;
+      const ptrdiff_t inc_flat = (ptrdiff_t)da * (ptrdiff_t)astride + dc * 32;
+      const ptrdiff_t inc_wrap = inc_flat - (ptrdiff_t)A * (ptrdiff_t)astride + 32;
       for (int w0 = warp; w0 < nw; w0 += kFusedWarps * U) {
         float x[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           x[u] = -INFINITY;
-          if (w0 + u * kFusedWarps < nw && c * 32 + lane < HW) x[u] = ldg_stream(p0 + a * astride + c * 32);
-          c += dc; a += da;
-          if (a >= A) { a -= A; ++c; }
+          if (w0 + u * kFusedWarps < nw && cell < HW) x[u] = ldg_stream(p);
+          a += da;
+          const bool wrap = a >= A;
+          a -= wrap ? A : 0;
+          p += wrap ? inc_wrap : inc_flat;
+          cell += wrap ? dc * 32 + 32 : dc * 32;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
