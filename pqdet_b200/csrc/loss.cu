@@ -37,12 +37,34 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   const int A = P.A, C = P.C, ch = 5 + C, LW = 6 + C;
   const int HW = P.H * P.W;
   float* sgt = smem;                                    // [kGtChunk][5]
-  __shared__ double sred[8][3];
+  __shared__ float sred[8][3];
   const int cell0 = tile * kLossTile;
   const int ncell = min(kLossTile, HW - cell0);
   const int lane = lane_id(), a = warp_id();
   const int cell = cell0 + lane;
   const bool active = lane < ncell;
+
+  // ---- class-channel gradient = 0 everywhere (responsible cells overwrite theirs further down, after at
+  // least one __syncthreads).  CTA-cooperative: every plane segment of the tile is 32 consecutive floats,
+  // written with 128-bit stores when the planes are 16-byte aligned.
+  if (P.grad) {
+    if (RAW) {
+      const bool vec = ((HW & 3) == 0) && (ncell == kLossTile);
+      for (int a2 = 0; a2 < A; ++a2) {
+        float* seg0 = P.grad + (((size_t)b * A + a2) * ch + 5) * HW + cell0;
+        if (vec) {
+          for (int i = threadIdx.x; i < C * 8; i += blockDim.x)
+            reinterpret_cast<float4*>(seg0 + (size_t)(i >> 3) * HW)[i & 7] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int i = threadIdx.x; i < C * 32; i += blockDim.x)
+            if ((i & 31) < ncell) seg0[(size_t)(i >> 5) * HW + (i & 31)] = 0.f;
+        }
+      }
+    } else if (active) {
+      float* gp = P.grad + (((size_t)b * HW + cell) * A + a) * ch + 5;
+      for (int c = 0; c < C; ++c) gp[c] = 0.f;
+    }
+  }
 
   // ---- label row: only [box(4), respond] and the trailing mixw are needed for every row; the class
   // targets are read at responsible cells only.  Rows are 4*(6+C) bytes apart (8-byte aligned for even C),
@@ -152,21 +174,35 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   if (active) lc = focal_bce_term(1.0f, 0.75f, respond, pconf, respond, bgd, &dconf);
 
   const float gw = mixw * P.inv_B;
-  // ---- class term (+ gradient stores for every class channel) ----
+  // ---- class term: only the rare responsible cells (their class gradients overwrite the zeros written at
+  // the top; the barriers in between order the two stores).  Logits/targets are fetched in batches of 8 so
+  // the scattered-plane load latency is paid once per batch, not once per class.
   float lp = 0.f;
-  for (int c = 0; c < C; ++c) {
-    float g = 0.f;
-    if (active && respond != 0.0f) {
-      const float t = __ldg(lab + 5 + c);
-      float p, dp;
-      if (RAW) p = sigmoidf_(P.x[plane0 + (size_t)(5 + c) * HW + cell]);
-      else p = P.x[prow + 5 + c];
-      lp = PQ_ADD(lp, focal_bce_term(2.0f, 0.5f, t, p, respond, -1.0f, &dp));
-      g = RAW ? dp * (p * (1.0f - p)) * gw : dp * gw;
-    }
-    if (active && P.grad) {
-      if (RAW) P.grad[plane0 + (size_t)(5 + c) * HW + cell] = g;
-      else P.grad[prow + 5 + c] = g;
+  if (active && respond != 0.0f) {
+    constexpr int U = 8;
+    for (int c0 = 0; c0 < C; c0 += U) {
+      float z[U], t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + u;
+        if (c < C) {
+          z[u] = RAW ? P.x[plane0 + (size_t)(5 + c) * HW + cell] : P.x[prow + 5 + c];
+          t[u] = __ldg(lab + 5 + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + u;
+        if (c < C) {
+          const float p = RAW ? sigmoidf_(z[u]) : z[u];
+          float dp;
+          lp = PQ_ADD(lp, focal_bce_term(2.0f, 0.5f, t[u], p, respond, -1.0f, &dp));
+          if (P.grad) {
+            if (RAW) P.grad[plane0 + (size_t)(5 + c) * HW + cell] = dp * (p * (1.0f - p)) * gw;
+            else P.grad[prow + 5 + c] = dp * gw;
+          }
+        }
+      }
     }
   }
   if (active && P.grad) {
@@ -179,16 +215,21 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
     else P.grad[prow + 4] = dconf * gw;
   }
 
-  // ---- partial sums (fp64, fixed order) ----
-  double v0 = active ? (double)PQ_MUL(lb, mixw) : 0.0;
-  double v1 = active ? (double)PQ_MUL(lc, mixw) : 0.0;
-  double v2 = active ? (double)PQ_MUL(lp, mixw) : 0.0;
-  v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+  // ---- partial sums: fixed-order fp32 butterfly inside the warp, fp64 across warps / CTAs ----
+  float v0 = active ? PQ_MUL(lb, mixw) : 0.0f;
+  float v1 = active ? PQ_MUL(lc, mixw) : 0.0f;
+  float v2 = active ? PQ_MUL(lp, mixw) : 0.0f;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 += __shfl_xor_sync(PQ_FULL, v0, d);
+    v1 += __shfl_xor_sync(PQ_FULL, v1, d);
+    v2 += __shfl_xor_sync(PQ_FULL, v2, d);
+  }
   if (lane == 0) { sred[a][0] = v0; sred[a][1] = v1; sred[a][2] = v2; }
   __syncthreads();
   if (threadIdx.x < 3) {
     double s = 0.0;
-    for (int w = 0; w < A; ++w) s += sred[w][threadIdx.x];
+    for (int w = 0; w < A; ++w) s += (double)sred[w][threadIdx.x];
     P.partials[((size_t)b * ntiles + tile) * 3 + threadIdx.x] = s;
   }
 }
@@ -201,9 +242,8 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossParams P) {
 }
 
 // ---- all FPN levels in ONE launch (DetectionModel.forward training branch, model/interpreter.py:77-85)
-// grid.x enumerates the tiles of every level back to back, grid.y = image.  The last CTA to finish
-// (atomic ticket) reduces every level's partial sums in index order - deterministic regardless of which
-// CTA happens to be last - and writes
+// grid.x enumerates the tiles of every level back to back, grid.y = image.  A second, single-CTA kernel
+// (loss_levels_finalize_kernel) reduces every level's partial sums in index order - deterministic - and writes
 //   out[0..3]            loss, bbox, conf, cls summed over levels in Python-sum order ((0+h0)+h1)+h2
 //   out[4+4l .. 7+4l]    the four (1,) losses of level l (what YOLOLayer.forward returns)
 //   out[4+4L+l]          loss_per_branch[l] = (bbox+conf)+cls of level l
@@ -220,38 +260,37 @@ struct MultiLossParams {
 __global__ void __launch_bounds__(256)
 loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ bool s_last;
-  __shared__ double s_fin[256][3];
   int l = 0;
 #pragma unroll
   for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
     if (i < M.n_levels && (int)blockIdx.x >= M.tile_off[i]) l = i;
   const int ntiles = M.tile_off[l + 1] - M.tile_off[l];
   loss_tile<true>(M.lv[l], blockIdx.x - M.tile_off[l], ntiles, blockIdx.y, smem);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(M.ticket, 1u) == M.total_blocks - 1u);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
+}
+
+// One CTA: reduce every level's partial sums in index order (deterministic) and write the outputs.
+__global__ void __launch_bounds__(256)
+loss_levels_finalize_kernel(const __grid_constant__ MultiLossParams M) {
+  __shared__ double s_fin[256][3];
   float tot[4] = {0.f, 0.f, 0.f, 0.f};
   bool nan = false;
   for (int q = 0; q < M.n_levels; ++q) {
     const LossParams& P = M.lv[q];
     const int64_t n = (int64_t)P.B * (M.tile_off[q + 1] - M.tile_off[q]);
     double acc[3] = {0.0, 0.0, 0.0};
-    const volatile double* part = P.partials;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      acc[0] += part[i * 3 + 0]; acc[1] += part[i * 3 + 1]; acc[2] += part[i * 3 + 2];
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
+      acc[0] += P.partials[i * 3 + 0]; acc[1] += P.partials[i * 3 + 1]; acc[2] += P.partials[i * 3 + 2];
     }
     for (int j = 0; j < 3; ++j) s_fin[threadIdx.x][j] = acc[j];
     __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+      if ((int)threadIdx.x < d)
+        for (int j = 0; j < 3; ++j) s_fin[threadIdx.x][j] += s_fin[threadIdx.x + d][j];
+      __syncthreads();
+    }
     if (threadIdx.x == 0) {
-      double sum[3] = {0.0, 0.0, 0.0};
-      for (unsigned t = 0; t < blockDim.x; ++t)
-        for (int j = 0; j < 3; ++j) sum[j] += s_fin[t][j];
       const double invB = 1.0 / (double)P.B;
-      const float lb = (float)(sum[0] * invB), lc = (float)(sum[1] * invB), lp = (float)(sum[2] * invB);
+      const float lb = (float)(s_fin[0][0] * invB), lc = (float)(s_fin[0][1] * invB), lp = (float)(s_fin[0][2] * invB);
       const float loss = PQ_ADD(PQ_ADD(lb, lc), lp);
       float* o = M.out + 4 + 4 * q;
       o[0] = loss; o[1] = lb; o[2] = lc; o[3] = lp;
@@ -265,7 +304,6 @@ loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   if (threadIdx.x == 0) {
     for (int j = 0; j < 4; ++j) M.out[j] = tot[j];
     *M.nan_flag = nan ? 1 : 0;
-    *M.ticket = 0u;                                  // re-arm for the next launch (stream ordered)
   }
 }
 
@@ -448,12 +486,14 @@ extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const fl
   M.n_levels = n_levels;
   M.total_blocks = (unsigned)tiles_total * (unsigned)B;
   M.out = out; M.nan_flag = nan_flag;
-  if (!workspace_initialised) PQ_CUDA(cudaMemsetAsync(M.ticket, 0, sizeof(unsigned), st));
+  (void)workspace_initialised;
   const size_t smem = (size_t)kGtChunk * 5 * sizeof(float);
   if (smem > 48 * 1024)
     PQ_CUDA(cudaFuncSetAttribute(loss_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tiles_total, B);
   loss_levels_kernel<<<grid, 32 * A, smem, st>>>(M);
+  PQ_LAUNCH_CHECK();
+  loss_levels_finalize_kernel<<<1, 256, 0, st>>>(M);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
