@@ -220,13 +220,27 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
     const bool va = t0 + lane < n;
     const int slot = va ? order[s + t0 + lane] : 0;
     const uint64_t mine = va ? keys[slot] : ~0ull;
+    const uint32_t ms = (uint32_t)(mine >> kHitBits);
     int rank = 0;
+    bool tie = false;
     for (int t1 = 0; t1 < n; t1 += 32) {
-      const uint64_t other = (t1 + lane < n) ? keys[order[s + t1 + lane]] : ~0ull;
+      const int op = t1 + lane;
+      const uint32_t other = (op < n) ? (uint32_t)(keys[order[s + op]] >> kHitBits) : 0xffffffffu;
 #pragma unroll 8
       for (int j = 0; j < 32; ++j) {
-        const uint64_t o = __shfl_sync(PQ_FULL, other, j);
-        rank += (o < mine) ? 1 : 0;
+        const uint32_t o = __shfl_sync(PQ_FULL, other, j);
+        rank += (o < ms) ? 1 : 0;
+        tie |= (o == ms) && (t1 + j != t0 + lane);
+      }
+    }
+    if (__any_sync(PQ_FULL, tie && va)) {                 // exact score tie somewhere: redo in 64 bits
+      rank = 0;
+      for (int t1 = 0; t1 < n; t1 += 32) {
+        const uint64_t other = (t1 + lane < n) ? keys[order[s + t1 + lane]] : ~0ull;
+        for (int j = 0; j < 32; ++j) {
+          const uint64_t o = __shfl_sync(PQ_FULL, other, j);
+          rank += (o < mine) ? 1 : 0;
+        }
       }
     }
     if (va) scratch[s + rank] = (uint16_t)slot;
@@ -234,6 +248,42 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
   __syncwarp();
   for (int i = lane; i < n; i += 32) order[s + i] = scratch[s + i];
   __syncwarp();
+}
+
+// Objectness scan of one image.  Word w of a level = (chunk c, anchor a), w = c*A + a.  All offsets are
+// 32-bit and stateless per word; AT == 3 (the only anchor count PQDet uses) turns the divmod into a
+// multiply-shift, AT == 0 is the run-time generic version.
+template <int AT>
+__device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int lane, int warp, uint32_t* hitw) {
+  constexpr int U = 8;
+  const int A = AT ? AT : P.A;
+  const int ch = P.ch;
+  for (int l = 0; l < P.n_levels; ++l) {
+    const LevelDev& L = P.lv[l];
+    const int HW = L.HW, nw = L.nchunk * A;
+    const unsigned astride = (unsigned)(ch * HW);                    // anchor a -> a + 1, in floats
+    const float* p0 = L.raw + ((size_t)b * A * ch + 4) * HW + lane;  // objectness plane of anchor 0
+    uint32_t* hw = hitw + L.group_off * A;
+    for (int w0 = warp; w0 < nw; w0 += kFusedWarps * U) {
+      float x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * kFusedWarps;
+        const int c = w / A;
+        const int a = w - c * A;
+        x[u] = -INFINITY;
+        if (w < nw && c * 32 + lane < HW) x[u] = ldg_stream(p0 + (a * astride + (unsigned)c * 32u));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * kFusedWarps;
+        bool pass = x[u] > P.logit_lo;
+        if (pass) pass = sigmoidf_(x[u]) > P.thr_f;
+        const unsigned word = __ballot_sync(PQ_FULL, pass);
+        if (lane == 0 && w < nw) hw[w] = word;
+      }
+    }
+  }
 }
 
 template <int ROUND>
@@ -259,45 +309,9 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     if (tid < 128) { S.cls_cnt[tid] = 0; S.cls_fill[tid] = 0; }
     __syncthreads();
 
-    // ---- 1. objectness scan: one ballot word per (level, chunk, anchor); no divisions -----------
-    for (int l = 0; l < P.n_levels; ++l) {
-      constexpr int U = 8;
-      const LevelDev& L = P.lv[l];
-      const int HW = L.HW, nw = L.nchunk * A;
-      const size_t astride = (size_t)ch * HW;                       // anchor a -> a + 1
-      const float* p0 = L.raw + ((size_t)b * A * ch + 4) * HW + lane;  // objectness plane of anchor 0
-      uint32_t* hw = hitw + L.group_off * A;
-      // word index w = warp + 8*i  <->  (chunk c, anchor a); pointer and cell advance incrementally with
-      // two loop-invariant strides (anchor wraps or not), so the inner loop has no multiplies.
-      const int c0 = warp / A;
-      int a = warp - c0 * A;
-      const int dc = kFusedWarps / A, da = kFusedWarps - dc * A;
-      const float* p = p0 + (size_t)a * astride + c0 * 32;
-      int cell = c0 * 32 + lane;
-      const ptrdiff_t inc_flat = (ptrdiff_t)da * (ptrdiff_t)astride + dc * 32;
-      const ptrdiff_t inc_wrap = inc_flat - (ptrdiff_t)A * (ptrdiff_t)astride + 32;
-      for (int w0 = warp; w0 < nw; w0 += kFusedWarps * U) {
-        float x[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          x[u] = -INFINITY;
-          if (w0 + u * kFusedWarps < nw && cell < HW) x[u] = ldg_stream(p);
-          a += da;
-          const bool wrap = a >= A;
-          a -= wrap ? A : 0;
-          p += wrap ? inc_wrap : inc_flat;
-          cell += wrap ? dc * 32 + 32 : dc * 32;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int w = w0 + u * kFusedWarps;
-          bool pass = x[u] > P.logit_lo;
-          if (pass) pass = sigmoidf_(x[u]) > P.thr_f;
-          const unsigned word = __ballot_sync(PQ_FULL, pass);
-          if (lane == 0 && w < nw) hw[w] = word;
-        }
-      }
-    }
+    // ---- 1. objectness scan: one ballot word per (level, chunk, anchor) ---------------------------
+    if (A == 3) scan_objectness<3>(P, b, lane, warp, hitw);
+    else scan_objectness<0>(P, b, lane, warp, hitw);
     __syncthreads();
 
     // ---- 2. deterministic slots: exclusive prefix of the per-group hit counts --------------------
@@ -733,31 +747,103 @@ gen_plan_kernel(const __grid_constant__ GenParams G, const __grid_constant__ Det
   }
 }
 
-constexpr int kSegThreads = 128;
-constexpr int kSegSmemKeys = 4096;   // buckets up to this size are sorted in shared memory
+// Two shared-memory tiers for the (image, class) buckets: up to 2048 candidates with 256 threads
+// (56 KB, 4 CTAs/SM) and up to 8192 with 512 threads (224 KB, 1 CTA/SM); anything larger runs on global arrays.
+constexpr int kSegSmallKeys = 2048, kSegSmallThreads = 256;
+constexpr int kSegBigKeys = 8192, kSegBigThreads = 512;
 
-// One CTA per (image, class) bucket: sort, greedy NMS (warp 0 resolves, all warps test against the
-// kept list), append kept keys to the image's kept region.
-template <int ROUND>
+// Greedy NMS over a sorted bucket of n candidates by one CTA.  box(pos) = trick-shifted box of sorted
+// position pos, kget/kset = kept-position list.  32 candidates per step:
+//   A. every warp tests the step's 32 candidates against its stripe of the kept list;
+//   B. every warp computes a slice of the step's 32x32 suppression matrix (row i = which later candidates box
+//      i would suppress), independent of A;
+//   C. warp 0 ORs the dead masks and walks the alive bits in order: keep i, clear the bits of row i.
+// Only C is serial and it is a handful of bit operations per kept box.
+template <int ROUND, int kSegWarps, typename Box, typename KGet, typename KSet>
+__device__ __forceinline__ int bucket_greedy(uint32_t n, float iou_f, double iou_d, Box box, KGet kget, KSet kset,
+                                             unsigned* s_dead, unsigned* s_rows, int* s_k) {
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  if (tid == 0) *s_k = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t p = base + lane;
+    const bool valid = p < n;
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) me = box(p);
+    bool dead = !valid;
+    const int k0 = *s_k;
+    for (int q = warp; q < k0; q += kSegWarps) {          // A
+      const float4 a = box(kget(q));
+      const float Sa = box_area(a.x, a.y, a.z, a.w);
+      if (!dead && nms_suppresses<ROUND>(a.x, a.y, a.z, a.w, Sa, me.x, me.y, me.z, me.w, iou_f, iou_d)) dead = true;
+    }
+    const unsigned dm = __ballot_sync(PQ_FULL, dead);
+    if (lane == 0) s_dead[warp] = dm;
+    for (int i = warp; i < 32; i += kSegWarps) {           // B: row i of the step's suppression matrix
+      const float ax1 = __shfl_sync(PQ_FULL, me.x, i), ay1 = __shfl_sync(PQ_FULL, me.y, i);
+      const float ax2 = __shfl_sync(PQ_FULL, me.z, i), ay2 = __shfl_sync(PQ_FULL, me.w, i);
+      const float Sa = box_area(ax1, ay1, ax2, ay2);
+      const bool sup = (lane > i) && valid &&
+                       nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, me.x, me.y, me.z, me.w, iou_f, iou_d);
+      const unsigned row = __ballot_sync(PQ_FULL, sup);
+      if (lane == 0) s_rows[i] = row;
+    }
+    __syncthreads();
+    if (warp == 0) {                                       // C
+      unsigned alldead = 0;
+#pragma unroll
+      for (int q = 0; q < kSegWarps; ++q) alldead |= s_dead[q];
+      const unsigned myrow = s_rows[lane];
+      unsigned alive = ~alldead, kept = 0;
+      while (alive) {
+        const int i = __ffs(alive) - 1;
+        kept |= 1u << i;
+        alive &= ~(1u << i);
+        alive &= ~__shfl_sync(PQ_FULL, myrow, i);
+      }
+      if ((kept >> lane) & 1u) kset(k0 + __popc(kept & ((1u << lane) - 1u)), p);
+      if (lane == 0) *s_k = k0 + __popc(kept);
+    }
+    __syncthreads();
+  }
+  return *s_k;
+}
+
+// One CTA per (image, class) bucket: sort, greedy NMS, append the kept keys to the image's kept region.
+// Buckets of up to kSegSmemKeys candidates keep keys, shifted boxes and the kept list in shared memory
+// (the inner loop then touches no global memory); larger ones run the same code on global arrays.
+template <int ROUND, int kSegSmemKeys, int kSegThreads>
 __global__ void __launch_bounds__(kSegThreads)
 gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
   if (*G.ok == 0) return;
-  __shared__ uint64_t skeys[kSegSmemKeys];
-  __shared__ unsigned s_dead[kSegThreads / 32];
+  constexpr int kSegWarps = kSegThreads / 32;
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(seg_smem);
+  float4* sbox = reinterpret_cast<float4*>(seg_smem + sizeof(uint64_t) * kSegSmemKeys);
+  uint32_t* skl = reinterpret_cast<uint32_t*>(seg_smem + (sizeof(uint64_t) + sizeof(float4)) * kSegSmemKeys);
+  __shared__ unsigned s_dead[kSegWarps];
+  __shared__ unsigned s_rows[32];
   __shared__ int s_k;
+  __shared__ uint32_t s_dst;
   const int C = G.C;
   const int ii = blockIdx.y, c = blockIdx.x;
   const uint32_t n = G.cls_count[(size_t)ii * C + c];
   if (n == 0) return;
   const int b = gen_image(G, ii);
   const uint32_t cap = G.seg_cap[(size_t)ii * C + c];
+  // tier dispatch: the small launch takes cap <= 2048 and the > 8192 leftovers, the big launch the middle
+  if (kSegSmemKeys == kSegSmallKeys) {
+    if (cap > (uint32_t)kSegSmallKeys && cap <= (uint32_t)kSegBigKeys) return;
+  } else {
+    if (cap <= (uint32_t)kSegSmallKeys || cap > (uint32_t)kSegBigKeys) return;
+  }
   uint64_t* gk = G.keys + G.seg_off[(size_t)ii * C + c];
   uint32_t* kl = G.klist + G.seg_off[(size_t)ii * C + c];
-  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-  uint64_t* keys = gk;
-  if (cap <= (uint32_t)kSegSmemKeys) {
+  const int tid = threadIdx.x;
+  const bool in_smem = cap <= (uint32_t)kSegSmemKeys;
+  uint64_t* keys = in_smem ? skeys : gk;
+  if (in_smem) {
     for (uint32_t i = tid; i < cap; i += kSegThreads) skeys[i] = (i < n) ? gk[i] : ~0ull;
-    keys = skeys;
   } else {
     for (uint32_t i = n + tid; i < cap; i += kSegThreads) gk[i] = ~0ull;
   }
@@ -771,68 +857,40 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
   if (trick) off = PQ_MUL((float)c, PQ_ADD(ordered_to_float(G.max_ord[ii]), 1.0f));
   const float4* rbox = G.from_heads ? G.rbox + (size_t)ii * G.N : nullptr;
   const float* bb = G.from_heads ? nullptr : G.bboxes + (size_t)b * G.N * (4 + C);
-  auto getbox = [&](uint32_t pos) -> float4 {
+  auto shifted_box = [&](uint32_t pos) -> float4 {            // global gather + coordinate-trick shift
     const uint32_t row = (uint32_t)keys[pos];
-    if (rbox) return rbox[row];
-    const float* r = bb + (size_t)row * (4 + C);
-    return make_float4(r[0], r[1], r[2], r[3]);
+    float4 r;
+    if (rbox) r = rbox[row];
+    else {
+      const float* q = bb + (size_t)row * (4 + C);
+      r = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    return make_float4(PQ_ADD(r.x, off), PQ_ADD(r.y, off), PQ_ADD(r.z, off), PQ_ADD(r.w, off));
   };
-  if (tid == 0) s_k = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t p = base + lane;
-    const bool valid = p < n;
-    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-    if (valid) {
-      const float4 bx = getbox(p);
-      x1 = PQ_ADD(bx.x, off); y1 = PQ_ADD(bx.y, off); x2 = PQ_ADD(bx.z, off); y2 = PQ_ADD(bx.w, off);
-    }
-    bool dead = !valid;
-    const int k0 = s_k;
-    for (int q = warp; q < k0; q += kSegThreads / 32) {     // kept list striped over the warps
-      const float4 a = getbox(kl[q]);
-      const float ax1 = PQ_ADD(a.x, off), ay1 = PQ_ADD(a.y, off), ax2 = PQ_ADD(a.z, off), ay2 = PQ_ADD(a.w, off);
-      const float Sa = box_area(ax1, ay1, ax2, ay2);
-      if (!dead && nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, G.iou_f, G.iou_d)) dead = true;
-    }
-    const unsigned dm = __ballot_sync(PQ_FULL, dead);
-    if (lane == 0) s_dead[warp] = dm;
+  int k;
+  if (in_smem) {
+    for (uint32_t i = tid; i < n; i += kSegThreads) sbox[i] = shifted_box(i);
     __syncthreads();
-    if (warp == 0) {
-      unsigned alldead = 0;
-#pragma unroll
-      for (int q = 0; q < kSegThreads / 32; ++q) alldead |= s_dead[q];
-      dead = (alldead >> lane) & 1u;
-      unsigned alive = ~alldead;
-      int k = k0;
-      while (alive) {
-        const int i = __ffs(alive) - 1;
-        alive &= alive - 1;
-        const float ax1 = __shfl_sync(PQ_FULL, x1, i), ay1 = __shfl_sync(PQ_FULL, y1, i);
-        const float ax2 = __shfl_sync(PQ_FULL, x2, i), ay2 = __shfl_sync(PQ_FULL, y2, i);
-        const float Sa = box_area(ax1, ay1, ax2, ay2);
-        if (lane == i) kl[k] = p;
-        ++k;
-        const bool sup = (lane > i) && !dead &&
-                         nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, G.iou_f, G.iou_d);
-        dead |= sup;
-        alive &= ~__ballot_sync(PQ_FULL, sup);
-      }
-      if (lane == 0) s_k = k;
-    }
-    __syncthreads();
+    k = bucket_greedy<ROUND, kSegWarps>(n, G.iou_f, G.iou_d,
+                             [&](uint32_t pos) { return sbox[pos]; },
+                             [&](int q) { return skl[q]; },
+                             [&](int q, uint32_t pos) { skl[q] = pos; }, s_dead, s_rows, &s_k);
+  } else {
+    k = bucket_greedy<ROUND, kSegWarps>(n, G.iou_f, G.iou_d, shifted_box,
+                             [&](int q) { return kl[q]; },
+                             [&](int q, uint32_t pos) { kl[q] = pos; }, s_dead, s_rows, &s_k);
   }
   // append kept keys (score desc, row asc, class asc order key) to the image's kept region
-  const int k = s_k;
-  __shared__ uint32_t s_dst;
   if (tid == 0) s_dst = atomicAdd(&G.kept_count[ii], (uint32_t)k);
   __syncthreads();
   uint64_t* kk = G.kkeys + G.img_off[ii] + s_dst;
   for (int q = tid; q < k; q += kSegThreads) {
-    const uint64_t key = keys[kl[q]];
+    const uint64_t key = keys[in_smem ? skl[q] : kl[q]];
     kk[q] = (key & 0xffffffff00000000ull) | ((uint64_t)((uint32_t)key) << 7) | (uint64_t)c;
   }
 }
+
+constexpr size_t kSegBytesPerKey = sizeof(uint64_t) + sizeof(float4) + sizeof(uint32_t);
 
 constexpr int kFinThreads = 256;
 constexpr int kFinSmemKeys = 4096;
@@ -1064,9 +1122,24 @@ extern "C" int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes
   gen_select_kernel<1><<<sel_grid, 256, 0, st>>>(G);
   PQ_LAUNCH_CHECK();
   dim3 seg_grid(G.C, n_images);
-  if (iou_round == PQDET_IOU_TV_CUDA) gen_bucket_nms_kernel<0><<<seg_grid, kSegThreads, 0, st>>>(G);
-  else gen_bucket_nms_kernel<1><<<seg_grid, kSegThreads, 0, st>>>(G);
-  PQ_LAUNCH_CHECK();
+  auto launch_buckets = [&](auto small, auto big) -> int {
+    const size_t sb = kSegBytesPerKey * kSegSmallKeys, bb = kSegBytesPerKey * kSegBigKeys;
+    PQ_CUDA(cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+    PQ_CUDA(cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb));
+    small<<<seg_grid, kSegSmallThreads, sb, st>>>(G);
+    PQ_LAUNCH_CHECK();
+    big<<<seg_grid, kSegBigThreads, bb, st>>>(G);
+    PQ_LAUNCH_CHECK();
+    return PQDET_OK;
+  };
+  int brc;
+  if (iou_round == PQDET_IOU_TV_CUDA)
+    brc = launch_buckets(gen_bucket_nms_kernel<0, kSegSmallKeys, kSegSmallThreads>,
+                         gen_bucket_nms_kernel<0, kSegBigKeys, kSegBigThreads>);
+  else
+    brc = launch_buckets(gen_bucket_nms_kernel<1, kSegSmallKeys, kSegSmallThreads>,
+                         gen_bucket_nms_kernel<1, kSegBigKeys, kSegBigThreads>);
+  if (brc != PQDET_OK) return brc;
   gen_finalize_kernel<<<n_images, kFinThreads, 0, st>>>(G, O);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;

@@ -19,10 +19,15 @@ FUSED_MAX_DET = 2048          # == kCapM of csrc/nms.cu: a fused image never kee
 class Detections:
     """Result of decode_nms: padded device buffers + per-image views after one host read."""
 
-    def __init__(self, det, idx, meta, B, spill=None):
+    def __init__(self, det, idx, meta, B):
         self.det, self.idx, self.meta, self.B = det, idx, meta, B
-        self._spill = spill or {}
+        self._spill_batch = None          # (det, idx, host meta, {image id: position}) of the general path
         self._host = None
+
+    @property
+    def _spill(self):
+        """image ids that were resolved by the general path (overflowed the fused kernel)."""
+        return self._spill_batch[3] if self._spill_batch else {}
 
     def host_meta(self) -> torch.Tensor:
         """(3,B) int32 on the host: counts, ncand, status.  The only device->host sync."""
@@ -39,14 +44,16 @@ class Detections:
 
     def __getitem__(self, b: int) -> torch.Tensor:
         """(K_b, 6) rows [x1,y1,x2,y2,score,class] of image b, descending score."""
-        if b in self._spill:
-            return self._spill[b][0]
+        if self._spill_batch and b in self._spill_batch[3]:
+            i = self._spill_batch[3][b]
+            return self._spill_batch[0][i, :int(self._spill_batch[2][0, i])]
         return self.det[b, :int(self.counts[b])]
 
     def indices(self, b: int) -> torch.Tensor:
         """row*C + class of every detection of image b (requires return_index=True)."""
-        if b in self._spill:
-            return self._spill[b][1]
+        if self._spill_batch and b in self._spill_batch[3]:
+            i = self._spill_batch[3][b]
+            return self._spill_batch[1][i, :int(self._spill_batch[2][0, i])].to(torch.int64)
         return self.idx[b, :int(self.counts[b])].to(torch.int64)
 
     def to_reference_list(self) -> List[torch.Tensor]:
@@ -58,47 +65,67 @@ class Detections:
         return out
 
 
+_DENSE_HINT = {}          # workload signature -> True when the last call mostly overflowed the fused kernel
+
+
+def _general(h, keep, ids, n_sel, return_index, by_position, cap, max_det):
+    """Run the general path until its workspace / output capacities fit (normally one attempt)."""
+    for _ in range(4):
+        gdet, gidx, gmeta, needed = _ops.nms_general(heads_t=h, keep_alive=keep, image_ids=ids, n_images=n_sel,
+                                                     max_det=max_det, cand_capacity=cap, want_index=return_index,
+                                                     out_by_position=by_position)
+        host = torch.cat([gmeta.to(torch.int64), needed]).cpu()           # the one device->host read
+        R = n_sel if by_position else h.B
+        gcounts, gncand, gstatus = host[0:R], host[R:2 * R], host[2 * R:3 * R]
+        if bool((gstatus & _lib.ST_CAND_OVERFLOW).any()):
+            cap = max(int(host[3 * R]), cap * 2)
+            continue
+        if bool((gstatus & _lib.ST_DET_TRUNCATED).any()):
+            max_det = int(gcounts.max())
+            continue
+        return gdet, gidx, gmeta, host[:3 * R].view(3, R).to(torch.int32)
+    raise _lib.PqdetError("general NMS path did not converge on a workspace size")
+
+
 def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classes: int, input_size,
                batch_original_size, dataset: str = "voc", score_threshold: float = 0.1,
                iou_threshold: float = 0.45, return_index: bool = False, resolve_overflow: bool = True,
-               nms_mode: Optional[str] = None, iou_round: Optional[str] = None) -> Detections:
+               nms_mode: Optional[str] = None, iou_round: Optional[str] = None,
+               strategy: str = "auto") -> Detections:
     """heads: raw [yolo] inputs (B, A*(5+C), H_l, W_l) in cfg order with their strides.
     input_size (h, w) -- pass a tuple/CPU tensor (a CUDA tensor costs a sync);
     batch_original_size (B,2) or (2,) (h, w).  dataset in {'voc','coco','visdrone'} picks the affine.
     With resolve_overflow (default) images whose candidates do not fit the on-chip lists are re-run
-    through the general path, so the result is always complete (costs the host read of `status`)."""
+    through the general path, so the result is always complete (costs the host read of `status`).
+    strategy: 'fused' (one-launch kernel + per-image fallback), 'general' (bucketed global-memory path for
+    every image: the right choice for dense scenes such as VisDrone), or 'auto' (fused first; remembers per
+    workload signature when most images overflowed and then goes straight to the general path)."""
     m, r = config.nms_modes()
     nms_mode, iou_round = nms_mode or m, iou_round or r
     h, keep = _ops.make_heads(heads, strides, num_classes, input_size, batch_original_size, dataset,
                               score_threshold, iou_threshold, nms_mode, iou_round)
     B = h.B
+    sig = (tuple(tuple(t.shape[1:]) for t in heads), num_classes, float(score_threshold), dataset)
+    if B and (strategy == "general" or (strategy == "auto" and _DENSE_HINT.get(sig, False))):
+        gdet, gidx, gmeta, hm = _general(h, keep, None, B, return_index, False, max(B * 32768, 1 << 16), 8192)
+        res = Detections(gdet, gidx, gmeta, B)
+        res._host = hm
+        _DENSE_HINT[sig] = bool(hm[1].max() > FUSED_MAX_DET or hm[1].float().mean() > FUSED_MAX_DET / 2)
+        return res
     det, idx, meta = _ops.decode_nms_fused(h, keep, FUSED_MAX_DET, return_index)
     res = Detections(det, idx, meta, B)
     if not resolve_overflow or B == 0:
         return res
     status = res.host_meta()[2]
     over = torch.nonzero(status & _lib.ST_CAND_OVERFLOW).reshape(-1)
+    _DENSE_HINT[sig] = bool(over.numel() * 2 > B)
     if over.numel() == 0:
         return res
     ids = over.to(torch.int32).to(det.device)
     n_sel = int(ids.numel())
-    cap, max_det = max(n_sel * 32768, 1 << 16), 8192
-    for _ in range(3):
-        gdet, gidx, gmeta, needed = _ops.nms_general(heads_t=h, keep_alive=keep, image_ids=ids, n_images=n_sel,
-                                                     max_det=max_det, cand_capacity=cap,
-                                                     want_index=return_index, out_by_position=True)
-        host = torch.cat([gmeta.to(torch.int64), needed]).cpu()
-        gcounts, gncand, gstatus = host[0:n_sel], host[n_sel:2 * n_sel], host[2 * n_sel:3 * n_sel]
-        if bool((gstatus & _lib.ST_CAND_OVERFLOW).any()):
-            cap = max(int(host[3 * n_sel]), cap * 2)
-            continue
-        if bool((gstatus & _lib.ST_DET_TRUNCATED).any()):
-            max_det = int(gcounts.max())
-            continue
-        hm = res.host_meta()
-        for i, b in enumerate(over.tolist()):
-            k = int(gcounts[i])
-            res._spill[b] = (gdet[i, :k], gidx[i, :k].to(torch.int64) if return_index else None)
-            hm[0, b], hm[1, b], hm[2, b] = k, int(gncand[i]), 0
-        return res
-    raise _lib.PqdetError("general NMS path did not converge on a workspace size")
+    gdet, gidx, _, ghm = _general(h, keep, ids, n_sel, return_index, True, max(n_sel * 32768, 1 << 16), 8192)
+    hm = res.host_meta()
+    res._spill_batch = (gdet, gidx, ghm, {int(b): i for i, b in enumerate(over.tolist())})
+    for i, b in enumerate(over.tolist()):
+        hm[0, b], hm[1, b], hm[2, b] = ghm[0, i], ghm[1, i], 0
+    return res

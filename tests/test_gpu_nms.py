@@ -83,6 +83,7 @@ def _fused_vs_chain(B, C, size, profile, kind, thr, iou, sem, seed, orig=None, s
     from pqdet_b200 import config, fused, synth
     from pqdet_b200.interpreter import DetectionHead
     config.nms_semantics = sem
+    fused._DENSE_HINT.clear()                                     # every case starts on the fused kernel
     strides = strides or synth.FPN_STRIDES
     heads = synth.make_heads(B, C, size, profile, seed=seed, strides=strides)
     dheads = [h.cuda() for h in heads]
@@ -96,6 +97,13 @@ def _fused_vs_chain(B, C, size, profile, kind, thr, iou, sem, seed, orig=None, s
     if mode:
         kw["nms_mode"] = mode
     dets = fused.decode_nms(dheads, strides, C, (size, size), cuda(orig), kind, thr, iou, return_index=True, **kw)
+    # the general path for every image must give the same rows (strategy='general', and what 'auto' switches to
+    # after a mostly-overflowing call)
+    for strat in ("general", "auto"):
+        alt = fused.decode_nms(dheads, strides, C, (size, size), cuda(orig), kind, thr, iou, return_index=True,
+                               strategy=strat, **kw)
+        for b in range(B):
+            assert torch.equal(alt[b], dets[b]) and torch.equal(alt.indices(b), dets.indices(b)), (strat, b)
     # decoded boxes themselves: within 1e-5 of the oracle's decode
     ref_dec = po.detect([h.numpy() for h in heads], C, strides)
     assert rel_close(decoded[..., :4], ref_dec[..., :4], 1e-5, scale=float(size))
