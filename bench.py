@@ -365,10 +365,17 @@ def bench_other_configs(device, peak):
             from pqdet_b200.train_dataset import pack_gt, assign_labels
             gt_dev, cnt_dev = pack_gt(gts, device)
             tgt = {}
-            def run_assign():
-                tgt["t"] = assign_labels(gt_dev, cnt_dev, out_sizes, C, la._anchors.tolist(), la._strides.tolist(), 0.3)
-            dt_a = wall(run_assign, 5)
-            target = tgt["t"]
+            def run_assign():                    # no host read: GT lists stay at capacity 3*n_max (trim=False)
+                tgt["t"] = assign_labels(gt_dev, cnt_dev, out_sizes, C, la._anchors.tolist(), la._strides.tolist(),
+                                         0.3, trim=False)
+            run_assign()
+            ta = []
+            for _ in range(10):
+                flush_a = torch.empty((256 << 20,), dtype=torch.uint8, device=device).zero_()
+                ta += time_steps(run_assign, 1)
+            del flush_a
+            dt_a = float(np.median(ta)) * 1e-3
+            target = assign_labels(gt_dev, cnt_dev, out_sizes, C, la._anchors.tolist(), la._strides.tolist(), 0.3)
             raws = [t.requires_grad_(True) for t in synth.make_train_heads(B, C, size, seed=0, device=device)]
             opts = [dict(classes=C, stride=s, bbox_loss=kind, ignore_thresh=0.5, l1_loss_gain=0.05) for s in STRIDES]
             g = GraphedLossStep(DetectionHead(opts), raws, target)
@@ -429,7 +436,6 @@ def run_ours(args):
     per_step = time_steps(step, args.steps)
     t_stop.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = torch.tensor([t_start.elapsed_time(t_stop)], device=device)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -471,6 +477,14 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = world * B * e2e_steps / (float(e2e_ms) * 1e-3)
+    # keep the GPU busy with the timed kernel for ~0.4 s more so that the 100 ms nvidia-smi sampler sees clocks
+    # and throttle reasons under exactly this load (the timed region itself lasts only a few ms)
+    t_busy = time.perf_counter()
+    while time.perf_counter() - t_busy < 0.4:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     h2d = sum(t.numel() * 4 for t in heads)
 
     if rank != 0:

@@ -350,8 +350,15 @@ def assign_labels(gt: torch.Tensor, gt_count: torch.Tensor, num_classes: int, an
     Hs = (ctypes.c_int * 3)(*[int(s[0]) for s in sizes_hw])
     Ws = (ctypes.c_int * 3)(*[int(s[1]) for s in sizes_hw])
     cap = int(list_capacity) if list_capacity else max(3 * n_max, 1)
-    labels = [torch.empty((B, Hs[i], Ws[i], 3, 6 + C), dtype=torch.float32, device=device) for i in range(3)]
-    lists = [torch.empty((B, cap, 4), dtype=torch.float32, device=device) for _ in range(3)]
+    # one allocation for the three label tensors (and one for the three lists): the library then fills the
+    # background with a single streaming launch
+    sizes = [B * Hs[i] * Ws[i] * 3 * (6 + C) for i in range(3)]
+    lbuf = torch.empty((sum(sizes),), dtype=torch.float32, device=device)
+    labels, off = [], 0
+    for i in range(3):
+        labels.append(lbuf[off:off + sizes[i]].view(B, Hs[i], Ws[i], 3, 6 + C))
+        off += sizes[i]
+    lists = list(torch.empty((3, B, cap, 4), dtype=torch.float32, device=device).unbind(0))
     list_len = torch.empty((B, 3), dtype=torch.int32, device=device)
     lib = _lib.load()
     owner = _workspace(device, "assign", lib.pqdet_assign_workspace(B, Hs, Ws))

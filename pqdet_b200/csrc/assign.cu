@@ -168,14 +168,32 @@ extern "C" int pqdet_assign_labels(const float* gt, const int32_t* gt_count, int
   P.list_capacity = list_capacity;
   P.list_len = list_len;
   PQ_CUDA(cudaMemsetAsync(owner, 0xff, own_total * sizeof(int32_t), st));
-  for (int s = 0; s < 3; ++s) {
-    PQ_CUDA(cudaMemsetAsync(lists[s], 0, (size_t)B * list_capacity * 4 * sizeof(float), st));
-    const int64_t total = (int64_t)B * H[s] * W[s] * 3 * (6 + C);
+  // Background fill.  When the caller carved the three label tensors (and the three GT lists) out of one
+  // allocation, back to back, everything is one streaming launch / one memset: rows have the same
+  // 6+C layout on every level.
+  int64_t ltot[3];
+  for (int s = 0; s < 3; ++s) ltot[s] = (int64_t)B * H[s] * W[s] * 3 * (6 + C);
+  const size_t list_floats = (size_t)B * list_capacity * 4;
+  const bool one_label_buf = (labels[1] == labels[0] + ltot[0]) && (labels[2] == labels[1] + ltot[1]);
+  const bool one_list_buf = (lists[1] == lists[0] + list_floats) && (lists[2] == lists[1] + list_floats);
+  if (one_list_buf) {
+    PQ_CUDA(cudaMemsetAsync(lists[0], 0, 3 * list_floats * sizeof(float), st));
+  } else {
+    for (int s = 0; s < 3; ++s) PQ_CUDA(cudaMemsetAsync(lists[s], 0, list_floats * sizeof(float), st));
+  }
+  auto fill = [&](float* dst, int64_t total) -> int {
     int64_t blocks = ((total >> 2) + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * 16) blocks = 148 * 16;           // grid-stride, whole waves on 148 SMs
     if (blocks < 1) blocks = 1;
-    assign_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels[s], total, 6 + C);
+    assign_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(dst, total, 6 + C);
     PQ_LAUNCH_CHECK();
+    return PQDET_OK;
+  };
+  if (one_label_buf) {
+    if (fill(labels[0], ltot[0] + ltot[1] + ltot[2]) != PQDET_OK) return PQDET_ERR_CUDA;
+  } else {
+    for (int s = 0; s < 3; ++s)
+      if (fill(labels[s], ltot[s]) != PQDET_OK) return PQDET_ERR_CUDA;
   }
   assign_kernel<0><<<B, 256, 0, st>>>(P);
   PQ_LAUNCH_CHECK();
