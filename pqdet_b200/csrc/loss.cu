@@ -268,29 +268,32 @@ loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   loss_tile<true>(M.lv[l], blockIdx.x - M.tile_off[l], ntiles, blockIdx.y, smem);
 }
 
-// One CTA: reduce every level's partial sums in index order (deterministic) and write the outputs.
-__global__ void __launch_bounds__(256)
+// One CTA of 1024 threads: reduce every level's partial sums in a fixed order (thread-strided accumulation,
+// warp butterfly, then a serial sum over the 32 warp results) - deterministic - and write the outputs.
+__global__ void __launch_bounds__(1024)
 loss_levels_finalize_kernel(const __grid_constant__ MultiLossParams M) {
-  __shared__ double s_fin[256][3];
+  __shared__ double s_w[32][3];
+  const int lane = lane_id(), warp = warp_id();
   float tot[4] = {0.f, 0.f, 0.f, 0.f};
   bool nan = false;
   for (int q = 0; q < M.n_levels; ++q) {
     const LossParams& P = M.lv[q];
     const int64_t n = (int64_t)P.B * (M.tile_off[q + 1] - M.tile_off[q]);
     double acc[3] = {0.0, 0.0, 0.0};
-    for (int64_t i = threadIdx.x; i < n; i += 256) {
+#pragma unroll 4
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
       acc[0] += P.partials[i * 3 + 0]; acc[1] += P.partials[i * 3 + 1]; acc[2] += P.partials[i * 3 + 2];
     }
-    for (int j = 0; j < 3; ++j) s_fin[threadIdx.x][j] = acc[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) { s_w[warp][0] = acc[0]; s_w[warp][1] = acc[1]; s_w[warp][2] = acc[2]; }
     __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-      if ((int)threadIdx.x < d)
-        for (int j = 0; j < 3; ++j) s_fin[threadIdx.x][j] += s_fin[threadIdx.x + d][j];
-      __syncthreads();
-    }
     if (threadIdx.x == 0) {
+      double sum[3] = {0.0, 0.0, 0.0};
+      for (int w = 0; w < 32; ++w)
+        for (int j = 0; j < 3; ++j) sum[j] += s_w[w][j];
       const double invB = 1.0 / (double)P.B;
-      const float lb = (float)(s_fin[0][0] * invB), lc = (float)(s_fin[0][1] * invB), lp = (float)(s_fin[0][2] * invB);
+      const float lb = (float)(sum[0] * invB), lc = (float)(sum[1] * invB), lp = (float)(sum[2] * invB);
       const float loss = PQ_ADD(PQ_ADD(lb, lc), lp);
       float* o = M.out + 4 + 4 * q;
       o[0] = loss; o[1] = lb; o[2] = lc; o[3] = lp;
@@ -493,7 +496,7 @@ extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const fl
   dim3 grid(tiles_total, B);
   loss_levels_kernel<<<grid, 32 * A, smem, st>>>(M);
   PQ_LAUNCH_CHECK();
-  loss_levels_finalize_kernel<<<1, 256, 0, st>>>(M);
+  loss_levels_finalize_kernel<<<1, 1024, 0, st>>>(M);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
