@@ -308,7 +308,41 @@ def bench_loss(device, steps, warmup, peak):
                          "eager_images_per_s": B / (ms * 1e-3), "eager_ms_per_step": ms}
     finally:
         pqcfg.nan_check = old
+    # the reference's own formulation (oracle/loss_ref.py: the same ATen op sequence as model/loss.py) on this
+    # box: host cores, and the stock CUDA kernels -- bounded to a few steps
+    base = {}
+    try:
+        from oracle import loss_ref
+        idx = {8: 0, 16: 1, 32: 2}
+        for dev_name in ("cpu", "cuda"):
+            dv = torch.device(dev_name) if dev_name == "cpu" else device
+            hs = [r.detach().to(dv) for r in raws]
+            tg = [t.to(dv) for t in target]
+            def ref_step():
+                tot = 0
+                for h, s in zip(hs, STRIDES):
+                    x = h.clone().requires_grad_(True)
+                    pred = loss_ref.decode_t(x, C, s)
+                    out = loss_ref.loss_per_scale_t(pred, tg[idx[s]], tg[3 + idx[s]], s, "l1", 0.5, 0.05)
+                    out[0].sum().backward()
+                    tot = tot + out[0].detach()
+                return tot
+            ref_step()
+            if dev_name == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 2 if dev_name == "cpu" else 5
+            for _ in range(reps):
+                ref_step()
+            if dev_name == "cuda":
+                torch.cuda.synchronize()
+            base[dev_name] = B * reps / (time.perf_counter() - t0)
+    except Exception as e:
+        base["error"] = repr(e)
     return {"workload": "BASELINE config B: VOC C=20 512x512 bs=16 decode+loss fwd+bwd, 3 levels, GT 1-12/img",
+            "reference_formulation_images_per_s": {"host_cpu_all_cores": base.get("cpu"), "stock_cuda_kernels": base.get("cuda"),
+                                                   "note": "oracle/loss_ref.py (model/loss.py's ATen op sequence + autograd), l1, "
+                                                           "same inputs", "error": base.get("error")},
             "algorithmic_bytes_per_image": 2 * raw_bytes(C, size) + label_bytes(C, size),
             "timing": "median of per-step CUDA events, L2 flushed between steps; headline = CUDA-graph replay of "
                       "forward+backward (pqdet_b200.graphs.GraphedLossStep), eager_* = the same step driven from "

@@ -56,6 +56,21 @@ class Detections:
             return self._spill_batch[1][i, :int(self._spill_batch[2][0, i])].to(torch.int64)
         return self.idx[b, :int(self.counts[b])].to(torch.int64)
 
+    def to_numpy_list(self):
+        """Evaluator ingest (eval/evaluator.py:53-61 without the per-image loop of device syncs): ONE
+        device->host copy of the padded rows, then per-image numpy views [(K_b, 6) float32]."""
+        counts = self.counts
+        kmax = int(counts.max()) if self.B else 0
+        host = self.det[:, :kmax].contiguous().cpu().numpy() if kmax else None
+        out = []
+        for b in range(self.B):
+            if self._spill_batch and b in self._spill_batch[3]:
+                out.append(self[b].cpu().numpy())
+            else:
+                k = int(counts[b])
+                out.append(host[b, :k] if k else __import__("numpy").zeros((0, 6), "float32"))
+        return out
+
     def to_reference_list(self) -> List[torch.Tensor]:
         """What the reference's per-image loop produces: tensors (K,6), or shape (0,) when empty."""
         out = []

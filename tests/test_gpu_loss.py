@@ -223,3 +223,50 @@ def test_numpy_nms_wrapper():
     out = tools.nms(rows, 0.1, 0.45)
     want = po.torch_nms(bb, 0.1, 0.45, device="cpu", mode="vanilla")
     assert sorted(map(bytes, out.astype(np.float32))) == sorted(map(bytes, want))
+
+
+def test_loss_and_assignment_full_size_configs():
+    """BASELINE configs B (VOC-512 bs=16, l1) and D-shard (COCO-608 bs=16, giou) at full size: GPU label
+    assignment bit-exact vs the oracle, losses within 1e-5, run-to-run determinism (bitwise), and shard
+    invariance (the batch mean equals the mean of the two half-batch means; gradients are the halves' / 2)."""
+    from pqdet_b200 import synth
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.train_dataset import DEFAULT_ANCHORS, LabelAssigner
+    for B, C, size, lo, hi, kind in ((16, 20, 512, 1, 12, "l1"), (16, 80, 608, 2, 38, "giou")):
+        gts = synth.make_gt(B, C, size, lo, hi, seed=1)
+        out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+        target = LabelAssigner(C).create_label_batch(gts, out_sizes)
+        wl, wg = po.create_label_batch(gts, out_sizes, C, DEFAULT_ANCHORS)
+        for i in range(3):
+            assert np.array_equal(target[i].cpu().numpy(), wl[i]) and np.array_equal(target[3 + i].cpu().numpy(), wg[i])
+        heads = synth.make_train_heads(B, C, size, seed=1)                      # strides 32, 16, 8
+        opts = [_opt(C, s, kind) for s in (32, 16, 8)]
+        head = DetectionHead(opts)
+
+        def run(hs, tg):
+            raws = [h.cuda().requires_grad_(True) for h in hs]
+            out = head(raws, tg)
+            out["loss"].sum().backward()
+            return out, [r.grad for r in raws]
+        out1, g1 = run(heads, target)
+        out2, g2 = run(heads, target)
+        assert all(torch.equal(a, b) for a, b in zip(g1, g2)) and torch.equal(out1["loss"], out2["loss"])
+        # oracle on the stride-32 level (the full (B,H,W,3,G) broadcast stays small there) + stride 16
+        idx = {8: 0, 16: 1, 32: 2}
+        tot = 0.0
+        for h, s in zip(heads, (32, 16, 8)):
+            want, _ = loss_ref.yolo_layer_loss(h, torch.from_numpy(wl[idx[s]]), torch.from_numpy(wg[idx[s]]), C, s,
+                                               kind, 0.5, 0.05, want_grad=False)
+            tot += float(want[0])
+        assert rel_close(float(out1["loss"]), tot, 2e-5), (float(out1["loss"]), tot)
+        # shard invariance
+        halves = []
+        for lo_b, hi_b in ((0, B // 2), (B // 2, B)):
+            tg = tuple(t[lo_b:hi_b].contiguous() for t in target)
+            halves.append(run([h[lo_b:hi_b] for h in heads], tg))
+        mean = 0.5 * (float(halves[0][0]["loss"]) + float(halves[1][0]["loss"]))
+        assert rel_close(float(out1["loss"]), mean, 1e-5)
+        for lvl in range(3):
+            cat = torch.cat([halves[0][1][lvl], halves[1][1][lvl]], dim=0) * 0.5
+            scale = float(g1[lvl].abs().max())
+            assert float((cat - g1[lvl]).abs().max()) <= 1e-6 * scale
