@@ -38,8 +38,9 @@ struct LevelDev {
   int H, W, HW;
   float stride;
   int row_off;    // first row of this level in the concatenated prediction
-  int group_off;  // first (level, chunk) group
-  int nchunk;     // ceil(HW/32)
+  int group_off;  // first group (128 cells) of this level
+  int nchunk;     // groups in this level = ceil(HW/128)
+  int vec4;       // objectness planes are 16-byte aligned (HW % 4 == 0 and an aligned base): 128-bit loads
 };
 
 struct HeadsDev {
@@ -47,7 +48,7 @@ struct HeadsDev {
   int n_levels;
   int B, A, C, ch;
   int N;       // rows per image
-  int G_tot;   // groups per image; words per image = G_tot * A
+  int G_tot;   // 128-cell groups per image; ballot words per image = G_tot * 4 * A
   int kind;
   float in_h, in_w;
   const float* orig;
@@ -177,7 +178,7 @@ struct FusedSmem {
   const float* pbase[PQDET_MAX_LEVELS * 8];   // objectness plane of (level, anchor) for this image
   float red[kFusedWarps];
   int b, H, M, K, maxcnt, next_class;
-  // followed by: uint32_t hitw[G_tot*A]; uint32_t gbase[G_tot];
+  // followed by: uint32_t hitw[G_tot*4*A]; uint32_t gbase[G_tot];
 };
 
 __device__ __forceinline__ uint32_t pack_meta(int level, int a, int cell) {
@@ -197,14 +198,15 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
     // hit index: count with one 32-bit shuffle per peer and redo in 64 bits in the (rare) tie case.
     const uint32_t ms = (uint32_t)(mine >> kHitBits);
     int rank = 0;
-    bool tie = false;
 #pragma unroll 8
     for (int j = 0; j < 32; ++j) {
       const uint32_t o = __shfl_sync(PQ_FULL, ms, j);
       rank += (o < ms) ? 1 : 0;
-      tie |= (o == ms) && (j != lane);
     }
-    if (__any_sync(PQ_FULL, tie && lane < n)) {
+    // distinct scores <=> distinct ranks; a shared rank among the real entries means an exact score tie
+    const unsigned same = __match_any_sync(PQ_FULL, (lane < n) ? rank : 64 + lane);   // all lanes take part
+    const bool tie = (lane < n) && (__popc(same) > 1);
+    if (__any_sync(PQ_FULL, tie)) {
       rank = 0;
       for (int j = 0; j < 32; ++j) {
         const uint64_t o = __shfl_sync(PQ_FULL, mine, j);
@@ -221,8 +223,7 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
     const int slot = va ? order[s + t0 + lane] : 0;
     const uint64_t mine = va ? keys[slot] : ~0ull;
     const uint32_t ms = (uint32_t)(mine >> kHitBits);
-    int rank = 0;
-    bool tie = false;
+    int rank = 0, eq = 0;
     for (int t1 = 0; t1 < n; t1 += 32) {
       const int op = t1 + lane;
       const uint32_t other = (op < n) ? (uint32_t)(keys[order[s + op]] >> kHitBits) : 0xffffffffu;
@@ -230,10 +231,10 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
       for (int j = 0; j < 32; ++j) {
         const uint32_t o = __shfl_sync(PQ_FULL, other, j);
         rank += (o < ms) ? 1 : 0;
-        tie |= (o == ms) && (t1 + j != t0 + lane);
+        eq += (o == ms) ? 1 : 0;
       }
     }
-    if (__any_sync(PQ_FULL, tie && va)) {                 // exact score tie somewhere: redo in 64 bits
+    if (__any_sync(PQ_FULL, va && eq > 1)) {               // exact score tie somewhere: redo in 64 bits
       rank = 0;
       for (int t1 = 0; t1 < n; t1 += 32) {
         const uint64_t other = (t1 + lane < n) ? keys[order[s + t1 + lane]] : ~0ull;
@@ -250,37 +251,59 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
   __syncwarp();
 }
 
-// Objectness scan of one image.  Word w of a level = (chunk c, anchor a), w = c*A + a.  All offsets are
-// 32-bit and stateless per word; AT == 3 (the only anchor count PQDet uses) turns the divmod into a
-// multiply-shift, AT == 0 is the run-time generic version.
+// Objectness scan of one image.  The cells of a level are cut into groups of 128; a unit = (group g,
+// anchor a): lane l reads cells g*128 + 4l .. 4l+3 of that anchor's objectness plane with one 128-bit load
+// (scalar loads when the planes are not 16-byte aligned, e.g. 19x19) and the warp emits four ballot words,
+// word k holding the cells 4l+k.  hitw layout: [group][a*4 + k].  AT == 3 (the only anchor count PQDet uses)
+// turns the unit divmod into a multiply-shift; AT == 0 is the run-time generic version.
 template <int AT>
 __device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int lane, int warp, uint32_t* hitw) {
-  constexpr int U = 8;
+  constexpr int U = 4;
   const int A = AT ? AT : P.A;
   const int ch = P.ch;
   for (int l = 0; l < P.n_levels; ++l) {
     const LevelDev& L = P.lv[l];
-    const int HW = L.HW, nw = L.nchunk * A;
+    const int HW = L.HW, nu = L.nchunk * A;
+    const bool vec = L.vec4 != 0;
     const unsigned astride = (unsigned)(ch * HW);                    // anchor a -> a + 1, in floats
-    const float* p0 = L.raw + ((size_t)b * A * ch + 4) * HW + lane;  // objectness plane of anchor 0
-    uint32_t* hw = hitw + L.group_off * A;
-    for (int w0 = warp; w0 < nw; w0 += kFusedWarps * U) {
-      float x[U];
+    const float* p0 = L.raw + ((size_t)b * A * ch + 4) * HW;         // objectness plane of anchor 0
+    uint4* hw = reinterpret_cast<uint4*>(hitw) + L.group_off * A;    // one uint4 (4 words) per unit
+    for (int u0 = warp; u0 < nu; u0 += kFusedWarps * U) {
+      float4 x[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int w = w0 + u * kFusedWarps;
-        const int c = w / A;
-        const int a = w - c * A;
-        x[u] = -INFINITY;
-        if (w < nw && c * 32 + lane < HW) x[u] = ldg_stream(p0 + (a * astride + (unsigned)c * 32u));
+        const int un = u0 + u * kFusedWarps;
+        const int g = un / A;
+        const int a = un - g * A;
+        const int cell = g * 128 + 4 * lane;
+        x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (un < nu && cell < HW) {
+          const float* p = p0 + (a * astride + (unsigned)cell);
+          if (vec) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(p));
+          } else {
+            x[u].x = ldg_stream(p);
+            if (cell + 1 < HW) x[u].y = ldg_stream(p + 1);
+            if (cell + 2 < HW) x[u].z = ldg_stream(p + 2);
+            if (cell + 3 < HW) x[u].w = ldg_stream(p + 3);
+          }
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int w = w0 + u * kFusedWarps;
-        bool pass = x[u] > P.logit_lo;
-        if (pass) pass = sigmoidf_(x[u]) > P.thr_f;
-        const unsigned word = __ballot_sync(PQ_FULL, pass);
-        if (lane == 0 && w < nw) hw[w] = word;
+        const int un = u0 + u * kFusedWarps;
+        bool p0b = x[u].x > P.logit_lo, p1b = x[u].y > P.logit_lo, p2b = x[u].z > P.logit_lo, p3b = x[u].w > P.logit_lo;
+        if (p0b | p1b | p2b | p3b) {                                   // rare: exact test of the survivors
+          if (p0b) p0b = sigmoidf_(x[u].x) > P.thr_f;
+          if (p1b) p1b = sigmoidf_(x[u].y) > P.thr_f;
+          if (p2b) p2b = sigmoidf_(x[u].z) > P.thr_f;
+          if (p3b) p3b = sigmoidf_(x[u].w) > P.thr_f;
+        }
+        uint4 wd;
+        wd.x = __ballot_sync(PQ_FULL, p0b); wd.y = __ballot_sync(PQ_FULL, p1b);
+        wd.z = __ballot_sync(PQ_FULL, p2b); wd.w = __ballot_sync(PQ_FULL, p3b);
+        if (lane == 0 && un < nu) hw[un] = wd;
       }
     }
   }
@@ -292,10 +315,11 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
   uint32_t* hitw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(FusedSmem));
-  uint32_t* gbase = hitw + P.G_tot * P.A;
+  uint32_t* gbase = hitw + P.G_tot * 4 * P.A;
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int A = P.A, C = P.C, ch = P.ch;
-  const int W_tot = P.G_tot * A;
+  const int WG = 4 * A;                    // ballot words per 128-cell group
+  const int W_tot = P.G_tot * WG;
 
   for (;;) {
     if (tid == 0) S.b = atomicAdd(work, 1);
@@ -321,7 +345,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         const int g = g0 + lane;
         int c = 0;
         if (g < P.G_tot)
-          for (int a = 0; a < A; ++a) c += __popc(hitw[g * A + a]);
+          for (int t = 0; t < WG; ++t) c += __popc(hitw[g * WG + t]);
         const int inc = warp_inclusive_sum(c);
         if (g < P.G_tot) gbase[g] = running + inc - c;
         running += __shfl_sync(PQ_FULL, inc, 31);
@@ -338,20 +362,24 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     for (int w = tid; w < W_tot; w += kFusedThreads) {
       unsigned word = hitw[w];
       if (!word) continue;
-      const int g = w / A, a = w - g * A;
+      const int g = w / WG, t = w - g * WG;
+      const int a = t >> 2, k = t & 3;                      // word t = a*4 + k holds cells 4*lane + k of anchor a
       const int l = level_of_group(P, g);
       const LevelDev& L = P.lv[l];
+      const uint32_t* gw = hitw + g * WG;
       while (word) {
         const int j = __ffs(word) - 1;
         word &= word - 1;
         const unsigned below = (1u << j) - 1u;
+        // slot = hits of the group that precede (lane j, k, a) in (cell, anchor) order
         int h = gbase[g];
-        for (int a2 = 0; a2 < A; ++a2) {
-          const unsigned w2 = hitw[g * A + a2];
+        for (int t2 = 0; t2 < WG; ++t2) {
+          const unsigned w2 = gw[t2];
           h += __popc(w2 & below);
-          if (a2 < a) h += (w2 >> j) & 1u;
+          const int a2 = t2 >> 2, k2 = t2 & 3;
+          if (k2 < k || (k2 == k && a2 < a)) h += (w2 >> j) & 1u;
         }
-        const int cell = (g - L.group_off) * 32 + j;
+        const int cell = (g - L.group_off) * 128 + 4 * j + k;
         S.hmeta[h] = pack_meta(l, a, cell);
         S.hconf[h] = sigmoidf_(S.pbase[l * A + a][cell]);
         S.hhas[h] = 0;
@@ -961,7 +989,8 @@ static int fill_heads(const pqdet_heads_t* h, HeadsDev* P) {
     L.H = h->H[l]; L.W = h->W[l]; L.HW = h->H[l] * h->W[l];
     L.stride = h->stride[l];
     L.row_off = (int)rows; L.group_off = (int)groups;
-    L.nchunk = (L.HW + 31) / 32;
+    L.nchunk = (L.HW + 127) / 128;
+    L.vec4 = ((L.HW & 3) == 0 && (reinterpret_cast<uintptr_t>(L.raw) & 15) == 0) ? 1 : 0;
     rows += (int64_t)L.HW * h->A;
     groups += L.nchunk;
   }
@@ -1004,7 +1033,7 @@ extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t*
   PQ_ENTER(device);
   cudaStream_t st = (cudaStream_t)stream;
   DetOut O{det, det_idx, max_det, counts, ncand, status};
-  const size_t smem = sizeof(FusedSmem) + (size_t)P.G_tot * (P.A + 1) * sizeof(uint32_t);
+  const size_t smem = sizeof(FusedSmem) + (size_t)P.G_tot * (4 * P.A + 1) * sizeof(uint32_t);
   if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
