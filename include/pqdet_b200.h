@@ -90,7 +90,10 @@ int pqdet_recover(const float* pred, float* out, int B, int64_t N, int C, int af
  * counts (B)             kept detections K per image
  * ncand  (B)             candidates M per image (score > thr)
  * status (B)             PQDET_ST_* bits
- * work_counter           one int32 of scratch (dynamic image scheduler), zeroed by the call  */
+ * work_counter           int32[2] of scratch (dynamic image scheduler).  counter_armed = 0: the call zeroes it
+ *                        first; = 1: the caller guarantees both words are 0 - true after every completed
+ *                        call on the same stream, because the last CTA to leave re-arms them - so a
+ *                        steady-state loop enqueues nothing but the kernel */
 typedef struct {
   const float* raw[PQDET_MAX_LEVELS];
   int H[PQDET_MAX_LEVELS], W[PQDET_MAX_LEVELS];
@@ -108,7 +111,7 @@ typedef struct {
 
 int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
-                     int device, void* stream);
+                     int counter_armed, int device, void* stream);
 
 /* General (any candidate count) path, same results as pqdet_decode_nms.  Works on the images
  * listed in image_ids (device int32[n_images]; NULL = images 0..n_images-1).  det/det_idx/counts/

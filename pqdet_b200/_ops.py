@@ -144,23 +144,33 @@ def make_heads(raws: Sequence[torch.Tensor], strides: Sequence[float], num_class
 
 
 def alloc_fused_outputs(B: int, max_det: int, want_index: bool, device):
+    """Output buffers of the fused kernel.  meta = [counts(B), ncand(B), status(B), scheduler words(2)]."""
     det = torch.empty((B, max_det, 6), dtype=torch.float32, device=device)
     idx = torch.empty((B, max_det), dtype=torch.int32, device=device) if want_index else None
-    meta = torch.empty((3 * B + 1,), dtype=torch.int32, device=device)
+    meta = torch.zeros((3 * B + 2,), dtype=torch.int32, device=device)
     return det, idx, meta
 
 
+_FUSED_ARMED = set()
+
+
 def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool, out=None):
-    """-> det (B,max_det,6), idx (B,max_det)|None, meta int32 (3B+1): counts, ncand, status, scheduler word.
-    `out` = buffers from alloc_fused_outputs to reuse across calls (no allocation in the hot loop)."""
+    """-> det (B,max_det,6), idx (B,max_det)|None, meta int32 (3B+2): counts, ncand, status, scheduler words.
+    `out` = buffers from alloc_fused_outputs to reuse across calls: no allocation in the hot loop, and from
+    the second call on nothing but the kernel is enqueued (the kernel re-arms its own scheduler words)."""
     raws, _ = keep_alive
     device = raws[0].device
     B = heads_t.B
     det, idx, meta = out if out is not None else alloc_fused_outputs(B, max_det, want_index, device)
     counts, ncand, status, work = meta[0:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:]
+    key = (work.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+    armed = 1 if (out is not None and key in _FUSED_ARMED) else 0
+    _FUSED_ARMED.discard(key)                       # if the call raises, the next one zeroes the words again
     _lib.check(_lib.load().pqdet_decode_nms(ctypes.byref(heads_t), _ptr(det), _ptr(idx), int(max_det),
-                                            _ptr(counts), _ptr(ncand), _ptr(status), _ptr(work),
+                                            _ptr(counts), _ptr(ncand), _ptr(status), _ptr(work), armed,
                                             _dev(raws[0]), _stream(device)), "pqdet_decode_nms")
+    if out is not None:
+        _FUSED_ARMED.add(key)
     return det, idx, meta
 
 

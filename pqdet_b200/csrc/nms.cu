@@ -22,6 +22,8 @@
 // lists bucketed by (image, class), one CTA per bucket.
 #include <string.h>
 
+#include <atomic>
+
 #include "pq_common.cuh"
 
 namespace pq {
@@ -566,6 +568,15 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     }
     __syncthreads();
   }
+  // re-arm the scheduler for the next launch on this stream: the last CTA to leave zeroes both words
+  // (work[0] = next image, work[1] = CTAs that have finished), so steady-state calls need no memset
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(work + 1, 1) == (int)gridDim.x - 1) {
+      work[0] = 0;
+      work[1] = 0;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1023,7 +1034,7 @@ static int fill_heads(const pqdet_heads_t* h, HeadsDev* P) {
 
 extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                                 int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
-                                int device, void* stream) {
+                                int counter_armed, int device, void* stream) {
   using namespace pq;
   HeadsDev P;
   int rc = fill_heads(heads, &P);
@@ -1035,22 +1046,35 @@ extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t*
   DetOut O{det, det_idx, max_det, counts, ncand, status};
   const size_t smem = sizeof(FusedSmem) + (size_t)P.G_tot * (4 * P.A + 1) * sizeof(uint32_t);
   if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
-  int sm_count = 148;
-  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
-  PQ_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
-  auto launch = [&](auto kern) -> int {
-    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    PQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    int grid = sm_count * per_sm;            // persistent: one resident wave, images pulled dynamically
+  // work_counter = int32[2].  counter_armed != 0: the caller guarantees both words are zero (they are after
+  // every completed call: the kernel re-arms them), so no memset is enqueued.
+  if (!counter_armed) PQ_CUDA(cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), st));
+  auto launch = [&](auto kern, int which) -> int {
+    // Launch geometry is a pure function of (device, kernel, smem); remember the last one per device as a
+    // single 64-bit word (smem << 32 | grid) so concurrent callers can only ever see a consistent pair.
+    static std::atomic<uint64_t> cache[2][16];
+    int per_sm_grid = 0;
+    if (device < 16) {
+      const uint64_t c = cache[which][device].load(std::memory_order_relaxed);
+      if ((c >> 32) == (uint64_t)smem) per_sm_grid = (int)(c & 0xffffffffu);
+    }
+    if (per_sm_grid == 0) {
+      PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1, sm_count = 148;
+      PQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem));
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+      if (per_sm < 1) per_sm = 1;
+      per_sm_grid = sm_count * per_sm;                      // persistent: one resident wave
+      if (device < 16) cache[which][device].store(((uint64_t)smem << 32) | (uint32_t)per_sm_grid, std::memory_order_relaxed);
+    }
+    int grid = per_sm_grid;
     if (grid > P.B) grid = P.B;
     kern<<<grid, kFusedThreads, smem, st>>>(P, O, work_counter);
     PQ_LAUNCH_CHECK();
     return PQDET_OK;
   };
-  if (heads->iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0>);
-  return launch(decode_nms_fused_kernel<1>);
+  if (heads->iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0>, 0);
+  return launch(decode_nms_fused_kernel<1>, 1);
 }
 
 namespace pq {
