@@ -355,7 +355,7 @@ def bench_other_configs(device, peak):
     C: regnetx-600m-fpn-visdrone 10-class 608x608 bs=64, dense profile (decode+NMS through the fused kernel with
        the general path for images that overflow its on-chip lists; and decode+loss fwd+bwd with 20-200 GT/img).
     D: COCO 80-class 608x608, 16 images per GPU (the bs=128 / 8-GPU shard): GPU label assignment + GIoU loss."""
-    from pqdet_b200 import fused, synth
+    from pqdet_b200 import _ops, fused, synth
     from pqdet_b200.graphs import GraphedLossStep
     from pqdet_b200.interpreter import DetectionHead
     from pqdet_b200.train_dataset import LabelAssigner
@@ -371,6 +371,29 @@ def bench_other_configs(device, peak):
             fn()
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / reps
+
+    # ---- A: mobilenetv2-fpn VOC 512x512 bs=1 (the reference's CPU-runnable case, predict.py): latency of one image
+    try:
+        from oracle import cpu_path
+        hA = synth.make_heads(1, C_VOC, SIZE, "sparse", seed=0, device=device)
+        oA = torch.tensor([375.0, 500.0], device=device)
+        hh, kk = _ops.make_heads(hA, STRIDES, C_VOC, (SIZE, SIZE), oA, "voc", THR, IOU, "auto_cpu", "tv_cpu")
+        bufA = _ops.alloc_fused_outputs(1, 2048, False, device)
+        for _ in range(5):
+            _ops.decode_nms_fused(hh, kk, 2048, False, out=bufA)
+        tA = time_steps(lambda: _ops.decode_nms_fused(hh, kk, 2048, False, out=bufA), 20)
+        hc = [t.cpu() for t in hA]
+        torch.set_num_threads(cpu_path.host_cores())
+        cpu_path.eval_chain(hc, STRIDES, C_VOC, (SIZE, SIZE), oA.cpu().reshape(1, 2), "voc", THR, IOU)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ref = cpu_path.eval_chain(hc, STRIDES, C_VOC, (SIZE, SIZE), oA.cpu().reshape(1, 2), "voc", THR, IOU)
+        dt_cpu = (time.perf_counter() - t0) / 10
+        out["A_bs1_latency"] = {"workload": "VOC C=20 512x512 bs=1 decode+recover+NMS, torchvision-CPU semantics",
+                                "gpu_kernel_us": float(np.median(tA)) * 1e3, "cpu_reference_path_us": dt_cpu * 1e6,
+                                "kept": int(bufA[2][0]), "cpu_kept": int(ref[0].shape[0])}
+    except Exception as e:
+        out["A_bs1_latency"] = {"error": repr(e)}
 
     # ---- C: dense decode + NMS
     B, C, size = 64, 10, 608

@@ -197,3 +197,39 @@ def test_fused_full_size_properties():
         want = eval_chain_oracle(None, synth.FPN_STRIDES, C, (size, size), np.array([size, size], np.float32),
                                  "voc", 0.1, 0.45, "cuda", decoded=dec)[0][0]
         assert_same_detections(full[b].cpu().numpy(), want, what="full-size img %d" % b)
+
+
+@pytest.mark.parametrize("size,C", [(320, 20), (352, 1), (416, 20), (480, 3), (544, 80), (576, 20)])
+def test_fused_multi_scale_input_sizes(size, C):
+    """The reference trains/evaluates at 320..608 (config.py:67): grids such as 11x11, 13x13, 19x19 exercise the
+    partial 128-cell groups and the unaligned (scalar) objectness loads of the scan."""
+    orig = np.array([[float(size) * 0.75, float(size)], [float(size), float(size) * 0.6]], np.float32)
+    _fused_vs_chain(2, C, size, "sparse", "voc", 0.1, 0.45, "cuda", seed=size + C, orig=orig)
+
+
+def test_fused_rectangular_heads_and_single_level():
+    """Non-square grids (H != W) and a single-level model: oracle on our own decode."""
+    from pqdet_b200 import config, fused
+    from pqdet_b200.parser import Decode
+    config.nms_semantics = "cuda"
+    fused._DENSE_HINT.clear()
+    g = torch.Generator().manual_seed(77)
+    C, B = 4, 3
+    shapes = [(12, 20, 32), (24, 40, 16)]                         # (H, W, stride): 384 x 640 input
+    heads = []
+    for h, w, s in shapes:
+        r = torch.randn((B, 3 * (5 + C), h, w), generator=g)
+        r[:, 4::(5 + C)] -= 2.5                                   # objectness logits: ~8% of rows pass
+        heads.append(r)
+    orig = np.array([[384., 640.], [300., 500.], [640., 384.]], np.float32)
+    for sub in (heads, heads[:1]):
+        strides = [s for _, _, s in shapes][:len(sub)]
+        dheads = [h.cuda() for h in sub]
+        dec = torch.cat([Decode(C, s)(h).reshape(B, -1, 5 + C) for h, s in zip(dheads, strides)], dim=1).cpu().numpy()
+        want = eval_chain_oracle(None, strides, C, (384, 640), orig, "coco", 0.1, 0.45, "cuda", decoded=dec)
+        dets = fused.decode_nms(dheads, strides, C, (384, 640), cuda(orig), "coco", 0.1, 0.45, return_index=True)
+        for b in range(B):
+            w, rows, cls = want[b]
+            ncand = int(dets.host_meta()[1, b])
+            assert_same_detections(dets[b].cpu().numpy(), w, ties_unordered=4 * ncand > 100000, what="rect %d" % b)
+            assert np.array_equal(dets.indices(b).cpu().numpy(), rows * C + cls)
