@@ -395,6 +395,31 @@ def bench_other_configs(device, peak):
     except Exception as e:
         out["A_bs1_latency"] = {"error": repr(e)}
 
+    # ---- drop-in route (no caller changes): DetectionHead eval -> recover ->
+    # tools.torch_nms per image (the reference's own loop) and tools.batched_torch_nms (one call per batch)
+    try:
+        from pqdet_b200 import base_sample, tools as pqtools
+        nB = 64
+        hD = synth.make_heads(nB, C_VOC, SIZE, "sparse", seed=4321, device=device)
+        oD = torch.tensor([[float(SIZE), float(SIZE)]], device=device).repeat(nB, 1)
+        headD = DetectionHead([dict(classes=C_VOC, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05)
+                               for s in STRIDES])
+        def loop_route():
+            with torch.no_grad():
+                rec = base_sample.recover_bboxes_prediction_voc(headD(hD), (SIZE, SIZE), oD)
+                return [pqtools.torch_nms(rec[b], THR, IOU).cpu() for b in range(nB)]
+        def batch_route():
+            with torch.no_grad():
+                rec = base_sample.recover_bboxes_prediction_voc(headD(hD), (SIZE, SIZE), oD)
+                return [t.cpu() for t in pqtools.batched_torch_nms(rec, THR, IOU)]
+        out["dropin_eval_path"] = {
+            "workload": "VOC C=20 512x512, 64 images: decode (materialised) -> recover -> NMS through the reference's "
+                        "own call signatures",
+            "per_image_torch_nms_loop_images_per_s": nB / wall(loop_route, 3),
+            "batched_torch_nms_images_per_s": nB / wall(batch_route, 3)}
+    except Exception as e:
+        out["dropin_eval_path"] = {"error": repr(e)}
+
     # ---- C: dense decode + NMS
     B, C, size = 64, 10, 608
     heads = synth.make_heads(B, C, size, "dense", seed=0, device=device)
