@@ -113,6 +113,15 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
                      int counter_armed, int device, void* stream);
 
+/* ---- a6: tools.torch_nms (tools.py:540-566) for a whole batch in ONE launch: bboxes (B, N, 4+C) recovered
+ * boxes + class scores -> detections, same outputs / status bits / scheduler-word contract as
+ * pqdet_decode_nms.  Images with more than 1024 hit rows or 2048 candidates are flagged
+ * PQDET_ST_CAND_OVERFLOW and must be re-run through pqdet_nms_general(bboxes=...). */
+int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, double score_threshold,
+                    double iou_threshold, int nms_mode, int iou_round, float* det, int32_t* det_idx,
+                    int max_det, int32_t* counts, int32_t* ncand, int32_t* status,
+                    int32_t* work_counter, int counter_armed, int device, void* stream);
+
 /* General (any candidate count) path, same results as pqdet_decode_nms.  Works on the images
  * listed in image_ids (device int32[n_images]; NULL = images 0..n_images-1).  det/det_idx/counts/
  * ncand/status are indexed by image id, or by position in image_ids when out_by_position != 0.

@@ -174,6 +174,28 @@ def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool, out=No
     return det, idx, meta
 
 
+def nms_fused(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float, nms_mode: str, iou_round: str,
+              max_det: int, want_index: bool, out=None):
+    """tools.torch_nms for a batch in one launch.  bboxes (B, N, 4+C) -> det, idx, meta (as decode_nms_fused)."""
+    bboxes = _req(bboxes, "bboxes")
+    if bboxes.dim() != 3:
+        raise ValueError("bboxes must be (B, N, 4+C)")
+    B, N, C = bboxes.shape[0], bboxes.shape[1], bboxes.shape[2] - 4
+    device = bboxes.device
+    det, idx, meta = out if out is not None else alloc_fused_outputs(B, max_det, want_index, device)
+    counts, ncand, status, work = meta[0:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:]
+    key = (work.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+    armed = 1 if (out is not None and key in _FUSED_ARMED) else 0
+    _FUSED_ARMED.discard(key)
+    _lib.check(_lib.load().pqdet_nms_fused(_ptr(bboxes), B, N, C, float(score_threshold), float(iou_threshold),
+                                           _lib.NMS_MODE[nms_mode], _lib.IOU_ROUND[iou_round], _ptr(det),
+                                           _ptr(idx), int(max_det), _ptr(counts), _ptr(ncand), _ptr(status),
+                                           _ptr(work), armed, _dev(bboxes), _stream(device)), "pqdet_nms_fused")
+    if out is not None:
+        _FUSED_ARMED.add(key)
+    return det, idx, meta
+
+
 def nms_general(heads_t=None, keep_alive=None, bboxes: Optional[torch.Tensor] = None,
                 score_threshold: float = 0.0, iou_threshold: float = 0.0, nms_mode: str = "auto_cuda",
                 iou_round: str = "tv_cuda", image_ids: Optional[torch.Tensor] = None,

@@ -60,6 +60,9 @@ struct HeadsDev {
   float iou_f;
   double iou_d;
   int nms_mode;
+  // SRC == 1 (scores source, the tools.torch_nms drop-in): recovered tensor (B, N, bb_row = 4+C)
+  const float* bboxes;
+  int bb_row;
 };
 
 struct DetOut {
@@ -311,33 +314,65 @@ __device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int la
   }
 }
 
-template <int ROUND>
+// SRC == 0: candidates come from the raw heads (decode + recover fused in).  SRC == 1: from a recovered
+// (B, N, 4+C) tensor, i.e. tools.torch_nms for a whole batch in one launch: the front end streams every row
+// once (no early-out is possible, the scores are already formed), the sort / NMS / output back end is shared.
+template <int ROUND, int SRC>
 __global__ void __launch_bounds__(kFusedThreads, 4)
 decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constant__ DetOut O, int32_t* work) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
   uint32_t* hitw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(FusedSmem));
-  uint32_t* gbase = hitw + P.G_tot * 4 * P.A;
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int A = P.A, C = P.C, ch = P.ch;
-  const int WG = 4 * A;                    // ballot words per 128-cell group
+  const int WG = SRC ? 1 : 4 * A;          // ballot words per group (128 cells x A anchors | 32 rows)
   const int W_tot = P.G_tot * WG;
+  uint32_t* gbase = hitw + W_tot;
 
   for (;;) {
     if (tid == 0) S.b = atomicAdd(work, 1);
     __syncthreads();
     const int b = S.b;
     if (b >= P.B) break;
-    if (tid < P.n_levels * A) {
+    if (SRC == 0 && tid < P.n_levels * A) {
       const int l = tid / A, a = tid - l * A;
       S.pbase[tid] = P.lv[l].raw + ((size_t)(b * A + a) * ch + 4) * P.lv[l].HW;
     }
     if (tid < 128) { S.cls_cnt[tid] = 0; S.cls_fill[tid] = 0; }
     __syncthreads();
+    const float* img = SRC ? P.bboxes + (size_t)b * P.N * P.bb_row : nullptr;
 
-    // ---- 1. objectness scan: one ballot word per (level, chunk, anchor) ---------------------------
-    if (A == 3) scan_objectness<3>(P, b, lane, warp, hitw);
-    else scan_objectness<0>(P, b, lane, warp, hitw);
+    // ---- 1. scan: one ballot word per (level, group, anchor, sub-cell) | per 32 rows ---------------
+    if (SRC == 0) {
+      if (A == 3) scan_objectness<3>(P, b, lane, warp, hitw);
+      else scan_objectness<0>(P, b, lane, warp, hitw);
+    } else {
+      // a row is a hit iff any of its C scores exceeds thr (tools.py:551); 128-bit loads when rows are aligned
+      const bool vec = ((P.bb_row & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.bboxes) & 15) == 0);
+      for (int w = warp; w < W_tot; w += kFusedWarps) {
+        const int row = w * 32 + lane;
+        bool pass = false;
+        if (row < P.N) {
+          const float* r = img + (size_t)row * P.bb_row;
+          if (vec) {
+            const float4* r4 = reinterpret_cast<const float4*>(r);
+            const int n4 = P.bb_row >> 2;
+#pragma unroll 4
+            for (int q = 1; q < n4; ++q) {
+              float4 v;
+              asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(r4 + q));
+              pass |= (v.x > P.thr_f) | (v.y > P.thr_f) | (v.z > P.thr_f) | (v.w > P.thr_f);
+            }
+          } else {
+#pragma unroll 4
+            for (int c = 0; c < C; ++c) pass |= ldg_stream(r + 4 + c) > P.thr_f;
+          }
+        }
+        const unsigned word = __ballot_sync(PQ_FULL, pass);
+        if (lane == 0) hitw[w] = word;
+      }
+    }
     __syncthreads();
 
     // ---- 2. deterministic slots: exclusive prefix of the per-group hit counts --------------------
@@ -364,6 +399,17 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     for (int w = tid; w < W_tot; w += kFusedThreads) {
       unsigned word = hitw[w];
       if (!word) continue;
+      if (SRC == 1) {                                       // word w = rows 32w .. 32w+31, already in row order
+        int h = gbase[w];
+        while (word) {
+          const int j = __ffs(word) - 1;
+          word &= word - 1;
+          S.hmeta[h] = (uint32_t)(w * 32 + j);
+          S.hhas[h] = 0;
+          ++h;
+        }
+        continue;
+      }
       const int g = w / WG, t = w - g * WG;
       const int a = t >> 2, k = t & 3;                      // word t = a*4 + k holds cells 4*lane + k of anchor a
       const int l = level_of_group(P, g);
@@ -390,7 +436,29 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     __syncthreads();
 
     // ---- 3. box + class channels of the hit rows only: 8 lanes per row, 4 rows per warp step ------
-    {
+    if (SRC == 1) {
+      const int CK = 4 + C;
+      const int sub = lane >> 3, k0 = lane & 7;
+      for (int h = warp * 4 + sub; h < H; h += kFusedWarps * 4) {
+        const float* r = img + (size_t)S.hmeta[h] * P.bb_row;
+        for (int k = k0; k < CK; k += 8) {
+          const float v = r[k];
+          if (k < 4) {
+            reinterpret_cast<float*>(&S.hbox[h])[k] = v;
+          } else if (v > P.thr_f) {
+            const unsigned peers = __activemask();
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&S.M, __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const int slot = base + __popc(peers & ((1u << lane) - 1u));
+            if (slot < kCapM) S.keys[slot] = cand_key(k - 4, v, (uint32_t)h);
+            atomicAdd(&S.cls_cnt[k - 4], 1);
+            S.hhas[h] = 1;
+          }
+        }
+      }
+    } else {
       const Affine af = image_affine(P, b);
       const int CK = 4 + C;
       const int sub = lane >> 3, k0 = lane & 7;
@@ -542,8 +610,11 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       const uint32_t low = (uint32_t)k2;
       const int h = low >> 7, c = low & 127;
       const uint32_t meta = S.hmeta[h];
-      const LevelDev& L = P.lv[meta >> 30];
-      const int64_t row = L.row_off + (int64_t)(meta & 0x7ffffff) * A + ((meta >> 27) & 7);
+      int64_t row = meta;
+      if (SRC == 0) {
+        const LevelDev& L = P.lv[meta >> 30];
+        row = L.row_off + (int64_t)(meta & 0x7ffffff) * A + ((meta >> 27) & 7);
+      }
       write_det(O, b, j, S.hbox[h], score, c, row, C);
     };
     if (K <= kRankOutMax) {                                // position = number of smaller keys
@@ -1032,19 +1103,13 @@ static int fill_heads(const pqdet_heads_t* h, HeadsDev* P) {
 
 }  // namespace pq
 
-extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
-                                int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
-                                int counter_armed, int device, void* stream) {
-  using namespace pq;
-  HeadsDev P;
-  int rc = fill_heads(heads, &P);
-  if (rc != PQDET_OK) return rc;
-  if (!det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
-  if (P.B == 0) return PQDET_OK;
-  PQ_ENTER(device);
-  cudaStream_t st = (cudaStream_t)stream;
-  DetOut O{det, det_idx, max_det, counts, ncand, status};
-  const size_t smem = sizeof(FusedSmem) + (size_t)P.G_tot * (4 * P.A + 1) * sizeof(uint32_t);
+namespace pq {
+
+// Shared launcher of the fused kernel (both sources, both rounding orders).
+static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counter, int counter_armed,
+                        int iou_round, int src, int device, cudaStream_t st) {
+  const int WG = src ? 1 : 4 * P.A;
+  const size_t smem = sizeof(FusedSmem) + (size_t)P.G_tot * (WG + 1) * sizeof(uint32_t);
   if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
   // work_counter = int32[2].  counter_armed != 0: the caller guarantees both words are zero (they are after
   // every completed call: the kernel re-arms them), so no memset is enqueued.
@@ -1052,7 +1117,7 @@ extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t*
   auto launch = [&](auto kern, int which) -> int {
     // Launch geometry is a pure function of (device, kernel, smem); remember the last one per device as a
     // single 64-bit word (smem << 32 | grid) so concurrent callers can only ever see a consistent pair.
-    static std::atomic<uint64_t> cache[2][16];
+    static std::atomic<uint64_t> cache[4][16];
     int per_sm_grid = 0;
     if (device < 16) {
       const uint64_t c = cache[which][device].load(std::memory_order_relaxed);
@@ -1073,8 +1138,63 @@ extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t*
     PQ_LAUNCH_CHECK();
     return PQDET_OK;
   };
-  if (heads->iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0>, 0);
-  return launch(decode_nms_fused_kernel<1>, 1);
+  if (src == 0) {
+    if (iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0, 0>, 0);
+    return launch(decode_nms_fused_kernel<1, 0>, 1);
+  }
+  if (iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0, 1>, 2);
+  return launch(decode_nms_fused_kernel<1, 1>, 3);
+}
+
+}  // namespace pq
+
+extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
+                                int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
+                                int counter_armed, int device, void* stream) {
+  using namespace pq;
+  HeadsDev P;
+  memset(&P, 0, sizeof(P));
+  int rc = fill_heads(heads, &P);
+  if (rc != PQDET_OK) return rc;
+  if (!det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
+  if (P.B == 0) return PQDET_OK;
+  PQ_ENTER(device);
+  DetOut O{det, det_idx, max_det, counts, ncand, status};
+  return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 0, device, (cudaStream_t)stream);
+}
+
+extern "C" int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, double score_threshold,
+                               double iou_threshold, int nms_mode, int iou_round, float* det, int32_t* det_idx,
+                               int max_det, int32_t* counts, int32_t* ncand, int32_t* status,
+                               int32_t* work_counter, int counter_armed, int device, void* stream) {
+  using namespace pq;
+  if (!bboxes || !det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
+  if (B < 0 || N < 0 || C < 1) return PQDET_ERR_INVALID_ARG;
+  if (C > PQDET_MAX_CLASSES || N >= (1ll << kHitBits) || N * C >= (1ll << 31)) return PQDET_ERR_UNSUPPORTED;
+  if (nms_mode < 0 || nms_mode > 3 || iou_round < 0 || iou_round > 1) return PQDET_ERR_INVALID_ARG;
+  if (!(iou_threshold >= 0.0)) return PQDET_ERR_UNSUPPORTED;
+  if (B == 0 || N == 0) {
+    if (B > 0) {
+      PQ_ENTER(device);
+      PQ_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * sizeof(int32_t), (cudaStream_t)stream));
+      PQ_CUDA(cudaMemsetAsync(ncand, 0, (size_t)B * sizeof(int32_t), (cudaStream_t)stream));
+      PQ_CUDA(cudaMemsetAsync(status, 0, (size_t)B * sizeof(int32_t), (cudaStream_t)stream));
+    }
+    return PQDET_OK;
+  }
+  HeadsDev P;
+  memset(&P, 0, sizeof(P));
+  P.n_levels = 0;
+  P.B = B; P.A = 1; P.C = C; P.ch = 5 + C;
+  P.N = (int)N;
+  P.G_tot = (int)((N + 31) / 32);
+  P.thr_f = (float)score_threshold;
+  P.iou_f = (float)iou_threshold; P.iou_d = iou_threshold;
+  P.nms_mode = nms_mode;
+  P.bboxes = bboxes; P.bb_row = 4 + C;
+  PQ_ENTER(device);
+  DetOut O{det, det_idx, max_det, counts, ncand, status};
+  return launch_fused(P, O, work_counter, counter_armed, iou_round, 1, device, (cudaStream_t)stream);
 }
 
 namespace pq {

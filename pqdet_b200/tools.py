@@ -15,40 +15,70 @@ from . import _lib, _ops, config
 # ------------------------------------------------------------------------------------------------
 # a6: tools.py:540-566
 # ------------------------------------------------------------------------------------------------
+_FUSED_MAX_DET = 2048            # == kCapM of csrc/nms.cu
+
+
+def _general_nms(bboxes, ids, n_sel, score_threshold, iou_threshold, nms_mode, iou_round, return_index, by_position):
+    """General path until its workspace / output capacities fit.  -> det, idx, host meta (3, R) int64."""
+    cap, max_det = max(n_sel * 8192, 1 << 16), 4096
+    for _ in range(4):
+        det, idx, meta, needed = _ops.nms_general(bboxes=bboxes, score_threshold=score_threshold,
+                                                  iou_threshold=iou_threshold, nms_mode=nms_mode,
+                                                  iou_round=iou_round, image_ids=ids, n_images=n_sel,
+                                                  max_det=max_det, cand_capacity=cap, want_index=return_index,
+                                                  out_by_position=by_position)
+        host = torch.cat([meta.to(torch.int64), needed]).cpu()
+        R = n_sel if by_position else bboxes.shape[0]
+        counts, status = host[0:R], host[2 * R:3 * R]
+        if bool((status & _lib.ST_CAND_OVERFLOW).any()):
+            cap = max(int(host[3 * R]), cap * 2)
+            continue
+        if bool((status & _lib.ST_DET_TRUNCATED).any()):
+            max_det = int(counts.max())
+            continue
+        return det, idx, host[:3 * R].view(3, R)
+    raise _lib.PqdetError("pqdet_nms_general did not converge on a workspace size")
+
+
 def batched_torch_nms(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float,
-                      return_index: bool = False, nms_mode: str = None, iou_round: str = None):
+                      return_index: bool = False, nms_mode: str = None, iou_round: str = None,
+                      strategy: str = "auto"):
     """Batched form of torch_nms: bboxes (B, N, 4+C) -> list of B tensors (K_b, 6)
-    (and, if return_index, a list of int64 tensors row*C+class).  One sync for the whole batch."""
+    (and, if return_index, a list of int64 tensors row*C+class).  One kernel launch and one host read for the
+    whole batch (csrc/nms.cu, scores source); images whose candidates do not fit the on-chip lists are re-run
+    through the general path.  strategy='general' forces the general path for every image."""
     if bboxes.dim() != 3:
         raise ValueError("bboxes must be (B, N, 4+C)")
     B, N, _ = bboxes.shape
     C = bboxes.shape[2] - 4
     m, r = config.nms_modes()
     nms_mode, iou_round = nms_mode or m, iou_round or r
+    empty = torch.zeros((0, 6), dtype=torch.float32, device=bboxes.device)
     if B == 0 or N == 0:
-        e = [torch.zeros((0, 6), dtype=torch.float32, device=bboxes.device) for _ in range(B)]
+        e = [empty for _ in range(B)]
         return (e, [torch.zeros((0,), dtype=torch.int64, device=bboxes.device) for _ in range(B)]) \
             if return_index else e
-    cap = max(B * 4096, 1 << 16)
-    max_det = 4096
-    for _ in range(3):
-        det, idx, meta, needed = _ops.nms_general(bboxes=bboxes, score_threshold=score_threshold,
-                                                  iou_threshold=iou_threshold, nms_mode=nms_mode,
-                                                  iou_round=iou_round, max_det=max_det, cand_capacity=cap,
-                                                  want_index=return_index)
-        host = torch.cat([meta.to(torch.int64), needed]).cpu()          # the one D2H of this call
-        counts, status, need = host[0:B], host[2 * B:3 * B], int(host[3 * B])
-        if bool((status & _lib.ST_CAND_OVERFLOW).any()):
-            cap = max(need, cap * 2)
-            continue
-        if bool((status & _lib.ST_DET_TRUNCATED).any()):
-            max_det = int(counts.max())
-            continue
-        outs = [det[b, :int(counts[b])] for b in range(B)]
-        if return_index:
-            return outs, [idx[b, :int(counts[b])].to(torch.int64) for b in range(B)]
-        return outs
-    raise _lib.PqdetError("pqdet_nms_general did not converge on a workspace size")
+    if strategy == "general":
+        det, idx, hm = _general_nms(bboxes, None, B, score_threshold, iou_threshold, nms_mode, iou_round,
+                                    return_index, False)
+        outs = [det[b, :int(hm[0, b])] for b in range(B)]
+        return (outs, [idx[b, :int(hm[0, b])].to(torch.int64) for b in range(B)]) if return_index else outs
+    det, idx, meta = _ops.nms_fused(bboxes, score_threshold, iou_threshold, nms_mode, iou_round, _FUSED_MAX_DET,
+                                    return_index)
+    hm = meta[:3 * B].view(3, B).cpu()                                # the one device->host read
+    outs = [det[b, :int(hm[0, b])] for b in range(B)]
+    idxs = [idx[b, :int(hm[0, b])].to(torch.int64) for b in range(B)] if return_index else None
+    over = torch.nonzero(hm[2] & _lib.ST_CAND_OVERFLOW).reshape(-1)
+    if over.numel():
+        ids = over.to(torch.int32).to(bboxes.device)
+        gdet, gidx, ghm = _general_nms(bboxes, ids, int(ids.numel()), score_threshold, iou_threshold, nms_mode,
+                                       iou_round, return_index, True)
+        for i, b in enumerate(over.tolist()):
+            k = int(ghm[0, i])
+            outs[b] = gdet[i, :k]
+            if return_index:
+                idxs[b] = gidx[i, :k].to(torch.int64)
+    return (outs, idxs) if return_index else outs
 
 
 def torch_nms(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float) -> torch.Tensor:
@@ -163,7 +193,7 @@ def nms(bboxes, score_threshold, iou_threshold, sigma=0.3, method='nms'):
     for r, c in enumerate(bboxes[:, 5].tolist()):
         dense[r, 4 + cmap[c]] = bboxes[r, 4]
     outs, idx = batched_torch_nms(_np_to_cuda(dense)[None], score_threshold, iou_threshold, return_index=True,
-                                  nms_mode="vanilla", iou_round="tv_cpu")
+                                  nms_mode="vanilla", iou_round="tv_cpu", strategy="general")
     rows = (idx[0] // C).cpu().numpy()
     kept = bboxes[rows]
     order = np.argsort([cmap[c] for c in kept[:, 5].tolist()], kind="stable")

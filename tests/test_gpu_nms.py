@@ -46,6 +46,9 @@ def test_torch_nms_dropin_vs_oracle(sem, profile, C, size, kind, iou):
     orig = np.array([[375., 500.], [float(size), float(size)]], np.float32)
     rec = po.recover(pred, (size, size), orig, kind)
     outs, idxs = tools.batched_torch_nms(cuda(rec), 0.1, iou, return_index=True)
+    g_outs, g_idxs = tools.batched_torch_nms(cuda(rec), 0.1, iou, return_index=True, strategy="general")
+    for b in range(B):
+        assert torch.equal(outs[b], g_outs[b]) and torch.equal(idxs[b], g_idxs[b])    # fused == general path
     for b in range(B):
         want, rows, cls = po.torch_nms(rec[b], 0.1, iou, device=sem, return_index=True)
         ncand = int((rec[b][:, 4:] > np.float32(0.1)).sum())
