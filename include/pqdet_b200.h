@@ -113,6 +113,17 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
                      int counter_armed, int device, void* stream);
 
+/* Host-buffer form of pqdet_decode_nms: the call predict.py:33-45 / eval/evaluator.py:48-61 would make when the
+ * head outputs and the detections live in HOST memory.  heads->raw[], heads->orig_hw, det, det_idx, counts, ncand
+ * and status may each be PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) or device
+ * memory; pageable host memory is rejected (PQDET_ERR_INVALID_ARG).  No staging copy is made: the kernel reads the
+ * objectness planes and the channels of the rows above threshold straight over PCIe (about an eighth of the head
+ * bytes on VOC-like inputs) and writes the detection rows straight back.  work_counter must be device memory.
+ * Outputs are valid after `stream` is synchronised. */
+int pqdet_decode_nms_host(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
+                          int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
+                          int counter_armed, int device, void* stream);
+
 /* ---- a6: tools.torch_nms (tools.py:540-566) for a whole batch in ONE launch: bboxes (B, N, 4+C) recovered
  * boxes + class scores -> detections, same outputs / status bits / scheduler-word contract as
  * pqdet_decode_nms.  Images with more than 1024 hit rows or 2048 candidates are flagged

@@ -174,6 +174,88 @@ def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool, out=No
     return det, idx, meta
 
 
+def _req_pinned(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if t.is_cuda:
+        return _req(t, name)
+    if not t.is_pinned():
+        raise _lib.PqdetError("%s is pageable host memory: the host-buffer path needs page-locked tensors "
+                              "(tensor.pin_memory()); pqdet_b200 has no CPU path" % name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError("%s must be contiguous float32" % name)
+    return t
+
+
+def make_heads_host(raws: Sequence[torch.Tensor], strides: Sequence[float], num_classes: int, input_size,
+                    original_size, kind: str, score_threshold: float, iou_threshold: float,
+                    nms_mode: str, iou_round: str):
+    """make_heads for head tensors that live in PINNED HOST memory (no staging copy is made)."""
+    raws = [_req_pinned(r, "head") for r in raws]
+    if not 1 <= len(raws) <= _lib.MAX_LEVELS or len(raws) != len(strides):
+        raise ValueError("need 1..%d heads with matching strides" % _lib.MAX_LEVELS)
+    B = raws[0].shape[0]
+    ch = 5 + num_classes
+    A = raws[0].shape[1] // ch
+    h = _lib.HeadsT()
+    for i, (r, s) in enumerate(zip(raws, strides)):
+        if r.shape[0] != B or r.shape[1] != A * ch:
+            raise ValueError("head %d has inconsistent shape" % i)
+        h.raw[i] = r.data_ptr()
+        h.H[i], h.W[i] = int(r.shape[2]), int(r.shape[3])
+        h.stride[i] = float(s)
+    h.n_levels = len(raws)
+    h.B, h.A, h.C = B, A, num_classes
+    h.affine_kind = _lib.AFFINE[kind]
+    h.in_h, h.in_w = _hw_pair(input_size, "input_size")
+    if not isinstance(original_size, torch.Tensor):
+        original_size = torch.tensor(original_size, dtype=torch.float32)
+    orig = original_size.detach().to(dtype=torch.float32).contiguous()
+    if not orig.is_cuda and not orig.is_pinned():
+        orig = orig.pin_memory()
+    if orig.dim() == 1 and orig.numel() == 2:
+        per = 0
+    elif orig.dim() == 2 and tuple(orig.shape) == (B, 2):
+        per = 1
+    else:
+        raise ValueError("batch_original_size must have shape (B,2) or (2,), got %s" % (tuple(orig.shape),))
+    h.orig_hw = orig.data_ptr()
+    h.orig_per_image = per
+    h.score_threshold = float(score_threshold)
+    h.iou_threshold = float(iou_threshold)
+    h.nms_mode = _lib.NMS_MODE[nms_mode]
+    h.iou_round = _lib.IOU_ROUND[iou_round]
+    return h, (raws, orig)
+
+
+def alloc_host_outputs(B: int, max_det: int, want_index: bool, device):
+    """Pinned-host outputs of decode_nms_host (+ the two device scheduler words)."""
+    det = torch.empty((B, max_det, 6), dtype=torch.float32, pin_memory=True)
+    idx = torch.empty((B, max_det), dtype=torch.int32, pin_memory=True) if want_index else None
+    meta = torch.zeros((3 * B,), dtype=torch.int32, pin_memory=True)
+    work = torch.zeros((2,), dtype=torch.int32, device=device)
+    return det, idx, meta, work
+
+
+def decode_nms_host(heads_t, keep_alive, max_det: int, want_index: bool, device, out=None):
+    """Host buffers in, host buffers out (pqdet_decode_nms_host).  -> det, idx, meta (pinned host), work (device).
+    Asynchronous on the current stream of `device`: synchronise before reading the outputs."""
+    device = torch.device(device)
+    B = heads_t.B
+    det, idx, meta, work = out if out is not None else alloc_host_outputs(B, max_det, want_index, device)
+    counts, ncand, status = meta[0:B], meta[B:2 * B], meta[2 * B:3 * B]
+    key = (work.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+    armed = 1 if (out is not None and key in _FUSED_ARMED) else 0
+    _FUSED_ARMED.discard(key)
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    _lib.check(_lib.load().pqdet_decode_nms_host(ctypes.byref(heads_t), _ptr(det), _ptr(idx), int(max_det),
+                                                 _ptr(counts), _ptr(ncand), _ptr(status), _ptr(work), armed,
+                                                 dev_index, _stream(device)), "pqdet_decode_nms_host")
+    if out is not None:
+        _FUSED_ARMED.add(key)
+    return det, idx, meta, work
+
+
 def nms_fused(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float, nms_mode: str, iou_round: str,
               max_det: int, want_index: bool, out=None):
     """tools.torch_nms for a batch in one launch.  bboxes (B, N, 4+C) -> det, idx, meta (as decode_nms_fused)."""

@@ -182,7 +182,7 @@ struct FusedSmem {
   int seg_start[128];
   const float* pbase[PQDET_MAX_LEVELS * 8];   // objectness plane of (level, anchor) for this image
   float red[kFusedWarps];
-  int b, H, M, K, maxcnt, next_class;
+  int b, H, M, K, maxcnt, next_class, nrec;
   // followed by: uint32_t hitw[G_tot*4*A]; uint32_t gbase[G_tot];
 };
 
@@ -262,7 +262,8 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
 // word k holding the cells 4l+k.  hitw layout: [group][a*4 + k].  AT == 3 (the only anchor count PQDet uses)
 // turns the unit divmod into a multiply-shift; AT == 0 is the run-time generic version.
 template <int AT>
-__device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int lane, int warp, uint32_t* hitw) {
+__device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int lane, int warp, uint32_t* hitw,
+                                                uint64_t* rec, int* nrec) {
   constexpr int U = 4;
   const int A = AT ? AT : P.A;
   const int ch = P.ch;
@@ -300,10 +301,19 @@ __device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int la
         const int un = u0 + u * kFusedWarps;
         bool p0b = x[u].x > P.logit_lo, p1b = x[u].y > P.logit_lo, p2b = x[u].z > P.logit_lo, p3b = x[u].w > P.logit_lo;
         if (p0b | p1b | p2b | p3b) {                                   // rare: exact test of the survivors
-          if (p0b) p0b = sigmoidf_(x[u].x) > P.thr_f;
-          if (p1b) p1b = sigmoidf_(x[u].y) > P.thr_f;
-          if (p2b) p2b = sigmoidf_(x[u].z) > P.thr_f;
-          if (p3b) p3b = sigmoidf_(x[u].w) > P.thr_f;
+          // a hit leaves a record (objectness, position) so that the plane is never read a second time
+          const uint32_t pos = ((uint32_t)(L.group_off + un / A) << 10) | ((uint32_t)(un % A) << 7) | ((uint32_t)lane << 2);
+          auto test = [&](float xv, uint32_t k) -> bool {
+            const float conf = sigmoidf_(xv);
+            if (!(conf > P.thr_f)) return false;
+            const int r = atomicAdd(nrec, 1);
+            if (r < kCapH) rec[r] = ((uint64_t)__float_as_uint(conf) << 32) | (pos | k);
+            return true;
+          };
+          if (p0b) p0b = test(x[u].x, 0);
+          if (p1b) p1b = test(x[u].y, 1);
+          if (p2b) p2b = test(x[u].z, 2);
+          if (p3b) p3b = test(x[u].w, 3);
         }
         uint4 wd;
         wd.x = __ballot_sync(PQ_FULL, p0b); wd.y = __ballot_sync(PQ_FULL, p1b);
@@ -339,13 +349,14 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       S.pbase[tid] = P.lv[l].raw + ((size_t)(b * A + a) * ch + 4) * P.lv[l].HW;
     }
     if (tid < 128) { S.cls_cnt[tid] = 0; S.cls_fill[tid] = 0; }
+    if (tid == 0) S.nrec = 0;
     __syncthreads();
     const float* img = SRC ? P.bboxes + (size_t)b * P.N * P.bb_row : nullptr;
 
     // ---- 1. scan: one ballot word per (level, group, anchor, sub-cell) | per 32 rows ---------------
     if (SRC == 0) {
-      if (A == 3) scan_objectness<3>(P, b, lane, warp, hitw);
-      else scan_objectness<0>(P, b, lane, warp, hitw);
+      if (A == 3) scan_objectness<3>(P, b, lane, warp, hitw, S.keys, &S.nrec);
+      else scan_objectness<0>(P, b, lane, warp, hitw, S.keys, &S.nrec);
     } else {
       // a row is a hit iff any of its C scores exceeds thr (tools.py:551); 128-bit loads when rows are aligned
       const bool vec = ((P.bb_row & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.bboxes) & 15) == 0);
@@ -396,10 +407,9 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       __syncthreads();
       continue;
     }
-    for (int w = tid; w < W_tot; w += kFusedThreads) {
-      unsigned word = hitw[w];
-      if (!word) continue;
-      if (SRC == 1) {                                       // word w = rows 32w .. 32w+31, already in row order
+    if (SRC == 1) {
+      for (int w = tid; w < W_tot; w += kFusedThreads) {    // word w = rows 32w .. 32w+31, already in row order
+        unsigned word = hitw[w];
         int h = gbase[w];
         while (word) {
           const int j = __ffs(word) - 1;
@@ -408,16 +418,27 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
           S.hhas[h] = 0;
           ++h;
         }
-        continue;
       }
-      const int g = w / WG, t = w - g * WG;
-      const int a = t >> 2, k = t & 3;                      // word t = a*4 + k holds cells 4*lane + k of anchor a
-      const int l = level_of_group(P, g);
-      const LevelDev& L = P.lv[l];
-      const uint32_t* gw = hitw + g * WG;
-      while (word) {
-        const int j = __ffs(word) - 1;
-        word &= word - 1;
+    } else {
+      // one hit record per thread: word a*4 + k of group g holds the cells 4*lane + k of anchor a
+      uint32_t pos[kCapH / kFusedThreads];
+      float cf[kCapH / kFusedThreads];
+#pragma unroll
+      for (int r = 0; r < kCapH / kFusedThreads; ++r) {
+        const int i = tid + r * kFusedThreads;
+        if (i < H) {
+          const uint64_t rc = S.keys[i];
+          pos[r] = (uint32_t)rc;
+          cf[r] = __uint_as_float((uint32_t)(rc >> 32));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kCapH / kFusedThreads; ++r) {
+        const int i = tid + r * kFusedThreads;
+        if (i >= H) continue;
+        const int g = pos[r] >> 10, a = (pos[r] >> 7) & 7, j = (pos[r] >> 2) & 31, k = pos[r] & 3;
+        const int l = level_of_group(P, g);
+        const uint32_t* gw = hitw + g * WG;
         const unsigned below = (1u << j) - 1u;
         // slot = hits of the group that precede (lane j, k, a) in (cell, anchor) order
         int h = gbase[g];
@@ -427,9 +448,8 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
           const int a2 = t2 >> 2, k2 = t2 & 3;
           if (k2 < k || (k2 == k && a2 < a)) h += (w2 >> j) & 1u;
         }
-        const int cell = (g - L.group_off) * 128 + 4 * j + k;
-        S.hmeta[h] = pack_meta(l, a, cell);
-        S.hconf[h] = sigmoidf_(S.pbase[l * A + a][cell]);
+        S.hmeta[h] = pack_meta(l, a, (g - P.lv[l].group_off) * 128 + 4 * j + k);
+        S.hconf[h] = cf[r];
         S.hhas[h] = 0;
       }
     }
@@ -459,44 +479,52 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         }
       }
     } else {
+      // A unit = (32 consecutive hit rows, 8 consecutive channels): lane = row, so one load instruction asks for
+      // the SAME channel of 32 rows.  Hit rows are in (cell, anchor) order and real objects light up runs of
+      // neighbouring cells, so the rows of one instruction fall into few 32-byte sectors of that channel plane
+      // (fewer memory requests; this is what bounds the kernel when the heads live in pinned host memory and
+      // every distinct sector is one PCIe read).  8 loads are in flight per lane.
       const Affine af = image_affine(P, b);
       const int CK = 4 + C;
-      const int sub = lane >> 3, k0 = lane & 7;
-      constexpr int V = 3;                                   // channel rounds in flight per row
-      for (int h = warp * 4 + sub; h < H; h += kFusedWarps * 4) {
+      constexpr int V = 8;
+      const int ncg = (CK + V - 1) / V;
+      const int nunit = ((H + 31) >> 5) * ncg;
+      for (int unit = warp; unit < nunit; unit += kFusedWarps) {
+        const int chunk = unit / ncg, k_lo = (unit - chunk * ncg) * V;
+        const int h = chunk * 32 + lane;
+        if (h >= H) continue;
         const uint32_t meta = S.hmeta[h];
         const int l = meta >> 30, a = (meta >> 27) & 7, cell = meta & 0x7ffffff;
         const LevelDev& L = P.lv[l];
         const float* base = S.pbase[l * A + a] + cell - (size_t)4 * L.HW;   // channel 0 of this row
         const float conf = S.hconf[h];
-        for (int kb = k0; kb < CK; kb += 8 * V) {
-          float v[V];
+        float v[V];
 #pragma unroll
-          for (int u = 0; u < V; ++u) {
-            const int k = kb + 8 * u;
-            if (k < CK) v[u] = ldg_stream(base + (size_t)((k < 4) ? k : k + 1) * L.HW);
-          }
+        for (int u = 0; u < V; ++u) {
+          const int k = k_lo + u;
+          if (k < CK) v[u] = ldg_stream(base + (size_t)((k < 4) ? k : k + 1) * L.HW);
+        }
+        int cx = 0, cy = 0;
+        if (k_lo == 0) { cy = cell / L.W; cx = cell - cy * L.W; }
 #pragma unroll
-          for (int u = 0; u < V; ++u) {
-            const int k = kb + 8 * u;
-            if (k >= CK) continue;
-            if (k < 4) {
-              const int cy = cell / L.W, cx = cell - cy * L.W;
-              reinterpret_cast<float*>(&S.hbox[h])[k] = recover_coord(k, decode_coord(k, v[u], cx, cy, L.stride), af);
-            } else {
-              const float sc = PQ_MUL(sigmoidf_(v[u]), conf);
-              if (sc > P.thr_f) {
-                // one shared-memory atomic per warp instead of one per candidate
-                const unsigned peers = __activemask();
-                const int leader = __ffs(peers) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&S.M, __popc(peers));
-                base = __shfl_sync(peers, base, leader);
-                const int slot = base + __popc(peers & ((1u << lane) - 1u));
-                if (slot < kCapM) S.keys[slot] = cand_key(k - 4, sc, (uint32_t)h);
-                atomicAdd(&S.cls_cnt[k - 4], 1);
-                S.hhas[h] = 1;
-              }
+        for (int u = 0; u < V; ++u) {
+          const int k = k_lo + u;
+          if (k >= CK) continue;
+          if (k < 4) {
+            reinterpret_cast<float*>(&S.hbox[h])[k] = recover_coord(k, decode_coord(k, v[u], cx, cy, L.stride), af);
+          } else {
+            const float sc = PQ_MUL(sigmoidf_(v[u]), conf);
+            if (sc > P.thr_f) {
+              // one shared-memory atomic per warp instead of one per candidate
+              const unsigned peers = __activemask();
+              const int leader = __ffs(peers) - 1;
+              int base = 0;
+              if (lane == leader) base = atomicAdd(&S.M, __popc(peers));
+              base = __shfl_sync(peers, base, leader);
+              const int slot = base + __popc(peers & ((1u << lane) - 1u));
+              if (slot < kCapM) S.keys[slot] = cand_key(k - 4, sc, (uint32_t)h);
+              atomicAdd(&S.cls_cnt[k - 4], 1);
+              S.hhas[h] = 1;
             }
           }
         }
@@ -1161,6 +1189,44 @@ extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t*
   PQ_ENTER(device);
   DetOut O{det, det_idx, max_det, counts, ncand, status};
   return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 0, device, (cudaStream_t)stream);
+}
+
+// Host-buffer entry: every pointer may be page-locked host memory; it is translated to its device alias and the
+// same kernel runs on it (the loads/stores then travel over PCIe, sector by sector, only where the kernel touches).
+namespace pq {
+template <typename T>
+static int device_alias(T** p, int allow_null) {
+  if (!*p) return allow_null ? PQDET_OK : PQDET_ERR_INVALID_ARG;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, (const void*)*p) != cudaSuccess) { cudaGetLastError(); return PQDET_ERR_INVALID_ARG; }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return PQDET_OK;
+  if (at.type == cudaMemoryTypeHost && at.devicePointer) { *p = (T*)at.devicePointer; return PQDET_OK; }
+  return PQDET_ERR_INVALID_ARG;          // pageable host memory: the device cannot read it
+}
+}  // namespace pq
+
+extern "C" int pqdet_decode_nms_host(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
+                                     int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
+                                     int counter_armed, int device, void* stream) {
+  using namespace pq;
+  if (!heads) return PQDET_ERR_INVALID_ARG;
+  PQ_ENTER(device);
+  pqdet_heads_t h = *heads;
+  int rc;
+  for (int l = 0; l < h.n_levels && l < PQDET_MAX_LEVELS; ++l)
+    if ((rc = device_alias(&h.raw[l], 0)) != PQDET_OK) return rc;
+  if ((rc = device_alias(&h.orig_hw, 0)) != PQDET_OK) return rc;
+  if ((rc = device_alias(&det, 0)) != PQDET_OK) return rc;
+  if ((rc = device_alias(&det_idx, 1)) != PQDET_OK) return rc;
+  if ((rc = device_alias(&counts, 0)) != PQDET_OK) return rc;
+  if ((rc = device_alias(&ncand, 0)) != PQDET_OK) return rc;
+  if ((rc = device_alias(&status, 0)) != PQDET_OK) return rc;
+  cudaPointerAttributes at;                   // the scheduler words are hammered with atomics: device memory only
+  if (!work_counter || cudaPointerGetAttributes(&at, work_counter) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return PQDET_ERR_INVALID_ARG;
+  }
+  return pqdet_decode_nms(&h, det, det_idx, max_det, counts, ncand, status, work_counter, counter_armed, device, stream);
 }
 
 extern "C" int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, double score_threshold,

@@ -144,3 +144,86 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
     for i, b in enumerate(over.tolist()):
         hm[0, b], hm[1, b], hm[2, b] = ghm[0, i], ghm[1, i], 0
     return res
+
+
+class HostDetections:
+    """Result of decode_nms_host: everything already sits in pinned host memory (numpy views, no copies)."""
+
+    def __init__(self, det, idx, meta, B, event):
+        self.det, self.idx, self.meta, self.B, self._event = det, idx, meta, B, event
+
+    def wait(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        return self
+
+    @property
+    def counts(self):
+        return self.wait().meta[:self.B]
+
+    @property
+    def status(self):
+        return self.wait().meta[2 * self.B:3 * self.B]
+
+    def __len__(self):
+        return self.B
+
+    def __getitem__(self, b: int) -> torch.Tensor:
+        return self.wait().det[b, :int(self.meta[b])]
+
+    def to_numpy_list(self):
+        self.wait()
+        det, cnt = self.det.numpy(), self.meta.numpy()
+        return [det[b, :cnt[b]] for b in range(self.B)]
+
+
+def decode_nms_host(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classes: int, input_size,
+                    batch_original_size, dataset: str = "voc", score_threshold: float = 0.1,
+                    iou_threshold: float = 0.45, return_index: bool = False, device=None, out=None,
+                    nms_mode: Optional[str] = None, iou_round: Optional[str] = None) -> HostDetections:
+    """decode_nms for head tensors in PINNED HOST memory; the detections come back in pinned host memory.
+    The GPU reads only what the kernel touches (objectness planes + the channels of rows above threshold) straight
+    over PCIe and writes the rows back, so there is no staging copy of the heads in either direction.  Images that
+    overflow the fused kernel's on-chip lists are re-run from a device copy of just those images through the
+    general path.  `out` = buffers of _ops.alloc_host_outputs to reuse across calls."""
+    m, r = config.nms_modes()
+    nms_mode, iou_round = nms_mode or m, iou_round or r
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    h, keep = _ops.make_heads_host(heads, strides, num_classes, input_size, batch_original_size, dataset,
+                                   score_threshold, iou_threshold, nms_mode, iou_round)
+    B = h.B
+    det, idx, meta, work = _ops.decode_nms_host(h, keep, FUSED_MAX_DET, return_index, device, out=out)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    res = HostDetections(det, idx, meta, B, ev)
+    res._keep = (keep, work)
+    if B == 0:
+        return res
+    status = res.status
+    over = torch.nonzero(status & _lib.ST_CAND_OVERFLOW).reshape(-1)
+    if over.numel():
+        # dense images: stage just those on the device and use the general path; rows land in the host buffers
+        sub = [t[over].to(device, non_blocking=True) for t in heads]
+        orig = batch_original_size if isinstance(batch_original_size, torch.Tensor) else torch.tensor(batch_original_size)
+        orig = orig.to(torch.float32)
+        o_sub = orig[over] if orig.dim() == 2 else orig
+        d = decode_nms(sub, strides, num_classes, input_size, o_sub.to(device), dataset, score_threshold, iou_threshold,
+                       return_index, True, nms_mode, iou_round, strategy="general")
+        hm = d.host_meta()
+        grow = int(hm[0].max())
+        if grow > res.det.shape[1]:
+            ndet = torch.empty((B, grow, 6), dtype=torch.float32, pin_memory=True)
+            ndet[:, :res.det.shape[1]] = res.det
+            res.det = ndet
+            if return_index:
+                nidx = torch.empty((B, grow), dtype=torch.int32, pin_memory=True)
+                nidx[:, :res.idx.shape[1]] = res.idx
+                res.idx = nidx
+        for i, b in enumerate(over.tolist()):
+            k = int(hm[0, i])
+            res.det[b, :k] = d[i].cpu()
+            if return_index:
+                res.idx[b, :k] = d.indices(i).to(torch.int32).cpu()
+            res.meta[b], res.meta[B + b], res.meta[2 * B + b] = k, int(hm[1, i]), 0
+    return res

@@ -236,3 +236,29 @@ def test_fused_rectangular_heads_and_single_level():
             ncand = int(dets.host_meta()[1, b])
             assert_same_detections(dets[b].cpu().numpy(), w, ties_unordered=4 * ncand > 100000, what="rect %d" % b)
             assert np.array_equal(dets.indices(b).cpu().numpy(), rows * C + cls)
+
+
+@pytest.mark.parametrize("profile,C,size,kind", [("sparse", 20, 512, "voc"), ("dense", 10, 608, "visdrone")])
+def test_host_buffer_path_equals_device_path(profile, C, size, kind):
+    """pqdet_decode_nms_host: pinned host heads in, pinned host detections out, identical rows to the
+    device-resident call (sparse: all images fused; dense: every image overflows -> general path)."""
+    from pqdet_b200 import fused, synth
+    B = 6
+    heads = synth.make_heads(B, C, size, profile, seed=5)
+    orig = torch.tensor([[375., 500.], [333., 500.], [float(size)] * 2, [500., 281.], [480., 480.], [300., 400.]])
+    dev = fused.decode_nms([h.cuda() for h in heads], synth.FPN_STRIDES, C, (size, size), orig.cuda(), kind, 0.1, 0.45,
+                           return_index=True)
+    pinned = [h.pin_memory() for h in heads]
+    host = fused.decode_nms_host(pinned, synth.FPN_STRIDES, C, (size, size), orig, kind, 0.1, 0.45, return_index=True)
+    rows = host.to_numpy_list()
+    for b in range(B):
+        assert np.array_equal(rows[b], dev[b].cpu().numpy()), (profile, b)
+        assert np.array_equal(host.idx[b, :int(host.counts[b])].numpy(), dev.indices(b).cpu().numpy().astype(np.int32))
+    assert int(host.counts.sum()) > 0
+
+
+def test_host_buffer_path_rejects_pageable_memory():
+    from pqdet_b200 import _lib, fused, synth
+    heads = synth.make_heads(1, 20, 512, "sparse", seed=1)
+    with pytest.raises(_lib.PqdetError):
+        fused.decode_nms_host(heads, synth.FPN_STRIDES, 20, (512, 512), (512., 512.), "voc")
