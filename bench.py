@@ -530,39 +530,64 @@ def run_ours(args):
     counts, ncand, status = meta[0], meta[1], meta[2]
     overflow = int((status != 0).sum())
 
-    # ---- end to end: pinned host heads -> H2D -> kernel -> D2H of the detections, every step ----
+    # ---- end to end, host buffers in -> host buffers out, every step (the reference-facing call:
+    # fused.decode_nms_host -> pqdet_decode_nms_host).  The heads sit in pinned host memory; the kernel pulls the
+    # objectness planes and the channels of rows above threshold straight over PCIe (no staging copy) and writes
+    # counts + detection rows straight into pinned host memory; the step ends with a stream synchronise, after
+    # which the caller owns the rows.  `staged` = the same result with a full H2D copy of the heads first, the
+    # device-resident kernel, then D2H of counts + rows (what this path cost before the zero-copy entry point).
     host_heads = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in heads]
     for hh, t in zip(host_heads, heads):
         hh.copy_(t)
+    torch.cuda.synchronize()
+    hz, keepz = _ops.make_heads_host(host_heads, STRIDES, C_VOC, (SIZE, SIZE), torch.tensor([float(SIZE), float(SIZE)]),
+                                     "voc", THR, IOU, "auto_cuda", "tv_cuda")
+    hout = _ops.alloc_host_outputs(B, MAXDET, False, device)
+
+    def e2e_step():
+        _ops.decode_nms_host(hz, keepz, MAXDET, False, device, out=hout)
+        torch.cuda.synchronize()
+        return hout
+
     dev_in = [torch.empty_like(t) for t in heads]
     h2, keep2 = _ops.make_heads(dev_in, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, "auto_cuda", "tv_cuda")
     host_meta = torch.empty((3 * B,), dtype=torch.int32, pin_memory=True)
-    d2h_bytes = [0]
 
-    def e2e_step():
+    def staged_step():
         for d, s in zip(dev_in, host_heads):
             d.copy_(s, non_blocking=True)
         det, _, m = _ops.decode_nms_fused(h2, keep2, MAXDET, False, out=out)
         host_meta.copy_(m[:3 * B], non_blocking=True)
         torch.cuda.synchronize()
         kmax = int(host_meta[:B].max())
-        rows = det[:, :kmax].contiguous().cpu()              # the detections a caller consumes
-        d2h_bytes[0] = host_meta.numel() * 4 + rows.numel() * 4
-        return rows
-    e2e_steps = max(3, min(args.steps, 5))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    es.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    ee.record()
-    torch.cuda.synchronize()
-    e2e_ms = torch.tensor([max(es.elapsed_time(ee), (time.perf_counter() - t0) * 1e3)], device=device)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * e2e_steps / (float(e2e_ms) * 1e-3)
+        return det[:, :kmax].contiguous().cpu()
+
+    def timed(fn, n):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es.record()
+        for _ in range(n):
+            fn()
+        ee.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([max(es.elapsed_time(ee), (time.perf_counter() - t0) * 1e3)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return world * B * n / (float(ms) * 1e-3)
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_val = timed(e2e_step, e2e_steps)
+    staged_val = timed(staged_step, 3)
+    e2e_same = bool(torch.equal(hout[2][:B], counts.to(torch.int32)) and
+                    all(torch.equal(hout[0][b, :int(counts[b])], out[0][b, :int(counts[b])].cpu()) for b in range(0, B, 61)))
+    # bytes that cross PCIe per step: the objectness planes (read in full, 128-byte lines) + one 32-byte sector per
+    # (hit row, box/class channel) as the upper bound of the gathers; results: 3 int32 per image + 24 B per row
+    n_hit = 0
+    for t in heads:
+        n_hit += int((torch.sigmoid(t.view(B, 3, 5 + C_VOC, -1)[:, :, 4]) > THR).sum())
+    h2d_pulled = sum(B * 3 * t.shape[2] * t.shape[3] * 4 for t in heads) + n_hit * (4 + C_VOC) * 32
+    d2h_bytes = [3 * B * 4 + int(counts.sum()) * 24]
     # keep the GPU busy with the timed kernel for ~0.4 s more so that the 100 ms nvidia-smi sampler sees clocks
     # and throttle reasons under exactly this load (the timed region itself lasts only a few ms)
     t_busy = time.perf_counter()
@@ -597,8 +622,14 @@ def run_ours(args):
                              "reads only the objectness planes plus the box/class channels of rows with conf > thr "
                              "(exact early-out), so DRAM traffic is far below the algorithmic bytes and frac can "
                              "exceed 1; achieved_dram = measured ncu DRAM bytes / time"},
-        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes[0],
-                "steps": e2e_steps, "note": "pinned host heads -> H2D -> fused kernel -> D2H counts + detection rows"},
+        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_pulled, "d2h_bytes_per_step": d2h_bytes[0],
+                "steps": e2e_steps, "host_input_bytes_per_step": h2d, "identical_to_resident_run": e2e_same,
+                "staged_full_copy_value": staged_val,
+                "note": "fused.decode_nms_host / pqdet_decode_nms_host: heads in pinned host memory, detections in "
+                        "pinned host memory, stream synchronised every step; the kernel reads host memory in place "
+                        "over PCIe (objectness planes + channels of the rows above threshold = h2d_bytes_per_step, "
+                        "of host_input_bytes_per_step) and writes counts + rows back; staged_full_copy_value = "
+                        "full H2D copy -> resident kernel -> D2H of counts + rows"},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "stats": {"kept_per_image": k_mean, "candidates_per_image": float(ncand.float().mean()),
