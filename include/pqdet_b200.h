@@ -217,6 +217,27 @@ int pqdet_assign_labels(const float* gt, const int32_t* gt_count, int B, int n_m
                         float* gtlist0, float* gtlist1, float* gtlist2, int list_capacity,
                         int32_t* list_len, void* owner, int device, void* stream);
 
+/* ---- sparse targets (keep GT as (B,G,6) lists end to end instead of the dense
+ * (B,H,W,3,6+C) tensors of dataset/train_dataset.py:26-43).  pqdet_assign_sparse runs the assignment of
+ * create_label (train_dataset.py:109-150) but emits, per scale, only
+ *   owner[s]  (B, 3, H_s*W_s) int32: index (into gt) of the GT whose row create_label would have left in that
+ *             label slot ("last writer wins", :145), -1 for background
+ *   gtlist[s] (B, list_capacity, 4) + list_len (B,3), exactly as pqdet_assign_labels.
+ * pqdet_loss_levels_sparse = pqdet_loss_levels with the label rows rebuilt on the fly from owner + gt
+ * ([gt box, 1, smoothed one-hot(class), mixw] / background [0.., mixw = 1]): same arithmetic, bit-identical
+ * outputs, without ever writing or reading the L bytes of dense labels.  A must be 3. */
+int pqdet_assign_sparse(const float* gt, const int32_t* gt_count, int B, int n_max,
+                        const float* anchors, const int* strides, const int* H, const int* W,
+                        float iou_threshold, int32_t* owner0, int32_t* owner1, int32_t* owner2,
+                        float* gtlist0, float* gtlist1, float* gtlist2, int list_capacity,
+                        int32_t* list_len, int device, void* stream);
+int pqdet_loss_levels_sparse(int n_levels, const float* const* raw, const int32_t* const* owner,
+                             const float* gt6, int n_max, const float* const* gtlist,
+                             float* const* grad, const int* H, const int* W, const int* G,
+                             const float* stride, int B, int A, int C, int bbox_loss,
+                             float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
+                             void* workspace, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

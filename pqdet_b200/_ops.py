@@ -481,3 +481,74 @@ def assign_labels(gt: torch.Tensor, gt_count: torch.Tensor, num_classes: int, an
                                        _ptr(lists[0]), _ptr(lists[1]), _ptr(lists[2]), cap, _ptr(list_len),
                                        _ptr(owner), _dev(gt), _stream(device)), "pqdet_assign_labels")
     return labels, lists, list_len
+
+
+def assign_sparse(gt: torch.Tensor, gt_count: torch.Tensor, anchors, strides, sizes_hw, iou_threshold: float,
+                  list_capacity: Optional[int] = None):
+    """gt (B,n_max,6) cuda, gt_count (B) -> owner maps [3] int32 (B,3,H_s,W_s), gtlists [3] (B,cap,4), list_len (B,3).
+    The dense label tensors are never produced (pqdet_assign_sparse)."""
+    gt = _req(gt, "gt")
+    if gt.dim() != 3 or gt.shape[2] != 6:
+        raise ValueError("gt must be (B, n_max, 6)")
+    B, n_max = gt.shape[0], gt.shape[1]
+    device = gt.device
+    gt_count = gt_count.to(device=device, dtype=torch.int32).contiguous()
+    anc = (ctypes.c_float * 18)(*[float(v) for wh in anchors for v in wh])
+    st = (ctypes.c_int * 3)(*[int(s) for s in strides])
+    Hs = (ctypes.c_int * 3)(*[int(s[0]) for s in sizes_hw])
+    Ws = (ctypes.c_int * 3)(*[int(s[1]) for s in sizes_hw])
+    cap = int(list_capacity) if list_capacity else max(3 * n_max, 1)
+    sizes = [B * 3 * Hs[i] * Ws[i] for i in range(3)]
+    obuf = torch.empty((sum(sizes),), dtype=torch.int32, device=device)
+    owners, off = [], 0
+    for i in range(3):
+        owners.append(obuf[off:off + sizes[i]].view(B, 3, Hs[i], Ws[i]))
+        off += sizes[i]
+    lists = list(torch.empty((3, B, cap, 4), dtype=torch.float32, device=device).unbind(0))
+    list_len = torch.empty((B, 3), dtype=torch.int32, device=device)
+    _lib.check(_lib.load().pqdet_assign_sparse(_ptr(gt), _ptr(gt_count), B, n_max, anc, st, Hs, Ws,
+                                               float(iou_threshold), _ptr(owners[0]), _ptr(owners[1]),
+                                               _ptr(owners[2]), _ptr(lists[0]), _ptr(lists[1]), _ptr(lists[2]), cap,
+                                               _ptr(list_len), _dev(gt), _stream(device)), "pqdet_assign_sparse")
+    return owners, lists, list_len
+
+
+def loss_levels_sparse(raws, owners, gt6: torch.Tensor, gts, num_classes: int, strides, bbox_loss: str,
+                       ignore_thresh: float, l1_loss_gain: float, want_grad: bool):
+    """loss_levels with sparse targets: owners[l] (B,3,H_l,W_l) int32, gt6 (B,n_max,6), gts[l] (B,G_l,4)."""
+    if bbox_loss == "ciou":
+        raise RuntimeError("NaN in loss")
+    if bbox_loss not in _lib.BBOX_LOSS:
+        raise NotImplementedError(bbox_loss)
+    raws = [_req(r, "head") for r in raws]
+    gts = [_req(x, "bboxes") for x in gts]
+    gt6 = _req(gt6, "gt")
+    L = len(raws)
+    C = num_classes
+    B = raws[0].shape[0]
+    A = raws[0].shape[1] // (5 + C)
+    device = raws[0].device
+    for r, o, g in zip(raws, owners, gts):
+        _, CH, H, W = r.shape
+        if r.shape[0] != B or CH != A * (5 + C) or tuple(o.shape) != (B, A, H, W) or o.dtype != torch.int32 \
+                or not o.is_cuda or not o.is_contiguous():
+            raise ValueError("head/owner shapes do not match: %s vs %s" % (tuple(r.shape), tuple(o.shape)))
+        if g.dim() != 3 or g.shape[0] != B or g.shape[2] != 4 or g.shape[1] < 1:
+            raise ValueError("bboxes must be (B, G>=1, 4)")
+    if gt6.dim() != 3 or gt6.shape[0] != B or gt6.shape[2] != 6:
+        raise ValueError("gt must be (B, n_max, 6)")
+    grads = [torch.empty_like(r) for r in raws] if want_grad else None
+    VP = ctypes.c_void_p * L
+    IP = ctypes.c_int * L
+    Hs, Ws = IP(*[r.shape[2] for r in raws]), IP(*[r.shape[3] for r in raws])
+    lib = _lib.load()
+    ws = _workspace(device, "loss_levels", lib.pqdet_loss_levels_workspace(L, B, A, Hs, Ws))
+    out = torch.empty((4 + 5 * L,), dtype=torch.float32, device=device)
+    flag = torch.empty((1,), dtype=torch.int32, device=device)
+    _lib.check(lib.pqdet_loss_levels_sparse(
+        L, VP(*[r.data_ptr() for r in raws]), VP(*[o.data_ptr() for o in owners]), _ptr(gt6), int(gt6.shape[1]),
+        VP(*[x.data_ptr() for x in gts]), VP(*[g.data_ptr() for g in grads]) if want_grad else None, Hs, Ws,
+        IP(*[g.shape[1] for g in gts]), (ctypes.c_float * L)(*[float(s) for s in strides]), B, A, C,
+        _lib.BBOX_LOSS[bbox_loss], float(ignore_thresh), float(l1_loss_gain), _ptr(out), _ptr(flag), _ptr(ws),
+        _dev(raws[0]), _stream(device)), "pqdet_loss_levels_sparse")
+    return out, flag, grads

@@ -7,6 +7,8 @@
 // owner map (atomicMax of the GT index per label slot) followed by a write pass in which only
 // the owner stores its row; the per-scale GT lists keep numpy's order (GT order, then anchor
 // order, one entry per hit) through a block prefix sum.
+#include <string.h>
+
 #include "pq_common.cuh"
 
 namespace pq {
@@ -23,8 +25,14 @@ struct AssignParams {
   float* gtlist[3];
   int list_capacity;
   int32_t* list_len;        // (B,3)
-  int32_t* owner[3];        // (B, H*W*3) each
+  int32_t* owner[3];        // (B, H*W*3) each; planar (B, 3, H*W) when owner_planar (sparse targets)
+  int owner_planar;
 };
+
+__device__ __forceinline__ size_t owner_slot(const AssignParams& P, int b, int s, int cell, int r) {
+  const size_t HW = (size_t)P.H[s] * P.W[s];
+  return P.owner_planar ? ((size_t)b * 3 + r) * HW + cell : (size_t)b * HW * 3 + (size_t)cell * 3 + r;
+}
 
 // background: zeros, mixw channel (last) = 1.0
 __global__ void __launch_bounds__(256)
@@ -84,7 +92,7 @@ assign_kernel(const __grid_constant__ AssignParams P) {
         for (int w = 0; w < warp; ++w) pos += s_warp[s][w];
         for (int r = 0; r < 3; ++r) {
           if (!((hit.mask >> (3 * s + r)) & 1u)) continue;
-          if (inb[s]) atomicMax(&P.owner[s][(size_t)b * P.H[s] * P.W[s] * 3 + (hit.cy[s] * P.W[s] + hit.cx[s]) * 3 + r], j);
+          if (inb[s]) atomicMax(&P.owner[s][owner_slot(P, b, s, hit.cy[s] * P.W[s] + hit.cx[s], r)], j);
           if (pos < P.list_capacity) {
             float* d = P.gtlist[s] + ((size_t)b * P.list_capacity + pos) * 4;
             d[0] = g[0]; d[1] = g[1]; d[2] = g[2]; d[3] = g[3];
@@ -158,6 +166,7 @@ extern "C" int pqdet_assign_labels(const float* gt, const int32_t* gt_count, int
     P.strides[s] = strides[s]; P.H[s] = H[s]; P.W[s] = W[s];
     P.label[s] = labels[s]; P.gtlist[s] = lists[s];
     P.owner[s] = own + own_total;
+    P.owner_planar = 0;
     own_total += (size_t)B * H[s] * W[s] * 3;
   }
   P.iou_thr = (double)iou_threshold;
@@ -198,6 +207,57 @@ extern "C" int pqdet_assign_labels(const float* gt, const int32_t* gt_count, int
   assign_kernel<0><<<B, 256, 0, st>>>(P);
   PQ_LAUNCH_CHECK();
   assign_kernel<1><<<B, 256, 0, st>>>(P);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
+// Sparse targets: the same assignment, but instead of the dense (B,H,W,3,6+C)
+// label tensors only an owner map is produced -- owner[s] (B, 3, H_s*W_s) int32 = index of the GT that
+// train_dataset.py:145 would have written last into that label slot, or -1 -- plus the per-scale GT lists.  The
+// loss kernel rebuilds the label row of a responsible cell from the GT row itself (pqdet_loss_levels_sparse).
+extern "C" int pqdet_assign_sparse(const float* gt, const int32_t* gt_count, int B, int n_max,
+                                   const float* anchors, const int* strides, const int* H, const int* W,
+                                   float iou_threshold, int32_t* owner0, int32_t* owner1, int32_t* owner2,
+                                   float* gtlist0, float* gtlist1, float* gtlist2, int list_capacity,
+                                   int32_t* list_len, int device, void* stream) {
+  using namespace pq;
+  if (!gt_count || !anchors || !strides || !H || !W || !owner0 || !owner1 || !owner2 || !gtlist0 || !gtlist1 ||
+      !gtlist2 || !list_len)
+    return PQDET_ERR_INVALID_ARG;
+  if (B < 1 || n_max < 0 || list_capacity < 1 || (n_max > 0 && !gt)) return PQDET_ERR_INVALID_ARG;
+  PQ_ENTER(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  AssignParams P;
+  memset(&P, 0, sizeof(P));
+  P.gt = gt; P.gt_count = gt_count; P.B = B; P.n_max = n_max; P.C = 1;
+  for (int i = 0; i < 18; ++i) P.anchors[i] = anchors[i];
+  int32_t* owners[3] = {owner0, owner1, owner2};
+  float* lists[3] = {gtlist0, gtlist1, gtlist2};
+  size_t slots[3];
+  for (int s = 0; s < 3; ++s) {
+    if (H[s] < 1 || W[s] < 1 || strides[s] < 1) return PQDET_ERR_INVALID_ARG;
+    P.strides[s] = strides[s]; P.H[s] = H[s]; P.W[s] = W[s];
+    P.gtlist[s] = lists[s];
+    P.owner[s] = owners[s];
+    slots[s] = (size_t)B * H[s] * W[s] * 3;
+  }
+  P.owner_planar = 1;
+  P.iou_thr = (double)iou_threshold;
+  P.list_capacity = list_capacity;
+  P.list_len = list_len;
+  // one memset each when the caller carved the three maps / lists out of one allocation, back to back
+  if (owners[1] == owners[0] + slots[0] && owners[2] == owners[1] + slots[1]) {
+    PQ_CUDA(cudaMemsetAsync(owners[0], 0xff, (slots[0] + slots[1] + slots[2]) * sizeof(int32_t), st));
+  } else {
+    for (int s = 0; s < 3; ++s) PQ_CUDA(cudaMemsetAsync(owners[s], 0xff, slots[s] * sizeof(int32_t), st));
+  }
+  const size_t list_floats = (size_t)B * list_capacity * 4;
+  if (lists[1] == lists[0] + list_floats && lists[2] == lists[1] + list_floats) {
+    PQ_CUDA(cudaMemsetAsync(lists[0], 0, 3 * list_floats * sizeof(float), st));
+  } else {
+    for (int s = 0; s < 3; ++s) PQ_CUDA(cudaMemsetAsync(lists[s], 0, list_floats * sizeof(float), st));
+  }
+  assign_kernel<0><<<B, 256, 0, st>>>(P);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }

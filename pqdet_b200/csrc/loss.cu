@@ -29,9 +29,14 @@ struct LossParams {
   int B, A, C, H, W, G;
   float stride, in_area, ignore_thresh, l1_gain, inv_B;
   int bbox_loss;
+  // sparse targets (pqdet_loss_levels_sparse): label rows are rebuilt from the owner map + the GT rows
+  const int32_t* owner;  // (B, A, H*W): index into gt6 of the GT owning the label slot, or -1
+  const float* gt6;      // (B, n_max, 6) rows [x1,y1,x2,y2,class,mixw]
+  int n_max;
+  float hot, cold;       // smoothed one-hot values (train_dataset.py:126-130)
 };
 
-template <bool RAW>
+template <bool RAW, bool SPARSE = false>
 __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, const int ntiles, const int b,
                                           float* smem) {
   const int A = P.A, C = P.C, ch = 5 + C, LW = 6 + C;
@@ -69,9 +74,25 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   // ---- label row: only [box(4), respond] and the trailing mixw are needed for every row; the class
   // targets are read at responsible cells only.  Rows are 4*(6+C) bytes apart (8-byte aligned for even C),
   // the three anchors of a cell are adjacent, so the three warps of the CTA share L1 lines.
-  const float* lab = P.label + (((size_t)b * HW + cell) * A + a) * LW;
+  const float* lab = SPARSE ? nullptr : P.label + (((size_t)b * HW + cell) * A + a) * LW;
   float tb[4] = {0.f, 0.f, 0.f, 0.f}, respond = 0.f, mixw = 0.f;
-  if (active) {
+  int cls = -1;
+  if (SPARSE) {
+    // the label row of train_dataset.py:135-145: [gt box, 1, smooth one-hot, mixw] where a GT owns the slot,
+    // [0, 0, 0, 0, 0, 0.., 1] (background, mixw = 1) elsewhere
+    if (active) {
+      const int j = __ldg(P.owner + ((size_t)b * A + a) * HW + cell);
+      mixw = 1.0f;
+      if (j >= 0) {
+        const float2* g = reinterpret_cast<const float2*>(P.gt6 + ((size_t)b * P.n_max + j) * 6);
+        const float2 g01 = __ldg(g), g23 = __ldg(g + 1), g45 = __ldg(g + 2);
+        tb[0] = g01.x; tb[1] = g01.y; tb[2] = g23.x; tb[3] = g23.y;
+        cls = (int)g45.x;
+        mixw = g45.y;
+        respond = 1.0f;
+      }
+    }
+  } else if (active) {
     if ((LW & 1) == 0) {
       const float2 t01 = __ldg(reinterpret_cast<const float2*>(lab));
       const float2 t23 = __ldg(reinterpret_cast<const float2*>(lab) + 1);
@@ -187,7 +208,7 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
         const int c = c0 + u;
         if (c < C) {
           z[u] = RAW ? P.x[plane0 + (size_t)(5 + c) * HW + cell] : P.x[prow + 5 + c];
-          t[u] = __ldg(lab + 5 + c);
+          t[u] = SPARSE ? ((c == cls) ? P.hot : P.cold) : __ldg(lab + 5 + c);
         }
       }
 #pragma unroll
@@ -257,6 +278,7 @@ struct MultiLossParams {
   int32_t* nan_flag;
 };
 
+template <bool SPARSE>
 __global__ void __launch_bounds__(256)
 loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   extern __shared__ __align__(16) float smem[];
@@ -265,7 +287,7 @@ loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
     if (i < M.n_levels && (int)blockIdx.x >= M.tile_off[i]) l = i;
   const int ntiles = M.tile_off[l + 1] - M.tile_off[l];
-  loss_tile<true>(M.lv[l], blockIdx.x - M.tile_off[l], ntiles, blockIdx.y, smem);
+  loss_tile<true, SPARSE>(M.lv[l], blockIdx.x - M.tile_off[l], ntiles, blockIdx.y, smem);
 }
 
 // One CTA of 1024 threads: reduce every level's partial sums in a fixed order (thread-strided accumulation,
@@ -451,15 +473,18 @@ extern "C" int64_t pqdet_loss_levels_workspace(int n_levels, int B, int A, const
   return bytes;
 }
 
-extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const float* const* label,
-                                 const float* const* gt, float* const* grad, const int* H, const int* W,
-                                 const int* G, const float* stride, int B, int A, int C, int bbox_loss,
-                                 float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
-                                 void* workspace, int workspace_initialised, int device, void* stream) {
-  using namespace pq;
-  if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || !raw || !label || !gt || !H || !W || !G || !stride ||
+namespace pq {
+static int loss_levels_impl(int n_levels, const float* const* raw, const float* const* label,
+                            const int32_t* const* owner, const float* gt6, int n_max,
+                            const float* const* gt, float* const* grad, const int* H, const int* W,
+                            const int* G, const float* stride, int B, int A, int C, int bbox_loss,
+                            float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
+                            void* workspace, int device, void* stream) {
+  const bool sparse = owner != nullptr;
+  if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || !raw || (!label && !owner) || !gt || !H || !W || !G || !stride ||
       !out || !nan_flag || !workspace)
     return PQDET_ERR_INVALID_ARG;
+  if (sparse && (n_max < 0 || (n_max > 0 && !gt6))) return PQDET_ERR_INVALID_ARG;
   if (B < 1 || B > 65535 || A < 1 || A > 8 || C < 1) return PQDET_ERR_INVALID_ARG;
   if (bbox_loss < 0 || bbox_loss > 3) return PQDET_ERR_UNSUPPORTED;
   PQ_ENTER(device);
@@ -470,10 +495,15 @@ extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const fl
   M.ticket = (unsigned*)ws;
   size_t off = 256;
   int tiles_total = 0;
+  const double deta = 0.01, uni = 1.0 / (double)C;         // train_dataset.py:126-130, fp64 then stored fp32
   for (int l = 0; l < n_levels; ++l) {
-    if (!raw[l] || !label[l] || !gt[l] || H[l] < 1 || W[l] < 1 || G[l] < 1) return PQDET_ERR_INVALID_ARG;
+    if (!raw[l] || !gt[l] || H[l] < 1 || W[l] < 1 || G[l] < 1) return PQDET_ERR_INVALID_ARG;
+    if (sparse ? !owner[l] : !label[l]) return PQDET_ERR_INVALID_ARG;
     LossParams& P = M.lv[l];
-    P.x = raw[l]; P.label = label[l]; P.gt = gt[l]; P.grad = grad ? grad[l] : nullptr;
+    P.x = raw[l]; P.label = sparse ? nullptr : label[l]; P.gt = gt[l]; P.grad = grad ? grad[l] : nullptr;
+    P.owner = sparse ? owner[l] : nullptr; P.gt6 = gt6; P.n_max = n_max;
+    P.hot = (float)(1.0 * (1 - deta) + deta * uni);
+    P.cold = (float)(0.0 * (1 - deta) + deta * uni);
     P.partials = (double*)(ws + off);
     const int tiles = (H[l] * W[l] + kLossTile - 1) / kLossTile;
     off += ((size_t)B * tiles * 3 * sizeof(double) + 255) / 256 * 256;
@@ -489,16 +519,38 @@ extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const fl
   M.n_levels = n_levels;
   M.total_blocks = (unsigned)tiles_total * (unsigned)B;
   M.out = out; M.nan_flag = nan_flag;
-  (void)workspace_initialised;
   const size_t smem = (size_t)kGtChunk * 5 * sizeof(float);
-  if (smem > 48 * 1024)
-    PQ_CUDA(cudaFuncSetAttribute(loss_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tiles_total, B);
-  loss_levels_kernel<<<grid, 32 * A, smem, st>>>(M);
+  if (sparse) loss_levels_kernel<true><<<grid, 32 * A, smem, st>>>(M);
+  else loss_levels_kernel<false><<<grid, 32 * A, smem, st>>>(M);
   PQ_LAUNCH_CHECK();
   loss_levels_finalize_kernel<<<1, 1024, 0, st>>>(M);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
+}
+}  // namespace pq
+
+extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const float* const* label,
+                                 const float* const* gt, float* const* grad, const int* H, const int* W,
+                                 const int* G, const float* stride, int B, int A, int C, int bbox_loss,
+                                 float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
+                                 void* workspace, int workspace_initialised, int device, void* stream) {
+  (void)workspace_initialised;
+  if (!label) return PQDET_ERR_INVALID_ARG;
+  return pq::loss_levels_impl(n_levels, raw, label, nullptr, nullptr, 0, gt, grad, H, W, G, stride, B, A, C,
+                              bbox_loss, ignore_thresh, l1_loss_gain, out, nan_flag, workspace, device, stream);
+}
+
+extern "C" int pqdet_loss_levels_sparse(int n_levels, const float* const* raw, const int32_t* const* owner,
+                                        const float* gt6, int n_max, const float* const* gtlist,
+                                        float* const* grad, const int* H, const int* W, const int* G,
+                                        const float* stride, int B, int A, int C, int bbox_loss,
+                                        float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
+                                        void* workspace, int device, void* stream) {
+  if (!owner) return PQDET_ERR_INVALID_ARG;
+  if (A != 3) return PQDET_ERR_UNSUPPORTED;          // the assignment has 3 anchors per scale (config.py:57)
+  return pq::loss_levels_impl(n_levels, raw, nullptr, owner, gt6, n_max, gtlist, grad, H, W, G, stride, B, A, C,
+                              bbox_loss, ignore_thresh, l1_loss_gain, out, nan_flag, workspace, device, stream);
 }
 
 extern "C" int pqdet_loss_levels_scale_grad(int n_levels, float* const* grad, const int* H, const int* W,

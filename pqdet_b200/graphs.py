@@ -20,7 +20,8 @@ class GraphedLossStep:
         """head: interpreter.DetectionHead; heads/target: example tensors (shapes are frozen)."""
         self.head = head
         self.static_heads = [h.detach().clone().requires_grad_(True) for h in heads]
-        self.static_target = tuple(t.detach().clone() for t in target)
+        self._sparse = hasattr(target, "tensors")                      # train_dataset.SparseTarget
+        self.static_target = target.clone() if self._sparse else tuple(t.detach().clone() for t in target)
         self.graph = torch.cuda.CUDAGraph()
         old = config.nan_check
         config.nan_check = "lazy"                 # no host read inside the captured region
@@ -53,6 +54,9 @@ class GraphedLossStep:
     def __call__(self, heads: Sequence[torch.Tensor], target: Sequence[torch.Tensor]):
         for s, h in zip(self.static_heads, heads):
             s.data.copy_(h, non_blocking=True)
+        if self._sparse:
+            self.static_target.copy_(target)
+            return self.replay()
         for s, t in zip(self.static_target, target):
             if s.shape != t.shape:
                 raise ValueError("target shape changed: %s vs %s (GT lists must be padded to the captured "

@@ -14,6 +14,7 @@ from torch import nn
 from . import _ops, config
 from .loss import _raise_if_nan
 from .parser import YOLOLayer
+from .train_dataset import SparseTarget
 
 
 def item_getter(*items):
@@ -56,6 +57,33 @@ class _MultiLossFn(torch.autograd.Function):
         return (None,) * 6 + tuple(grads) + (None,) * (2 * L)
 
 
+class _MultiLossSparseFn(torch.autograd.Function):
+    """_MultiLossFn on a SparseTarget: inputs are L raw heads, then gt6, L owner maps, L GT lists."""
+
+    @staticmethod
+    def forward(ctx, L, num_classes, strides, bbox_loss, ignore_thresh, l1_gain, *tensors):
+        raws, gt6 = tensors[:L], tensors[L]
+        owners, gts = tensors[L + 1:2 * L + 1], tensors[2 * L + 1:3 * L + 1]
+        want_grad = any(r.requires_grad for r in raws)
+        out, flag, grads = _ops.loss_levels_sparse([r.detach() for r in raws], owners, gt6, gts, num_classes,
+                                                   strides, bbox_loss, ignore_thresh, l1_gain, want_grad)
+        ctx.pq = (L, num_classes, grads)
+        ctx.mark_non_differentiable(flag)
+        return out, flag
+
+    @staticmethod
+    def backward(ctx, g_out, _g_flag):
+        L, num_classes, grads = ctx.pq
+        if grads is None:
+            raise RuntimeError("pqdet loss: backward called twice (the fused gradient is consumed in place)")
+        ctx.pq = (L, num_classes, None)
+        _ops.loss_levels_scale_grad(grads, num_classes, g_out.contiguous())
+        return (None,) * 6 + tuple(grads) + (None,) * (2 * L + 1)
+
+
+_SCALE_SLOT = {8: 0, 16: 1, 32: 2}
+
+
 class DetectionHead(nn.Module):
     def __init__(self, opts: Sequence[dict], onnx: bool = False):
         """opts: one [yolo] option dict per level, in cfg order (FPN: strides 32, 16, 8)."""
@@ -83,6 +111,19 @@ class DetectionHead(nn.Module):
             return out
         L = len(self.layers)
         opt0 = self.layers[0].opt
+        if isinstance(target, SparseTarget):
+            same_opts = all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
+                            and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in self.layers)
+            if not same_opts:
+                raise ValueError("sparse targets need the same loss options on every [yolo] level")
+            if opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
+                raise NotImplementedError
+            slots = [_SCALE_SLOT[l.opt['stride']] for l in self.layers]
+            out, flag = _MultiLossSparseFn.apply(L, target.num_classes, [l.opt['stride'] for l in self.layers],
+                                                 opt0['bbox_loss'], opt0['ignore_thresh'],
+                                                 opt0.get('l1_loss_gain', 0.1), *heads, target.gt,
+                                                 *[target.owner[i] for i in slots], *[target.bboxes[i] for i in slots])
+            return self._result(out, flag, L)
         same = all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
                    and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in self.layers)
         if not same or opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
@@ -92,6 +133,10 @@ class DetectionHead(nn.Module):
         out, flag = _MultiLossFn.apply(L, C, [l.opt['stride'] for l in self.layers], opt0['bbox_loss'],
                                        opt0['ignore_thresh'], opt0.get('l1_loss_gain', 0.1),
                                        *heads, *[p[0] for p in pairs], *[p[1] for p in pairs])
+        return self._result(out, flag, L)
+
+    @staticmethod
+    def _result(out, flag, L):
         if config.nan_check == "sync" and int(flag.item()) != 0:
             for l in range(L):                                        # model/loss.py:110-114
                 lo = out[4 + 4 * l:8 + 4 * l]

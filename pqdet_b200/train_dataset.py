@@ -54,6 +54,47 @@ def assign_labels(gt: torch.Tensor, gt_count: torch.Tensor, output_sizes, num_cl
     return (labels[0], labels[1], labels[2], lists[0], lists[1], lists[2])
 
 
+class SparseTarget:
+    """Training target without dense labels: what DetectionHead.forward accepts in
+    place of the 6-tuple (label_s, label_m, label_l, sbboxes, mbboxes, lbboxes).
+      gt      (B, n_max, 6)  the GT rows [x1,y1,x2,y2,class,mixw] themselves
+      owner   3 x (B, 3, H_s, W_s) int32, scales in ascending stride order (8, 16, 32): GT index or -1
+      bboxes  3 x (B, G_s, 4) per-scale GT lists (what loss_per_scale's ignore mask consumes)
+    The loss kernel rebuilds each responsible cell's label row from gt[owner]; results are bit-identical to the
+    dense path, L bytes per image are neither written nor read."""
+
+    def __init__(self, gt, owner, bboxes, num_classes):
+        self.gt, self.owner, self.bboxes, self.num_classes = gt, list(owner), list(bboxes), num_classes
+
+    def tensors(self):
+        return [self.gt] + self.owner + self.bboxes
+
+    def clone(self):
+        return SparseTarget(self.gt.clone(), [o.clone() for o in self.owner], [b.clone() for b in self.bboxes],
+                            self.num_classes)
+
+    def copy_(self, other):
+        for d, s in zip(self.tensors(), other.tensors()):
+            if d.shape != s.shape:
+                raise ValueError("target shape changed: %s vs %s (use trim=False for a fixed capacity)"
+                                 % (tuple(s.shape), tuple(d.shape)))
+            d.copy_(s, non_blocking=True)
+        return self
+
+
+def assign_sparse(gt: torch.Tensor, gt_count: torch.Tensor, output_sizes, num_classes: int,
+                  anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, anchors_iou_threshold: float = 0.3,
+                  trim: bool = True) -> SparseTarget:
+    """The assignment of create_label + collate_batch without the dense label tensors."""
+    owners, lists, list_len = _ops.assign_sparse(gt, gt_count, anchors, strides,
+                                                 [tuple(int(v) for v in s) for s in output_sizes],
+                                                 anchors_iou_threshold)
+    if trim:
+        mx = list_len.max(dim=0)[0].cpu().tolist()
+        lists = [l[:, :max(int(m), 1)].contiguous() for l, m in zip(lists, mx)]
+    return SparseTarget(gt, owners, lists, num_classes)
+
+
 class LabelAssigner:
     """Holds what TrainDataset.__init__ reads from the config (train_dataset.py:47-56) and exposes
     create_label with the reference's signature."""
@@ -83,6 +124,11 @@ class LabelAssigner:
     def create_label_batch(self, batch_bboxes: List[np.ndarray], output_sizes, trim: bool = True):
         gt, cnt = pack_gt(batch_bboxes, self.device)
         return assign_labels(gt, cnt, output_sizes, self._num_classes, self._anchors.tolist(),
+                             self._strides.tolist(), self._anchors_iou_threshold, trim=trim)
+
+    def create_sparse_batch(self, batch_bboxes: List[np.ndarray], output_sizes, trim: bool = True) -> SparseTarget:
+        gt, cnt = pack_gt(batch_bboxes, self.device)
+        return assign_sparse(gt, cnt, output_sizes, self._num_classes, self._anchors.tolist(),
                              self._strides.tolist(), self._anchors_iou_threshold, trim=trim)
 
 

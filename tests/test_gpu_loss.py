@@ -270,3 +270,45 @@ def test_loss_and_assignment_full_size_configs():
             cat = torch.cat([halves[0][1][lvl], halves[1][1][lvl]], dim=0) * 0.5
             scale = float(g1[lvl].abs().max())
             assert float((cat - g1[lvl]).abs().max()) <= 1e-6 * scale
+
+
+VIS_ANCHORS = [(9, 13), (25, 17), (16, 31), (47, 29), (32, 51), (83, 48), (61, 91), (131, 99), (210, 189)]
+
+
+@pytest.mark.parametrize("kind", ["l1", "giou"])
+@pytest.mark.parametrize("C,size,B,lo,hi,anchors", [(20, 512, 5, 1, 12, None), (10, 608, 3, 20, 200, VIS_ANCHORS),
+                                                     (80, 608, 2, 0, 38, None)])
+def test_sparse_targets_bit_identical_to_dense_labels(kind, C, size, B, lo, hi, anchors):
+    """SparseTarget (owner maps + GT rows) through pqdet_loss_levels_sparse gives exactly the
+    losses and gradients of the dense (B,H,W,3,6+C) labels, including images without GT and cell collisions."""
+    from pqdet_b200 import synth
+    from pqdet_b200.graphs import GraphedLossStep
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.train_dataset import LabelAssigner
+    gts = synth.make_gt(B, C, size, lo, hi, seed=3)
+    gts[0] = np.concatenate([gts[0], gts[0][:1]]) if len(gts[0]) else gts[0]      # duplicate GT -> slot collision
+    out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+    la = LabelAssigner(C) if anchors is None else LabelAssigner(C, anchors=anchors)
+    dense = la.create_label_batch(gts, out_sizes)
+    sparse = la.create_sparse_batch(gts, out_sizes)
+    for i in range(3):
+        assert torch.equal(dense[3 + i], sparse.bboxes[i])
+        own = sparse.owner[i].permute(0, 2, 3, 1)                                   # (B,H,W,3)
+        assert torch.equal(own >= 0, dense[i][..., 4] == 1.0)
+    head = DetectionHead([_opt(C, s, kind) for s in synth.FPN_STRIDES])
+    theads = synth.make_train_heads(B, C, size, seed=1, device="cuda")
+    r1 = [t.clone().requires_grad_(True) for t in theads]
+    r2 = [t.clone().requires_grad_(True) for t in theads]
+    o1, o2 = head(r1, dense), head(r2, sparse)
+    up = torch.tensor([0.7], device="cuda")
+    (o1["loss"] * up + o1["conf_loss"]).sum().backward()
+    (o2["loss"] * up + o2["conf_loss"]).sum().backward()
+    for k in ("loss", "giou_loss", "conf_loss", "class_loss"):
+        assert torch.equal(o1[k], o2[k]), k
+    assert all(torch.equal(a, b) for a, b in zip(o1["loss_per_branch"], o2["loss_per_branch"]))
+    assert all(torch.equal(a.grad, b.grad) for a, b in zip(r1, r2))
+    # CUDA-graph replay on sparse targets
+    g = GraphedLossStep(head, theads, sparse)
+    out, grads = g(theads, sparse)
+    assert torch.equal(out["loss"], head([t.requires_grad_(True) for t in theads], dense)["loss"].detach())
+    assert all(bool(torch.isfinite(x).all()) for x in grads)
