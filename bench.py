@@ -268,6 +268,7 @@ def bench_loss(device, steps, warmup, peak):
     gts = synth.make_gt(B, C, size, 1, 12, seed=0)
     out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
     target = LabelAssigner(C, device=device).create_label_batch(gts, out_sizes)
+    sparse_target = LabelAssigner(C, device=device).create_sparse_batch(gts, out_sizes)
     raws = [t.requires_grad_(True) for t in synth.make_train_heads(B, C, size, seed=0, device=device)]
     res = {}
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=device)
@@ -291,20 +292,32 @@ def bench_loss(device, steps, warmup, peak):
                 flush.zero_()
                 ts += time_steps(step, 1)
             ms = float(np.median(ts))
-            # the same step captured into a CUDA graph (pqdet_b200.graphs): host glue out of the loop
+            # the same step captured into CUDA graphs (pqdet_b200.graphs): host glue out of the loop.
+            #   direct   = head.loss_and_grad: the one fused kernel (loss + d loss/d head), dense labels
+            #   sparse   = the same on SparseTarget (owner maps + GT rows instead of the dense labels)
+            #   autograd = forward(...)['loss'].mean().backward(), i.e. the reference's call sequence incl. torch's
+            #              autograd glue kernels
             from pqdet_b200.graphs import GraphedLossStep
-            gstep = GraphedLossStep(head, raws, target)
-            for _ in range(warmup):
-                gstep.replay()
-            tg = []
-            for _ in range(steps):
-                flush.zero_()
-                tg += time_steps(gstep.replay, 1)
-            msg = float(np.median(tg))
+
+            def graph_ms(gstep):
+                for _ in range(warmup):
+                    gstep.replay()
+                tg = []
+                for _ in range(steps):
+                    flush.zero_()
+                    tg += time_steps(gstep.replay, 1)
+                return float(np.median(tg))
+            msg = graph_ms(GraphedLossStep(head, raws, target))
+            mss = graph_ms(GraphedLossStep(head, raws, sparse_target))
+            msa = graph_ms(GraphedLossStep(head, raws, target, autograd=True))
             alg = 2 * raw_bytes(C, size) + label_bytes(C, size)
+            alg_sparse = 2 * raw_bytes(C, size) + 4 * 3 * cells(size)
             res[kind] = {"images_per_s": B / (msg * 1e-3), "ms_per_step": msg,
                          "roofline_frac": (alg * B / (msg * 1e-3)) / (peak * 1e9),
                          "achieved_gbs": alg * B / (msg * 1e-3) / 1e9,
+                         "sparse_targets_images_per_s": B / (mss * 1e-3), "sparse_targets_ms_per_step": mss,
+                         "sparse_targets_roofline_frac": (alg_sparse * B / (mss * 1e-3)) / (peak * 1e9),
+                         "autograd_graph_images_per_s": B / (msa * 1e-3), "autograd_graph_ms_per_step": msa,
                          "eager_images_per_s": B / (ms * 1e-3), "eager_ms_per_step": ms}
     finally:
         pqcfg.nan_check = old
@@ -344,10 +357,13 @@ def bench_loss(device, steps, warmup, peak):
                                                    "note": "oracle/loss_ref.py (model/loss.py's ATen op sequence + autograd), l1, "
                                                            "same inputs", "error": base.get("error")},
             "algorithmic_bytes_per_image": 2 * raw_bytes(C, size) + label_bytes(C, size),
+            "algorithmic_bytes_per_image_sparse_targets": 2 * raw_bytes(C, size) + 4 * 3 * cells(size),
             "timing": "median of per-step CUDA events, L2 flushed between steps; headline = CUDA-graph replay of "
-                      "forward+backward (pqdet_b200.graphs.GraphedLossStep), eager_* = the same step driven from "
-                      "Python/autograd",
-            "kernels_per_step": 3, "by_bbox_loss": res}
+                      "DetectionHead.loss_and_grad (one fused kernel: losses + d loss/d head); sparse_targets_* = the "
+                      "same on SparseTarget (SURVEY 8f-3); autograd_graph_* = the reference's call sequence "
+                      "loss.mean().backward() captured with torch's autograd glue; eager_* = that sequence driven "
+                      "from Python",
+            "kernels_per_step": 1, "by_bbox_loss": res}
 
 
 def bench_other_configs(device, peak):
@@ -462,21 +478,35 @@ def bench_other_configs(device, peak):
             target = assign_labels(gt_dev, cnt_dev, out_sizes, C, la._anchors.tolist(), la._strides.tolist(), 0.3)
             raws = [t.requires_grad_(True) for t in synth.make_train_heads(B, C, size, seed=0, device=device)]
             opts = [dict(classes=C, stride=s, bbox_loss=kind, ignore_thresh=0.5, l1_loss_gain=0.05) for s in STRIDES]
-            g = GraphedLossStep(DetectionHead(opts), raws, target)
-            ts = []
             flush = torch.empty((256 << 20,), dtype=torch.uint8, device=device)
+
+            def graph_ms(g):
+                ts = []
+                for _ in range(10):
+                    flush.zero_()
+                    ts += time_steps(g.replay, 1)
+                return float(np.median(ts))
+            g = GraphedLossStep(DetectionHead(opts), raws, target)
+            ms = graph_ms(g)
+            from pqdet_b200.train_dataset import assign_sparse
+            sp = assign_sparse(gt_dev, cnt_dev, out_sizes, C, la._anchors.tolist(), la._strides.tolist(), 0.3)
+            ms_sparse = graph_ms(GraphedLossStep(DetectionHead(opts), raws, sp))
+            tsa = []
             for _ in range(10):
                 flush.zero_()
-                ts += time_steps(g.replay, 1)
-            ms = float(np.median(ts))
+                tsa += time_steps(lambda: assign_sparse(gt_dev, cnt_dev, out_sizes, C, la._anchors.tolist(),
+                                                        la._strides.tolist(), 0.3, trim=False), 1)
+            dt_as = float(np.median(tsa)) * 1e-3
             alg = 2 * raw_bytes(C, size) + label_bytes(C, size)
             out[name] = {"workload": "C=%d %dx%d bs=%d bbox_loss=%s GT %d-%d/img" % (C, size, size, B, kind, lo, hi),
                          "loss_images_per_s": B / (ms * 1e-3), "loss_ms_per_step": ms,
                          "loss_roofline_frac": alg * B / (ms * 1e-3) / (peak * 1e9),
+                         "sparse_targets_loss_images_per_s": B / (ms_sparse * 1e-3), "sparse_targets_loss_ms": ms_sparse,
+                         "sparse_targets_assign_images_per_s": B / dt_as, "sparse_targets_assign_ms": dt_as * 1e3,
                          "gt_list_len": [int(t.shape[1]) for t in target[3:]],
                          "assign_images_per_s": B / dt_a, "assign_ms": dt_a * 1e3,
                          "assign_roofline_frac": label_bytes(C, size) * B / dt_a / (peak * 1e9)}
-            del raws, g, target, tgt
+            del raws, g, target, tgt, sp
     finally:
         pqcfg.nan_check = old
     return out

@@ -192,7 +192,8 @@ int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A, int C, in
  *   [4+4l..7+4l]    the four per-level losses YOLOLayer returns
  *   [4+4L+l]        loss_per_branch[l] = bbox+conf+cls of level l
  * workspace: pqdet_loss_levels_workspace() bytes; pass workspace_initialised=0 the first time a buffer is
- * used (its scheduler word is then zeroed by the call), 1 afterwards (the kernel re-arms it itself). */
+ * used (its completion tickets are then zeroed by the call), 1 afterwards (the kernel re-arms them itself:
+ * the reduction over tiles and images happens inside the one launch, by the last CTAs to finish). */
 int64_t pqdet_loss_levels_workspace(int n_levels, int B, int A, const int* H, const int* W);
 int pqdet_loss_levels(int n_levels, const float* const* raw, const float* const* label,
                       const float* const* gt, float* const* grad, const int* H, const int* W,
@@ -236,7 +237,7 @@ int pqdet_loss_levels_sparse(int n_levels, const float* const* raw, const int32_
                              float* const* grad, const int* H, const int* W, const int* G,
                              const float* stride, int B, int A, int C, int bbox_loss,
                              float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
-                             void* workspace, int device, void* stream);
+                             void* workspace, int workspace_initialised, int device, void* stream);
 
 #ifdef __cplusplus
 }

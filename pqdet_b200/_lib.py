@@ -89,7 +89,7 @@ SIGNATURES = {
     "pqdet_loss_levels_sparse": (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int,
                                          POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int),
                                          POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, c_int, c_float,
-                                         c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                         c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 _LIB = None

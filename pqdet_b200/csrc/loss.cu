@@ -18,7 +18,6 @@
 namespace pq {
 
 constexpr int kLossTile = 32;
-constexpr int kGtChunk = 128;
 
 struct LossParams {
   const float* x;       // raw (B, A*ch, H, W) or decoded (B,H,W,A,ch)
@@ -36,62 +35,33 @@ struct LossParams {
   float hot, cold;       // smoothed one-hot values (train_dataset.py:126-130)
 };
 
+// Every warp is autonomous: warp = anchor, lane = cell of the tile.  There is no CTA-wide barrier until the
+// final 3-value reduction, so a warp never waits for its siblings' memory latency (at 16 images per GPU the
+// kernel is latency bound: every dependent DRAM round trip that can be overlapped or dropped is step time).
 template <bool RAW, bool SPARSE = false>
 __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, const int ntiles, const int b,
                                           float* smem) {
   const int A = P.A, C = P.C, ch = 5 + C, LW = 6 + C;
   const int HW = P.H * P.W;
-  float* sgt = smem;                                    // [kGtChunk][5]
   __shared__ float sred[8][3];
   const int cell0 = tile * kLossTile;
   const int ncell = min(kLossTile, HW - cell0);
   const int lane = lane_id(), a = warp_id();
+  float* sgt = smem + a * (32 * 5);                     // this warp's culled GT boxes of the current round
   const int cell = cell0 + lane;
   const bool active = lane < ncell;
 
-  // ---- class-channel gradient = 0 everywhere (responsible cells overwrite theirs further down, after at
-  // least one __syncthreads).  CTA-cooperative: every plane segment of the tile is 32 consecutive floats,
-  // written with 128-bit stores when the planes are 16-byte aligned.
-  if (P.grad) {
-    if (RAW) {
-      const bool vec = ((HW & 3) == 0) && (ncell == kLossTile);
-      for (int a2 = 0; a2 < A; ++a2) {
-        float* seg0 = P.grad + (((size_t)b * A + a2) * ch + 5) * HW + cell0;
-        if (vec) {
-          for (int i = threadIdx.x; i < C * 8; i += blockDim.x)
-            reinterpret_cast<float4*>(seg0 + (size_t)(i >> 3) * HW)[i & 7] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          for (int i = threadIdx.x; i < C * 32; i += blockDim.x)
-            if ((i & 31) < ncell) seg0[(size_t)(i >> 5) * HW + (i & 31)] = 0.f;
-        }
-      }
-    } else if (active) {
-      float* gp = P.grad + (((size_t)b * HW + cell) * A + a) * ch + 5;
-      for (int c = 0; c < C; ++c) gp[c] = 0.f;
-    }
-  }
-
-  // ---- label row: only [box(4), respond] and the trailing mixw are needed for every row; the class
-  // targets are read at responsible cells only.  Rows are 4*(6+C) bytes apart (8-byte aligned for even C),
-  // the three anchors of a cell are adjacent, so the three warps of the CTA share L1 lines.
+  // ---- loads first, all independent: GT boxes of the first round, label row (or owner), raw planes ----
+  const float4* gtb = reinterpret_cast<const float4*>(P.gt + (size_t)b * P.G * 4);
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < P.G) q = __ldg(gtb + lane);
+  // label row: only [box(4), respond] and the trailing mixw are needed for every row; the class
+  // targets are read at responsible cells only.
   const float* lab = SPARSE ? nullptr : P.label + (((size_t)b * HW + cell) * A + a) * LW;
   float tb[4] = {0.f, 0.f, 0.f, 0.f}, respond = 0.f, mixw = 0.f;
-  int cls = -1;
+  int cls = -1, own = -1;
   if (SPARSE) {
-    // the label row of train_dataset.py:135-145: [gt box, 1, smooth one-hot, mixw] where a GT owns the slot,
-    // [0, 0, 0, 0, 0, 0.., 1] (background, mixw = 1) elsewhere
-    if (active) {
-      const int j = __ldg(P.owner + ((size_t)b * A + a) * HW + cell);
-      mixw = 1.0f;
-      if (j >= 0) {
-        const float2* g = reinterpret_cast<const float2*>(P.gt6 + ((size_t)b * P.n_max + j) * 6);
-        const float2 g01 = __ldg(g), g23 = __ldg(g + 1), g45 = __ldg(g + 2);
-        tb[0] = g01.x; tb[1] = g01.y; tb[2] = g23.x; tb[3] = g23.y;
-        cls = (int)g45.x;
-        mixw = g45.y;
-        respond = 1.0f;
-      }
-    }
+    if (active) own = __ldg(P.owner + ((size_t)b * A + a) * HW + cell);
   } else if (active) {
     if ((LW & 1) == 0) {
       const float2 t01 = __ldg(reinterpret_cast<const float2*>(lab));
@@ -104,16 +74,57 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
     respond = __ldg(lab + 4);
     mixw = __ldg(lab + 5 + C);
   }
-  // ---- prediction: box + objectness ----
-  float pb[4] = {0.f, 0.f, 1.f, 1.f}, es[4] = {0.f, 0.f, 0.f, 0.f}, pconf = 0.5f;
   const size_t plane0 = ((size_t)b * A + a) * ch * HW;             // RAW: first plane of this anchor
   const size_t prow = (((size_t)b * HW + cell) * A + a) * ch;      // !RAW: this row
+  float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (active) {
+    if (RAW) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[k] = ldg_stream(P.x + plane0 + (size_t)k * HW + cell);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[k] = P.x[prow + k];
+    }
+  }
+
+  // ---- class-channel gradient = 0 (responsible cells overwrite theirs further down, after a __syncwarp).
+  // Each plane segment of the tile is 32 consecutive floats: 128-bit stores when the planes are aligned.
+  if (P.grad) {
+    if (RAW) {
+      const bool vec = ((HW & 3) == 0) && (ncell == kLossTile);
+      float* seg0 = P.grad + plane0 + (size_t)5 * HW + cell0;
+      if (vec) {
+        for (int i = lane; i < C * 8; i += 32)
+          reinterpret_cast<float4*>(seg0 + (size_t)(i >> 3) * HW)[i & 7] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (active) {
+        for (int c = 0; c < C; ++c) seg0[(size_t)c * HW + lane] = 0.f;
+      }
+    } else if (active) {
+      float* gp = P.grad + prow + 5;
+      for (int c = 0; c < C; ++c) gp[c] = 0.f;
+    }
+  }
+
+  if (SPARSE) {
+    // the label row of train_dataset.py:135-145: [gt box, 1, smooth one-hot, mixw] where a GT owns the slot,
+    // [0, 0, 0, 0, 0, 0.., 1] (background, mixw = 1) elsewhere
+    if (active) {
+      mixw = 1.0f;
+      if (own >= 0) {
+        const float2* g = reinterpret_cast<const float2*>(P.gt6 + ((size_t)b * P.n_max + own) * 6);
+        const float2 g01 = __ldg(g), g23 = __ldg(g + 1), g45 = __ldg(g + 2);
+        tb[0] = g01.x; tb[1] = g01.y; tb[2] = g23.x; tb[3] = g23.y;
+        cls = (int)g45.x;
+        mixw = g45.y;
+        respond = 1.0f;
+      }
+    }
+  }
+  // ---- prediction: box + objectness ----
+  float pb[4] = {0.f, 0.f, 1.f, 1.f}, es[4] = {0.f, 0.f, 0.f, 0.f}, pconf = 0.5f;
   if (active) {
     if (RAW) {
       const int cy = cell / P.W, cx = cell - cy * P.W;
-      float v[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) v[k] = ldg_stream(P.x + plane0 + (size_t)k * HW + cell);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         pb[k] = decode_coord(k, v[k], cx, cy, P.stride);
@@ -123,8 +134,8 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
       pconf = sigmoidf_(v[4]);
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pb[k] = P.x[prow + k];
-      pconf = P.x[prow + 4];
+      for (int k = 0; k < 4; ++k) pb[k] = v[k];
+      pconf = v[4];
     }
   }
   // ---- box term ----
@@ -133,15 +144,13 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
   if (active) lb = bbox_loss_row(P.bbox_loss, pb, tb, respond, P.in_area, P.l1_gain, dbox);
 
   // ---- ignore mask: every GT has iou < thr (NaN -> false), only needed where respond != 1 ----
-  // Exact culling: a GT that does not strictly overlap the union bounding box of this CTA's predictions
-  // has inter == 0 with every one of them, i.e. iou == +0 < thr, and cannot change the mask - provided
-  // thr > 0, the prediction areas are positive finite numbers and the GT area is a finite number >= 0
-  // (otherwise 0/0 or NaN could appear, so culling is switched off for the CTA / that GT).
+  // Exact culling per warp: a GT that does not strictly overlap the union bounding box of this warp's
+  // predictions has inter == 0 with every one of them, i.e. iou == +0 < thr, and cannot change the mask -
+  // provided thr > 0, the prediction areas are positive finite numbers and the GT area is a finite number
+  // >= 0 (otherwise 0/0 or NaN could appear, so culling is switched off for the warp / that GT).
   bool below = true;
   const bool need = active && (respond != 1.0f);
   const float a1 = box_area(pb[0], pb[1], pb[2], pb[3]);
-  __shared__ float s_u[8][4];
-  __shared__ int s_ng;
   float ux1 = INFINITY, uy1 = INFINITY, ux2 = -INFINITY, uy2 = -INFINITY;
   if (need) {
     const bool sane = (a1 > 0.0f) && (a1 < INFINITY) && (P.ignore_thresh > 0.0f);
@@ -153,39 +162,33 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
     ux1 = fminf(ux1, __shfl_xor_sync(PQ_FULL, ux1, d)); uy1 = fminf(uy1, __shfl_xor_sync(PQ_FULL, uy1, d));
     ux2 = fmaxf(ux2, __shfl_xor_sync(PQ_FULL, ux2, d)); uy2 = fmaxf(uy2, __shfl_xor_sync(PQ_FULL, uy2, d));
   }
-  if (lane == 0) { s_u[a][0] = ux1; s_u[a][1] = uy1; s_u[a][2] = ux2; s_u[a][3] = uy2; }
-  __syncthreads();
-  for (int w = 0; w < A; ++w) {
-    ux1 = fminf(ux1, s_u[w][0]); uy1 = fminf(uy1, s_u[w][1]);
-    ux2 = fmaxf(ux2, s_u[w][2]); uy2 = fmaxf(uy2, s_u[w][3]);
-  }
-  for (int g0 = 0; g0 < P.G; g0 += kGtChunk) {
-    const int ng = min(kGtChunk, P.G - g0);
-    __syncthreads();
-    if (threadIdx.x == 0) s_ng = 0;
-    __syncthreads();
-    for (int e = threadIdx.x; e < ng; e += blockDim.x) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(P.gt + ((size_t)b * P.G + g0 + e) * 4));
-      const float a2 = box_area(q.x, q.y, q.z, q.w);
-      const bool cullable = (a2 >= 0.0f) && (a2 < INFINITY);
-      const bool overlaps = (q.z > ux1) && (q.x < ux2) && (q.w > uy1) && (q.y < uy2);
-      if (!cullable || overlaps) {
-        const int pos = atomicAdd(&s_ng, 1);
-        sgt[pos * 5 + 0] = q.x; sgt[pos * 5 + 1] = q.y; sgt[pos * 5 + 2] = q.z; sgt[pos * 5 + 3] = q.w;
-        sgt[pos * 5 + 4] = a2;
-      }
+  for (int g0 = 0; g0 < P.G; g0 += 32) {
+    if (!__any_sync(PQ_FULL, need && below)) break;
+    if (g0 > 0) {
+      q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g0 + lane < P.G) q = __ldg(gtb + g0 + lane);
     }
-    __syncthreads();
-    const int nk = s_ng;
+    const float a2 = box_area(q.x, q.y, q.z, q.w);
+    const bool cullable = (a2 >= 0.0f) && (a2 < INFINITY);
+    const bool overlaps = (q.z > ux1) && (q.x < ux2) && (q.w > uy1) && (q.y < uy2);
+    const bool take = (g0 + lane < P.G) && (!cullable || overlaps);
+    const unsigned tm = __ballot_sync(PQ_FULL, take);
+    if (take) {
+      float* d = sgt + __popc(tm & ((1u << lane) - 1u)) * 5;
+      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w; d[4] = a2;
+    }
+    __syncwarp();
+    const int nk = __popc(tm);
     if (need && below) {
       for (int g = 0; g < nk; ++g) {
-        const float* q = sgt + g * 5;
-        if (!iou_below(pb[0], pb[1], pb[2], pb[3], a1, q[0], q[1], q[2], q[3], q[4], P.ignore_thresh)) {
+        const float* e = sgt + g * 5;
+        if (!iou_below(pb[0], pb[1], pb[2], pb[3], a1, e[0], e[1], e[2], e[3], e[4], P.ignore_thresh)) {
           below = false;
           break;
         }
       }
     }
+    __syncwarp();
   }
   // torch.max over an empty GT axis would raise; collate always pads to G >= 1.
   const float bgd = PQ_MUL(PQ_SUB(1.0f, respond), below ? 1.0f : 0.0f);
@@ -196,7 +199,7 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
 
   const float gw = mixw * P.inv_B;
   // ---- class term: only the rare responsible cells (their class gradients overwrite the zeros written at
-  // the top; the barriers in between order the two stores).  Logits/targets are fetched in batches of 8 so
+  // the top; __syncwarp orders the two stores).  Logits/targets are fetched in batches of 8 so
   // the scattered-plane load latency is paid once per batch, not once per class.
   float lp = 0.f;
   if (active && respond != 0.0f) {
@@ -226,16 +229,6 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
       }
     }
   }
-  if (active && P.grad) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (RAW) P.grad[plane0 + (size_t)k * HW + cell] = dbox[k] * es[k] * gw;
-      else P.grad[prow + k] = dbox[k] * gw;
-    }
-    if (RAW) P.grad[plane0 + (size_t)4 * HW + cell] = dconf * (pconf * (1.0f - pconf)) * gw;
-    else P.grad[prow + 4] = dconf * gw;
-  }
-
   // ---- partial sums: fixed-order fp32 butterfly inside the warp, fp64 across warps / CTAs ----
   float v0 = active ? PQ_MUL(lb, mixw) : 0.0f;
   float v1 = active ? PQ_MUL(lc, mixw) : 0.0f;
@@ -252,19 +245,32 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
     double s = 0.0;
     for (int w = 0; w < A; ++w) s += (double)sred[w][threadIdx.x];
     P.partials[((size_t)b * ntiles + tile) * 3 + threadIdx.x] = s;
+    // make the partial visible before this warp takes its completion ticket (loss_levels_kernel).  Only these
+    // three lanes fence, and they do it BEFORE issuing their box/objectness gradient stores, so the fence
+    // waits for little more than the 8-byte store above.
+    __threadfence();
+  }
+  if (active && P.grad) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (RAW) P.grad[plane0 + (size_t)k * HW + cell] = dbox[k] * es[k] * gw;
+      else P.grad[prow + k] = dbox[k] * gw;
+    }
+    if (RAW) P.grad[plane0 + (size_t)4 * HW + cell] = dconf * (pconf * (1.0f - pconf)) * gw;
+    else P.grad[prow + 4] = dconf * gw;
   }
 }
 
 template <bool RAW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 loss_fwd_bwd_kernel(const __grid_constant__ LossParams P) {
   extern __shared__ __align__(16) float smem[];
   loss_tile<RAW>(P, blockIdx.x, gridDim.x, blockIdx.y, smem);
 }
 
 // ---- all FPN levels in ONE launch (DetectionModel.forward training branch, model/interpreter.py:77-85)
-// grid.x enumerates the tiles of every level back to back, grid.y = image.  A second, single-CTA kernel
-// (loss_levels_finalize_kernel) reduces every level's partial sums in index order - deterministic - and writes
+// grid.x enumerates the tiles of every level back to back, grid.y = image.  The last CTAs to finish reduce the
+// partial sums in a fixed order - deterministic - inside the same launch (ticket counters) and write
 //   out[0..3]            loss, bbox, conf, cls summed over levels in Python-sum order ((0+h0)+h1)+h2
 //   out[4+4l .. 7+4l]    the four (1,) losses of level l (what YOLOLayer.forward returns)
 //   out[4+4L+l]          loss_per_branch[l] = (bbox+conf)+cls of level l
@@ -273,13 +279,14 @@ struct MultiLossParams {
   int tile_off[PQDET_MAX_LEVELS + 1];
   int n_levels;
   unsigned total_blocks;
-  unsigned* ticket;
+  unsigned* ticket;        // [0] = images finished (all levels); [1 + l*B + b] = tiles of (level l, image b) finished
+  double* img_partials;    // [n_levels][B][3]
   float* out;
   int32_t* nan_flag;
 };
 
 template <bool SPARSE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   extern __shared__ __align__(16) float smem[];
   int l = 0;
@@ -287,49 +294,66 @@ loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
     if (i < M.n_levels && (int)blockIdx.x >= M.tile_off[i]) l = i;
   const int ntiles = M.tile_off[l + 1] - M.tile_off[l];
-  loss_tile<true, SPARSE>(M.lv[l], blockIdx.x - M.tile_off[l], ntiles, blockIdx.y, smem);
-}
+  const int b = blockIdx.y;
+  const LossParams& P = M.lv[l];
+  loss_tile<true, SPARSE>(P, blockIdx.x - M.tile_off[l], ntiles, b, smem);
 
-// One CTA of 1024 threads: reduce every level's partial sums in a fixed order (thread-strided accumulation,
-// warp butterfly, then a serial sum over the 32 warp results) - deterministic - and write the outputs.
-__global__ void __launch_bounds__(1024)
-loss_levels_finalize_kernel(const __grid_constant__ MultiLossParams M) {
-  __shared__ double s_w[32][3];
-  const int lane = lane_id(), warp = warp_id();
-  float tot[4] = {0.f, 0.f, 0.f, 0.f};
-  bool nan = false;
-  for (int q = 0; q < M.n_levels; ++q) {
-    const LossParams& P = M.lv[q];
-    const int64_t n = (int64_t)P.B * (M.tile_off[q + 1] - M.tile_off[q]);
-    double acc[3] = {0.0, 0.0, 0.0};
-#pragma unroll 4
-    for (int64_t i = threadIdx.x; i < n; i += 1024) {
-      acc[0] += P.partials[i * 3 + 0]; acc[1] += P.partials[i * 3 + 1]; acc[2] += P.partials[i * 3 + 2];
-    }
+  // ---- in-kernel finalisation (no second launch): the last tile of an image to finish reduces that image's
+  // partial sums, the last image to finish reduces over the batch and writes the outputs.  All orders are
+  // fixed (lane-strided accumulation + butterfly), so the result is run-to-run deterministic.
+  // Only warp 0 takes part (its lanes 0..2 wrote and fenced this CTA's partials); the other warps are done.
+  if (warp_id() != 0) return;
+  const int lane = lane_id();
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) last = (atomicAdd(&M.ticket[1 + l * P.B + b], 1u) == (unsigned)ntiles - 1u) ? 1 : 0;
+  if (!__shfl_sync(PQ_FULL, last, 0)) return;
+  __threadfence();
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int t = lane; t < ntiles; t += 32) {
+    const double* pp = P.partials + ((size_t)b * ntiles + t) * 3;
+    acc[0] += __ldcg(pp); acc[1] += __ldcg(pp + 1); acc[2] += __ldcg(pp + 2);
+  }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) { s_w[warp][0] = acc[0]; s_w[warp][1] = acc[1]; s_w[warp][2] = acc[2]; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double sum[3] = {0.0, 0.0, 0.0};
-      for (int w = 0; w < 32; ++w)
-        for (int j = 0; j < 3; ++j) sum[j] += s_w[w][j];
-      const double invB = 1.0 / (double)P.B;
-      const float lb = (float)(sum[0] * invB), lc = (float)(sum[1] * invB), lp = (float)(sum[2] * invB);
-      const float loss = PQ_ADD(PQ_ADD(lb, lc), lp);
-      float* o = M.out + 4 + 4 * q;
-      o[0] = loss; o[1] = lb; o[2] = lc; o[3] = lp;
-      M.out[4 + 4 * M.n_levels + q] = PQ_ADD(PQ_ADD(lb, lc), lp);
-      tot[0] = q ? PQ_ADD(tot[0], loss) : loss; tot[1] = q ? PQ_ADD(tot[1], lb) : lb;
-      tot[2] = q ? PQ_ADD(tot[2], lc) : lc;     tot[3] = q ? PQ_ADD(tot[3], lp) : lp;
-      nan |= (loss != loss);
+  for (int j = 0; j < 3; ++j) acc[j] = warp_sum(acc[j]);
+  if (lane < 3) {
+    M.img_partials[((size_t)l * P.B + b) * 3 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
+    __threadfence();
+  }
+  __syncwarp();
+  if (lane == 0) last = (atomicAdd(&M.ticket[0], 1u) == (unsigned)(M.n_levels * P.B) - 1u) ? 1 : 0;
+  if (!__shfl_sync(PQ_FULL, last, 0)) return;
+  __threadfence();
+  {
+    float tot[4] = {0.f, 0.f, 0.f, 0.f};
+    bool nan = false;
+    for (int q = 0; q < M.n_levels; ++q) {
+      double sum[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double a2 = 0.0;
+        for (int i = lane; i < P.B; i += 32) a2 += __ldcg(M.img_partials + ((size_t)q * P.B + i) * 3 + j);
+        sum[j] = warp_sum(a2);
+      }
+      if (lane == 0) {
+        const double invB = 1.0 / (double)P.B;
+        const float lb = (float)(sum[0] * invB), lc = (float)(sum[1] * invB), lp = (float)(sum[2] * invB);
+        const float loss = PQ_ADD(PQ_ADD(lb, lc), lp);          // model/loss.py:108
+        float* o = M.out + 4 + 4 * q;
+        o[0] = loss; o[1] = lb; o[2] = lc; o[3] = lp;
+        M.out[4 + 4 * M.n_levels + q] = PQ_ADD(PQ_ADD(lb, lc), lp);
+        tot[0] = q ? PQ_ADD(tot[0], loss) : loss; tot[1] = q ? PQ_ADD(tot[1], lb) : lb;
+        tot[2] = q ? PQ_ADD(tot[2], lc) : lc;     tot[3] = q ? PQ_ADD(tot[3], lp) : lp;
+        nan |= (loss != loss);
+      }
     }
-    __syncthreads();
+    if (lane == 0) {
+      for (int j = 0; j < 4; ++j) M.out[j] = tot[j];
+      *M.nan_flag = nan ? 1 : 0;
+    }
   }
-  if (threadIdx.x == 0) {
-    for (int j = 0; j < 4; ++j) M.out[j] = tot[j];
-    *M.nan_flag = nan ? 1 : 0;
-  }
+  // re-arm the tickets for the next launch on this stream
+  for (int i = lane; i < 1 + M.n_levels * P.B; i += 32) M.ticket[i] = 0u;
 }
 
 // Chain rule for the multi-level outputs.  g = upstream gradient of out (device, 4+5L floats).  Level l's
@@ -432,15 +456,11 @@ extern "C" int pqdet_loss_fwd_bwd(const float* x, int input_is_raw, const float*
   P.ignore_thresh = ignore_thresh; P.l1_gain = l1_loss_gain; P.inv_B = 1.0f / (float)B;
   P.bbox_loss = bbox_loss;
   const int tiles = (H * W + kLossTile - 1) / kLossTile;
-  const size_t smem = (size_t)kGtChunk * 5 * sizeof(float);
+  const size_t smem = (size_t)A * 32 * 5 * sizeof(float);
   dim3 grid(tiles, B);
   if (input_is_raw) {
-    if (smem > 48 * 1024)
-      PQ_CUDA(cudaFuncSetAttribute(loss_fwd_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     loss_fwd_bwd_kernel<true><<<grid, 32 * A, smem, st>>>(P);
   } else {
-    if (smem > 48 * 1024)
-      PQ_CUDA(cudaFuncSetAttribute(loss_fwd_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     loss_fwd_bwd_kernel<false><<<grid, 32 * A, smem, st>>>(P);
   }
   PQ_LAUNCH_CHECK();
@@ -463,9 +483,14 @@ extern "C" int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A
   return PQDET_OK;
 }
 
+namespace pq {
+static inline size_t ticket_bytes(int n_levels, int B) { return ((size_t)(1 + n_levels * B) * 4 + 255) / 256 * 256; }
+static inline size_t imgpart_bytes(int n_levels, int B) { return ((size_t)n_levels * B * 3 * 8 + 255) / 256 * 256; }
+}  // namespace pq
+
 extern "C" int64_t pqdet_loss_levels_workspace(int n_levels, int B, int A, const int* H, const int* W) {
   if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || B < 0 || A < 1 || !H || !W) return PQDET_ERR_INVALID_ARG;
-  int64_t bytes = 256;   // ticket
+  int64_t bytes = (int64_t)(pq::ticket_bytes(n_levels, B) + pq::imgpart_bytes(n_levels, B));
   for (int l = 0; l < n_levels; ++l) {
     const int64_t tiles = ((int64_t)H[l] * W[l] + pq::kLossTile - 1) / pq::kLossTile;
     bytes += ((int64_t)B * tiles * 3 * (int64_t)sizeof(double) + 255) / 256 * 256;
@@ -479,7 +504,7 @@ static int loss_levels_impl(int n_levels, const float* const* raw, const float* 
                             const float* const* gt, float* const* grad, const int* H, const int* W,
                             const int* G, const float* stride, int B, int A, int C, int bbox_loss,
                             float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
-                            void* workspace, int device, void* stream) {
+                            void* workspace, int workspace_initialised, int device, void* stream) {
   const bool sparse = owner != nullptr;
   if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || !raw || (!label && !owner) || !gt || !H || !W || !G || !stride ||
       !out || !nan_flag || !workspace)
@@ -493,7 +518,11 @@ static int loss_levels_impl(int n_levels, const float* const* raw, const float* 
   memset(&M, 0, sizeof(M));
   unsigned char* ws = (unsigned char*)workspace;
   M.ticket = (unsigned*)ws;
-  size_t off = 256;
+  size_t off = ticket_bytes(n_levels, B);
+  M.img_partials = (double*)(ws + off);
+  off += imgpart_bytes(n_levels, B);
+  // the tickets must be zero on entry: the kernel re-arms them itself, so only a fresh buffer needs the memset
+  if (!workspace_initialised) PQ_CUDA(cudaMemsetAsync(ws, 0, ticket_bytes(n_levels, B), st));
   int tiles_total = 0;
   const double deta = 0.01, uni = 1.0 / (double)C;         // train_dataset.py:126-130, fp64 then stored fp32
   for (int l = 0; l < n_levels; ++l) {
@@ -519,12 +548,10 @@ static int loss_levels_impl(int n_levels, const float* const* raw, const float* 
   M.n_levels = n_levels;
   M.total_blocks = (unsigned)tiles_total * (unsigned)B;
   M.out = out; M.nan_flag = nan_flag;
-  const size_t smem = (size_t)kGtChunk * 5 * sizeof(float);
+  const size_t smem = (size_t)A * 32 * 5 * sizeof(float);
   dim3 grid(tiles_total, B);
   if (sparse) loss_levels_kernel<true><<<grid, 32 * A, smem, st>>>(M);
   else loss_levels_kernel<false><<<grid, 32 * A, smem, st>>>(M);
-  PQ_LAUNCH_CHECK();
-  loss_levels_finalize_kernel<<<1, 1024, 0, st>>>(M);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
@@ -535,10 +562,10 @@ extern "C" int pqdet_loss_levels(int n_levels, const float* const* raw, const fl
                                  const int* G, const float* stride, int B, int A, int C, int bbox_loss,
                                  float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
                                  void* workspace, int workspace_initialised, int device, void* stream) {
-  (void)workspace_initialised;
   if (!label) return PQDET_ERR_INVALID_ARG;
   return pq::loss_levels_impl(n_levels, raw, label, nullptr, nullptr, 0, gt, grad, H, W, G, stride, B, A, C,
-                              bbox_loss, ignore_thresh, l1_loss_gain, out, nan_flag, workspace, device, stream);
+                              bbox_loss, ignore_thresh, l1_loss_gain, out, nan_flag, workspace,
+                              workspace_initialised, device, stream);
 }
 
 extern "C" int pqdet_loss_levels_sparse(int n_levels, const float* const* raw, const int32_t* const* owner,
@@ -546,11 +573,12 @@ extern "C" int pqdet_loss_levels_sparse(int n_levels, const float* const* raw, c
                                         float* const* grad, const int* H, const int* W, const int* G,
                                         const float* stride, int B, int A, int C, int bbox_loss,
                                         float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
-                                        void* workspace, int device, void* stream) {
+                                        void* workspace, int workspace_initialised, int device, void* stream) {
   if (!owner) return PQDET_ERR_INVALID_ARG;
   if (A != 3) return PQDET_ERR_UNSUPPORTED;          // the assignment has 3 anchors per scale (config.py:57)
   return pq::loss_levels_impl(n_levels, raw, nullptr, owner, gt6, n_max, gtlist, grad, H, W, G, stride, B, A, C,
-                              bbox_loss, ignore_thresh, l1_loss_gain, out, nan_flag, workspace, device, stream);
+                              bbox_loss, ignore_thresh, l1_loss_gain, out, nan_flag, workspace,
+                              workspace_initialised, device, stream);
 }
 
 extern "C" int pqdet_loss_levels_scale_grad(int n_levels, float* const* grad, const int* H, const int* W,

@@ -16,9 +16,15 @@ from . import config
 
 
 class GraphedLossStep:
-    def __init__(self, head, heads: Sequence[torch.Tensor], target: Sequence[torch.Tensor], warmup: int = 3):
-        """head: interpreter.DetectionHead; heads/target: example tensors (shapes are frozen)."""
+    def __init__(self, head, heads: Sequence[torch.Tensor], target: Sequence[torch.Tensor], warmup: int = 3,
+                 autograd: bool = False):
+        """head: interpreter.DetectionHead; heads/target: example tensors (shapes are frozen).
+        autograd=False (default): the step is head.loss_and_grad -- one kernel in the graph.
+        autograd=True: the reference's own call sequence, forward(heads, target)['loss'].mean().backward(),
+        captured with its autograd glue kernels (same numbers, a few microseconds more per replay)."""
         self.head = head
+        self.autograd = autograd
+        self.static_grads = None
         self.static_heads = [h.detach().clone().requires_grad_(True) for h in heads]
         self._sparse = hasattr(target, "tensors")                      # train_dataset.SparseTarget
         self.static_target = target.clone() if self._sparse else tuple(t.detach().clone() for t in target)
@@ -35,13 +41,18 @@ class GraphedLossStep:
             torch.cuda.synchronize()
             for h in self.static_heads:
                 h.grad = None
-            with torch.cuda.graph(self.graph):
+            # capture on the stream the warm-up ran on: the library's per-stream workspace is then already
+            # allocated and armed (its completion tickets are zero), so the graph holds nothing but the kernels
+            with torch.cuda.graph(self.graph, stream=side):
                 self.static_out = self._step()
         finally:
             config.nan_check = old
         self.nan_flag = getattr(self.static_out['loss'], 'pq_nan_flag', None)
 
     def _step(self):
+        if not self.autograd:
+            out, self.static_grads = self.head.loss_and_grad(self.static_heads, self.static_target)
+            return out
         out = self.head(self.static_heads, self.static_target)
         out['loss'].mean().backward()
         return out
@@ -49,6 +60,8 @@ class GraphedLossStep:
     def replay(self):
         """Re-run on whatever is in the static buffers.  -> (loss dict, [d loss / d head])."""
         self.graph.replay()
+        if not self.autograd:
+            return self.static_out, self.static_grads
         return self.static_out, [h.grad for h in self.static_heads]
 
     def __call__(self, heads: Sequence[torch.Tensor], target: Sequence[torch.Tensor]):

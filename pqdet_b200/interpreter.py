@@ -135,6 +135,35 @@ class DetectionHead(nn.Module):
                                        *heads, *[p[0] for p in pairs], *[p[1] for p in pairs])
         return self._result(out, flag, L)
 
+    def loss_and_grad(self, heads: Sequence[torch.Tensor], target):
+        """The training branch without autograd glue: ONE kernel launch gives the loss dict of forward(heads,
+        target) and d loss.mean() / d head for every level (the kernel always computes both).  A trainer continues
+        into the backbone with torch.autograd.backward(list(heads), grads) instead of loss.mean().backward()
+        (trainer.py:233) -- same gradients, minus ~8 tiny autograd kernels per step.
+        target: the reference's 6-tuple or a train_dataset.SparseTarget.  -> (dict, [grad per level])"""
+        L = len(self.layers)
+        opt0 = self.layers[0].opt
+        if not all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
+                   and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in self.layers):
+            raise ValueError("loss_and_grad needs the same loss options on every [yolo] level")
+        if opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
+            raise NotImplementedError
+        strides = [l.opt['stride'] for l in self.layers]
+        raws = [h.detach() for h in heads]
+        if isinstance(target, SparseTarget):
+            slots = [_SCALE_SLOT[s] for s in strides]
+            out, flag, grads = _ops.loss_levels_sparse(raws, [target.owner[i] for i in slots], target.gt,
+                                                       [target.bboxes[i] for i in slots], target.num_classes, strides,
+                                                       opt0['bbox_loss'], opt0['ignore_thresh'],
+                                                       opt0.get('l1_loss_gain', 0.1), True)
+        else:
+            pairs = [_TARGET_MAP[s](target) for s in strides]
+            C = pairs[0][0].shape[-1] - 6
+            out, flag, grads = _ops.loss_levels(raws, [p[0] for p in pairs], [p[1] for p in pairs], C, strides,
+                                                opt0['bbox_loss'], opt0['ignore_thresh'],
+                                                opt0.get('l1_loss_gain', 0.1), True)
+        return self._result(out, flag, L), grads
+
     @staticmethod
     def _result(out, flag, L):
         if config.nan_check == "sync" and int(flag.item()) != 0:

@@ -41,6 +41,21 @@ def main():
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(); call(); e.record(); torch.cuda.synchronize()
             ts.append(s.elapsed_time(e))
+        sp = la.create_sparse_batch(gts, out_sizes)
+        owners = [sp.owner[idx[s]] for s in STRIDES]
+        sgl = [sp.bboxes[idx[s]] for s in STRIDES]
+
+        def call_sparse():
+            return _ops.loss_levels_sparse(raws, owners, sp.gt, sgl, C, STRIDES, kind, 0.5, 0.05, True)
+        for _ in range(3):
+            call_sparse()
+        tsp = []
+        for _ in range(10):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); call_sparse(); e.record(); torch.cuda.synchronize()
+            tsp.append(s.elapsed_time(e))
+        print("%s: sparse targets        launch %.1f us" % (name, float(np.median(tsp)) * 1e3))
         cells = sum((size // s) ** 2 for s in STRIDES)
         alg = (2 * 12 * (5 + C) + 12 * (6 + C)) * cells * B
         ms = float(np.median(ts))

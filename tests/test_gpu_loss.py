@@ -312,3 +312,34 @@ def test_sparse_targets_bit_identical_to_dense_labels(kind, C, size, B, lo, hi, 
     out, grads = g(theads, sparse)
     assert torch.equal(out["loss"], head([t.requires_grad_(True) for t in theads], dense)["loss"].detach())
     assert all(bool(torch.isfinite(x).all()) for x in grads)
+
+
+def test_loss_and_grad_equals_autograd_path_and_graph_modes():
+    """DetectionHead.loss_and_grad (no autograd glue) == forward(...)['loss'].mean().backward(), eagerly and
+    through both CUDA-graph modes; repeated replays are bit-stable (in-kernel deterministic reduction)."""
+    from pqdet_b200 import synth
+    from pqdet_b200.graphs import GraphedLossStep
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.train_dataset import LabelAssigner
+    C, size, B = 20, 512, 16
+    gts = synth.make_gt(B, C, size, 1, 12, seed=0)
+    out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+    target = LabelAssigner(C).create_label_batch(gts, out_sizes)
+    head = DetectionHead([_opt(C, s, "giou") for s in synth.FPN_STRIDES])
+    theads = synth.make_train_heads(B, C, size, seed=0, device="cuda")
+    raws = [t.clone().requires_grad_(True) for t in theads]
+    out = head(raws, target)
+    out["loss"].mean().backward()
+    d_out, d_grads = head.loss_and_grad(theads, target)
+    assert torch.equal(out["loss"].detach(), d_out["loss"])
+    assert all(torch.equal(r.grad, g) for r, g in zip(raws, d_grads))
+    for autograd in (False, True):
+        g = GraphedLossStep(head, theads, target, autograd=autograd)
+        for _ in range(3):
+            o, gr = g(theads, target)
+            assert torch.equal(o["loss"].detach(), d_out["loss"]) and torch.equal(o["class_loss"].detach(), d_out["class_loss"])
+            assert all(torch.equal(a, b) for a, b in zip(gr, d_grads))
+    # a different batch size on the same stream re-uses the workspace: its completion tickets must be re-zeroed
+    o2, _ = head.loss_and_grad([t[:5].contiguous() for t in theads], tuple(t[:5].contiguous() for t in target))
+    o3, _ = head.loss_and_grad(theads, target)
+    assert torch.equal(o3["loss"], d_out["loss"]) and bool(torch.isfinite(o2["loss"]).all())
