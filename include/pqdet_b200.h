@@ -191,9 +191,8 @@ int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A, int C, in
  *   [0..3]          loss, bbox(giou_loss), conf_loss, class_loss summed over levels, ((0+h0)+h1)+h2
  *   [4+4l..7+4l]    the four per-level losses YOLOLayer returns
  *   [4+4L+l]        loss_per_branch[l] = bbox+conf+cls of level l
- * workspace: pqdet_loss_levels_workspace() bytes; pass workspace_initialised=0 the first time a buffer is
- * used (its completion tickets are then zeroed by the call), 1 afterwards (the kernel re-arms them itself:
- * the reduction over tiles and images happens inside the one launch, by the last CTAs to finish). */
+ * workspace: pqdet_loss_levels_workspace() bytes of scratch (per-CTA partial sums, reduced in a fixed order by a
+ * second single-CTA launch); workspace_initialised is accepted for ABI stability and ignored (no state is kept). */
 int64_t pqdet_loss_levels_workspace(int n_levels, int B, int A, const int* H, const int* W);
 int pqdet_loss_levels(int n_levels, const float* const* raw, const float* const* label,
                       const float* const* gt, float* const* grad, const int* H, const int* W,

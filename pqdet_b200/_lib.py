@@ -96,7 +96,8 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; PQDET_B200_LIB overrides it (A/B runs of differently compiled kernels)."""
+    return os.environ.get("PQDET_B200_LIB") or _build.LIB_PATH
 
 
 def load():

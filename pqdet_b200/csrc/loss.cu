@@ -229,6 +229,16 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
       }
     }
   }
+  if (active && P.grad) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (RAW) P.grad[plane0 + (size_t)k * HW + cell] = dbox[k] * es[k] * gw;
+      else P.grad[prow + k] = dbox[k] * gw;
+    }
+    if (RAW) P.grad[plane0 + (size_t)4 * HW + cell] = dconf * (pconf * (1.0f - pconf)) * gw;
+    else P.grad[prow + 4] = dconf * gw;
+  }
+
   // ---- partial sums: fixed-order fp32 butterfly inside the warp, fp64 across warps / CTAs ----
   float v0 = active ? PQ_MUL(lb, mixw) : 0.0f;
   float v1 = active ? PQ_MUL(lc, mixw) : 0.0f;
@@ -245,19 +255,6 @@ __device__ __forceinline__ void loss_tile(const LossParams& P, const int tile, c
     double s = 0.0;
     for (int w = 0; w < A; ++w) s += (double)sred[w][threadIdx.x];
     P.partials[((size_t)b * ntiles + tile) * 3 + threadIdx.x] = s;
-    // make the partial visible before this warp takes its completion ticket (loss_levels_kernel).  Only these
-    // three lanes fence, and they do it BEFORE issuing their box/objectness gradient stores, so the fence
-    // waits for little more than the 8-byte store above.
-    __threadfence();
-  }
-  if (active && P.grad) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (RAW) P.grad[plane0 + (size_t)k * HW + cell] = dbox[k] * es[k] * gw;
-      else P.grad[prow + k] = dbox[k] * gw;
-    }
-    if (RAW) P.grad[plane0 + (size_t)4 * HW + cell] = dconf * (pconf * (1.0f - pconf)) * gw;
-    else P.grad[prow + 4] = dconf * gw;
   }
 }
 
@@ -269,8 +266,8 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossParams P) {
 }
 
 // ---- all FPN levels in ONE launch (DetectionModel.forward training branch, model/interpreter.py:77-85)
-// grid.x enumerates the tiles of every level back to back, grid.y = image.  The last CTAs to finish reduce the
-// partial sums in a fixed order - deterministic - inside the same launch (ticket counters) and write
+// grid.x enumerates the tiles of every level back to back, grid.y = image.  A second, single-CTA kernel
+// (loss_levels_finalize_kernel) reduces every level's partial sums in a fixed order - deterministic - and writes
 //   out[0..3]            loss, bbox, conf, cls summed over levels in Python-sum order ((0+h0)+h1)+h2
 //   out[4+4l .. 7+4l]    the four (1,) losses of level l (what YOLOLayer.forward returns)
 //   out[4+4L+l]          loss_per_branch[l] = (bbox+conf)+cls of level l
@@ -279,14 +276,15 @@ struct MultiLossParams {
   int tile_off[PQDET_MAX_LEVELS + 1];
   int n_levels;
   unsigned total_blocks;
-  unsigned* ticket;        // [0] = images finished (all levels); [1 + l*B + b] = tiles of (level l, image b) finished
-  double* img_partials;    // [n_levels][B][3]
   float* out;
   int32_t* nan_flag;
 };
 
+#ifndef PQ_LOSS_MINB
+#define PQ_LOSS_MINB 4
+#endif
 template <bool SPARSE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, PQ_LOSS_MINB)
 loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   extern __shared__ __align__(16) float smem[];
   int l = 0;
@@ -297,63 +295,64 @@ loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   const int b = blockIdx.y;
   const LossParams& P = M.lv[l];
   loss_tile<true, SPARSE>(P, blockIdx.x - M.tile_off[l], ntiles, b, smem);
+}
 
-  // ---- in-kernel finalisation (no second launch): the last tile of an image to finish reduces that image's
-  // partial sums, the last image to finish reduces over the batch and writes the outputs.  All orders are
-  // fixed (lane-strided accumulation + butterfly), so the result is run-to-run deterministic.
-  // Only warp 0 takes part (its lanes 0..2 wrote and fenced this CTA's partials); the other warps are done.
-  if (warp_id() != 0) return;
-  const int lane = lane_id();
-  __syncwarp();
-  int last = 0;
-  if (lane == 0) last = (atomicAdd(&M.ticket[1 + l * P.B + b], 1u) == (unsigned)ntiles - 1u) ? 1 : 0;
-  if (!__shfl_sync(PQ_FULL, last, 0)) return;
-  __threadfence();
-  double acc[3] = {0.0, 0.0, 0.0};
-  for (int t = lane; t < ntiles; t += 32) {
-    const double* pp = P.partials + ((size_t)b * ntiles + t) * 3;
-    acc[0] += __ldcg(pp); acc[1] += __ldcg(pp + 1); acc[2] += __ldcg(pp + 2);
+// One CTA of 1024 threads finishes the step: every thread accumulates its share of every level's per-CTA partial
+// sums (all loads independent, one L2 round trip), then warp butterflies and a fixed-order sum over the 32 warp
+// results - deterministic - and thread 0 writes the outputs.  Measured alternatives: doing this inside the main
+// kernel with completion tickets costs more (every CTA then holds its SM slot for a fence + atomic round trip).
+__global__ void __launch_bounds__(1024)
+loss_levels_finalize_kernel(const __grid_constant__ MultiLossParams M) {
+  __shared__ double s_w[32][PQDET_MAX_LEVELS * 3];
+  const int lane = lane_id(), warp = warp_id();
+  double acc[PQDET_MAX_LEVELS * 3];
+#pragma unroll
+  for (int i = 0; i < PQDET_MAX_LEVELS * 3; ++i) acc[i] = 0.0;
+#pragma unroll
+  for (int q = 0; q < PQDET_MAX_LEVELS; ++q) {
+    if (q >= M.n_levels) break;
+    const LossParams& P = M.lv[q];
+    const int64_t n = (int64_t)P.B * (M.tile_off[q + 1] - M.tile_off[q]);
+#pragma unroll 4
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+      acc[q * 3 + 0] += P.partials[i * 3 + 0]; acc[q * 3 + 1] += P.partials[i * 3 + 1];
+      acc[q * 3 + 2] += P.partials[i * 3 + 2];
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 3; ++j) acc[j] = warp_sum(acc[j]);
-  if (lane < 3) {
-    M.img_partials[((size_t)l * P.B + b) * 3 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
-    __threadfence();
+  for (int i = 0; i < PQDET_MAX_LEVELS * 3; ++i) {
+    if (i >= M.n_levels * 3) break;
+    const double v = warp_sum(acc[i]);
+    if (lane == 0) s_w[warp][i] = v;
   }
-  __syncwarp();
-  if (lane == 0) last = (atomicAdd(&M.ticket[0], 1u) == (unsigned)(M.n_levels * P.B) - 1u) ? 1 : 0;
-  if (!__shfl_sync(PQ_FULL, last, 0)) return;
-  __threadfence();
-  {
+  __syncthreads();
+  if (warp == 0) {
+    // lane i < 3L sums component i over the 32 warps in index order
+    double sum = 0.0;
+    if (lane < M.n_levels * 3)
+      for (int w = 0; w < 32; ++w) sum += s_w[w][lane];
     float tot[4] = {0.f, 0.f, 0.f, 0.f};
     bool nan = false;
     for (int q = 0; q < M.n_levels; ++q) {
-      double sum[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double a2 = 0.0;
-        for (int i = lane; i < P.B; i += 32) a2 += __ldcg(M.img_partials + ((size_t)q * P.B + i) * 3 + j);
-        sum[j] = warp_sum(a2);
-      }
+      const double invB = 1.0 / (double)M.lv[q].B;
+      const float lb = (float)(__shfl_sync(PQ_FULL, sum, q * 3 + 0) * invB);
+      const float lc = (float)(__shfl_sync(PQ_FULL, sum, q * 3 + 1) * invB);
+      const float lp = (float)(__shfl_sync(PQ_FULL, sum, q * 3 + 2) * invB);
+      const float loss = PQ_ADD(PQ_ADD(lb, lc), lp);            // model/loss.py:108
       if (lane == 0) {
-        const double invB = 1.0 / (double)P.B;
-        const float lb = (float)(sum[0] * invB), lc = (float)(sum[1] * invB), lp = (float)(sum[2] * invB);
-        const float loss = PQ_ADD(PQ_ADD(lb, lc), lp);          // model/loss.py:108
         float* o = M.out + 4 + 4 * q;
         o[0] = loss; o[1] = lb; o[2] = lc; o[3] = lp;
         M.out[4 + 4 * M.n_levels + q] = PQ_ADD(PQ_ADD(lb, lc), lp);
-        tot[0] = q ? PQ_ADD(tot[0], loss) : loss; tot[1] = q ? PQ_ADD(tot[1], lb) : lb;
-        tot[2] = q ? PQ_ADD(tot[2], lc) : lc;     tot[3] = q ? PQ_ADD(tot[3], lp) : lp;
-        nan |= (loss != loss);
       }
+      tot[0] = q ? PQ_ADD(tot[0], loss) : loss; tot[1] = q ? PQ_ADD(tot[1], lb) : lb;
+      tot[2] = q ? PQ_ADD(tot[2], lc) : lc;     tot[3] = q ? PQ_ADD(tot[3], lp) : lp;
+      nan |= (loss != loss);
     }
     if (lane == 0) {
       for (int j = 0; j < 4; ++j) M.out[j] = tot[j];
       *M.nan_flag = nan ? 1 : 0;
     }
   }
-  // re-arm the tickets for the next launch on this stream
-  for (int i = lane; i < 1 + M.n_levels * P.B; i += 32) M.ticket[i] = 0u;
 }
 
 // Chain rule for the multi-level outputs.  g = upstream gradient of out (device, 4+5L floats).  Level l's
@@ -483,14 +482,9 @@ extern "C" int pqdet_loss_scale_grad(float* grad, int input_is_raw, int B, int A
   return PQDET_OK;
 }
 
-namespace pq {
-static inline size_t ticket_bytes(int n_levels, int B) { return ((size_t)(1 + n_levels * B) * 4 + 255) / 256 * 256; }
-static inline size_t imgpart_bytes(int n_levels, int B) { return ((size_t)n_levels * B * 3 * 8 + 255) / 256 * 256; }
-}  // namespace pq
-
 extern "C" int64_t pqdet_loss_levels_workspace(int n_levels, int B, int A, const int* H, const int* W) {
   if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || B < 0 || A < 1 || !H || !W) return PQDET_ERR_INVALID_ARG;
-  int64_t bytes = (int64_t)(pq::ticket_bytes(n_levels, B) + pq::imgpart_bytes(n_levels, B));
+  int64_t bytes = 256;
   for (int l = 0; l < n_levels; ++l) {
     const int64_t tiles = ((int64_t)H[l] * W[l] + pq::kLossTile - 1) / pq::kLossTile;
     bytes += ((int64_t)B * tiles * 3 * (int64_t)sizeof(double) + 255) / 256 * 256;
@@ -517,12 +511,8 @@ static int loss_levels_impl(int n_levels, const float* const* raw, const float* 
   MultiLossParams M;
   memset(&M, 0, sizeof(M));
   unsigned char* ws = (unsigned char*)workspace;
-  M.ticket = (unsigned*)ws;
-  size_t off = ticket_bytes(n_levels, B);
-  M.img_partials = (double*)(ws + off);
-  off += imgpart_bytes(n_levels, B);
-  // the tickets must be zero on entry: the kernel re-arms them itself, so only a fresh buffer needs the memset
-  if (!workspace_initialised) PQ_CUDA(cudaMemsetAsync(ws, 0, ticket_bytes(n_levels, B), st));
+  (void)workspace_initialised;                  // the workspace carries no state between calls
+  size_t off = 256;
   int tiles_total = 0;
   const double deta = 0.01, uni = 1.0 / (double)C;         // train_dataset.py:126-130, fp64 then stored fp32
   for (int l = 0; l < n_levels; ++l) {
@@ -552,6 +542,8 @@ static int loss_levels_impl(int n_levels, const float* const* raw, const float* 
   dim3 grid(tiles_total, B);
   if (sparse) loss_levels_kernel<true><<<grid, 32 * A, smem, st>>>(M);
   else loss_levels_kernel<false><<<grid, 32 * A, smem, st>>>(M);
+  PQ_LAUNCH_CHECK();
+  loss_levels_finalize_kernel<<<1, 1024, 0, st>>>(M);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
