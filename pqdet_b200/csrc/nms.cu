@@ -737,71 +737,107 @@ __device__ __forceinline__ bool gen_row_from_index(const HeadsDev& P, int64_t i,
   return true;
 }
 
-// pass 0: count candidates per (image, class) + max picked coordinate; pass 1: scatter keys.
+// pass 0: count candidates per (image, class) + max picked coordinate; pass 1: scatter keys into the buckets.
+// Every thread evaluates one row and remembers which classes pass as a 128-bit mask.  Counts and slot
+// reservations go through a per-CTA shared-memory histogram, so the global counters see one atomic per
+// (CTA, class) instead of one per candidate (dense scenes: ~12k candidates per image on C counters).
 template <int PASS>
 __global__ void __launch_bounds__(256)
 gen_select_kernel(const __grid_constant__ GenParams G) {
   if (PASS == 1 && *G.ok == 0) return;
+  __shared__ unsigned s_cnt[128];
+  __shared__ unsigned s_base[128];
+  __shared__ unsigned s_max;
   const int ii = blockIdx.y;
   const int b = gen_image(G, ii);
   const int C = G.C;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float box[4];
+  const int tid = threadIdx.x;
+  if (tid < 128) s_cnt[tid] = 0;
+  if (tid == 0) s_max = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
+  float box[4] = {0.f, 0.f, 0.f, 0.f};
   float conf = 1.0f;
-  int row;
+  int row = 0;
   const float* scores = nullptr;   // !from_heads: pointer to the C scores of the row
-  int level = 0, a = 0, cell = 0;
+  const float* cls0 = nullptr;     // from_heads: first class plane element of the row (stride HW between classes)
+  int HW = 0;
+  bool live = false;
   if (G.from_heads) {
     const HeadsDev& P = G.heads;
-    if (!gen_row_from_index(P, i, level, a, cell, row)) return;
-    const LevelDev& L = P.lv[level];
-    const float x = L.raw[((size_t)(b * P.A + a) * P.ch + 4) * L.HW + cell];
-    if (!(x > P.logit_lo)) return;
-    conf = sigmoidf_(x);
-    if (!(conf > G.thr_f)) return;
-    const Affine af = image_affine(P, b);
-    const int cy = cell / L.W, cx = cell - cy * L.W;
+    int level = 0, a = 0, cell = 0;
+    if (gen_row_from_index(P, i, level, a, cell, row)) {
+      const LevelDev& L = P.lv[level];
+      HW = L.HW;
+      const float* r0 = L.raw + (size_t)(b * P.A + a) * P.ch * L.HW + cell;
+      const float x = r0[(size_t)4 * L.HW];
+      if (x > P.logit_lo) {
+        conf = sigmoidf_(x);
+        if (conf > G.thr_f) {
+          live = true;
+          cls0 = r0 + (size_t)5 * L.HW;
+          {
+            const Affine af = image_affine(P, b);
+            const int cy = cell / L.W, cx = cell - cy * L.W;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      box[k] = recover_coord(k, decode_coord(k, L.raw[((size_t)(b * P.A + a) * P.ch + k) * L.HW + cell],
-                                             cx, cy, L.stride), af);
-  } else {
-    if (i >= G.N) return;
+            for (int k = 0; k < 4; ++k)
+              box[k] = recover_coord(k, decode_coord(k, r0[(size_t)k * L.HW], cx, cy, L.stride), af);
+          }
+        }
+      }
+    }
+  } else if (i < G.N) {
+    live = true;
     row = (int)i;
     const float* r = G.bboxes + ((size_t)b * G.N + i) * (4 + C);
 #pragma unroll
     for (int k = 0; k < 4; ++k) box[k] = r[k];
     scores = r + 4;
   }
-  bool any = false;
-  for (int c = 0; c < C; ++c) {
-    float s;
-    if (G.from_heads) {
-      const HeadsDev& P = G.heads;
-      const LevelDev& L = P.lv[level];
-      s = PQ_MUL(sigmoidf_(L.raw[((size_t)(b * P.A + a) * P.ch + 5 + c) * L.HW + cell]), conf);
-    } else {
-      s = scores[c];
-    }
-    if (s > G.thr_f) {
-      any = true;
-      if (PASS == 0) {
-        atomicAdd(&G.cls_count[(size_t)ii * C + c], 1u);
-      } else {
-        const uint32_t slot = atomicAdd(&G.cls_fill[(size_t)ii * C + c], 1u);
-        G.keys[G.seg_off[(size_t)ii * C + c] + slot] =
-            ((uint64_t)(~__float_as_uint(s)) << 32) | (uint32_t)row;
+  auto score_of = [&](int c) -> float {
+    return G.from_heads ? PQ_MUL(sigmoidf_(cls0[(size_t)c * HW]), conf) : scores[c];
+  };
+  uint64_t m0 = 0, m1 = 0;          // classes of this row with score > thr
+  if (live) {
+    for (int c = 0; c < C; ++c) {
+      if (score_of(c) > G.thr_f) {
+        if (c < 64) m0 |= 1ull << c; else m1 |= 1ull << (c - 64);
+        atomicAdd(&s_cnt[c], 1u);
       }
     }
   }
-  if (any) {
-    if (PASS == 0) {
-      float mx = fmaxf(fmaxf(box[0], box[1]), fmaxf(box[2], box[3]));
-      atomicMax(&G.max_ord[ii], float_to_ordered(mx));
-    } else if (G.from_heads) {
-      G.rbox[(size_t)ii * G.N + row] = make_float4(box[0], box[1], box[2], box[3]);
+  const bool any = (m0 | m1) != 0;
+  if (PASS == 0) {
+    // max picked coordinate of the image: warp max, one shared atomic per warp, one global atomic per CTA
+    unsigned mo = any ? float_to_ordered(fmaxf(fmaxf(box[0], box[1]), fmaxf(box[2], box[3]))) : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mo = max(mo, __shfl_xor_sync(PQ_FULL, mo, d));
+    if (lane_id() == 0 && mo) atomicMax(&s_max, mo);
+  }
+  __syncthreads();
+  if (PASS == 0) {
+    if (tid < C && s_cnt[tid]) atomicAdd(&G.cls_count[(size_t)ii * C + tid], s_cnt[tid]);
+    if (tid == 0 && s_max) atomicMax(&G.max_ord[ii], s_max);
+    return;
+  }
+  if (tid < C) {
+    const unsigned n = s_cnt[tid];
+    s_base[tid] = n ? atomicAdd(&G.cls_fill[(size_t)ii * C + tid], n) : 0u;
+    s_cnt[tid] = 0;
+  }
+  __syncthreads();
+  if (!any) return;
+  for (int h = 0; h < 2; ++h) {
+    uint64_t m = h ? m1 : m0;
+    while (m) {
+      const int c = __ffsll((long long)m) - 1 + 64 * h;
+      m &= m - 1;
+      const float sc = score_of(c);                        // same expression as above: bit-identical
+      const unsigned slot = s_base[c] + atomicAdd(&s_cnt[c], 1u);
+      G.keys[G.seg_off[(size_t)ii * C + c] + slot] = ((uint64_t)(~__float_as_uint(sc)) << 32) | (uint32_t)row;
     }
   }
+  if (G.from_heads) G.rbox[(size_t)ii * G.N + row] = make_float4(box[0], box[1], box[2], box[3]);
 }
 
 // Block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix
@@ -911,7 +947,7 @@ __device__ __forceinline__ int bucket_greedy(uint32_t n, float iou_f, double iou
     bool dead = !valid;
     const int k0 = *s_k;
     for (int q = warp; q < k0; q += kSegWarps) {          // A
-      const float4 a = box(kget(q));
+      const float4 a = kget(q);
       const float Sa = box_area(a.x, a.y, a.z, a.w);
       if (!dead && nms_suppresses<ROUND>(a.x, a.y, a.z, a.w, Sa, me.x, me.y, me.z, me.w, iou_f, iou_d)) dead = true;
     }
@@ -939,7 +975,7 @@ __device__ __forceinline__ int bucket_greedy(uint32_t n, float iou_f, double iou
         alive &= ~(1u << i);
         alive &= ~__shfl_sync(PQ_FULL, myrow, i);
       }
-      if ((kept >> lane) & 1u) kset(k0 + __popc(kept & ((1u << lane) - 1u)), p);
+      if ((kept >> lane) & 1u) kset(k0 + __popc(kept & ((1u << lane) - 1u)), p, me);
       if (lane == 0) *s_k = k0 + __popc(kept);
     }
     __syncthreads();
@@ -1009,14 +1045,17 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
   if (in_smem) {
     for (uint32_t i = tid; i < n; i += kSegThreads) sbox[i] = shifted_box(i);
     __syncthreads();
+    // the kept boxes are compacted in place at the front of sbox (kept count <= candidates already consumed, and
+    // every warp holds the current step's boxes in registers), so the inner loop reads them without indirection
     k = bucket_greedy<ROUND, kSegWarps>(n, G.iou_f, G.iou_d,
                              [&](uint32_t pos) { return sbox[pos]; },
-                             [&](int q) { return skl[q]; },
-                             [&](int q, uint32_t pos) { skl[q] = pos; }, s_dead, s_rows, &s_k);
+                             [&](int q) { return sbox[q]; },
+                             [&](int q, uint32_t pos, const float4& bx) { skl[q] = pos; sbox[q] = bx; },
+                             s_dead, s_rows, &s_k);
   } else {
     k = bucket_greedy<ROUND, kSegWarps>(n, G.iou_f, G.iou_d, shifted_box,
-                             [&](int q) { return kl[q]; },
-                             [&](int q, uint32_t pos) { kl[q] = pos; }, s_dead, s_rows, &s_k);
+                             [&](int q) { return shifted_box(kl[q]); },
+                             [&](int q, uint32_t pos, const float4&) { kl[q] = pos; }, s_dead, s_rows, &s_k);
   }
   // append kept keys (score desc, row asc, class asc order key) to the image's kept region
   if (tid == 0) s_dst = atomicAdd(&G.kept_count[ii], (uint32_t)k);
@@ -1030,7 +1069,7 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
 
 constexpr size_t kSegBytesPerKey = sizeof(uint64_t) + sizeof(float4) + sizeof(uint32_t);
 
-constexpr int kFinThreads = 256;
+constexpr int kFinThreads = 1024;
 constexpr int kFinSmemKeys = 4096;
 
 __global__ void __launch_bounds__(kFinThreads)

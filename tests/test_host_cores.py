@@ -77,6 +77,41 @@ def test_nms_pair_core_matches_c_oracle(hh):
     assert n_dis >= 0
 
 
+def test_nms_pair_core_borderline_quotients(hh):
+    """Walk the shift of box b float by float across the point where I/D crosses thr and compare every step with
+    the reference formulas (both rounding orders): the pair test must agree on every borderline quotient."""
+    hh.hh_nms_suppresses.argtypes = [F, F, ctypes.c_double, ctypes.c_int]
+    n_flip = 0
+    for (W, H, y) in ((37.25, 21.5, 0.0), (103.0, 64.75, 3.5), (9.125, 300.0, -2.25)):
+        for thr in (0.45, 0.65, 0.5, 0.1, 1.0 / 3.0):
+            a = np.array([10.0, 5.0, 10.0 + W, 5.0 + H], np.float32)
+            hb = H - abs(y)
+            # IoU(x) = (W-x)*hb / (2*W*H - (W-x)*hb) = thr  ->  x analytically, then +-150 floats around it
+            inter = thr * 2 * W * H / (1 + thr)
+            x0 = np.float32(W - inter / hb)
+            x = x0
+            for _ in range(150):
+                x = np.nextafter(x, np.float32(-1e9))
+            seen = set()
+            for _ in range(300):
+                b = np.array([10.0 + x, 5.0 + y, 10.0 + x + W, 5.0 + y + H], np.float32)
+                l, t = max(a[0], b[0]), max(a[1], b[1])
+                r, d = min(a[2], b[2]), min(a[3], b[3])
+                w, h = max(np.float32(r - l), np.float32(0)), max(np.float32(d - t), np.float32(0))
+                I = np.float32(w * h)
+                Sa = np.float32(np.float32(a[2] - a[0]) * np.float32(a[3] - a[1]))
+                bw, bh = np.float32(b[2] - b[0]), np.float32(b[3] - b[1])
+                fma = np.float32(np.float64(bw) * np.float64(bh) + np.float64(Sa))
+                cuda_q = bool(np.float32(I / np.float32(fma - I)) > np.float32(thr))
+                cpu_q = bool(float(np.float32(I / np.float32(np.float32(Sa + np.float32(bw * bh)) - I))) > thr)
+                got = [hh.hh_nms_suppresses(fp(a), fp(np.ascontiguousarray(b)), thr, rnd) for rnd in (0, 1)]
+                assert got == [int(cuda_q), int(cpu_q)], (W, H, y, thr, float(x))
+                seen.add(cuda_q)
+                x = np.nextafter(x, np.float32(1e9))
+            n_flip += int(len(seen) == 2)
+    assert n_flip >= 10          # the walks really straddle the threshold
+
+
 def test_iou_family_core(hh):
     g = load_golden("iou")
     b1, b2 = np.ascontiguousarray(g["b1"]), np.ascontiguousarray(g["b2"])
