@@ -33,11 +33,12 @@ decode_fwd_kernel(const float* __restrict__ raw, float* __restrict__ out, int A,
     }
   }
   __syncthreads();
+  // the tile is one contiguous run of ncell*A*ch floats in the output: warp = cell, lanes sweep its A*ch values
   float* dst = out + ((size_t)b * rows_total + row_off + (size_t)cell0 * A) * ch;
-  const int n = ncell * ACH;
-  for (int e = threadIdx.x; e < n; e += kDecodeThreads) {
-    int r = e / ACH, c = e - r * ACH;
-    dst[e] = tile[r * ST + c];
+  for (int r = warp_id(); r < ncell; r += kDecodeThreads / 32) {
+    const float* trow = tile + r * ST;
+    float* drow = dst + (size_t)r * ACH;
+    for (int c = lane; c < ACH; c += 32) drow[c] = trow[c];
   }
 }
 
@@ -54,13 +55,13 @@ decode_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ gout,
   const int cell0 = blockIdx.x * kTileCells;
   const int ncell = min(kTileCells, HW - cell0);
   const float* gsrc = gout + ((size_t)b * rows_total + row_off + (size_t)cell0 * A) * ch;
-  const int n = ncell * ACH;
-  for (int e = threadIdx.x; e < n; e += kDecodeThreads) {
-    int r = e / ACH, c = e - r * ACH;
-    tile[r * ST + c] = gsrc[e];
+  const int lane = lane_id();
+  for (int r = warp_id(); r < ncell; r += kDecodeThreads / 32) {
+    const float* grow = gsrc + (size_t)r * ACH;
+    float* trow = tile + r * ST;
+    for (int c = lane; c < ACH; c += 32) trow[c] = grow[c];
   }
   __syncthreads();
-  const int lane = lane_id();
   const int cell = cell0 + lane;
   const size_t base = (size_t)b * ACH * HW;
   for (int c = warp_id(); c < ACH; c += kDecodeThreads / 32) {
@@ -81,24 +82,38 @@ decode_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ gout,
   }
 }
 
-// One thread per output element of (B, N, 4+C).
-__global__ void __launch_bounds__(256)
+// recover: a CTA takes kRecRows consecutive rows of one image.  The input rows are one contiguous run of
+// kRecRows*(5+C) floats: staged in shared memory with coalesced loads, then every warp sweeps the 4+C output values
+// of its rows (contiguous in the output as well).  The affine of the image is evaluated once per CTA.
+constexpr int kRecRows = 64;
+constexpr int kRecThreads = 256;
+
+__global__ void __launch_bounds__(kRecThreads)
 recover_kernel(const float* __restrict__ pred, float* __restrict__ out, int64_t N, int C, int kind,
-               float in_h, float in_w, const float* __restrict__ orig_hw, int orig_per_image, int64_t total) {
-  const int oc = 4 + C;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = e / oc;
-    int k = (int)(e - row * oc);
-    const float* p = pred + row * (5 + C);
-    if (k < 4) {
-      int64_t b = row / N;
-      const float* o = orig_hw + (orig_per_image ? 2 * b : 0);
-      Affine a = affine_params(kind, in_h, in_w, o[0], o[1]);
-      out[e] = recover_coord(k, p[k], a);
-    } else {
-      out[e] = PQ_MUL(p[k + 1], p[4]);
-    }
+               float in_h, float in_w, const float* __restrict__ orig_hw, int orig_per_image) {
+  extern __shared__ float rtile[];          // [kRecRows][5+C]
+  __shared__ Affine s_af;
+  const int ic = 5 + C, oc = 4 + C;
+  const int b = blockIdx.y;
+  const int64_t row0 = (int64_t)blockIdx.x * kRecRows;
+  const int nrow = (int)min((int64_t)kRecRows, N - row0);
+  if (threadIdx.x == 0) {
+    const float* o = orig_hw + (orig_per_image ? 2 * b : 0);
+    s_af = affine_params(kind, in_h, in_w, o[0], o[1]);
+  }
+  const float* src = pred + ((size_t)b * N + row0) * ic;
+  const int n_in = nrow * ic;
+  for (int e = threadIdx.x; e < n_in; e += kRecThreads) rtile[e] = ldg_stream(src + e);
+  __syncthreads();
+  const Affine af = s_af;
+  float* dst = out + ((size_t)b * N + row0) * oc;
+  const int lane = lane_id();
+  for (int r = warp_id(); r < nrow; r += kRecThreads / 32) {
+    const float* trow = rtile + r * ic;
+    const float conf = trow[4];
+    float* drow = dst + (size_t)r * oc;
+    for (int k = lane; k < oc; k += 32)
+      drow[k] = (k < 4) ? recover_coord(k, trow[k], af) : PQ_MUL(trow[k + 1], conf);
   }
 }
 
@@ -146,13 +161,15 @@ extern "C" int pqdet_recover(const float* pred, float* out, int B, int64_t N, in
                              int device, void* stream) {
   if (!pred || !out || !orig_hw || B < 0 || N < 0 || C < 0) return PQDET_ERR_INVALID_ARG;
   if (affine_kind < 0 || affine_kind > 2) return PQDET_ERR_INVALID_ARG;
-  const int64_t total = (int64_t)B * N * (4 + C);
-  if (total == 0) return PQDET_OK;
+  if ((int64_t)B * N == 0) return PQDET_OK;
+  if (B > 65535) return PQDET_ERR_UNSUPPORTED;
   PQ_ENTER(device);
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 64) blocks = 148 * 64;   // grid-stride: a whole number of waves on 148 SMs
-  pq::recover_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      pred, out, N, C, affine_kind, in_h, in_w, orig_hw, orig_per_image, total);
+  const size_t smem = (size_t)pq::kRecRows * (5 + C) * sizeof(float);
+  if (smem > 48 * 1024)
+    PQ_CUDA(cudaFuncSetAttribute(pq::recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((N + pq::kRecRows - 1) / pq::kRecRows), B);
+  pq::recover_kernel<<<grid, pq::kRecThreads, smem, (cudaStream_t)stream>>>(
+      pred, out, N, C, affine_kind, in_h, in_w, orig_hw, orig_per_image);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
