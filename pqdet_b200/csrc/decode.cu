@@ -121,9 +121,10 @@ recover_kernel(const float* __restrict__ pred, float* __restrict__ out, int64_t 
 
 extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int C, int H, int W, float stride,
                                 int64_t out_rows_total, int64_t out_row_offset, int device, void* stream) {
-  if (!raw || !out || B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
+  if (B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
   if (out_row_offset < 0 || out_row_offset + (int64_t)H * W * A > out_rows_total) return PQDET_ERR_INVALID_ARG;
-  if (B == 0) return PQDET_OK;
+  if (B == 0) return PQDET_OK;                       // empty batch: tensors without storage are fine
+  if (!raw || !out) return PQDET_ERR_INVALID_ARG;
   if (B > 65535) return PQDET_ERR_UNSUPPORTED;
   PQ_ENTER(device);
   const int ch = 5 + C;
@@ -140,9 +141,10 @@ extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int 
 extern "C" int pqdet_decode_bwd(const float* raw, const float* grad_out, float* grad_raw, int B, int A, int C,
                                 int H, int W, float stride, int64_t out_rows_total, int64_t out_row_offset,
                                 int device, void* stream) {
-  if (!raw || !grad_out || !grad_raw || B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
+  if (B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
   if (out_row_offset < 0 || out_row_offset + (int64_t)H * W * A > out_rows_total) return PQDET_ERR_INVALID_ARG;
   if (B == 0) return PQDET_OK;
+  if (!raw || !grad_out || !grad_raw) return PQDET_ERR_INVALID_ARG;
   if (B > 65535) return PQDET_ERR_UNSUPPORTED;
   PQ_ENTER(device);
   const int ch = 5 + C;
@@ -159,9 +161,10 @@ extern "C" int pqdet_decode_bwd(const float* raw, const float* grad_out, float* 
 extern "C" int pqdet_recover(const float* pred, float* out, int B, int64_t N, int C, int affine_kind,
                              float in_h, float in_w, const float* orig_hw, int orig_per_image,
                              int device, void* stream) {
-  if (!pred || !out || !orig_hw || B < 0 || N < 0 || C < 0) return PQDET_ERR_INVALID_ARG;
+  if (B < 0 || N < 0 || C < 0) return PQDET_ERR_INVALID_ARG;
   if (affine_kind < 0 || affine_kind > 2) return PQDET_ERR_INVALID_ARG;
   if ((int64_t)B * N == 0) return PQDET_OK;
+  if (!pred || !out || !orig_hw) return PQDET_ERR_INVALID_ARG;
   if (B > 65535) return PQDET_ERR_UNSUPPORTED;
   PQ_ENTER(device);
   const size_t smem = (size_t)pq::kRecRows * (5 + C) * sizeof(float);

@@ -1132,7 +1132,7 @@ static int fill_heads(const pqdet_heads_t* h, HeadsDev* P) {
   if (!(h->iou_threshold >= 0.0)) return PQDET_ERR_UNSUPPORTED;  // cross-class pairs have IoU 0: skipping them needs thr >= 0
   int64_t rows = 0, groups = 0;
   for (int l = 0; l < h->n_levels; ++l) {
-    if (!h->raw[l] || h->H[l] < 1 || h->W[l] < 1) return PQDET_ERR_INVALID_ARG;
+    if ((!h->raw[l] && h->B > 0) || h->H[l] < 1 || h->W[l] < 1) return PQDET_ERR_INVALID_ARG;   // B == 0: empty tensors have no storage
     LevelDev& L = P->lv[l];
     L.raw = h->raw[l];
     L.H = h->H[l]; L.W = h->W[l]; L.HW = h->H[l] * h->W[l];

@@ -120,6 +120,11 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
     h, keep = _ops.make_heads(heads, strides, num_classes, input_size, batch_original_size, dataset,
                               score_threshold, iou_threshold, nms_mode, iou_round)
     B = h.B
+    if B == 0:                                       # empty batch: nothing to launch
+        dev = heads[0].device
+        return Detections(torch.empty((0, FUSED_MAX_DET, 6), device=dev),
+                          torch.empty((0, FUSED_MAX_DET), dtype=torch.int32, device=dev) if return_index else None,
+                          torch.zeros((2,), dtype=torch.int32, device=dev), 0)
     sig = (tuple(tuple(t.shape[1:]) for t in heads), num_classes, float(score_threshold), dataset)
     if B and (strategy == "general" or (strategy == "auto" and _DENSE_HINT.get(sig, False))):
         gdet, gidx, gmeta, hm = _general(h, keep, None, B, return_index, False, max(B * 32768, 1 << 16), 8192)

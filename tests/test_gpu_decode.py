@@ -95,3 +95,17 @@ def test_cpu_tensor_is_rejected():
     from pqdet_b200._lib import PqdetError
     with pytest.raises(PqdetError):
         Decode(20, 8)(torch.zeros(1, 75, 2, 2))
+
+
+def test_empty_batch_through_the_materialising_route():
+    """B = 0 tensors have no storage (data_ptr 0): decode, the eval concat and recover return empty results."""
+    from pqdet_b200 import base_sample
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.parser import Decode
+    C = 20
+    assert tuple(Decode(C, 8)(torch.zeros((0, 75, 64, 64), device="cuda")).shape) == (0, 64, 64, 3, 25)
+    head = DetectionHead([dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in (32, 16, 8)])
+    pred = head([torch.zeros((0, 75, 512 // s, 512 // s), device="cuda") for s in (32, 16, 8)])
+    assert tuple(pred.shape) == (0, 16128, 25)
+    rec = base_sample.recover_bboxes_prediction_voc(pred, (512, 512), torch.zeros((0, 2), device="cuda"))
+    assert tuple(rec.shape) == (0, 16128, 24)

@@ -262,3 +262,45 @@ def test_host_buffer_path_rejects_pageable_memory():
     heads = synth.make_heads(1, 20, 512, "sparse", seed=1)
     with pytest.raises(_lib.PqdetError):
         fused.decode_nms_host(heads, synth.FPN_STRIDES, 20, (512, 512), (512., 512.), "voc")
+
+
+@pytest.mark.parametrize("sem", ["cuda", "cpu"])
+def test_tie_break_identical_scores_and_shuffled_positions(sem):
+    """SURVEY 8a' 'NMS tie-break': equal scores are visited in candidate order (row, then class); clusters of
+    overlapping boxes with identical scores keep the first row, wherever the cluster sits in the tensor."""
+    from pqdet_b200 import config, tools
+    config.nms_semantics = sem
+    rng = np.random.default_rng(5)
+    N, C = 300, 4
+    bb = np.zeros((N, 4 + C), np.float32)
+    bb[:, :4] = np.array([1000., 1000., 1001., 1001.], np.float32)                 # far-away filler boxes
+    rows = rng.permutation(N)[:100]
+    for j, r in enumerate(rows):                                                    # 2 clusters x 50 boxes
+        base = np.array([10., 10., 60., 60.], np.float32) if j < 50 else np.array([200., 200., 280., 260.], np.float32)
+        bb[r, :4] = base + rng.uniform(-2, 2, 4).astype(np.float32)
+        bb[r, 4 + (j % 2)] = np.float32(0.7)                                        # identical scores, two classes
+    got, idx = tools.batched_torch_nms(cuda(bb[None]), 0.1, 0.45, return_index=True)
+    want, wr, wc = po.torch_nms(bb, 0.1, 0.45, device=sem, return_index=True)
+    assert_same_detections(got[0].cpu().numpy(), want, what="ties/" + sem)
+    assert np.array_equal(idx[0].cpu().numpy(), wr * C + wc)
+    first = {(j < 50, j % 2): min(r for jj, r in enumerate(rows) if (jj < 50) == (j < 50) and jj % 2 == j % 2)
+             for j in range(100)}
+    assert sorted(int(i) // C for i in idx[0].cpu().numpy()) == sorted(first.values())
+
+
+def test_empty_batch_empty_rows_and_truncation():
+    from pqdet_b200 import _lib, _ops, fused, synth, tools
+    C, size = 20, 512
+    heads = [h.cuda() for h in synth.make_heads(3, C, size, "sparse", seed=40)]
+    orig = torch.tensor([float(size), float(size)]).cuda()
+    d0 = fused.decode_nms([h[:0] for h in heads], synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45)
+    assert len(d0) == 0 and d0.to_numpy_list() == []
+    assert tuple(tools.torch_nms(torch.zeros((0, 4 + C), device="cuda"), 0.1, 0.45).shape) == (0,)
+    # max_det smaller than the kept count: rows are truncated, counts[] still holds the true K, status says so
+    full = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45)
+    h, keep = _ops.make_heads(heads, synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45, "auto_cuda", "tv_cuda")
+    det, _, meta = _ops.decode_nms_fused(h, keep, 16, False)
+    m = meta[:9].view(3, 3).cpu()
+    assert m[0].tolist() == full.counts.tolist() and all(int(s) & _lib.ST_DET_TRUNCATED for s in m[2])
+    for b in range(3):
+        assert torch.equal(det[b], full[b][:16])
