@@ -393,7 +393,6 @@ def loss_scale_grad(grad: torch.Tensor, input_is_raw: bool, num_classes: int, g_
     return grad
 
 
-_WS_ARMED = {}          # (workspace ptr, stream) -> launch signature whose completion tickets the buffer holds (all zero)
 
 
 def loss_levels(raws, labels, gts, num_classes: int, strides, bbox_loss: str, ignore_thresh: float,
@@ -423,8 +422,6 @@ def loss_levels(raws, labels, gts, num_classes: int, strides, bbox_loss: str, ig
     Hs, Ws = IP(*[r.shape[2] for r in raws]), IP(*[r.shape[3] for r in raws])
     lib = _lib.load()
     ws = _workspace(device, "loss_levels", lib.pqdet_loss_levels_workspace(L, B, A, Hs, Ws))
-    armed = (ws.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
-    sig = (L, B, A, tuple(Hs), tuple(Ws))      # the ticket region's size depends on (L, B): re-zero it when they change
     out = torch.empty((4 + 5 * L,), dtype=torch.float32, device=device)
     flag = torch.empty((1,), dtype=torch.int32, device=device)
     _lib.check(lib.pqdet_loss_levels(
@@ -432,8 +429,7 @@ def loss_levels(raws, labels, gts, num_classes: int, strides, bbox_loss: str, ig
         VP(*[g.data_ptr() for g in grads]) if want_grad else None, Hs, Ws, IP(*[g.shape[1] for g in gts]),
         (ctypes.c_float * L)(*[float(s) for s in strides]), B, A, C, _lib.BBOX_LOSS[bbox_loss],
         float(ignore_thresh), float(l1_loss_gain), _ptr(out), _ptr(flag), _ptr(ws),
-        1 if _WS_ARMED.get(armed) == sig else 0, _dev(raws[0]), _stream(device)), "pqdet_loss_levels")
-    _WS_ARMED[armed] = sig
+        1, _dev(raws[0]), _stream(device)), "pqdet_loss_levels")
     return out, flag, grads
 
 
@@ -544,8 +540,6 @@ def loss_levels_sparse(raws, owners, gt6: torch.Tensor, gts, num_classes: int, s
     Hs, Ws = IP(*[r.shape[2] for r in raws]), IP(*[r.shape[3] for r in raws])
     lib = _lib.load()
     ws = _workspace(device, "loss_levels", lib.pqdet_loss_levels_workspace(L, B, A, Hs, Ws))
-    armed = (ws.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
-    sig = (L, B, A, tuple(Hs), tuple(Ws))      # the ticket region's size depends on (L, B): re-zero it when they change
     out = torch.empty((4 + 5 * L,), dtype=torch.float32, device=device)
     flag = torch.empty((1,), dtype=torch.int32, device=device)
     _lib.check(lib.pqdet_loss_levels_sparse(
@@ -553,6 +547,5 @@ def loss_levels_sparse(raws, owners, gt6: torch.Tensor, gts, num_classes: int, s
         VP(*[x.data_ptr() for x in gts]), VP(*[g.data_ptr() for g in grads]) if want_grad else None, Hs, Ws,
         IP(*[g.shape[1] for g in gts]), (ctypes.c_float * L)(*[float(s) for s in strides]), B, A, C,
         _lib.BBOX_LOSS[bbox_loss], float(ignore_thresh), float(l1_loss_gain), _ptr(out), _ptr(flag), _ptr(ws),
-        1 if _WS_ARMED.get(armed) == sig else 0, _dev(raws[0]), _stream(device)), "pqdet_loss_levels_sparse")
-    _WS_ARMED[armed] = sig
+        1, _dev(raws[0]), _stream(device)), "pqdet_loss_levels_sparse")
     return out, flag, grads

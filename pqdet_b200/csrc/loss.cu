@@ -275,7 +275,6 @@ struct MultiLossParams {
   LossParams lv[PQDET_MAX_LEVELS];
   int tile_off[PQDET_MAX_LEVELS + 1];
   int n_levels;
-  unsigned total_blocks;
   float* out;
   int32_t* nan_flag;
 };
@@ -287,6 +286,9 @@ template <bool SPARSE>
 __global__ void __launch_bounds__(256, PQ_LOSS_MINB)
 loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
   extern __shared__ __align__(16) float smem[];
+  // programmatic dependent launch: let the finalize kernel be scheduled while this grid drains (it waits in
+  // cudaGridDependencySynchronize() until every CTA here has completed and its partials are visible)
+  cudaTriggerProgrammaticLaunchCompletion();
   int l = 0;
 #pragma unroll
   for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
@@ -304,6 +306,7 @@ loss_levels_kernel(const __grid_constant__ MultiLossParams M) {
 __global__ void __launch_bounds__(1024)
 loss_levels_finalize_kernel(const __grid_constant__ MultiLossParams M) {
   __shared__ double s_w[32][PQDET_MAX_LEVELS * 3];
+  cudaGridDependencySynchronize();
   const int lane = lane_id(), warp = warp_id();
   double acc[PQDET_MAX_LEVELS * 3];
 #pragma unroll
@@ -536,14 +539,25 @@ static int loss_levels_impl(int n_levels, const float* const* raw, const float* 
   }
   for (int l = n_levels; l <= PQDET_MAX_LEVELS; ++l) M.tile_off[l] = tiles_total;
   M.n_levels = n_levels;
-  M.total_blocks = (unsigned)tiles_total * (unsigned)B;
   M.out = out; M.nan_flag = nan_flag;
   const size_t smem = (size_t)A * 32 * 5 * sizeof(float);
   dim3 grid(tiles_total, B);
   if (sparse) loss_levels_kernel<true><<<grid, 32 * A, smem, st>>>(M);
   else loss_levels_kernel<false><<<grid, 32 * A, smem, st>>>(M);
   PQ_LAUNCH_CHECK();
-  loss_levels_finalize_kernel<<<1, 1024, 0, st>>>(M);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PQ_CUDA(cudaLaunchKernelEx(&cfg, loss_levels_finalize_kernel, M));
+  }
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
