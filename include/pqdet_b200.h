@@ -238,6 +238,22 @@ int pqdet_loss_levels_sparse(int n_levels, const float* const* raw, const int32_
                              float ignore_thresh, float l1_loss_gain, float* out, int32_t* nan_flag,
                              void* workspace, int workspace_initialised, int device, void* stream);
 
+/* ---- evaluator statistics: the per-detection matching loop of Evaluator.AP,
+ * eval/evaluator.py:69-124, for all classes, images and IoU thresholds in one launch.  The caller (see
+ * pqdet_b200/evaluator.py) orders the detections per class by (-score, insertion index) exactly like
+ * tools.PriorityQueue (tools.py:654-679) and groups the labels per (image, class) like add_labels (:164-175):
+ *   det_box      (D,4)     detections, class-sorted order
+ *   grp_det      (..)      detection indices ordered by (group, class rank); grp_det_off (G+1)
+ *   gt_box       (sumGT,4) float32 or float64 (gt_is_f64), groups back to back; gt_difficult (sumGT); gt_off (G+1)
+ *   thresholds   (T)       DEVICE doubles (np.linspace(0.5, 0.95, 10), :13)
+ *   seen         (T,sumGT) scratch, tp / fp (T,D): all three zero on entry; tp/fp receive the reference's flags
+ * Overlaps follow numpy's promotion (float32 GT: float32 arithmetic; float64 GT: only the detection's own area
+ * stays float32), so tp/fp - and the AP computed from them - are identical to the reference's. */
+int pqdet_ap_match(const float* det_box, int64_t D, const int32_t* grp_det, const int64_t* grp_det_off,
+                   const void* gt_box, int gt_is_f64, const uint8_t* gt_difficult, const int64_t* gt_off,
+                   int64_t sum_gt, int G, const double* thresholds, int T, uint8_t* seen, uint8_t* tp,
+                   uint8_t* fp, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

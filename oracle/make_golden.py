@@ -183,12 +183,33 @@ def gen_iou(ref):
     return d
 
 
+def gen_ap(ref):
+    """Evaluator.add_detections / add_labels / AP on synthetic evaluation sets (float32 and float64 GT)."""
+    import contextlib
+    import io
+    d = {}
+    for tag, dt, C, n, seed in (("f32", np.float32, 5, 40, 3), ("f64", np.float64, 20, 60, 4)):
+        ev = rh.make_evaluator(["c%d" % i for i in range(C)])
+        data = synth.make_eval_set(n, C, 512, seed=seed, gt_dtype=dt)
+        for f, gt, diffs, dets in data:
+            ev.add_detections(f, dets)
+            ev.add_labels(f, gt, diffs)
+        with contextlib.redirect_stderr(io.StringIO()):
+            ap = ev.AP()
+        d["raw_" + tag] = ap.raw
+        d["mAPs_" + tag] = np.asarray(ap.mAPs)
+        d["APs_" + tag] = np.asarray(ap.APs)
+        d["AP_" + tag] = np.float64(ap.AP)
+        d["cfg_" + tag] = np.array([n, C, 512, seed], np.int64)
+    return d
+
+
 def main():
     import torchvision
     ref = rh.load()
     os.makedirs(OUT, exist_ok=True)
     parts = {"decode": gen_decode, "recover": gen_recover, "nms": gen_nms,
-             "train": gen_label_and_loss, "iou": gen_iou}
+             "train": gen_label_and_loss, "iou": gen_iou, "ap": gen_ap}
     sizes = {}
     for name, fn in parts.items():
         path = os.path.join(OUT, name + ".npz")

@@ -97,3 +97,14 @@ def make_label_dataset(num_classes: int, anchors=VOC_ANCHORS, iou_threshold: flo
     ds._anchors = np.array(anchors, dtype=np.float32)
     ds._anchors_iou_threshold = iou_threshold
     return ds
+
+
+def make_evaluator(class_names):
+    """The reference Evaluator with only the fields its statistics code reads (eval/evaluator.py:31-36, 64-175):
+    no model, no dataset, no config."""
+    load()
+    from eval.evaluator import Evaluator
+    ev = Evaluator.__new__(Evaluator)
+    ev._classes = list(class_names)
+    ev.init_statics()
+    return ev

@@ -90,6 +90,8 @@ SIGNATURES = {
                                          POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), POINTER(c_int),
                                          POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, c_int, c_float,
                                          c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "pqdet_ap_match": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64,
+                               c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 _LIB = None

@@ -109,3 +109,39 @@ def make_train_heads(batch: int, num_classes: int, size: int, seed: int = 0, dev
     g.manual_seed(seed + 104729)
     return [torch.randn((batch, anchors_per_cell * (5 + num_classes), size // s, size // s),
                         dtype=torch.float32, device=dev, generator=g) * 0.5 for s in strides]
+
+
+def make_eval_set(n_images: int, num_classes: int, size: int = 512, seed: int = 0, gt_dtype=np.float32,
+                  n_obj=(1, 12), tie_scores: bool = True):
+    """Synthetic evaluation set for the AP bookkeeping (eval/evaluator.py:64-183): per image a file name, GT rows
+    [x1,y1,x2,y2,class] (gt_dtype), `difficult` flags, and detections (K,6) float32 [x1,y1,x2,y2,score,class] in
+    descending score like tools.torch_nms returns them: jittered copies of the GT (some duplicated, some with the
+    wrong class), random false positives, and - with tie_scores - scores quantised so that exact ties occur."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_images):
+        n = int(rng.integers(n_obj[0], n_obj[1] + 1))
+        wh = np.exp(rng.normal(3.8, 0.8, (n, 2))).clip(6, 0.7 * size)
+        c = rng.uniform(0, size, (n, 2))
+        x1y1 = (c - wh / 2).clip(0, size - 3)
+        x2y2 = np.maximum((c + wh / 2).clip(2, size - 1), x1y1 + 2)
+        cls = rng.integers(0, num_classes, n)
+        gt = np.concatenate([x1y1, x2y2, cls[:, None]], axis=1).astype(gt_dtype)
+        diffs = (rng.random(n) < 0.2).astype(np.int64)
+        dets = []
+        for j in range(n):
+            for _ in range(int(rng.integers(0, 4))):                      # 0-3 detections per object
+                jit = rng.normal(0, 0.08, 4) * np.repeat(wh[j], 2)
+                box = gt[j, :4].astype(np.float64) + jit
+                k = cls[j] if rng.random() < 0.9 else rng.integers(0, num_classes)
+                dets.append([box[0], box[1], max(box[2], box[0] + 1), max(box[3], box[1] + 1), rng.uniform(0.1, 1.0), k])
+        for _ in range(int(rng.integers(0, 6))):                          # background false positives
+            w, h = np.exp(rng.normal(3.5, 0.7, 2))
+            x, y = rng.uniform(0, size - 10, 2)
+            dets.append([x, y, x + w, y + h, rng.uniform(0.1, 0.6), rng.integers(0, num_classes)])
+        d = np.array(dets, dtype=np.float32).reshape(-1, 6)
+        if tie_scores and len(d):
+            d[:, 4] = np.round(d[:, 4] * 20) / 20 + np.float32(0.01)      # 19 distinct scores: plenty of exact ties
+        d = d[np.argsort(-d[:, 4], kind="stable")]
+        out.append(("img_%05d" % i, gt, diffs, d))
+    return out

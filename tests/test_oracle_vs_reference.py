@@ -96,3 +96,19 @@ def test_nms_oracle_matches_installed_torchvision_cpu():
             want_b = tv.ops.batched_nms(boxes, scores, cls, thr).numpy()
             got_b = po.batched_nms(boxes.numpy(), scores.numpy(), cls.numpy(), thr, device="cpu")
             assert np.array_equal(got_b, want_b)
+
+
+def test_ap_oracle_vs_live_reference_evaluator():
+    import contextlib
+    import io
+    from oracle import ap_oracle
+    from pqdet_b200 import synth
+    for dt, C, n, seed in ((np.float32, 7, 30, 11), (np.float64, 3, 25, 12), (np.int64, 4, 20, 13)):
+        ev = rh.make_evaluator(["c%d" % i for i in range(C)])
+        orc = ap_oracle.ApOracle(C)
+        for f, gt, diffs, dets in synth.make_eval_set(n, C, 512, seed=seed, gt_dtype=dt, n_obj=(1, 25)):
+            ev.add_detections(f, dets); ev.add_labels(f, gt, diffs)
+            orc.add_detections(f, dets); orc.add_labels(f, gt, diffs)
+        with contextlib.redirect_stderr(io.StringIO()):
+            ap = ev.AP()
+        assert np.array_equal(ap.raw, orc.AP()), dt
