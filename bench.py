@@ -481,6 +481,34 @@ def bench_other_configs(device, peak):
     except Exception as e:
         out["dropin_eval_path"] = {"error": repr(e)}
 
+    # ---- evaluator statistics: AP over a VOC-sized synthetic evaluation set
+    try:
+        from oracle import ap_oracle
+        from pqdet_b200.evaluator import DetectionAccumulator
+        data = synth.make_eval_set(2000, C_VOC, SIZE, seed=0)
+        acc, orc = DetectionAccumulator(["c%d" % i for i in range(C_VOC)], device=device), ap_oracle.ApOracle(C_VOC)
+        for f, gt, diffs, dets in data:
+            acc.add_detections(f, dets); acc.add_labels(f, gt, diffs)
+            orc.add_detections(f, dets); orc.add_labels(f, gt, diffs)
+        n_det = acc.detections_count
+        t0 = time.perf_counter()
+        raw_cpu = orc.AP()
+        t_cpu = time.perf_counter() - t0
+        acc2 = DetectionAccumulator(["c%d" % i for i in range(C_VOC)], device=device)      # warm-up instance
+        for f, gt, diffs, dets in data[:50]:
+            acc2.add_detections(f, dets); acc2.add_labels(f, gt, diffs)
+        acc2.AP()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = acc.AP()
+        t_gpu = time.perf_counter() - t0
+        out["evaluator_ap"] = {"workload": "Evaluator.AP over 2000 images / %d detections, 10 IoU thresholds" % n_det,
+                               "ours_ms": t_gpu * 1e3, "reference_loop_port_ms": t_cpu * 1e3,
+                               "identical_table": bool(np.array_equal(got.raw, raw_cpu, equal_nan=True)),
+                               "mAP": float(got.AP)}
+    except Exception as e:
+        out["evaluator_ap"] = {"error": repr(e)}
+
     # ---- C: dense decode + NMS
     B, C, size = 64, 10, 608
     heads = synth.make_heads(B, C, size, "dense", seed=0, device=device)
