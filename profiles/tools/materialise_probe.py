@@ -38,6 +38,9 @@ def main():
             t_rec = ev(lambda: base_sample.recover_bboxes_prediction_voc(pred, (size, size), orig))
             out = _ops.alloc_fused_outputs(B, 2048, False, dev)
             t_nms = ev(lambda: _ops.nms_fused(rec, 0.1, 0.45, "auto_cuda", "tv_cuda", 2048, False, out=out))
+            t_cp = ev(lambda: pred.clone())
+        print("B=%d: torch clone of the decoded tensor (%.0f MB read + write): %.1f us = %.0f GB/s" % (
+            B, pred.numel() * 4 / 1e6, t_cp * 1e3, 2 * pred.numel() * 4 / t_cp / 1e6))
         print("B=%d: decode %.1f us (%.0f GB/s of 2R), recover %.1f us (%.0f GB/s), nms_fused %.1f us (%.0f GB/s read) -> %.0f img/s kernel time"
               % (B, t_dec * 1e3, 2 * R / t_dec / 1e6, t_rec * 1e3, (pred.numel() + rec.numel()) * 4 / t_rec / 1e6,
                  t_nms * 1e3, rec.numel() * 4 / t_nms / 1e6, B / ((t_dec + t_rec + t_nms) * 1e-3)))
