@@ -63,6 +63,7 @@ struct HeadsDev {
   // SRC == 1 (scores source, the tools.torch_nms drop-in): recovered tensor (B, N, bb_row = 4+C)
   const float* bboxes;
   int bb_row;
+  uint32_t magic_n4;   // ceil(2^32 / (bb_row / 4)): word index -> row by multiply-high
 };
 
 struct DetOut {
@@ -360,6 +361,35 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     } else {
       // a row is a hit iff any of its C scores exceeds thr (tools.py:551); 128-bit loads when rows are aligned
       const bool vec = ((P.bb_row & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.bboxes) & 15) == 0);
+      if (vec && P.magic_n4 != 0) {
+        // The image is one contiguous run of N * n4 128-bit words (n4 per row): consecutive threads read consecutive
+        // words, so every byte crosses L2 once, fully coalesced; a word with a score above thr sets its row's bit.
+        const int n4 = P.bb_row >> 2;
+        for (int w = tid; w < W_tot; w += kFusedThreads) hitw[w] = 0u;
+        __syncthreads();
+        const float4* img4 = reinterpret_cast<const float4*>(img);
+        const int total4 = P.N * n4;
+        constexpr int U = 4;
+        for (int e0 = tid; e0 < total4; e0 += kFusedThreads * U) {
+          float4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * kFusedThreads;
+            if (e < total4)
+              asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(img4 + e));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * kFusedThreads;
+            if (e >= total4) continue;
+            const int row = (int)__umulhi((unsigned)e, P.magic_n4);           // e / n4
+            if (e == row * n4) continue;                                       // word 0 of a row = the box
+            if ((v[u].x > P.thr_f) | (v[u].y > P.thr_f) | (v[u].z > P.thr_f) | (v[u].w > P.thr_f))
+              atomicOr(&hitw[row >> 5], 1u << (row & 31));
+          }
+        }
+      } else
       for (int w = warp; w < W_tot; w += kFusedWarps) {
         const int row = w * 32 + lane;
         bool pass = false;
@@ -1297,6 +1327,10 @@ extern "C" int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, dou
   P.iou_f = (float)iou_threshold; P.iou_d = iou_threshold;
   P.nms_mode = nms_mode;
   P.bboxes = bboxes; P.bb_row = 4 + C;
+  // multiply-high division of the word index by n4 = (4+C)/4 <= 32 is exact below 2^27 words; larger inputs (or
+  // rows that are not a whole number of 128-bit words) take the row-per-lane scan
+  if (((4 + C) & 3) == 0 && N * ((4 + C) >> 2) < (1ll << 27))
+    P.magic_n4 = (uint32_t)(((1ull << 32) + (uint64_t)((4 + C) >> 2) - 1) / (uint64_t)((4 + C) >> 2));
   PQ_ENTER(device);
   DetOut O{det, det_idx, max_det, counts, ncand, status};
   return launch_fused(P, O, work_counter, counter_armed, iou_round, 1, device, (cudaStream_t)stream);
