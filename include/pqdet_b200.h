@@ -69,6 +69,11 @@ const char* pqdet_strerror(int code);
 int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int C, int H, int W, float stride,
                      int64_t out_rows_total, int64_t out_row_offset, int device, void* stream);
 
+/* DetectionModel.forward eval branch (model/interpreter.py:72-76): every level's Decode + view + cat in ONE launch.
+ * raw/H/W/stride: HOST arrays of n_levels entries in cfg order; out (B, N, 5+C), N = sum of H*W*A. */
+int pqdet_decode_levels(int n_levels, const float* const* raw, const int* H, const int* W, const float* stride,
+                        float* out, int B, int A, int C, int device, void* stream);
+
 /* autograd of Decode.forward: grad_raw = grad_out * d out / d raw (needs raw, not out). */
 int pqdet_decode_bwd(const float* raw, const float* grad_out, float* grad_raw, int B, int A, int C,
                      int H, int W, float stride, int64_t out_rows_total, int64_t out_row_offset,

@@ -48,6 +48,8 @@ SIGNATURES = {
     "pqdet_strerror": (c_char_p, [c_int]),
     "pqdet_decode_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_int64, c_int64, c_int, c_void_p]),
+    "pqdet_decode_levels": (c_int, [c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), POINTER(c_float),
+                                    c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pqdet_decode_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                  c_int64, c_int64, c_int, c_void_p]),
     "pqdet_recover": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_float,

@@ -86,6 +86,26 @@ def decode_fwd(raw: torch.Tensor, num_classes: int, stride: float, out: Optional
     return out
 
 
+def decode_levels(raws: Sequence[torch.Tensor], num_classes: int, strides: Sequence[float]) -> torch.Tensor:
+    """Every level decoded straight into its row range of (B, N, 5+C): one launch (pqdet_decode_levels)."""
+    raws = [_req(r, "conv") for r in raws]
+    ch = 5 + num_classes
+    B = raws[0].shape[0]
+    A = raws[0].shape[1] // ch
+    for r in raws:
+        if r.shape[0] != B or r.shape[1] != A * ch or r.device != raws[0].device:
+            raise ValueError("heads have inconsistent shapes/devices")
+    L = len(raws)
+    N = sum(r.shape[2] * r.shape[3] * A for r in raws)
+    out = torch.empty((B, N, ch), dtype=torch.float32, device=raws[0].device)
+    VP, IP, FP = ctypes.c_void_p * L, ctypes.c_int * L, ctypes.c_float * L
+    _lib.check(_lib.load().pqdet_decode_levels(L, VP(*[r.data_ptr() for r in raws]), IP(*[r.shape[2] for r in raws]),
+                                               IP(*[r.shape[3] for r in raws]), FP(*[float(s) for s in strides]),
+                                               _ptr(out), B, A, num_classes, _dev(raws[0]), _stream(raws[0].device)),
+               "pqdet_decode_levels")
+    return out
+
+
 def decode_bwd(raw: torch.Tensor, grad_out: torch.Tensor, num_classes: int, stride: float) -> torch.Tensor:
     raw = _req(raw, "conv")
     grad_out = _req(grad_out, "grad_out")

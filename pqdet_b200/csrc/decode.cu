@@ -4,6 +4,10 @@
 // each warp reads 32 consecutive cells of one channel plane (one 128-byte line), applies the
 // decode function, and the tile is written back as one contiguous run of 32*A*(5+C) floats.
 // HBM traffic is the algorithmic 2R (read once, write once); there is no reuse to exploit.
+#include <string.h>
+
+#include <atomic>
+
 #include "pq_common.cuh"
 
 namespace pq {
@@ -11,15 +15,13 @@ namespace pq {
 constexpr int kTileCells = 32;
 constexpr int kDecodeThreads = 256;
 
-__global__ void __launch_bounds__(kDecodeThreads)
-decode_fwd_kernel(const float* __restrict__ raw, float* __restrict__ out, int A, int ch, int H, int W,
-                  float stride, int64_t rows_total, int64_t row_off) {
-  extern __shared__ __align__(16) float tile[];  // [kTileCells][ST]
+__device__ __forceinline__ void decode_tile(const float* __restrict__ raw, float* __restrict__ out, int A, int ch,
+                                            int H, int W, float stride, int64_t rows_total, int64_t row_off,
+                                            int tile_index, int b, float* tile) {
   const int HW = H * W;
   const int ACH = A * ch;
   const int ST = ACH | 1;  // odd row stride: conflict-free column writes (== ACH whenever ACH is odd)
-  const int b = blockIdx.y;
-  const int cell0 = blockIdx.x * kTileCells;
+  const int cell0 = tile_index * kTileCells;
   const int ncell = min(kTileCells, HW - cell0);
   const int lane = lane_id();
   const int cell = cell0 + lane;
@@ -65,6 +67,36 @@ decode_fwd_kernel(const float* __restrict__ raw, float* __restrict__ out, int A,
       for (int c = lane; c < ACH; c += 32) drow[c] = trow[c];
     }
   }
+}
+
+__global__ void __launch_bounds__(kDecodeThreads)
+decode_fwd_kernel(const float* __restrict__ raw, float* __restrict__ out, int A, int ch, int H, int W,
+                  float stride, int64_t rows_total, int64_t row_off) {
+  extern __shared__ __align__(16) float tile[];  // [kTileCells][ST]
+  decode_tile(raw, out, A, ch, H, W, stride, rows_total, row_off, blockIdx.x, blockIdx.y, tile);
+}
+
+// All levels of the eval concat (model/interpreter.py:75-76) in ONE launch: grid.x enumerates the tiles of every
+// level back to back, grid.y = image; each level writes its own row range of the (B, N, 5+C) output.
+struct DecodeLevels {
+  const float* raw[PQDET_MAX_LEVELS];
+  int H[PQDET_MAX_LEVELS], W[PQDET_MAX_LEVELS];
+  float stride[PQDET_MAX_LEVELS];
+  int64_t row_off[PQDET_MAX_LEVELS];
+  int tile_off[PQDET_MAX_LEVELS + 1];
+  int n_levels;
+};
+
+__global__ void __launch_bounds__(kDecodeThreads)
+decode_levels_kernel(const __grid_constant__ DecodeLevels L, float* __restrict__ out, int A, int ch,
+                     int64_t rows_total) {
+  extern __shared__ __align__(16) float tile[];
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < PQDET_MAX_LEVELS; ++i)
+    if (i < L.n_levels && (int)blockIdx.x >= L.tile_off[i]) l = i;
+  decode_tile(L.raw[l], out, A, ch, L.H[l], L.W[l], L.stride[l], rows_total, L.row_off[l],
+              (int)blockIdx.x - L.tile_off[l], blockIdx.y, tile);
 }
 
 // grad_raw[b][c][cell] = grad_out[b][cell][a][k] * d out/d raw:
@@ -275,6 +307,38 @@ extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int 
   return PQDET_OK;
 }
 
+extern "C" int pqdet_decode_levels(int n_levels, const float* const* raw, const int* H, const int* W,
+                                   const float* stride, float* out, int B, int A, int C, int device, void* stream) {
+  using namespace pq;
+  if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || !raw || !H || !W || !stride) return PQDET_ERR_INVALID_ARG;
+  if (B < 0 || A <= 0 || C < 0) return PQDET_ERR_INVALID_ARG;
+  if (B == 0) return PQDET_OK;
+  if (B > 65535) return PQDET_ERR_UNSUPPORTED;
+  if (!out) return PQDET_ERR_INVALID_ARG;
+  DecodeLevels L;
+  memset(&L, 0, sizeof(L));
+  int64_t rows = 0;
+  int tiles = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!raw[l] || H[l] < 1 || W[l] < 1) return PQDET_ERR_INVALID_ARG;
+    L.raw[l] = raw[l]; L.H[l] = H[l]; L.W[l] = W[l]; L.stride[l] = stride[l];
+    L.row_off[l] = rows; L.tile_off[l] = tiles;
+    rows += (int64_t)H[l] * W[l] * A;
+    tiles += (H[l] * W[l] + kTileCells - 1) / kTileCells;
+  }
+  for (int l = n_levels; l <= PQDET_MAX_LEVELS; ++l) L.tile_off[l] = tiles;
+  L.n_levels = n_levels;
+  PQ_ENTER(device);
+  const int ch = 5 + C;
+  const size_t smem = (size_t)kTileCells * ((A * ch) | 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    PQ_CUDA(cudaFuncSetAttribute(decode_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(tiles, B);
+  decode_levels_kernel<<<grid, kDecodeThreads, smem, (cudaStream_t)stream>>>(L, out, A, ch, rows);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
 extern "C" int pqdet_decode_bwd(const float* raw, const float* grad_out, float* grad_raw, int B, int A, int C,
                                 int H, int W, float stride, int64_t out_rows_total, int64_t out_row_offset,
                                 int device, void* stream) {
@@ -318,11 +382,21 @@ extern "C" int pqdet_recover(const float* pred, float* out, int B, int64_t N, in
     if (aligned && tsm <= 200 * 1024 && ((N + pq::kRecRows - 1) / pq::kRecRows) * B < (1ll << 31)) {
       const int64_t tiles_per_image = (N + pq::kRecRows - 1) / pq::kRecRows;
       const int64_t total_tiles = tiles_per_image * B;
-      PQ_CUDA(cudaFuncSetAttribute(pq::recover_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-      int per_sm = 1, sm_count = 148;
-      PQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pq::recover_tma_kernel, pq::kRecThreads, tsm));
-      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
-      int64_t grid = (int64_t)sm_count * (per_sm < 1 ? 1 : per_sm);
+      // launch geometry is a pure function of (device, smem): remember the last one per device
+      static std::atomic<uint64_t> cache[16];
+      int64_t grid = 0;
+      if (device < 16) {
+        const uint64_t c = cache[device].load(std::memory_order_relaxed);
+        if ((c >> 32) == (uint64_t)tsm) grid = (int64_t)(c & 0xffffffffu);
+      }
+      if (grid == 0) {
+        PQ_CUDA(cudaFuncSetAttribute(pq::recover_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        int per_sm = 1, sm_count = 148;
+        PQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pq::recover_tma_kernel, pq::kRecThreads, tsm));
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+        grid = (int64_t)sm_count * (per_sm < 1 ? 1 : per_sm);
+        if (device < 16) cache[device].store(((uint64_t)tsm << 32) | (uint32_t)grid, std::memory_order_relaxed);
+      }
       if (grid > total_tiles) grid = total_tiles;
       pq::recover_tma_kernel<<<(unsigned)grid, pq::kRecThreads, tsm, (cudaStream_t)stream>>>(
           pred, out, N, C, affine_kind, in_h, in_w, orig_hw, orig_per_image, (unsigned)tiles_per_image,

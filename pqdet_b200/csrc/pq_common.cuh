@@ -121,7 +121,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     if (ok) return;
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

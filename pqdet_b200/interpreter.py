@@ -97,8 +97,10 @@ class DetectionHead(nn.Module):
             if any(h.requires_grad for h in heads) and torch.is_grad_enabled():
                 outs = [l(h) for l, h in zip(self.layers, heads)]
                 return torch.cat([o.view((o.shape[0], -1, o.shape[-1])) for o in outs], dim=1)
-            # eval: decode every level straight into its row range of (B, N, 5+C) -- no cat pass
+            # eval: every level decoded straight into its row range of (B, N, 5+C): no cat pass, one launch
             C = self.layers[0].opt['classes']
+            if all(l.opt['classes'] == C for l in self.layers) and len(heads) <= 4:
+                return _ops.decode_levels(heads, C, [l.opt['stride'] for l in self.layers])
             ch = 5 + C
             B = heads[0].shape[0]
             rows = [h.shape[2] * h.shape[3] * (h.shape[1] // ch) for h in heads]
