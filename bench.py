@@ -509,6 +509,41 @@ def bench_other_configs(device, peak):
     except Exception as e:
         out["evaluator_ap"] = {"error": repr(e)}
 
+    # ---- eval pre-processing: letterbox + normalise + CHW for a batch of VOC-sized uint8 images
+    try:
+        from pqdet_b200 import augment as pqaug
+        rng = np.random.default_rng(0)
+        shapes = [(375, 500), (500, 333), (333, 500), (500, 375)] * 16
+        imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+        pqaug.letterbox_normalize(imgs, SIZE, device=device)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            got, _ = pqaug.letterbox_normalize(imgs, SIZE, device=device)
+        torch.cuda.synchronize()
+        t_gpu = (time.perf_counter() - t0) / 3
+        entry = {"workload": "Resize(512)+Normalize+ToTensor of 64 VOC-sized uint8 images (host bytes in, device tensor out)",
+                 "ours_images_per_s": len(imgs) / t_gpu}
+        try:
+            import cv2
+            mean, std = np.array(pqaug.VOC_MEAN, np.float32), np.array(pqaug.VOC_STD, np.float32)
+
+            def cpu_chain(im):
+                ratio, dh, dw, du, dl = pqaug.letterbox_geometry(im.shape[:2], (SIZE, SIZE))
+                r = cv2.resize(im, dsize=(dw, dh), interpolation=cv2.INTER_LINEAR)
+                r = np.pad(r, ((du, SIZE - dh - du), (dl, SIZE - dw - dl), (0, 0)), 'constant', constant_values=128)
+                return np.transpose((r.astype(np.float32) / 255. - mean) / std, (2, 0, 1)).astype(np.float32)
+            t0 = time.perf_counter()
+            ref = [cpu_chain(im) for im in imgs]
+            t_cpu = time.perf_counter() - t0
+            entry["reference_cv2_numpy_images_per_s_one_core"] = len(imgs) / t_cpu
+            entry["identical"] = bool(all(np.array_equal(got[i].cpu().numpy(), ref[i]) for i in range(0, len(imgs), 7)))
+        except ImportError:
+            pass
+        out["eval_preprocess"] = entry
+    except Exception as e:
+        out["eval_preprocess"] = {"error": repr(e)}
+
     # ---- C: dense decode + NMS
     B, C, size = 64, 10, 608
     heads = synth.make_heads(B, C, size, "dense", seed=0, device=device)

@@ -259,6 +259,22 @@ int pqdet_ap_match(const float* det_box, int64_t D, const int32_t* grp_det, cons
                    int64_t sum_gt, int G, const double* thresholds, int T, uint8_t* seen, uint8_t* tp,
                    uint8_t* fp, int device, void* stream);
 
+/* ---- eval pre-processing: augment.Resize (dataset/augment.py:227-259: cv2.resize
+ * INTER_LINEAR to the letterbox size + constant padding), augment.Normalize (:206-215) and augment.ToTensor
+ * (:390-398), i.e. eval_augment_voc / eval_augment_coco (dataset/voc_sample.py:85-90), for a batch of uint8 HWC images
+ * of different sizes in one launch.
+ *   src     packed device buffer holding the images back to back (3 channels, HWC)
+ *   images  device array of B records {int64 src_off; int32 sh, sw, dh, dw, du, dl; double scale_y, scale_x}
+ *           (48 bytes each, naturally aligned) filled by the caller exactly as Resize.__call__ / cv::resize derive them
+ *   mean3/std3  HOST float[3]
+ *   out_chw     (B, 3, target_h, target_w) float32, normalised (may be NULL)
+ *   out_hwc_u8  (B, target_h, target_w, 3) uint8, the padded resized image (may be NULL)
+ * The resize reproduces OpenCV's 8-bit fixed-point bilinear arithmetic: out_hwc_u8 is bit-identical to
+ * np.pad(cv2.resize(...)), out_chw to the reference chain. */
+int pqdet_letterbox_normalize(const uint8_t* src, const void* images, int B, int target_h, int target_w,
+                              int pad_val, const float* mean3, const float* std3, float* out_chw,
+                              uint8_t* out_hwc_u8, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

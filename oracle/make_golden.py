@@ -204,12 +204,34 @@ def gen_ap(ref):
     return d
 
 
+def gen_letterbox(ref):
+    """augment.Resize -> Normalize -> HWCtoCHW (= ToTensor without the device copy) of the reference on small random
+    uint8 images: up-scaling, down-scaling, tall, wide, already-square."""
+    import sys as _sys
+    _sys.path.insert(0, rh.REFERENCE_ROOT)
+    from dataset import augment as raug
+    rng = np.random.default_rng(21)
+    d = {}
+    shapes = [(37, 53), (120, 45), (64, 64), (23, 111), (150, 97), (9, 14)]
+    for i, (h, w) in enumerate(shapes):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        bb = rng.uniform(0, min(h, w), (4, 4)).astype(np.float32)
+        rimg, rbb = raug.Resize((64, 96))(img.copy(), bb.copy())
+        nimg, _ = raug.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])(rimg, rbb)
+        timg, _ = raug.HWCtoCHW()(nimg, rbb)
+        d["img%d" % i], d["bb%d" % i] = img, bb
+        d["resized%d" % i], d["rbb%d" % i], d["tensor%d" % i] = rimg, rbb, timg
+    d["n"] = np.int64(len(shapes))
+    d["target_hw"] = np.array([64, 96], np.int64)
+    return d
+
+
 def main():
     import torchvision
     ref = rh.load()
     os.makedirs(OUT, exist_ok=True)
     parts = {"decode": gen_decode, "recover": gen_recover, "nms": gen_nms,
-             "train": gen_label_and_loss, "iou": gen_iou, "ap": gen_ap}
+             "train": gen_label_and_loss, "iou": gen_iou, "ap": gen_ap, "letterbox": gen_letterbox}
     sizes = {}
     for name, fn in parts.items():
         path = os.path.join(OUT, name + ".npz")

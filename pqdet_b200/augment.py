@@ -1,0 +1,109 @@
+"""Drop-in for the eval pre-processing of dataset/augment.py:
+Resize (:227-259) -> Normalize (:206-215) -> ToTensor (:390-398), the chain eval_augment_voc / eval_augment_coco
+build (dataset/voc_sample.py:85-90), for a whole batch of uint8 HWC images in one kernel launch (csrc/augment.cu).
+
+The host only does what Resize.__call__ does in Python before calling OpenCV: the letterbox geometry per image
+(resize ratio, rounded size, padding) - with the same Python arithmetic - and packs the raw bytes; the bilinear
+resize (OpenCV's 8-bit fixed-point arithmetic, reproduced bit-exactly), the padding, the normalisation and the
+HWC -> CHW transpose run on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+IMAGE_REC = np.dtype([("off", "<i8"), ("sh", "<i4"), ("sw", "<i4"), ("dh", "<i4"), ("dw", "<i4"), ("du", "<i4"),
+                      ("dl", "<i4"), ("scale_y", "<f8"), ("scale_x", "<f8")], align=True)
+VOC_MEAN, VOC_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)          # dataset/voc_sample.py:88
+
+
+def letterbox_geometry(img_hw: Tuple[int, int], target_hw: Tuple[int, int]):
+    """dataset/augment.py:236-249 -> (resize_ratio, resize_h, resize_w, du, dl)."""
+    img_h, img_w = img_hw
+    target_h, target_w = target_hw
+    resize_ratio = min(target_w / img_w, target_h / img_h)
+    resize_w = round(resize_ratio * img_w)
+    resize_h = round(resize_ratio * img_h)
+    dl = (target_w - resize_w) // 2
+    du = (target_h - resize_h) // 2
+    return resize_ratio, resize_h, resize_w, du, dl
+
+
+def resize_bboxes(bboxes: np.ndarray, resize_ratio: float, du: int, dl: int) -> np.ndarray:
+    """dataset/augment.py:256-258 (in place, like the reference)."""
+    if len(bboxes) != 0:
+        bboxes[:, [0, 2]] = bboxes[:, [0, 2]] * resize_ratio + dl
+        bboxes[:, [1, 3]] = bboxes[:, [1, 3]] * resize_ratio + du
+    return bboxes
+
+
+def _pack(images: Sequence[np.ndarray], target_hw):
+    recs = np.zeros((len(images),), IMAGE_REC)
+    off = 0
+    geo = []
+    for i, im in enumerate(images):
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+            raise TypeError("images must be uint8 HWC with 3 channels, got %s %s" % (im.dtype, im.shape))
+        sh, sw = im.shape[:2]
+        ratio, dh, dw, du, dl = letterbox_geometry((sh, sw), target_hw)
+        if dh < 1 or dw < 1:
+            raise ValueError("image %d (%dx%d) vanishes at input size %s" % (i, sh, sw, target_hw))
+        # cv::resize: inv_scale = dsize / ssize (double), scale = 1 / inv_scale
+        recs[i] = (off, sh, sw, dh, dw, du, dl, 1.0 / (dh / sh), 1.0 / (dw / sw))
+        geo.append((ratio, du, dl))
+        off += sh * sw * 3
+    packed = np.empty((off,), np.uint8)
+    for r, im in zip(recs, images):
+        packed[r["off"]:r["off"] + im.size] = np.ascontiguousarray(im).reshape(-1)
+    return packed, recs, geo
+
+
+def letterbox_normalize(images: Sequence[np.ndarray], input_size, mean=VOC_MEAN, std=VOC_STD, pad_val: int = 128,
+                        device="cuda", want_uint8: bool = False):
+    """images: list of uint8 HWC arrays (any sizes).  input_size: int or (h, w).
+    -> float32 tensor (B, 3, h, w) = ToTensor(Normalize(Resize(img))) of every image
+       [, uint8 tensor (B, h, w, 3) = the padded resized images], geometry [(resize_ratio, du, dl)] per image."""
+    th, tw = (input_size, input_size) if isinstance(input_size, int) else (int(input_size[0]), int(input_size[1]))
+    device = torch.device(device)
+    B = len(images)
+    out = torch.empty((B, 3, th, tw), dtype=torch.float32, device=device)
+    out_u8 = torch.empty((B, th, tw, 3), dtype=torch.uint8, device=device) if want_uint8 else None
+    if B == 0:
+        return (out, out_u8, []) if want_uint8 else (out, [])
+    packed, recs, geo = _pack(images, (th, tw))
+    pin = device.type == "cuda"
+    t_src = torch.from_numpy(packed)
+    t_rec = torch.from_numpy(recs.view(np.uint8).reshape(-1))
+    if pin:
+        t_src, t_rec = t_src.pin_memory(), t_rec.pin_memory()
+    t_src, t_rec = t_src.to(device, non_blocking=True), t_rec.to(device, non_blocking=True)
+    if not t_src.is_cuda:
+        raise _lib.PqdetError("letterbox_normalize needs a CUDA device: pqdet_b200 has no CPU path")
+    m = (ctypes.c_float * 3)(*[float(np.float32(v)) for v in mean])
+    s = (ctypes.c_float * 3)(*[float(np.float32(v)) for v in std])
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().pqdet_letterbox_normalize(p(t_src), p(t_rec), B, th, tw, int(pad_val), m, s, p(out), p(out_u8),
+                                                     dev_index, ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
+               "pqdet_letterbox_normalize")
+    return (out, out_u8, geo) if want_uint8 else (out, geo)
+
+
+class Resize:
+    """dataset/augment.py:227-259 with the reference's call signature (one image, numpy in / numpy out)."""
+
+    def __init__(self, size, pad_val: int = 128, nopad: bool = False):
+        if nopad:
+            raise NotImplementedError("nopad=True (train-time multi-scale) is not on the eval path")
+        self.size, self.pad_val = size, pad_val
+
+    def __call__(self, img: np.ndarray, bboxes):
+        size = self.size() if callable(self.size) else self.size
+        _, u8, geo = letterbox_normalize([img], size, pad_val=self.pad_val, want_uint8=True)
+        ratio, du, dl = geo[0]
+        return u8[0].cpu().numpy(), resize_bboxes(bboxes, ratio, du, dl)

@@ -112,3 +112,17 @@ def test_ap_oracle_vs_live_reference_evaluator():
         with contextlib.redirect_stderr(io.StringIO()):
             ap = ev.AP()
         assert np.array_equal(ap.raw, orc.AP()), dt
+
+
+def test_resize_oracle_is_bit_exact_against_cv2():
+    """The third-party arithmetic on this path: cv2.resize(INTER_LINEAR) on uint8 (OpenCV fixed-point bilinear)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import augment_oracle as ao
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        sh, sw = int(rng.integers(5, 400)), int(rng.integers(5, 400))
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        T = int(rng.choice([64, 160, 320, 512]))
+        r = min(T / sw, T / sh)
+        dw, dh = max(round(r * sw), 1), max(round(r * sh), 1)
+        assert np.array_equal(ao.resize_linear_u8(img, dw, dh), cv2.resize(img, dsize=(dw, dh), interpolation=cv2.INTER_LINEAR))
