@@ -42,7 +42,22 @@ def resize_bboxes(bboxes: np.ndarray, resize_ratio: float, du: int, dl: int) -> 
     return bboxes
 
 
-def _pack(images: Sequence[np.ndarray], target_hw):
+_STAGE = {}          # device -> [pinned uint8 staging tensor, event of the last copy out of it]
+
+
+def _staging(device, nbytes: int) -> np.ndarray:
+    """A reusable page-locked staging buffer (allocating pinned memory per call costs more than the copy).  The
+    previous asynchronous copy out of it must have completed before it is overwritten."""
+    st = _STAGE.get(device)
+    if st is not None and st[1] is not None:
+        st[1].synchronize()
+    if st is None or st[0].numel() < nbytes:
+        st = [torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8, pin_memory=True), None]
+        _STAGE[device] = st
+    return st[0]
+
+
+def _pack(images: Sequence[np.ndarray], target_hw, stage=None):
     recs = np.zeros((len(images),), IMAGE_REC)
     off = 0
     geo = []
@@ -57,7 +72,7 @@ def _pack(images: Sequence[np.ndarray], target_hw):
         recs[i] = (off, sh, sw, dh, dw, du, dl, 1.0 / (dh / sh), 1.0 / (dw / sw))
         geo.append((ratio, du, dl))
         off += sh * sw * 3
-    packed = np.empty((off,), np.uint8)
+    packed = np.empty((off,), np.uint8) if stage is None else stage(off + recs.nbytes + 8)[:off].numpy()
     for r, im in zip(recs, images):
         packed[r["off"]:r["off"] + im.size] = np.ascontiguousarray(im).reshape(-1)
     return packed, recs, geo
@@ -75,15 +90,20 @@ def letterbox_normalize(images: Sequence[np.ndarray], input_size, mean=VOC_MEAN,
     out_u8 = torch.empty((B, th, tw, 3), dtype=torch.uint8, device=device) if want_uint8 else None
     if B == 0:
         return (out, out_u8, []) if want_uint8 else (out, [])
-    packed, recs, geo = _pack(images, (th, tw))
-    pin = device.type == "cuda"
-    t_src = torch.from_numpy(packed)
-    t_rec = torch.from_numpy(recs.view(np.uint8).reshape(-1))
-    if pin:
-        t_src, t_rec = t_src.pin_memory(), t_rec.pin_memory()
-    t_src, t_rec = t_src.to(device, non_blocking=True), t_rec.to(device, non_blocking=True)
-    if not t_src.is_cuda:
+    if device.type != "cuda":
         raise _lib.PqdetError("letterbox_normalize needs a CUDA device: pqdet_b200 has no CPU path")
+    packed, recs, geo = _pack(images, (th, tw), stage=lambda n: _staging(device, n))
+    stage = _STAGE[device][0]
+    nsrc, nrec = packed.size, recs.nbytes
+    rec_at = (nsrc + 7) & ~7                                   # records right behind the pixels, 8-byte aligned
+    if rec_at + nrec > stage.numel():
+        raise _lib.PqdetError("internal: staging buffer too small")
+    stage[rec_at:rec_at + nrec].numpy()[:] = recs.view(np.uint8).reshape(-1)
+    dev_buf = stage[:rec_at + nrec].to(device, non_blocking=True)      # ONE host->device copy: pixels + records
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    _STAGE[device][1] = ev
+    t_src, t_rec = dev_buf[:nsrc], dev_buf[rec_at:]
     m = (ctypes.c_float * 3)(*[float(np.float32(v)) for v in mean])
     s = (ctypes.c_float * 3)(*[float(np.float32(v)) for v in std])
     dev_index = device.index if device.index is not None else torch.cuda.current_device()
