@@ -275,6 +275,17 @@ int pqdet_letterbox_normalize(const uint8_t* src, const void* images, int B, int
                               int pad_val, const float* mean3, const float* std3, float* out_chw,
                               uint8_t* out_hwc_u8, int device, void* stream);
 
+/* ---- head 1x1 convolution + decode: the `filters = A*(5+C), size = 1, linear`
+ * convolution in front of every [yolo] layer (model/cfg/regnetx-600m-fpn.cfg:646-651) fused with Decode.forward
+ * (model/parser.py:206-235) on the tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM).
+ *   x (B, Cin, H, W), weight (A*(5+C), Cin) [the conv's (O, Cin, 1, 1) weight], bias (A*(5+C)) or NULL
+ *   out_decoded: rows [out_row_offset, +H*W*A) of a (B, out_rows_total, 5+C) prediction (may be NULL)
+ *   out_raw    : (B, A*(5+C), H, W), what the convolution alone would produce (may be NULL)
+ * TF32 products, fp32 accumulation - the precision PyTorch's own convolution runs at by default. */
+int pqdet_head_conv_decode(const float* x, const float* weight, const float* bias, float* out_decoded,
+                           float* out_raw, int B, int Cin, int H, int W, int A, int C, float stride,
+                           int64_t out_rows_total, int64_t out_row_offset, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

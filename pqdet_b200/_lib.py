@@ -96,6 +96,8 @@ SIGNATURES = {
                                c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pqdet_letterbox_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float),
                                           POINTER(c_float), c_void_p, c_void_p, c_int, c_void_p]),
+    "pqdet_head_conv_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, c_float, c_int64, c_int64, c_int, c_void_p]),
 }
 
 _LIB = None

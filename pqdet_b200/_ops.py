@@ -106,6 +106,32 @@ def decode_levels(raws: Sequence[torch.Tensor], num_classes: int, strides: Seque
     return out
 
 
+def head_conv_decode(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], num_classes: int,
+                     stride: float, out: Optional[torch.Tensor] = None, rows_total: Optional[int] = None,
+                     row_offset: int = 0, want_raw: bool = False):
+    """1x1 head convolution + Decode on the tensor cores (pqdet_head_conv_decode).
+    x (B,Cin,H,W), weight (A*(5+C), Cin[,1,1]), bias (A*(5+C))|None -> decoded (B,H,W,A,5+C) [or rows of `out`],
+    raw (B, A*(5+C), H, W) if want_raw."""
+    x = _req(x, "x")
+    weight = _req(weight.reshape(weight.shape[0], -1), "weight")
+    if bias is not None:
+        bias = _req(bias, "bias")
+    B, Cin, H, W = x.shape
+    ch = 5 + num_classes
+    ACH = weight.shape[0]
+    if ACH % ch or weight.shape[1] != Cin:
+        raise ValueError("weight %s does not match Cin=%d / 5+classes=%d" % (tuple(weight.shape), Cin, ch))
+    A = ACH // ch
+    if out is None:
+        out = torch.empty((B, H, W, A, ch), dtype=torch.float32, device=x.device)
+        rows_total, row_offset = H * W * A, 0
+    raw = torch.empty((B, ACH, H, W), dtype=torch.float32, device=x.device) if want_raw else None
+    _lib.check(_lib.load().pqdet_head_conv_decode(_ptr(x), _ptr(weight), _ptr(bias), _ptr(out), _ptr(raw), B, Cin, H, W,
+                                                  A, num_classes, float(stride), int(rows_total), int(row_offset),
+                                                  _dev(x), _stream(x.device)), "pqdet_head_conv_decode")
+    return (out, raw) if want_raw else out
+
+
 def decode_bwd(raw: torch.Tensor, grad_out: torch.Tensor, num_classes: int, stride: float) -> torch.Tensor:
     raw = _req(raw, "conv")
     grad_out = _req(grad_out, "grad_out")

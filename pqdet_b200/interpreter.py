@@ -137,6 +137,24 @@ class DetectionHead(nn.Module):
                                        *heads, *[p[0] for p in pairs], *[p[1] for p in pairs])
         return self._result(out, flag, L)
 
+    def forward_from_features(self, features: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
+                              biases: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Eval branch starting one layer earlier: features[l] = the input of level l's 1x1 head
+        convolution (`filters = A*(5+C), size = 1, activation = linear`, model/cfg/*.cfg), weights/biases = that
+        convolution's parameters.  Convolution (TF32 tensor cores, like PyTorch's own default) + Decode + the concat
+        of model/interpreter.py:75-76 without the raw head ever being written: -> (B, N, 5+C)."""
+        C = self.layers[0].opt['classes']
+        ch = 5 + C
+        B = features[0].shape[0]
+        rows = [f.shape[2] * f.shape[3] * (w.shape[0] // ch) for f, w in zip(features, weights)]
+        N = sum(rows)
+        out = torch.empty((B, N, ch), dtype=torch.float32, device=features[0].device)
+        off = 0
+        for l, f, w, bi, r in zip(self.layers, features, weights, biases, rows):
+            _ops.head_conv_decode(f, w, bi, C, l.opt['stride'], out=out, rows_total=N, row_offset=off)
+            off += r
+        return out
+
     def loss_and_grad(self, heads: Sequence[torch.Tensor], target):
         """The training branch without autograd glue: ONE kernel launch gives the loss dict of forward(heads,
         target) and d loss.mean() / d head for every level (the kernel always computes both).  A trainer continues

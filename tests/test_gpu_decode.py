@@ -109,3 +109,43 @@ def test_empty_batch_through_the_materialising_route():
     assert tuple(pred.shape) == (0, 16128, 25)
     rec = base_sample.recover_bboxes_prediction_voc(pred, (512, 512), torch.zeros((0, 2), device="cuda"))
     assert tuple(rec.shape) == (0, 16128, 24)
+
+
+@pytest.mark.parametrize("B,Cin,H,W,C,stride", [(2, 80, 64, 64, 20, 8), (3, 352, 16, 16, 20, 32), (2, 176, 19, 19, 10, 16),
+                                                  (1, 80, 38, 38, 80, 8), (2, 30, 7, 9, 1, 16)])
+def test_head_conv_decode_tensor_cores(B, Cin, H, W, C, stride):
+    """1x1 head convolution + Decode on tcgen05 (TF32 products, fp32 accumulation in TMEM).
+    raw vs an fp64 convolution within TF32 precision (2^-10 per operand; tolerance stated below); the decoded
+    output is bit-identical to Decode applied to the kernel's own raw output (same epilogue arithmetic)."""
+    from pqdet_b200 import _ops
+    g = torch.Generator(device="cuda").manual_seed(Cin + H)
+    A = 3
+    ACH = A * (5 + C)
+    x = torch.randn((B, Cin, H, W), device="cuda", generator=g)
+    w = torch.randn((ACH, Cin, 1, 1), device="cuda", generator=g) * 0.05
+    bias = torch.randn((ACH,), device="cuda", generator=g) * 0.1
+    dec, raw = _ops.head_conv_decode(x, w, bias, C, stride, want_raw=True)
+    ref = torch.einsum("bchw,oc->bohw", x.double(), w.view(ACH, Cin).double()) + bias.double().view(1, -1, 1, 1)
+    # |error| <= 2 * 2^-11 * sum_c |x_c * w_c| (both operands rounded to TF32) + fp32 accumulation noise
+    bound = 2.0 ** -10 * torch.einsum("bchw,oc->bohw", x.double().abs(), w.view(ACH, Cin).double().abs()) + 1e-5
+    assert bool(((raw.double() - ref).abs() <= bound).all())
+    assert torch.equal(dec, _ops.decode_fwd(raw, C, stride))
+    no_bias = _ops.head_conv_decode(x, w, None, C, stride, want_raw=True)[1]
+    assert torch.allclose(no_bias + bias.view(1, -1, 1, 1), raw, rtol=0, atol=1e-5)
+
+
+def test_forward_from_features_equals_conv_then_decode():
+    from pqdet_b200 import _ops
+    from pqdet_b200.interpreter import DetectionHead
+    C, B, size = 20, 2, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    head = DetectionHead([dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in (32, 16, 8)])
+    cins = (352, 176, 80)
+    feats = [torch.randn((B, c, size // s, size // s), device="cuda", generator=g) for c, s in zip(cins, (32, 16, 8))]
+    ws = [torch.randn((75, c, 1, 1), device="cuda", generator=g) * 0.03 for c in cins]
+    bs = [torch.randn((75,), device="cuda", generator=g) * 0.1 for _ in cins]
+    pred = head.forward_from_features(feats, ws, bs)
+    raws = [_ops.head_conv_decode(f, w, b, C, s, want_raw=True)[1] for f, w, b, s in zip(feats, ws, bs, (32, 16, 8))]
+    assert torch.equal(pred, head(raws))                       # same rows as Decode + concat of the raw heads
+    conv = [torch.nn.functional.conv2d(f, w, b) for f, w, b in zip(feats, ws, bs)]     # PyTorch's own (TF32) conv
+    assert torch.allclose(head(conv)[..., 4:], pred[..., 4:], rtol=0, atol=5e-3)
