@@ -6,11 +6,12 @@
 // adds the bias, applies Decode (model/parser.py:206-235) and writes the rows of the (B, N, 5+C) prediction, so the
 // raw head never makes the round trip through HBM.
 //
-// Operand staging (plain loads; both operands use the un-swizzled "interleave" canonical layouts, in 16-byte units):
+// Operand staging (cp.async; both operands use the un-swizzled "interleave" canonical layouts, in 16-byte units):
 //   A = X tile, K-major: unit(m, j = k/4) = 4 consecutive channels of cell m, at j*128 + m        (SBO 8, LBO 128)
 //   B = weights, K-major: unit(n, j = k/4) = 4 consecutive input channels of output n, at j*N + n (SBO 8, LBO N)
-// One tcgen05.mma consumes K = 8 tf32 values; the K loop runs in chunks of 32 channels through one smem stage,
-// each chunk committed to an mbarrier before the stage is refilled.
+// One tcgen05.mma consumes K = 8 tf32 values; the K loop runs in chunks of 32 channels through two smem stages: the
+// MMAs of a chunk (committed to that stage's mbarrier) run while the other stage is being filled.  The epilogue
+// tile reuses the stages; all 8 warps read the accumulator (warps w and w+4 share TMEM lane quadrant w%4).
 #include <string.h>
 
 #include "pq_common.cuh"
@@ -44,16 +45,17 @@ __device__ __forceinline__ uint64_t hc_smem_desc(uint32_t smem_addr, uint32_t lb
 __global__ void __launch_bounds__(kHcThreads)
 head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
   extern __shared__ __align__(128) unsigned char hsm[];
-  __shared__ __align__(8) uint64_t mma_done;
+  __shared__ __align__(8) uint64_t mma_done[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int HW = P.H * P.W, ACH = P.A * (5 + P.C), ch = 5 + P.C, N = P.N;
   const int b = blockIdx.y;
   const int cell0 = blockIdx.x * kHcM;
   const int ncell = min(kHcM, HW - cell0);
-  float4* sA = reinterpret_cast<float4*>(hsm);                                   // kHcKC * 32 units
-  float4* sB = reinterpret_cast<float4*>(hsm + (size_t)kHcKC * 32 * 16);          // (kHcKC/4) * N units
-  float* tile = reinterpret_cast<float*>(hsm + (size_t)kHcKC * 32 * 16 + (size_t)(kHcKC / 4) * N * 16);
+  // two operand stages (A: kHcKC/4 x 128 units, B: kHcKC/4 x N units of 16 bytes); the epilogue tile reuses them
+  const size_t a_bytes = (size_t)(kHcKC / 4) * kHcM * 16, b_bytes = (size_t)(kHcKC / 4) * N * 16;
+  const size_t stage_bytes = a_bytes + b_bytes;
+  float* tile = reinterpret_cast<float*>(hsm);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -61,61 +63,80 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(&mma_done, 1);
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
     mbar_init_fence();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
                          ((uint32_t)(kHcM >> 4) << 24);
   const float* xb = P.x + (size_t)b * P.Cin * HW;
   const bool vecB = ((P.Cin & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.w) & 15) == 0);
-  uint32_t phase = 0;
-  for (int kc0 = 0; kc0 < P.Cin; kc0 += kHcKC) {
-    // ---- stage the X tile (MN-major) and the weight chunk (K-major) --------------------------------------
+  const int nchunk = (P.Cin + kHcKC - 1) / kHcKC;
+  // Operand staging with cp.async (no registers, zero fill outside the tensor): chunk i+1 is in flight while the
+  // MMAs of chunk i are issued and run.
+  auto stage_chunk = [&](int i) {
+    const int kc0 = i * kHcKC, st = i & 1;
+    const uint32_t sA = smem_u32(hsm + (size_t)st * stage_bytes);
+    const uint32_t sB = smem_u32(hsm + (size_t)st * stage_bytes + a_bytes);
     for (int u = tid; u < (kHcKC / 4) * kHcM; u += kHcThreads) {
       const int j = u >> 7, m = u & (kHcM - 1);            // unit = 4 consecutive channels of one cell
       const int k = kc0 + 4 * j, cell = cell0 + m;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (cell < HW) {
-        const float* p = xb + (size_t)k * HW + cell;       // consecutive threads -> consecutive cells: coalesced
-        if (k < P.Cin) v.x = ldg_stream(p);
-        if (k + 1 < P.Cin) v.y = ldg_stream(p + HW);
-        if (k + 2 < P.Cin) v.z = ldg_stream(p + 2 * (size_t)HW);
-        if (k + 3 < P.Cin) v.w = ldg_stream(p + 3 * (size_t)HW);
+      const float* p = xb + (size_t)k * HW + cell;         // consecutive threads -> consecutive cells: coalesced
+      const uint32_t d = sA + (uint32_t)(j * kHcM + m) * 16u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (cell < HW) && (k + e < P.Cin);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                     ::"r"(d + 4u * e), "l"(ok ? p + (size_t)e * HW : xb), "r"(ok ? 4u : 0u) : "memory");
       }
-      sA[j * kHcM + m] = v;
     }
     for (int u = tid; u < (kHcKC / 4) * N; u += kHcThreads) {
       const int j = u / N, n = u - j * N;
       const int k = kc0 + 4 * j;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n < ACH && k < P.Cin) {
-        const float* p = P.w + (size_t)n * P.Cin + k;
-        if (vecB) {
-          v = *reinterpret_cast<const float4*>(p);
-        } else {
-          v.x = p[0];
-          if (k + 1 < P.Cin) v.y = p[1];
-          if (k + 2 < P.Cin) v.z = p[2];
-          if (k + 3 < P.Cin) v.w = p[3];
+      const float* p = P.w + (size_t)n * P.Cin + k;
+      const uint32_t d = sB + (uint32_t)(j * N + n) * 16u;
+      if (vecB) {
+        const bool ok = (n < ACH) && (k < P.Cin);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(d), "l"(ok ? p : P.w), "r"(ok ? 16u : 0u) : "memory");
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool ok = (n < ACH) && (k + e < P.Cin);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                       ::"r"(d + 4u * e), "l"(ok ? p + e : P.w), "r"(ok ? 4u : 0u) : "memory");
         }
       }
-      sB[j * N + n] = v;
     }
-    fence_async_smem();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_chunk(0);
+  for (int i = 0; i < nchunk; ++i) {
+    const int st = i & 1;
+    if (i + 1 < nchunk) {
+      // the MMAs that read the other stage (chunk i-1) must have finished before it is refilled
+      if (i >= 1) mbar_wait(&mma_done[st ^ 1], (uint32_t)(((i - 1) >> 1) & 1));
+      stage_chunk(i + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // chunk i has landed, chunk i+1 may be in flight
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    fence_async_smem();                       // writes of this thread -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+      const uint32_t a0 = smem_u32(hsm + (size_t)st * stage_bytes), b0 = a0 + (uint32_t)a_bytes;
 #pragma unroll
       for (int kb = 0; kb < kHcKC / 8; ++kb) {
         const uint64_t da = hc_smem_desc(a0 + (uint32_t)(2 * kb) * (uint32_t)kHcM * 16u, (uint32_t)kHcM, 8u);
         const uint64_t db = hc_smem_desc(b0 + (uint32_t)(2 * kb) * (uint32_t)N * 16u, (uint32_t)N, 8u);
-        const uint32_t accumulate = (kc0 > 0 || kb > 0) ? 1u : 0u;
+        const uint32_t accumulate = (i > 0 || kb > 0) ? 1u : 0u;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
@@ -125,23 +146,31 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
       // the commit makes the mbarrier track completion of everything issued so far (and implies the
       // before_thread_sync fence)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                   ::"r"(smem_u32(&mma_done)) : "memory");
+                   ::"r"(smem_u32(&mma_done[st])) : "memory");
     }
-    mbar_wait(&mma_done, phase);              // the stage may be refilled / the accumulator read
-    phase ^= 1u;
+  }
+  // the last commit covers every MMA issued before it
+  {
+    const int last = nchunk - 1;
+    mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();                            // nobody is still staging operands: the tile may reuse the stages
 
-  // ---- epilogue: accumulator row = cell, column = output channel ------------------------------------------
+  // ---- epilogue: accumulator row = cell, column = output channel; warps w and w+4 share TMEM lane quadrant
+  // w%4 and split the columns ------------------------------------------------------------------------------
   const int ST = ACH | 1;
-  if (warp < 4) {
-    const int r = warp * 32 + lane;                       // TMEM lane == row of the tile
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;                          // TMEM lane == row of the tile
     const int cell = cell0 + r;
     const int cy = cell / P.W, cx = cell - cy * P.W;
     const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
-    for (int c0 = 0; c0 < N; c0 += 16) {
+    const int nblk = N / 16, blk_lo = half ? (nblk + 1) / 2 : 0, blk_hi = half ? nblk : (nblk + 1) / 2;
+    for (int blk = blk_lo; blk < blk_hi; ++blk) {
+      const int c0 = blk * 16;
       uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -149,23 +178,25 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
           : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (r < ncell) {
+        int k = c0 % ch;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int c = c0 + i;
-          if (c >= ACH) break;
-          float raw = __uint_as_float(v[i]);
-          if (P.bias) raw = PQ_ADD(raw, __ldg(P.bias + c));
-          if (P.out_raw) P.out_raw[((size_t)b * ACH + c) * HW + cell] = raw;
-          const int k = c % ch;
-          float o;
-          if (k < 4) {
-            const float e = expf(raw);
-            const float g = (k & 1) ? gy : gx;
-            o = PQ_MUL((k < 2) ? PQ_SUB(g, e) : PQ_ADD(g, e), P.stride);      // decode_coord
-          } else {
-            o = __frcp_rn(PQ_ADD(1.0f, expf(-raw)));                          // sigmoidf_
+          if (c < ACH) {
+            float raw = __uint_as_float(v[i]);
+            if (P.bias) raw = PQ_ADD(raw, __ldg(P.bias + c));
+            if (P.out_raw) P.out_raw[((size_t)b * ACH + c) * HW + cell] = raw;
+            float o;
+            if (k < 4) {
+              const float e = expf(raw);
+              const float g = (k & 1) ? gy : gx;
+              o = PQ_MUL((k < 2) ? PQ_SUB(g, e) : PQ_ADD(g, e), P.stride);      // decode_coord
+            } else {
+              o = __frcp_rn(PQ_ADD(1.0f, expf(-raw)));                          // sigmoidf_
+            }
+            tile[r * ST + c] = o;
           }
-          tile[r * ST + c] = o;
+          if (++k == ch) k = 0;
         }
       }
     }
@@ -174,10 +205,17 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
   __syncthreads();
   if (P.out_dec) {
     float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch;
-    for (int r = warp; r < ncell; r += kHcThreads / 32) {
-      const float* trow = tile + r * ST;
-      float* drow = dst + (size_t)r * ACH;
-      for (int c = lane; c < ACH; c += 32) drow[c] = trow[c];
+    const int n = ncell * ACH;
+    if (ST == ACH && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0)) {
+      const float4* t4 = reinterpret_cast<const float4*>(tile);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int e = tid; e < (n >> 2); e += kHcThreads) d4[e] = t4[e];
+    } else {
+      for (int r = warp; r < ncell; r += kHcThreads / 32) {
+        const float* trow = tile + r * ST;
+        float* drow = dst + (size_t)r * ACH;
+        for (int c = lane; c < ACH; c += 32) drow[c] = trow[c];
+      }
     }
   }
   if (warp == 0) {
@@ -208,7 +246,10 @@ extern "C" int pqdet_head_conv_decode(const float* x, const float* weight, const
   while (P.tmem_cols < P.N) P.tmem_cols <<= 1;
   P.stride = stride; P.rows_total = out_rows_total; P.row_off = out_row_offset;
   PQ_ENTER(device);
-  const size_t smem = (size_t)kHcKC * 32 * 16 + (size_t)(kHcKC / 4) * P.N * 16 + (size_t)kHcM * (ACH | 1) * sizeof(float);
+  const size_t stages = 2 * ((size_t)(kHcKC / 4) * kHcM * 16 + (size_t)(kHcKC / 4) * P.N * 16);
+  const size_t tile_bytes = (size_t)kHcM * (ACH | 1) * sizeof(float);
+  const size_t smem = stages > tile_bytes ? stages : tile_bytes;
+  if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
   PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((H * W + kHcM - 1) / kHcM, B);
   head_conv_decode_kernel<<<grid, kHcThreads, smem, (cudaStream_t)stream>>>(P);
