@@ -1022,9 +1022,12 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
   if (*G.ok == 0) return;
   constexpr int kSegWarps = kSegThreads / 32;
   extern __shared__ __align__(16) unsigned char seg_smem[];
+  // one region of 16 bytes per key: the keys while sorting, then (the sorted keys parked in global memory, they are
+  // only needed again for the output) the trick-shifted boxes; behind it the kept positions.  18 bytes per key =
+  // 36 KB for the small tier: 6 CTAs per SM, so that 64 images x 10 classes run as a single wave.
   uint64_t* skeys = reinterpret_cast<uint64_t*>(seg_smem);
-  float4* sbox = reinterpret_cast<float4*>(seg_smem + sizeof(uint64_t) * kSegSmemKeys);
-  uint32_t* skl = reinterpret_cast<uint32_t*>(seg_smem + (sizeof(uint64_t) + sizeof(float4)) * kSegSmemKeys);
+  float4* sbox = reinterpret_cast<float4*>(seg_smem);
+  uint16_t* skl = reinterpret_cast<uint16_t*>(seg_smem + sizeof(float4) * kSegSmemKeys);
   __shared__ unsigned s_dead[kSegWarps];
   __shared__ unsigned s_rows[32];
   __shared__ int s_k;
@@ -1061,8 +1064,7 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
   if (trick) off = PQ_MUL((float)c, PQ_ADD(ordered_to_float(G.max_ord[ii]), 1.0f));
   const float4* rbox = G.from_heads ? G.rbox + (size_t)ii * G.N : nullptr;
   const float* bb = G.from_heads ? nullptr : G.bboxes + (size_t)b * G.N * (4 + C);
-  auto shifted_box = [&](uint32_t pos) -> float4 {            // global gather + coordinate-trick shift
-    const uint32_t row = (uint32_t)keys[pos];
+  auto shifted_row = [&](uint32_t row) -> float4 {            // global gather + coordinate-trick shift
     float4 r;
     if (rbox) r = rbox[row];
     else {
@@ -1071,16 +1073,34 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
     }
     return make_float4(PQ_ADD(r.x, off), PQ_ADD(r.y, off), PQ_ADD(r.z, off), PQ_ADD(r.w, off));
   };
+  auto shifted_box = [&](uint32_t pos) -> float4 { return shifted_row((uint32_t)keys[pos]); };
   int k;
   if (in_smem) {
-    for (uint32_t i = tid; i < n; i += kSegThreads) sbox[i] = shifted_box(i);
+    // keys -> registers (and global), barrier, then the boxes take over the region
+    constexpr int R = kSegSmemKeys / kSegThreads;
+    uint32_t rows[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t i = tid + r * kSegThreads;
+      if (i < n) {
+        const uint64_t key = skeys[i];
+        gk[i] = key;
+        rows[r] = (uint32_t)key;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t i = tid + r * kSegThreads;
+      if (i < n) sbox[i] = shifted_row(rows[r]);
+    }
     __syncthreads();
     // the kept boxes are compacted in place at the front of sbox (kept count <= candidates already consumed, and
     // every warp holds the current step's boxes in registers), so the inner loop reads them without indirection
     k = bucket_greedy<ROUND, kSegWarps>(n, G.iou_f, G.iou_d,
                              [&](uint32_t pos) { return sbox[pos]; },
                              [&](int q) { return sbox[q]; },
-                             [&](int q, uint32_t pos, const float4& bx) { skl[q] = pos; sbox[q] = bx; },
+                             [&](int q, uint32_t pos, const float4& bx) { skl[q] = (uint16_t)pos; sbox[q] = bx; },
                              s_dead, s_rows, &s_k);
   } else {
     k = bucket_greedy<ROUND, kSegWarps>(n, G.iou_f, G.iou_d, shifted_box,
@@ -1092,12 +1112,12 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
   __syncthreads();
   uint64_t* kk = G.kkeys + G.img_off[ii] + s_dst;
   for (int q = tid; q < k; q += kSegThreads) {
-    const uint64_t key = keys[in_smem ? skl[q] : kl[q]];
+    const uint64_t key = gk[in_smem ? (uint32_t)skl[q] : kl[q]];
     kk[q] = (key & 0xffffffff00000000ull) | ((uint64_t)((uint32_t)key) << 7) | (uint64_t)c;
   }
 }
 
-constexpr size_t kSegBytesPerKey = sizeof(uint64_t) + sizeof(float4) + sizeof(uint32_t);
+constexpr size_t kSegBytesPerKey = sizeof(float4) + sizeof(uint16_t);
 
 constexpr int kFinThreads = 1024;
 constexpr int kFinSmemKeys = 4096;
