@@ -16,8 +16,11 @@ import sys
 from . import base_sample, loss, parser, tools as pq_tools
 
 
-def install(strict: bool = False) -> dict:
-    """Patch every reference module that is importable; returns {attribute path: True/False}."""
+def install(strict: bool = False, patch_augment: bool = False) -> dict:
+    """Patch every reference module that is importable; returns {attribute path: True/False}.
+    patch_augment: also replace dataset.augment.Resize by the GPU letterbox.  Off by default: DataLoader worker
+    processes (where the training pipeline calls Resize) must not touch CUDA; turn it on for single-process eval /
+    predict scripts, or call pqdet_b200.augment.letterbox_normalize on whole batches instead."""
     done = {}
 
     def patch(modname, attr, value):
@@ -48,4 +51,43 @@ def install(strict: bool = False) -> dict:
             if strict:
                 raise
             done["dataset.RECOVER_BBOXES_REGISTER[%s]" % ds] = False
+    # the steps either side of the path: evaluator statistics and the eval letterbox
+    try:
+        _patch_evaluator()
+        done["eval.evaluator.Evaluator.{init_statics,add_detections,add_labels,AP}"] = True
+    except Exception:
+        if strict:
+            raise
+        done["eval.evaluator.Evaluator.{init_statics,add_detections,add_labels,AP}"] = False
+    if patch_augment:
+        from . import augment as pq_augment
+        patch("dataset.augment", "Resize", pq_augment.Resize)
     return done
+
+
+def _patch_evaluator():
+    """Evaluator keeps its loop (eval/evaluator.py:44-62); its statistics go through DetectionAccumulator, so AP()
+    runs the matching on the GPU and returns the same tools.AP tuple."""
+    ev_mod = importlib.import_module("eval.evaluator")
+    ref_tools = sys.modules.get("tools") or importlib.import_module("tools")
+    from .evaluator import DetectionAccumulator
+
+    def init_statics(self):
+        self._pq_acc = DetectionAccumulator(self._classes)
+        self.detections_count = 0
+
+    def add_detections(self, file_name, bboxes):
+        self._pq_acc.add_detections(file_name, bboxes)
+        self.detections_count = self._pq_acc.detections_count
+
+    def add_labels(self, file_name, bboxes, diffs):
+        self._pq_acc.add_labels(file_name, bboxes, diffs)
+
+    def AP(self):
+        m = self._pq_acc.AP()
+        self.init_statics()
+        return ref_tools.AP(m.mAPs, m.APs, m.AP, m.raw, m.class_names, m.iou_thresholds)
+
+    for name, fn in (("init_statics", init_statics), ("add_detections", add_detections),
+                     ("add_labels", add_labels), ("AP", AP)):
+        setattr(ev_mod.Evaluator, name, fn)

@@ -21,7 +21,7 @@ def test_install_patches_the_reference_hook_points():
         ref = rh.load()
         import pqdet_b200.install as inst
         from pqdet_b200 import parser as pqp, tools as pqt, base_sample as pqb, loss as pql
-        done = inst.install(strict=True)
+        done = inst.install(strict=True, patch_augment=True)
         assert all(done.values()), done
         import tools, model.parser, model.loss, dataset, dataset.base_sample
         assert model.parser.YOLOLayer is pqp.YOLOLayer and model.parser.Decode is pqp.Decode
@@ -35,6 +35,14 @@ def test_install_patches_the_reference_hook_points():
         assert len(yolo) == 3 and all(isinstance(l, pqp.YOLOLayer) for l in yolo)
         assert [l.opt['stride'] for l in yolo] == [32, 16, 8]
         assert yolo[0].opt['classes'] == 20 and yolo[0].opt['bbox_loss'] == 'l1'
+        # section 8f hooks: the evaluator's statistics and the eval letterbox
+        import eval.evaluator, dataset.augment
+        from pqdet_b200 import augment as pqa
+        assert dataset.augment.Resize is pqa.Resize
+        ev = eval.evaluator.Evaluator.__new__(eval.evaluator.Evaluator)
+        ev._classes = ['a', 'b']
+        ev.init_statics()
+        assert type(ev._pq_acc).__name__ == 'DetectionAccumulator' and ev.detections_count == 0
         print('ok')
     """) % (ROOT, os.path.join(rh.REFERENCE_ROOT, "model", "cfg", "regnetx-600m-fpn.cfg"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=rh.REFERENCE_ROOT, timeout=300)
