@@ -362,6 +362,43 @@ def bench_loss(device, steps, warmup, peak):
                          "sparse_targets_roofline_frac": (alg_sparse * B / (mss * 1e-3)) / (peak * 1e9),
                          "autograd_graph_images_per_s": B / (msa * 1e-3), "autograd_graph_ms_per_step": msa,
                          "eager_images_per_s": B / (ms * 1e-3), "eager_ms_per_step": ms}
+        # ---- training step end to end for the targets: host GT boxes in, loss scalars out (raw heads resident, as
+        # they come out of the backbone).  sparse = pack GT -> H2D -> pqdet_assign_sparse -> loss+grad -> D2H of the
+        # 19 floats; dense = the same through the dense label tensors built on the GPU.  What crosses PCIe per step is
+        # the GT rows only (the reference ships the dense labels: label_bytes per image).
+        try:
+            from pqdet_b200.train_dataset import assign_labels, assign_sparse, pack_gt
+            la2 = LabelAssigner(C, device=device)
+            head = DetectionHead([dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in STRIDES])
+            heads_d = [r.detach() for r in raws]
+
+            def step_sparse():
+                gt_d, cnt_d = pack_gt(gts, device)
+                tgt = assign_sparse(gt_d, cnt_d, out_sizes, C, la2._anchors.tolist(), la2._strides.tolist(), 0.3, trim=False)
+                o, _ = head.loss_and_grad(heads_d, tgt)
+                return float(o["loss"])
+
+            def step_dense():
+                gt_d, cnt_d = pack_gt(gts, device)
+                tgt = assign_labels(gt_d, cnt_d, out_sizes, C, la2._anchors.tolist(), la2._strides.tolist(), 0.3, trim=False)
+                o, _ = head.loss_and_grad(heads_d, tgt)
+                return float(o["loss"])
+            e2e_t = {}
+            for name, fn in (("sparse_targets", step_sparse), ("dense_labels_built_on_gpu", step_dense)):
+                for _ in range(3):
+                    v0 = fn()
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    fn()
+                e2e_t[name] = {"ms_per_step": (time.perf_counter() - t0) / 20 * 1e3, "loss": v0}
+            n_gt = int(sum(len(g) for g in gts))
+            res["targets_e2e"] = {"what": "host GT rows -> H2D -> assignment -> loss + d loss/d head -> D2H of the loss scalars, bs=16 "
+                                          "(wall clock incl. Python); heads resident",
+                                  "h2d_bytes_per_step": int(B * max(len(g) for g in gts) * 24 + B * 4),
+                                  "reference_h2d_bytes_per_step_dense_labels": int(B * label_bytes(C, size)),
+                                  "gt_rows": n_gt, **e2e_t}
+        except Exception as e:
+            res["targets_e2e"] = {"error": repr(e)}
     finally:
         pqcfg.nan_check = old
     # the reference's own formulation (oracle/loss_ref.py: the same ATen op sequence as model/loss.py) on this
@@ -406,7 +443,8 @@ def bench_loss(device, steps, warmup, peak):
                       "same on SparseTarget (SURVEY 8f-3); autograd_graph_* = the reference's call sequence "
                       "loss.mean().backward() captured with torch's autograd glue; eager_* = that sequence driven "
                       "from Python",
-            "kernels_per_step": 1, "by_bbox_loss": res, "steady_state": steady}
+            "kernels_per_step": 1, "targets_e2e": res.pop("targets_e2e", None), "by_bbox_loss": res,
+            "steady_state": steady}
 
 
 def bench_other_configs(device, peak):
