@@ -163,7 +163,7 @@ __device__ __forceinline__ void recover_tile(const float* rtile, float* otile, i
   const int n = nrow * C;
 #pragma unroll 2
   for (int e = tid; e < n; e += kRecThreads) {
-    const int r = (int)__umulhi((unsigned)e, magic_c);
+    const int r = (C == 1) ? e : (int)__umulhi((unsigned)e, magic_c);   // ceil(2^32 / 1) does not fit 32 bits
     const int c = e - r * C;
     const float* trow = rtile + r * ic;
     otile[r * oc + 4 + c] = PQ_MUL(trow[5 + c], trow[4]);

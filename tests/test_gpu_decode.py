@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from conftest import load_golden, rel_close
+from gpu_util import cuda
 from oracle import pqdet_oracle as po
 from oracle import loss_ref
 
@@ -149,3 +150,17 @@ def test_forward_from_features_equals_conv_then_decode():
     assert torch.equal(pred, head(raws))                       # same rows as Decode + concat of the raw heads
     conv = [torch.nn.functional.conv2d(f, w, b) for f, w, b in zip(feats, ws, bs)]     # PyTorch's own (TF32) conv
     assert torch.allclose(head(conv)[..., 4:], pred[..., 4:], rtol=0, atol=5e-3)
+
+
+@pytest.mark.parametrize("C", [1, 2, 3, 7])
+def test_recover_small_class_counts(C):
+    """The score pass maps element -> row by multiply-high with ceil(2^32 / C); C = 1 needs the special case."""
+    from pqdet_b200 import base_sample
+    rng = np.random.default_rng(C)
+    B, N = 3, 4032
+    pred = rng.uniform(0, 200, (B, N, 5 + C)).astype(np.float32)
+    pred[..., 4:] = rng.uniform(0, 1, (B, N, 1 + C)).astype(np.float32)
+    orig = np.array([[375., 500.], [480., 480.], [200., 333.]], np.float32)
+    for kind in ("voc", "visdrone"):
+        got = base_sample.RECOVER_BBOXES_REGISTER[kind](cuda(pred), (256, 256), cuda(orig)).cpu().numpy()
+        assert np.array_equal(got, po.recover(pred, (256, 256), orig, kind)), (C, kind)
