@@ -281,7 +281,8 @@ int pqdet_letterbox_normalize(const uint8_t* src, const void* images, int B, int
  *   x (B, Cin, H, W), weight (A*(5+C), Cin) [the conv's (O, Cin, 1, 1) weight], bias (A*(5+C)) or NULL
  *   out_decoded: rows [out_row_offset, +H*W*A) of a (B, out_rows_total, 5+C) prediction (may be NULL)
  *   out_raw    : (B, A*(5+C), H, W), what the convolution alone would produce (may be NULL)
- * TF32 products, fp32 accumulation - the precision PyTorch's own convolution runs at by default. */
+ * TF32 products (fp32 operands truncated to 10 mantissa bits), fp32 accumulation - the precision PyTorch's own
+ * convolution runs at by default; |error| <= 2^-9 * sum_c |x_c * w_c|. */
 int pqdet_head_conv_decode(const float* x, const float* weight, const float* bias, float* out_decoded,
                            float* out_raw, int B, int Cin, int H, int W, int A, int C, float stride,
                            int64_t out_rows_total, int64_t out_row_offset, int device, void* stream);

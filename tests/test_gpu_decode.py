@@ -116,7 +116,7 @@ def test_empty_batch_through_the_materialising_route():
                                                   (1, 80, 38, 38, 80, 8), (2, 30, 7, 9, 1, 16)])
 def test_head_conv_decode_tensor_cores(B, Cin, H, W, C, stride):
     """1x1 head convolution + Decode on tcgen05 (TF32 products, fp32 accumulation in TMEM).
-    raw vs an fp64 convolution within TF32 precision (2^-10 per operand; tolerance stated below); the decoded
+    raw vs an fp64 convolution within TF32 precision (operands truncated to 10 mantissa bits: up to 2^-10 each); the decoded
     output is bit-identical to Decode applied to the kernel's own raw output (same epilogue arithmetic)."""
     from pqdet_b200 import _ops
     g = torch.Generator(device="cuda").manual_seed(Cin + H)
@@ -127,8 +127,9 @@ def test_head_conv_decode_tensor_cores(B, Cin, H, W, C, stride):
     bias = torch.randn((ACH,), device="cuda", generator=g) * 0.1
     dec, raw = _ops.head_conv_decode(x, w, bias, C, stride, want_raw=True)
     ref = torch.einsum("bchw,oc->bohw", x.double(), w.view(ACH, Cin).double()) + bias.double().view(1, -1, 1, 1)
-    # |error| <= 2 * 2^-11 * sum_c |x_c * w_c| (both operands rounded to TF32) + fp32 accumulation noise
-    bound = 2.0 ** -10 * torch.einsum("bchw,oc->bohw", x.double().abs(), w.view(ACH, Cin).double().abs()) + 1e-5
+    # |error| <= 2 * 2^-10 * sum_c |x_c * w_c| (the tensor core truncates both operands to TF32; measured worst
+    # ratio 1.4e-3) + fp32 accumulation noise
+    bound = 2.0 ** -9 * torch.einsum("bchw,oc->bohw", x.double().abs(), w.view(ACH, Cin).double().abs()) + 1e-5
     assert bool(((raw.double() - ref).abs() <= bound).all())
     assert torch.equal(dec, _ops.decode_fwd(raw, C, stride))
     no_bias = _ops.head_conv_decode(x, w, None, C, stride, want_raw=True)[1]
