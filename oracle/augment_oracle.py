@@ -67,3 +67,17 @@ def normalize_to_chw(img_u8: np.ndarray, mean, std) -> np.ndarray:
     img = img_u8.astype(np.float32, copy=False)
     img = (img / 255. - mean) / std
     return np.transpose(img, (2, 0, 1)).astype(np.float32)
+
+
+def resize_ratio_pad(img: np.ndarray, ratio=(1.25, 1.25), pad_val: int = 128, divisor: int = 32):
+    """augment.ResizeRatio (dataset/augment.py:261-273) + augment.PadNearestDivisor (:275-298) without the bboxes."""
+    from math import ceil
+    target_h, target_w = [round(a * b) for a, b in zip(ratio, img.shape[:2])]
+    resized = resize_linear_u8(img, target_w, target_h)
+    img_h, img_w = resized.shape[:2]
+    th, tw = int(ceil(img_h / divisor) * divisor), int(ceil(img_w / divisor) * divisor)
+    dl = (tw - img_w) // 2
+    dr = tw - img_w - dl
+    du = (th - img_h) // 2
+    dd = th - img_h - du
+    return np.pad(resized, ((du, dd), (dl, dr), (0, 0)), 'constant', constant_values=pad_val), (du, dl)

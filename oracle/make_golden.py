@@ -223,6 +223,19 @@ def gen_letterbox(ref):
         d["resized%d" % i], d["rbb%d" % i], d["tensor%d" % i] = rimg, rbb, timg
     d["n"] = np.int64(len(shapes))
     d["target_hw"] = np.array([64, 96], np.int64)
+    # eval_augment_visdrone: ResizeRatio(1.25) -> PadNearestDivisor -> Normalize -> HWCtoCHW
+    rng = np.random.default_rng(22)
+    vshapes = [(37, 53), (100, 80), (51, 26)]
+    for i, (h, w) in enumerate(vshapes):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        bb = rng.uniform(0, min(h, w), (3, 4)).astype(np.float32)
+        r, rbb = raug.ResizeRatio(1.25)(img.copy(), bb.copy())
+        r, rbb = raug.PadNearestDivisor()(r, rbb)
+        nimg, _ = raug.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])(r, rbb)
+        timg, _ = raug.HWCtoCHW()(nimg, rbb)
+        d["vis_img%d" % i], d["vis_bb%d" % i] = img, bb
+        d["vis_padded%d" % i], d["vis_rbb%d" % i], d["vis_tensor%d" % i] = r, rbb, timg
+    d["vis_n"] = np.int64(len(vshapes))
     return d
 
 

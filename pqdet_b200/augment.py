@@ -57,7 +57,18 @@ def _staging(device, nbytes: int) -> np.ndarray:
     return st[0]
 
 
-def _pack(images: Sequence[np.ndarray], target_hw, stage=None):
+def ratio_pad_geometry(img_hw: Tuple[int, int], ratio=(1.25, 1.25), divisor: int = 32):
+    """dataset/augment.py:266-268 (ResizeRatio) + :281-289 (PadNearestDivisor) -> (resize_h, resize_w, canvas_h,
+    canvas_w, du, dl): the eval geometry of eval_augment_visdrone (dataset/visdrone_sample.py:76-82)."""
+    from math import ceil
+    img_h, img_w = img_hw
+    resize_h, resize_w = round(ratio[0] * img_h), round(ratio[1] * img_w)
+    canvas_h = int(ceil(resize_h / divisor) * divisor)
+    canvas_w = int(ceil(resize_w / divisor) * divisor)
+    return resize_h, resize_w, canvas_h, canvas_w, (canvas_h - resize_h) // 2, (canvas_w - resize_w) // 2
+
+
+def _pack(images: Sequence[np.ndarray], target_hw, stage=None, geometry=None):
     recs = np.zeros((len(images),), IMAGE_REC)
     off = 0
     geo = []
@@ -65,7 +76,7 @@ def _pack(images: Sequence[np.ndarray], target_hw, stage=None):
         if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
             raise TypeError("images must be uint8 HWC with 3 channels, got %s %s" % (im.dtype, im.shape))
         sh, sw = im.shape[:2]
-        ratio, dh, dw, du, dl = letterbox_geometry((sh, sw), target_hw)
+        ratio, dh, dw, du, dl = geometry[i] if geometry is not None else letterbox_geometry((sh, sw), target_hw)
         if dh < 1 or dw < 1:
             raise ValueError("image %d (%dx%d) vanishes at input size %s" % (i, sh, sw, target_hw))
         # cv::resize: inv_scale = dsize / ssize (double), scale = 1 / inv_scale
@@ -79,7 +90,7 @@ def _pack(images: Sequence[np.ndarray], target_hw, stage=None):
 
 
 def letterbox_normalize(images: Sequence[np.ndarray], input_size, mean=VOC_MEAN, std=VOC_STD, pad_val: int = 128,
-                        device="cuda", want_uint8: bool = False):
+                        device="cuda", want_uint8: bool = False, _geometry=None):
     """images: list of uint8 HWC arrays (any sizes).  input_size: int or (h, w).
     -> float32 tensor (B, 3, h, w) = ToTensor(Normalize(Resize(img))) of every image
        [, uint8 tensor (B, h, w, 3) = the padded resized images], geometry [(resize_ratio, du, dl)] per image."""
@@ -92,7 +103,7 @@ def letterbox_normalize(images: Sequence[np.ndarray], input_size, mean=VOC_MEAN,
         return (out, out_u8, []) if want_uint8 else (out, [])
     if device.type != "cuda":
         raise _lib.PqdetError("letterbox_normalize needs a CUDA device: pqdet_b200 has no CPU path")
-    packed, recs, geo = _pack(images, (th, tw), stage=lambda n: _staging(device, n))
+    packed, recs, geo = _pack(images, (th, tw), stage=lambda n: _staging(device, n), geometry=_geometry)
     stage = _STAGE[device][0]
     nsrc, nrec = packed.size, recs.nbytes
     rec_at = (nsrc + 7) & ~7                                   # records right behind the pixels, 8-byte aligned
@@ -112,6 +123,30 @@ def letterbox_normalize(images: Sequence[np.ndarray], input_size, mean=VOC_MEAN,
                                                      dev_index, ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
                "pqdet_letterbox_normalize")
     return (out, out_u8, geo) if want_uint8 else (out, geo)
+
+
+def resize_ratio_pad_normalize(images: Sequence[np.ndarray], ratio=1.25, divisor: int = 32, mean=VOC_MEAN, std=VOC_STD,
+                               pad_val: int = 128, device="cuda", want_uint8: bool = False):
+    """eval_augment_visdrone (dataset/visdrone_sample.py:76-82): ResizeRatio(ratio) -> PadNearestDivisor(pad_val,
+    divisor) -> Normalize -> ToTensor.  Every image gets its own canvas (its resized size rounded up to a multiple of
+    `divisor`); images that share a canvas size share a launch.
+    -> list of float32 tensors (3, H_i, W_i) [, list of uint8 (H_i, W_i, 3)], geometry [(ratio_h, ratio_w, du, dl)]."""
+    r = (ratio, ratio) if not isinstance(ratio, (tuple, list)) else tuple(ratio)
+    geos = [ratio_pad_geometry(im.shape[:2], r, divisor) for im in images]
+    outs, u8s = [None] * len(images), [None] * len(images)
+    groups = {}
+    for i, g in enumerate(geos):
+        groups.setdefault((g[2], g[3]), []).append(i)
+    for (ch, cw), idx in groups.items():
+        geometry = [(None, geos[i][0], geos[i][1], geos[i][4], geos[i][5]) for i in idx]
+        res = letterbox_normalize([images[i] for i in idx], (ch, cw), mean, std, pad_val, device, want_uint8,
+                                  _geometry=geometry)
+        for j, i in enumerate(idx):
+            outs[i] = res[0][j]
+            if want_uint8:
+                u8s[i] = res[1][j]
+    info = [(r[0], r[1], g[4], g[5]) for g in geos]
+    return (outs, u8s, info) if want_uint8 else (outs, info)
 
 
 class Resize:

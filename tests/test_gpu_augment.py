@@ -50,3 +50,26 @@ def test_letterbox_edge_cases():
     one = np.full((1, 1, 3), 200, np.uint8)                                    # a single pixel blown up to 64x64
     out, u8, _ = pa.letterbox_normalize([one], 64, want_uint8=True)
     assert bool((u8 == 200).all())
+
+
+def test_visdrone_resize_ratio_pad_golden_and_oracle():
+    """eval_augment_visdrone: ResizeRatio(1.25) -> PadNearestDivisor(128, 32) -> Normalize -> ToTensor; every image has
+    its own canvas."""
+    from pqdet_b200 import augment as pa
+    g = load_golden("letterbox")
+    imgs = [g["vis_img%d" % i] for i in range(int(g["vis_n"]))]
+    outs, u8s, info = pa.resize_ratio_pad_normalize(imgs, want_uint8=True)
+    for i in range(len(imgs)):
+        assert np.array_equal(u8s[i].cpu().numpy(), g["vis_padded%d" % i]), i
+        assert np.array_equal(outs[i].cpu().numpy(), g["vis_tensor%d" % i]), i
+        bb = g["vis_bb%d" % i].copy()                                  # augment.py:270-272, 295-297
+        bb[:, [0, 2]] *= info[i][1]; bb[:, [1, 3]] *= info[i][0]
+        bb[:, [0, 2]] += info[i][3]; bb[:, [1, 3]] += info[i][2]
+        assert np.array_equal(bb, g["vis_rbb%d" % i])
+    rng = np.random.default_rng(9)
+    big = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((540, 960), (540, 960), (765, 1360), (101, 77))]
+    outs, u8s, _ = pa.resize_ratio_pad_normalize(big, want_uint8=True)
+    for k, im in enumerate(big):
+        padded, _ = ao.resize_ratio_pad(im)
+        assert np.array_equal(u8s[k].cpu().numpy(), padded), im.shape
+        assert np.array_equal(outs[k].cpu().numpy(), ao.normalize_to_chw(padded, pa.VOC_MEAN, pa.VOC_STD))
