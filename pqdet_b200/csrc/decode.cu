@@ -28,27 +28,48 @@ __device__ __forceinline__ void decode_tile(const float* __restrict__ raw, float
   const int cy = cell / W, cx = cell - cy * W;
   const float* src = raw + (size_t)b * ACH * HW + cell;
   float* tcol = tile + lane * ST;
-  // The kernel is issue bound before it is HBM bound (ncu: 81 % of the issue slots at 2.3 TB/s), so the loop
-  // carries the channel-within-anchor index along instead of dividing, and 1/(1+e) uses the correctly rounded
-  // reciprocal (bit-identical to the IEEE division of sigmoidf_, fewer instructions).
+  // The kernel is issue bound before it is HBM bound, so the per-element bookkeeping is kept to an increment: every
+  // warp owns a contiguous run of channels (the channel-within-anchor index k walks with a wrap, no division), four
+  // channels per iteration with their loads issued together and their exp / reciprocal chains interleaved
+  // (rcp_rn_core = __frcp_rn without its per-call range check; out-of-range values redo the group with __frcp_rn,
+  // so the result is bit-identical to sigmoidf_ / decode_coord).
   constexpr int W8 = kDecodeThreads / 32;
   if (lane < ncell) {
-    int k = warp_id() % ch;
-    const float* p = src + (size_t)warp_id() * HW;        // walking pointers: no per-element 64-bit multiplies
-    float* t = tcol + warp_id();
-    const size_t pstep = (size_t)W8 * HW;
+    const int cpw = (ACH + W8 - 1) / W8;                  // channels per warp
+    const int c_lo = warp_id() * cpw, c_hi = min(ACH, c_lo + cpw);
+    int k = c_lo % ch;
+    const float* p = src + (size_t)c_lo * HW;
+    float* t = tcol + c_lo;
     const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
-    for (int c = warp_id(); c < ACH; c += W8, p += pstep, t += W8) {
-      const float v = ldg_stream(p);
-      if (k < 4) {
-        const float e = expf(v);
-        const float g = (k & 1) ? gy : gx;
-        *t = PQ_MUL((k < 2) ? PQ_SUB(g, e) : PQ_ADD(g, e), stride);      // == decode_coord(k, v, cx, cy, stride)
-      } else {
-        *t = __frcp_rn(PQ_ADD(1.0f, expf(-v)));                          // == sigmoidf_(v)
+    constexpr int U = 4;
+    for (int c = c_lo; c < c_hi; c += U, p += (size_t)U * HW, t += U) {
+      float v[U], e[U], rr[U];
+      int kk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        kk[u] = k;
+        if (++k == ch) k = 0;
+        v[u] = (c + u < c_hi) ? ldg_stream(p + (size_t)u * HW) : 0.0f;
       }
-      k += W8;
-      while (k >= ch) k -= ch;
+#pragma unroll
+      for (int u = 0; u < U; ++u) e[u] = expf(kk[u] < 4 ? v[u] : -v[u]);
+      bool slow = false;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float x = PQ_ADD(1.0f, e[u]);
+        rr[u] = rcp_rn_core(x);
+        slow |= (kk[u] >= 4) && !(x < kRcpCoreMax);
+      }
+      if (slow) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) rr[u] = __frcp_rn(PQ_ADD(1.0f, e[u]));               // == sigmoidf_(v)
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float g = (kk[u] & 1) ? gy : gx;
+        const float oc = PQ_MUL((kk[u] < 2) ? PQ_SUB(g, e[u]) : PQ_ADD(g, e[u]), stride);   // == decode_coord(k, v, cx, cy, stride)
+        if (c + u < c_hi) t[u] = kk[u] < 4 ? oc : rr[u];
+      }
     }
   }
   __syncthreads();

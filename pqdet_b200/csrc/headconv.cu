@@ -12,6 +12,16 @@
 // One tcgen05.mma consumes K = 8 tf32 values; the K loop runs in chunks of 32 channels through two smem stages: the
 // MMAs of a chunk (committed to that stage's mbarrier) run while the other stage is being filled.  The epilogue
 // tile reuses the stages; all 8 warps read the accumulator (warps w and w+4 share TMEM lane quadrant w%4).
+//
+// Two kernels.  `head_conv_decode_ws_kernel` (the fast path: H*W a multiple of 128, weights fit in shared memory) is
+// persistent and warp specialised: one CTA per SM keeps the whole weight matrix resident in shared memory, warp 0
+// streams X tiles with TMA tensor-map loads (the NCHW planes are MN-major for this GEMM; tf32 takes an MN-major
+// operand only in the "128-byte swizzle, 32-byte atom" layout = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, UMMA layout
+// type 1) through an mbarrier ring, warp 1 issues the MMAs into one of two TMEM accumulators, and 4*wq epilogue warps
+// decode the other accumulator and hand the finished (128 cells x A x (5+C)) tile - one contiguous run of the output -
+// to a TMA bulk store.  `head_conv_decode_kernel` is the general kernel (any shape; cp.async staging).
+#include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pq_common.cuh"
@@ -40,6 +50,20 @@ __device__ __forceinline__ uint64_t hc_smem_desc(uint32_t smem_addr, uint32_t lb
   // base offset 0, layout type [61,64) = 0 (no swizzle); addresses and offsets in 16-byte units
   return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(lbo_units & 0x3fffu) << 16) |
          ((uint64_t)(sbo_units & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// One tf32 MMA, descriptors passed as 32-bit halves: only the low word (start address, LBO) changes between the MMAs
+// of a tile, so the issue loop is one add per operand.  (Measured, profiles/tools/umma_rate_probe.cu: rebuilding the
+// 64-bit descriptors per MMA costs ~190 cycles of dependent uniform-datapath arithmetic, 4x the MMA itself.)
+__device__ __forceinline__ void hc_mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __global__ void __launch_bounds__(kHcThreads)
@@ -132,16 +156,14 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a0 = smem_u32(hsm + (size_t)st * stage_bytes), b0 = a0 + (uint32_t)a_bytes;
+      const uint64_t da = hc_smem_desc(a0, (uint32_t)kHcM, 8u), db = hc_smem_desc(b0, (uint32_t)N, 8u);
+      uint32_t a_lo = (uint32_t)da, b_lo = (uint32_t)db;
+      const uint32_t a_hi = (uint32_t)(da >> 32), b_hi = (uint32_t)(db >> 32);
 #pragma unroll
       for (int kb = 0; kb < kHcKC / 8; ++kb) {
-        const uint64_t da = hc_smem_desc(a0 + (uint32_t)(2 * kb) * (uint32_t)kHcM * 16u, (uint32_t)kHcM, 8u);
-        const uint64_t db = hc_smem_desc(b0 + (uint32_t)(2 * kb) * (uint32_t)N * 16u, (uint32_t)N, 8u);
-        const uint32_t accumulate = (i > 0 || kb > 0) ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+        hc_mma_tf32(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, (i > 0 || kb > 0) ? 1u : 0u);
+        a_lo += 2u * (uint32_t)kHcM;       // two 16-byte units of K further, in 16-byte address units
+        b_lo += 2u * (uint32_t)N;
       }
       // the commit makes the mbarrier track completion of everything issued so far (and implies the
       // before_thread_sync fence)
@@ -224,7 +246,391 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised fast path
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWsMaxStages = 12;
+
+struct HeadConvWsParams {
+  const float* w;
+  const float* bias;
+  float* out_dec;
+  float* out_raw;
+  int B, Cin, HW, Wd, A, C;
+  int N;               // A*(5+C) rounded up to 16
+  int KC;              // channels per stage: 32, 16 or 8 (divides Cin)
+  int stages;
+  int wq;              // epilogue warps per TMEM lane quadrant
+  int tile_bufs;       // 1 or 2 staging tiles for the output
+  int buf_cols;        // TMEM column stride between the two accumulators
+  int tiles_per_img, ntiles;
+  float stride;
+  int64_t rows_total, row_off;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// One lane of a converged warp; the surrounding loop stays warp-uniform so that descriptors and addresses live in
+// uniform registers (a loop run by `lane == 0` alone pays register -> uniform-register moves in front of every MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+template <bool WANT_RAW>
+__global__ void __launch_bounds__(768, 1)
+head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __grid_constant__ CUtensorMap tmap_x) {
+  extern __shared__ __align__(1024) unsigned char hsm_ws[];
+  __shared__ __align__(8) uint64_t full_bar[kWsMaxStages], empty_bar[kWsMaxStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const int ACH = P.A * (5 + P.C), ch = 5 + P.C, N = P.N, KC = P.KC, S = P.stages;
+  const int nchunk = P.Cin / KC;
+  const uint32_t stage_bytes = (uint32_t)KC * 512u;
+  // dynamic smem: [X ring, 1024-byte aligned][W: Cin/4 x N units][1 or 2 output tiles: 128 x ACH floats][bias]
+  const uint32_t base = (smem_u32(hsm_ws) + 1023u) & ~1023u;
+  unsigned char* aligned = hsm_ws + (base - smem_u32(hsm_ws));
+  const uint32_t sX = base;
+  const uint32_t sW = base + (uint32_t)S * stage_bytes;
+  float* tile0 = reinterpret_cast<float*>(aligned + (size_t)S * stage_bytes + (size_t)P.Cin * N * 4);
+  float* sbias = tile0 + P.tile_bufs * kHcM * ACH;          // N + 8 floats, zero beyond ACH or without a bias
+  const int n_epi = 4 * P.wq * 32;
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(2 * P.buf_cols)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 4 * P.wq);
+    mbar_init(&acc_empty[1], 4 * P.wq);
+    mbar_init_fence();
+  }
+  // the weights stay resident: K-major, unit(n, j = k/4) at j*N + n, rows n >= ACH zero
+  for (int u = tid; u < (P.Cin / 4) * N; u += blockDim.x) {
+    const int j = u / N, n = u - j * N;
+    const bool ok = n < ACH;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;"
+                 ::"r"(sW + (uint32_t)u * 16u), "l"(ok ? P.w + (size_t)n * P.Cin + 4 * j : P.w), "r"(ok ? 16u : 0u)
+                 : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int c = tid; c < N + 8; c += blockDim.x) sbias[c] = (P.bias && c < ACH) ? P.bias[c] : 0.0f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  fence_async_smem();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ---- producer: one thread keeps the ring full -------------------------------------------------------------
+    {
+      uint32_t s = 0, ph = 0;
+      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+        const int b = t / P.tiles_per_img, cell0 = (t - b * P.tiles_per_img) * kHcM;
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[s], stage_bytes);
+            const uint32_t dst = sX + s * stage_bytes;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              tma_load_2d(dst + (uint32_t)g * (uint32_t)KC * 128u, &tmap_x, cell0 + 32 * g, b * P.Cin + c * KC, &full_bar[s]);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (warp-uniform loop, one elected lane issues) --------------------------------------------------
+    {
+      // D = F32, A = B = TF32, A MN-major (bit 15), B K-major, N, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) |
+                             ((uint32_t)(kHcM >> 4) << 24);
+      // A: SW128 with 32-byte atoms (layout type 1): rows of 128 bytes, 4-row atoms 512 bytes apart (SBO 32 units),
+      // 32-cell groups KC*128 bytes apart (LBO); one K step (8 rows) = 1024 bytes = 64 units
+      const uint64_t da0 = (uint64_t)((sX >> 4) & 0x3fffu) | ((uint64_t)(((uint32_t)KC * 8u) & 0x3fffu) << 16) |
+                           ((uint64_t)32u << 32) | (1ull << 46) | (1ull << 61);
+      const uint64_t db0 = hc_smem_desc(sW, (uint32_t)N, 8u);
+      const uint32_t a_hi = (uint32_t)(da0 >> 32), b_hi = (uint32_t)(db0 >> 32);
+      const uint32_t stage_units = stage_bytes >> 4;
+      const int kpc = KC / 8;
+      uint32_t s = 0, ph = 0, a_stage = (uint32_t)da0, tl = 0;
+      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1u;
+        mbar_wait(&acc_empty[buf], ((tl >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)P.buf_cols;
+        uint32_t b_lo = (uint32_t)db0, accumulate = 0;
+        for (int c = 0; c < nchunk; ++c) {
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            uint32_t a_lo = a_stage, bb = b_lo, acc = accumulate;
+            for (int kb = 0; kb < kpc; ++kb) {
+              hc_mma_tf32(d_tmem, a_lo, a_hi, bb, b_hi, idesc, acc);
+              acc = 1;
+              a_lo += 64u;
+              bb += 2u * (uint32_t)N;
+            }
+            // frees the stage once the MMAs that read it are done
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         ::"r"(smem_u32(&empty_bar[s])) : "memory");
+          }
+          __syncwarp();
+          accumulate = 1;
+          b_lo += 2u * (uint32_t)N * (uint32_t)kpc;
+          a_stage += stage_units;
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1u; a_stage = (uint32_t)da0; }
+        }
+        if (elect_one())
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                       ::"r"(smem_u32(&acc_full[buf])) : "memory");
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: warp%4 = TMEM lane quadrant; the wq warps of a quadrant take the 8-column blocks round robin ----
+    const int q = warp & 3, jq = (warp - 4) >> 2;
+    const int etid = tid - 128;
+    const int r = q * 32 + lane;
+    const int nblk = (ACH + 7) / 8;
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++tl) {
+      const uint32_t buf = tl & 1u;
+      const int b = t / P.tiles_per_img, cell0 = (t - b * P.tiles_per_img) * kHcM;
+      const int cell = cell0 + r;
+      const int cy = cell / P.Wd, cx = cell - cy * P.Wd;
+      const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
+      mbar_wait(&acc_full[buf], (tl >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // the bulk store that last used this staging tile must have read it before it is overwritten
+      float* tile = tile0 + (P.tile_bufs == 2 ? (int)buf * kHcM * ACH : 0);
+      if (etid == 0) {
+        if (P.tile_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+      }
+      epi_bar_sync(n_epi);
+      for (int blk = jq; blk < nblk; blk += P.wq) {
+        const int c0 = blk * 8;
+        uint32_t v[8];
+        const uint32_t taddr = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int k0 = c0 % ch;
+        const float* bs = sbias + c0;
+        float* trow = tile + r * ACH + c0;
+        float raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), bs[i]);       // bias 0 where there is none
+        if (WANT_RAW) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (c0 + i < ACH) P.out_raw[((size_t)b * ACH + c0 + i) * P.HW + cell] = raw[i];
+        }
+        // 1 / (1 + e) through rcp_rn_core (pq_math.cuh) so that the 8 chains interleave instead of being serialised
+        // by __frcp_rn's per-call range check; x >= 2^126 (raw < -87: a denormal sigmoid) and NaN redo the block
+        // with __frcp_rn itself.
+        float e[8], rr[8];
+        bool slow = false;
+        if (k0 >= 4 && k0 + 8 <= ch && c0 + 8 <= ACH) {
+          // the common block: 8 objectness / class columns of one anchor -> 8 independent sigmoid chains
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = PQ_ADD(1.0f, expf(-raw[i]));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rr[i] = rcp_rn_core(e[i]);
+            slow |= !(e[i] < kRcpCoreMax);
+          }
+          if (slow) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr[i] = __frcp_rn(e[i]);                          // sigmoidf_
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) trow[i] = rr[i];
+        } else {
+          // a block that straddles the box channels of an anchor (or the padding): same chains, the kind of each
+          // column selected at the end
+          int kk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { int k = k0 + i; if (k >= ch) k -= ch; kk[i] = k; }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = expf(kk[i] < 4 ? raw[i] : -raw[i]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x = PQ_ADD(1.0f, e[i]);
+            rr[i] = rcp_rn_core(x);
+            slow |= (kk[i] >= 4) && !(x < kRcpCoreMax);
+          }
+          if (slow) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr[i] = __frcp_rn(PQ_ADD(1.0f, e[i]));           // sigmoidf_
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float g = (kk[i] & 1) ? gy : gx;
+            const float oc = PQ_MUL((kk[i] < 2) ? PQ_SUB(g, e[i]) : PQ_ADD(g, e[i]), P.stride);   // decode_coord
+            if (c0 + i < ACH) trow[i] = kk[i] < 4 ? oc : rr[i];
+          }
+        }
+      }
+      // this warp no longer needs the accumulator: the MMA warp may start the tile after next in it
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (P.out_dec) {
+        fence_async_smem();
+        epi_bar_sync(n_epi);
+        if (etid == 0) {
+          float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch;
+          tma_store_1d(dst, tile, (uint32_t)(kHcM * ACH * sizeof(float)));
+          tma_store_commit();
+        }
+      }
+    }
+    if (etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * P.buf_cols)) : "memory");
+  }
+}
+
 }  // namespace pq
+
+namespace {
+
+typedef CUresult (*PqEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PqEncodeTiledFn encode_tiled_fn() {
+  static PqEncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (PqEncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// Launches the persistent kernel when the shape qualifies; returns 1 if it did, 0 if the general kernel must run,
+// < 0 on error.
+int try_head_conv_ws(const float* x, const float* weight, const float* bias, float* out_decoded, float* out_raw,
+                     int B, int Cin, int H, int W, int A, int C, float stride, int64_t rows_total, int64_t row_off,
+                     int device, cudaStream_t stream) {
+  using namespace pq;
+  const int HW = H * W, ACH = A * (5 + C), N = (ACH + 15) / 16 * 16;
+  if (HW % kHcM != 0 || Cin % 8 != 0 || N > 256) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15)) return 0;
+  if (out_decoded) {
+    const size_t img_bytes = (size_t)rows_total * (5 + C) * 4, off_bytes = (size_t)row_off * (5 + C) * 4;
+    if ((reinterpret_cast<uintptr_t>(out_decoded) & 15) || (img_bytes & 15) || (off_bytes & 15)) return 0;
+  }
+  if ((int64_t)B * Cin > 0x7fffffff || (int64_t)B * (HW / kHcM) > 0x7fffffff) return 0;
+  PqEncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return 0;
+  HeadConvWsParams P;
+  memset(&P, 0, sizeof(P));
+  const size_t w_bytes = (size_t)Cin * N * 4, tile_bytes = (size_t)kHcM * ACH * 4, bias_bytes = (size_t)(N + 8) * 4;
+  int max_smem = 0;
+  PQ_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  // Stage = KC channels x 128 cells.  Every stage costs the MMA warp a fixed ~400 cycles of waits / fences / commit
+  // (measured), so stages are as large as the budget allows: KC = the largest multiple of 8 that divides Cin with
+  // at least 3 stages (>= 48 KB in flight) in what the resident weights and the output staging leave; two output
+  // staging tiles (the decode of tile i+1 overlaps the bulk store of tile i) when that still holds.
+  auto plan = [&](int bufs, int min_kc, int* kc_out, int* st_out) {
+    const size_t fixed = 1024 + w_bytes + (size_t)bufs * tile_bytes + bias_bytes + 1024;   // alignment slack + static
+    if (fixed >= (size_t)max_smem) return false;
+    const size_t room = (size_t)max_smem - fixed;
+    for (int kc = Cin > 256 ? 256 : Cin; kc >= min_kc; --kc) {
+      if (kc % 8 || Cin % kc) continue;
+      const size_t sb = (size_t)kc * 512;
+      size_t st = room / sb;
+      if (st > (size_t)kWsMaxStages) st = kWsMaxStages;
+      if (st >= 3 && st * sb >= 48 * 1024) {
+        while (st > 3 && (st - 1) * sb >= 128 * 1024) --st;
+        *kc_out = kc; *st_out = (int)st;
+        return true;
+      }
+    }
+    return false;
+  };
+  // preference: large stages (>= 48 channels keep the MMA warp ahead of HBM) with two staging tiles, large stages
+  // with one, then whatever fits
+  P.tile_bufs = 2;
+  if (!plan(2, 48, &P.KC, &P.stages)) {
+    P.tile_bufs = 1;
+    if (!plan(1, 48, &P.KC, &P.stages)) {
+      P.tile_bufs = 2;
+      if (!plan(2, 8, &P.KC, &P.stages)) {
+        P.tile_bufs = 1;
+        if (!plan(1, 8, &P.KC, &P.stages)) return 0;
+      }
+    }
+  }
+  const size_t stage_bytes = (size_t)P.KC * 512;
+  const int nblk = (ACH + 7) / 8;
+  int best = 1, waste = 1 << 30;
+  for (int wq = 5; wq >= 1; --wq) {
+    const int per = (nblk + wq - 1) / wq, w_ = per * wq - nblk;
+    if (per >= 1 && wq <= nblk && w_ < waste) { waste = w_; best = wq; }
+  }
+  P.wq = best;
+  P.w = weight; P.bias = bias; P.out_dec = out_decoded; P.out_raw = out_raw;
+  P.B = B; P.Cin = Cin; P.HW = HW; P.Wd = W; P.A = A; P.C = C; P.N = N;
+  P.buf_cols = 32;
+  while (P.buf_cols < N) P.buf_cols <<= 1;
+  P.tiles_per_img = HW / kHcM;
+  P.ntiles = B * P.tiles_per_img;
+  P.stride = stride; P.rows_total = rows_total; P.row_off = row_off;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)B * Cin}, strides[1] = {(cuuint64_t)HW * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)P.KC}, estr[2] = {1u, 1u};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 0;
+  int sms = 0;
+  PQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const size_t smem = 1024 + (size_t)P.stages * stage_bytes + w_bytes + (size_t)P.tile_bufs * tile_bytes + bias_bytes;
+  const int grid = P.ntiles < sms ? P.ntiles : sms;
+  if (out_raw) {
+    PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_conv_decode_ws_kernel<true><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
+  } else {
+    PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_conv_decode_ws_kernel<false><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
+  }
+  PQ_LAUNCH_CHECK();
+  return 1;
+}
+
+}  // namespace
 
 extern "C" int pqdet_head_conv_decode(const float* x, const float* weight, const float* bias, float* out_decoded,
                                       float* out_raw, int B, int Cin, int H, int W, int A, int C, float stride,
@@ -246,6 +652,11 @@ extern "C" int pqdet_head_conv_decode(const float* x, const float* weight, const
   while (P.tmem_cols < P.N) P.tmem_cols <<= 1;
   P.stride = stride; P.rows_total = out_rows_total; P.row_off = out_row_offset;
   PQ_ENTER(device);
+  if (!getenv("PQDET_HEADCONV_GENERAL")) {
+    const int rc = try_head_conv_ws(x, weight, bias, out_decoded, out_raw, B, Cin, H, W, A, C, stride, out_rows_total,
+                                    out_row_offset, device, (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : PQDET_OK;
+  }
   const size_t stages = 2 * ((size_t)(kHcKC / 4) * kHcM * 16 + (size_t)(kHcKC / 4) * P.N * 16);
   const size_t tile_bytes = (size_t)kHcM * (ACH | 1) * sizeof(float);
   const size_t smem = stages > tile_bytes ? stages : tile_bytes;

@@ -38,11 +38,17 @@ def main():
             raws = [torch.nn.functional.conv2d(f, w, b) for f, w, b in zip(feats, ws, bs)]
             t_dec = ev(lambda: head(raws))
             t_fused = ev(lambda: head.forward_from_features(feats, ws, bs))
+            per_level = [ev(lambda f=f, w=w, b=b, s=s: _ops.head_conv_decode(f, w, b, C, s)) for f, w, b, s in zip(feats, ws, bs, STRIDES)]
+            os.environ["PQDET_HEADCONV_GENERAL"] = "1"
+            t_general = ev(lambda: head.forward_from_features(feats, ws, bs))
+            del os.environ["PQDET_HEADCONV_GENERAL"]
         x_bytes = sum(f.numel() for f in feats) * 4
         o_bytes = sum(r.numel() for r in raws) * 4
         print("B=%d: torch conv2d x3 %.1f us + decode %.1f us = %.1f us | fused tcgen05 conv+decode %.1f us "
               "(%.0f GB/s of X read + decoded write; %.2fx)" % (B, t_conv * 1e3, t_dec * 1e3, (t_conv + t_dec) * 1e3,
               t_fused * 1e3, (x_bytes + o_bytes) / t_fused / 1e6, (t_conv + t_dec) / t_fused))
+        print("      persistent kernel per level (stride 32/16/8): %s us; general kernel (cp.async staging) all levels %.1f us"
+              % (" / ".join("%.1f" % (t * 1e3) for t in per_level), t_general * 1e3))
 
 
 if __name__ == "__main__":

@@ -113,7 +113,8 @@ def test_empty_batch_through_the_materialising_route():
 
 
 @pytest.mark.parametrize("B,Cin,H,W,C,stride", [(2, 80, 64, 64, 20, 8), (3, 352, 16, 16, 20, 32), (2, 176, 19, 19, 10, 16),
-                                                  (1, 80, 38, 38, 80, 8), (2, 30, 7, 9, 1, 16)])
+                                                  (1, 80, 38, 38, 80, 8), (2, 30, 7, 9, 1, 16),
+                                                  (9, 176, 64, 64, 20, 8), (5, 40, 32, 32, 10, 16), (2, 96, 16, 24, 3, 16)])
 def test_head_conv_decode_tensor_cores(B, Cin, H, W, C, stride):
     """1x1 head convolution + Decode on tcgen05 (TF32 products, fp32 accumulation in TMEM).
     raw vs an fp64 convolution within TF32 precision (operands truncated to 10 mantissa bits: up to 2^-10 each); the decoded
@@ -134,6 +135,55 @@ def test_head_conv_decode_tensor_cores(B, Cin, H, W, C, stride):
     assert torch.equal(dec, _ops.decode_fwd(raw, C, stride))
     no_bias = _ops.head_conv_decode(x, w, None, C, stride, want_raw=True)[1]
     assert torch.allclose(no_bias + bias.view(1, -1, 1, 1), raw, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,Cin,H,W,C", [(3, 352, 16, 16, 20), (7, 176, 32, 32, 20), (40, 80, 64, 64, 20), (2, 48, 16, 16, 10)])
+def test_head_conv_persistent_kernel_equals_general_kernel(B, Cin, H, W, C, monkeypatch):
+    """H*W a multiple of 128 takes the persistent warp-specialised kernel (TMA ring, resident weights, two TMEM
+    accumulators); PQDET_HEADCONV_GENERAL forces the general kernel.  Same K order of the same tf32 MMAs: identical
+    raw heads and decoded rows; more tiles than SMs (40 x 32) exercises the ring / accumulator phases."""
+    from pqdet_b200 import _ops
+    g = torch.Generator(device="cuda").manual_seed(B + Cin)
+    ACH = 3 * (5 + C)
+    x = torch.randn((B, Cin, H, W), device="cuda", generator=g)
+    w = torch.randn((ACH, Cin, 1, 1), device="cuda", generator=g) * 0.05
+    bias = torch.randn((ACH,), device="cuda", generator=g) * 0.1
+    dec, raw = _ops.head_conv_decode(x, w, bias, C, 8.0, want_raw=True)
+    dec_only = _ops.head_conv_decode(x, w, bias, C, 8.0)
+    dec_only = dec_only[0] if isinstance(dec_only, tuple) else dec_only
+    monkeypatch.setenv("PQDET_HEADCONV_GENERAL", "1")
+    dec_g, raw_g = _ops.head_conv_decode(x, w, bias, C, 8.0, want_raw=True)
+    torch.cuda.synchronize()
+    assert torch.equal(raw, raw_g)
+    assert torch.equal(dec, dec_g) and torch.equal(dec_only, dec_g)
+
+
+def test_sigmoid_reciprocal_out_of_range_logits(monkeypatch):
+    """The decode kernels interleave several 1/(1+e) chains with the range check of __frcp_rn hoisted out
+    (pq_math.cuh rcp_rn_core); logits below -87 (1+e >= 2^126: denormal / zero sigmoid), +-inf-producing values and
+    NaN must take the checked path and give exactly what the plain __frcp_rn formulation (general head conv
+    kernel) gives."""
+    from pqdet_b200 import _ops
+    C, Cin, H, W = 20, 16, 16, 16
+    ACH = 3 * (5 + C)
+    vals = torch.tensor([-104.0, -100.0, -95.0, -88.8, -88.0, -87.4, -87.3, -87.0, -50.0, -1.0, 0.0, 3.0, 50.0, 88.0, 89.0,
+                         100.0, float("nan"), float("inf"), float("-inf")], device="cuda")
+    bias = vals[torch.arange(ACH, device="cuda") % vals.numel()].contiguous()
+    x = torch.randn((2, Cin, H, W), device="cuda")
+    w = torch.zeros((ACH, Cin, 1, 1), device="cuda")
+    dec_ws, raw_ws = _ops.head_conv_decode(x, w, bias, C, 8.0, want_raw=True)
+    assert torch.equal(raw_ws.nan_to_num(7.0), bias.view(1, -1, 1, 1).expand_as(raw_ws).nan_to_num(7.0))
+    dec_mat = _ops.decode_fwd(raw_ws, C, 8.0)                        # materialising decode kernel, 4 chains interleaved
+    monkeypatch.setenv("PQDET_HEADCONV_GENERAL", "1")
+    dec_gen = _ops.head_conv_decode(x, w, bias, C, 8.0)               # plain __frcp_rn per element
+    torch.cuda.synchronize()
+    for got in (dec_ws, dec_mat):
+        assert torch.equal(got.view(torch.int32), dec_gen.view(torch.int32))     # bit patterns, NaN included
+    sig = dec_gen.view(2, H, W, 3, 5 + C)[0, 0, 0].reshape(-1)
+    ref = 1.0 / (1.0 + torch.exp(-bias.double()))
+    keep = (torch.arange(ACH, device="cuda") % (5 + C)) >= 4
+    ok = torch.isfinite(ref) & keep
+    assert torch.allclose(sig[ok].double(), ref[ok], rtol=1e-5, atol=1e-37)
 
 
 def test_forward_from_features_equals_conv_then_decode():
