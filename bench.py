@@ -583,29 +583,33 @@ def bench_other_configs(device, peak):
     except Exception as e:
         out["eval_preprocess"] = {"error": repr(e)}
 
-    # ---- head 1x1 convolution + decode on the tensor cores, regnetx-600m-fpn VOC shapes, bs=64
+    # ---- head 1x1 convolution + decode on the tensor cores, regnetx-600m-fpn VOC shapes
     try:
         cins = (352, 176, 80)
-        nB = 64
-        feats = [torch.randn((nB, c, SIZE // s, SIZE // s), device=device) for c, s in zip(cins, STRIDES)]
         ws = [torch.randn((75, c, 1, 1), device=device) * 0.03 for c in cins]
         bs = [torch.randn((75,), device=device) * 0.1 for _ in cins]
         headF = DetectionHead([dict(classes=C_VOC, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05)
                                for s in STRIDES])
-        with torch.no_grad():
-            def stock():
-                return headF([torch.nn.functional.conv2d(f, w, b) for f, w, b in zip(feats, ws, bs)])
-            stock(); headF.forward_from_features(feats, ws, bs)
-            t_stock = float(np.median([time_steps(stock, 1)[0] for _ in range(10)]))
-            t_fused = float(np.median([time_steps(lambda: headF.forward_from_features(feats, ws, bs), 1)[0] for _ in range(10)]))
-        xb = sum(f.numel() for f in feats) * 4
-        ob = nB * cells(SIZE) * 3 * (5 + C_VOC) * 4
-        out["head_conv_decode"] = {
-            "workload": "1x1 head conv (Cin 352/176/80 -> 75) + decode, VOC 512x512 bs=64, TF32 tensor cores",
-            "fused_tcgen05_images_per_s": nB / (t_fused * 1e-3), "fused_ms": t_fused,
-            "torch_conv2d_plus_our_decode_images_per_s": nB / (t_stock * 1e-3), "torch_conv2d_plus_our_decode_ms": t_stock,
-            "fused_gbs_features_read_plus_decoded_write": (xb + ob) / (t_fused * 1e-3) / 1e9}
-        del feats
+        entry = {"workload": "1x1 head conv (Cin 352/176/80 -> 75) + decode, VOC 512x512, TF32 tensor cores",
+                 "kernel": "head_conv_decode_ws_kernel: persistent, warp specialised (TMA ring of MN-major X tiles, resident "
+                           "weights, tcgen05.mma kind::tf32 into two TMEM accumulators, decode epilogue, bulk store)"}
+        for nB in (64, 256):
+            feats = [torch.randn((nB, c, SIZE // s, SIZE // s), device=device) for c, s in zip(cins, STRIDES)]
+            with torch.no_grad():
+                def stock():
+                    return headF([torch.nn.functional.conv2d(f, w, b) for f, w, b in zip(feats, ws, bs)])
+                stock(); headF.forward_from_features(feats, ws, bs)
+                t_stock = float(np.median([time_steps(stock, 1)[0] for _ in range(10)]))
+                t_fused = float(np.median([time_steps(lambda: headF.forward_from_features(feats, ws, bs), 1)[0] for _ in range(10)]))
+            xb = sum(f.numel() for f in feats) * 4
+            ob = nB * cells(SIZE) * 3 * (5 + C_VOC) * 4
+            entry["bs%d" % nB] = {
+                "fused_tcgen05_images_per_s": nB / (t_fused * 1e-3), "fused_ms": t_fused,
+                "torch_conv2d_plus_our_decode_images_per_s": nB / (t_stock * 1e-3), "torch_conv2d_plus_our_decode_ms": t_stock,
+                "fused_gbs_features_read_plus_decoded_write": (xb + ob) / (t_fused * 1e-3) / 1e9,
+                "frac_of_hbm_peak": (xb + ob) / (t_fused * 1e-3) / 1e9 / measured_peak()[0]}
+            del feats
+        out["head_conv_decode"] = entry
     except Exception as e:
         out["head_conv_decode"] = {"error": repr(e)}
 
