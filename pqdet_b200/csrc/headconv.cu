@@ -472,7 +472,12 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
           // column selected at the end
           int kk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { int k = k0 + i; if (k >= ch) k -= ch; kk[i] = k; }
+          for (int i = 0; i < 8; ++i) {            // 5 + C >= 5, so k0 + i < 3 * (5 + C): two conditional wraps
+            int k = k0 + i;
+            if (k >= ch) k -= ch;
+            if (k >= ch) k -= ch;
+            kk[i] = k;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = expf(kk[i] < 4 ? raw[i] : -raw[i]);
 #pragma unroll
@@ -594,11 +599,9 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
   }
   const size_t stage_bytes = (size_t)P.KC * 512;
   const int nblk = (ACH + 7) / 8;
-  int best = 1, waste = 1 << 30;
-  for (int wq = 5; wq >= 1; --wq) {
-    const int per = (nblk + wq - 1) / wq, w_ = per * wq - nblk;
-    if (per >= 1 && wq <= nblk && w_ < waste) { waste = w_; best = wq; }
-  }
+  // epilogue warps per TMEM lane quadrant: up to 5, fewer when that does not lengthen the longest column-block list
+  int best = nblk < 5 ? nblk : 5;
+  while (best > 1 && (nblk + best - 2) / (best - 1) == (nblk + best - 1) / best) --best;
   P.wq = best;
   P.w = weight; P.bias = bias; P.out_dec = out_decoded; P.out_raw = out_raw;
   P.B = B; P.Cin = Cin; P.HW = HW; P.Wd = W; P.A = A; P.C = C; P.N = N;
