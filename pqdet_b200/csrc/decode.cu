@@ -8,6 +8,8 @@
 
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "pq_common.cuh"
 
 namespace pq {
@@ -307,6 +309,127 @@ recover_tma_kernel(const float* __restrict__ pred, float* __restrict__ out, int6
   if (tid == 0) tma_store_wait_read<0>();                       // smem must stay alive until the stores have read it
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent TMA pipeline for the eval concat (all levels, every level's H*W a multiple of 128): one CTA per SM, a
+// producer warp streams (A*(5+C) channels x 128 cells) tiles of the raw heads with one 2-D tensor-map load each
+// through an mbarrier ring, 4*wq compute warps decode them (thread = cell, 8 consecutive channels per step, the
+// interleaved chains of decode_block8) into a staging tile that is one contiguous run of the output and leaves as
+// one bulk store; two staging tiles, so the decode of tile i+1 overlaps the store of tile i.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDtmCells = 128;
+constexpr int kDtmMaxStages = 4;
+
+struct DecodeTmaParams {
+  float* out;
+  int A, ch, n_levels;
+  int Wd[PQDET_MAX_LEVELS];
+  uint32_t magic_w[PQDET_MAX_LEVELS];     // ceil(2^32 / W): cell / W by multiply-high (0 when W == 1)
+  float stride[PQDET_MAX_LEVELS];
+  int64_t row_off[PQDET_MAX_LEVELS];
+  int tile_off[PQDET_MAX_LEVELS + 1];     // tiles of one image, levels concatenated
+  int tiles_img, ntiles;
+  int64_t rows_total;
+  int stages, wq;
+};
+struct DecodeTmaMaps {
+  CUtensorMap m[PQDET_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(768, 1)
+decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid_constant__ DecodeTmaMaps maps) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ __align__(8) uint64_t full_bar[kDtmMaxStages], empty_bar[kDtmMaxStages];
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const int ch = P.ch, ACH = P.A * ch, S = P.stages;
+  const uint32_t stage_bytes = (uint32_t)ACH * kDtmCells * 4u;
+  // dynamic smem: [S input stages: ACH x 128 floats][2 staging tiles: 128 x ACH floats]
+  float* tile0 = reinterpret_cast<float*>(dsm + (size_t)S * stage_bytes);
+  const int n_cmp = 4 * P.wq * 32;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 4 * P.wq);
+    }
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // ---- producer ----------------------------------------------------------------------------------------------
+    uint32_t s = 0, ph = 0;
+    for (int g = blockIdx.x; g < P.ntiles; g += gridDim.x) {
+      const int b = g / P.tiles_img, t = g - b * P.tiles_img;
+      int l = 0;
+      while (l + 1 < P.n_levels && t >= P.tile_off[l + 1]) ++l;
+      const int cell0 = (t - P.tile_off[l]) * kDtmCells;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_2d(smem_u32(dsm) + s * stage_bytes, &maps.m[l], cell0, b * ACH, &full_bar[s]);
+      }
+      __syncwarp();
+      if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ---- compute: warp%4 = which 32 cells of the tile, the wq warps of a quarter take the 8-channel blocks round robin
+    const int q = warp & 3, jq = (warp - 4) >> 2;
+    const int ctid = tid - 128;
+    const int r = q * 32 + lane;
+    const int nblk = (ACH + 7) / 8;
+    const int k_first = (jq * 8) % ch;                      // channel-within-anchor of this warp's first block
+    const int k_step = (P.wq * 8) % ch;
+    uint32_t s = 0, ph = 0, tl = 0;
+    // per-tile bookkeeping without divisions: (image, tile within image) advance by gridDim.x with carries
+    int b = blockIdx.x / P.tiles_img, t = blockIdx.x - b * P.tiles_img;
+    const int step_b = gridDim.x / P.tiles_img, step_t = gridDim.x - step_b * P.tiles_img;
+    for (int g = blockIdx.x; g < P.ntiles; g += gridDim.x, ++tl) {
+      int l = 0;
+      while (l + 1 < P.n_levels && t >= P.tile_off[l + 1]) ++l;
+      const int cell0 = (t - P.tile_off[l]) * kDtmCells;
+      const int cell = cell0 + r;
+      const int Wd = P.Wd[l];
+      const int cy = P.magic_w[l] ? (int)__umulhi((uint32_t)cell, P.magic_w[l]) : cell, cx = cell - cy * Wd;
+      const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
+      const float stride = P.stride[l];
+      float* tile = tile0 + (size_t)(tl & 1u) * kDtmCells * ACH;
+      float* dst = P.out + ((size_t)b * P.rows_total + P.row_off[l] + (size_t)cell0 * P.A) * ch;
+      // the bulk store that last used this staging tile must have read it before it is overwritten
+      if (ctid == 0) tma_store_wait_read<1>();
+      epi_bar_sync(n_cmp);
+      mbar_wait(&full_bar[s], ph);
+      const float* src = reinterpret_cast<const float*>(dsm + (size_t)s * stage_bytes) + r;
+      int k0 = k_first;
+      for (int blk = jq; blk < nblk; blk += P.wq) {
+        const int c0 = blk * 8;
+        const float* sp = src + c0 * kDtmCells;
+        float raw[8];
+        if (c0 + 8 <= ACH) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) raw[i] = sp[i * kDtmCells];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) raw[i] = (c0 + i < ACH) ? sp[i * kDtmCells] : 0.0f;
+        }
+        decode_block8(raw, k0, c0, ACH, ch, gx, gy, stride, tile + r * ACH + c0);
+        k0 += k_step;
+        if (k0 >= ch) k0 -= ch;
+      }
+      t += step_t; b += step_b;
+      if (t >= P.tiles_img) { t -= P.tiles_img; ++b; }
+      // this warp has read its part of the stage: the producer may refill it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
+      fence_async_smem();
+      epi_bar_sync(n_cmp);
+      if (ctid == 0) {
+        tma_store_1d(dst, tile, (uint32_t)(kDtmCells * ACH * sizeof(float)));
+        tma_store_commit();
+      }
+    }
+    if (ctid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
 }  // namespace pq
 
 extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int C, int H, int W, float stride,
@@ -327,6 +450,67 @@ extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int 
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
+
+namespace {
+
+// Launches the persistent TMA kernel when every level qualifies; 1 = launched, 0 = use the general kernel, < 0 = error.
+int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, const int* W, const float* stride,
+                          float* out, int B, int A, int C, int64_t rows, int device, cudaStream_t stream) {
+  using namespace pq;
+  const int ch = 5 + C, ACH = A * ch;
+  if (ACH > 256) return 0;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (((size_t)rows * ch * 4) & 15)) return 0;
+  PqEncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return 0;
+  DecodeTmaParams P;
+  DecodeTmaMaps maps;
+  memset(&P, 0, sizeof(P));
+  memset(&maps, 0, sizeof(maps));
+  int tiles = 0;
+  int64_t row_off = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const int HW = H[l] * W[l];
+    if (HW % kDtmCells != 0 || (reinterpret_cast<uintptr_t>(raw[l]) & 15)) return 0;
+    if ((int64_t)B * ACH > 0x7fffffff) return 0;
+    if (((size_t)row_off * ch * 4) & 15) return 0;
+    P.Wd[l] = W[l]; P.stride[l] = stride[l]; P.row_off[l] = row_off; P.tile_off[l] = tiles;
+    P.magic_w[l] = W[l] == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)W[l] - 1) / (uint64_t)W[l]);
+    if ((int64_t)HW * W[l] >= 0x100000000ll) return 0;          // multiply-high exact for cell < 2^32 / W
+    tiles += HW / kDtmCells;
+    row_off += (int64_t)HW * A;
+    cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)B * ACH}, strides[1] = {(cuuint64_t)HW * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kDtmCells, (cuuint32_t)ACH}, estr[2] = {1u, 1u};
+    if (enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(raw[l]), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 0;
+  }
+  for (int l = n_levels; l <= PQDET_MAX_LEVELS; ++l) P.tile_off[l] = tiles;
+  if ((int64_t)B * tiles > 0x7fffffff) return 0;
+  P.out = out; P.A = A; P.ch = ch; P.n_levels = n_levels;
+  P.tiles_img = tiles; P.ntiles = B * tiles; P.rows_total = rows;
+  int max_smem = 0, sms = 0;
+  PQ_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  PQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const size_t tile_bytes = (size_t)kDtmCells * ACH * 4;
+  const size_t room = (size_t)max_smem - 1024;                      // static barriers
+  if (room < 4 * tile_bytes) return 0;                              // 2 input stages + 2 staging tiles at least
+  size_t st = room / tile_bytes - 2;
+  if (st > (size_t)kDtmMaxStages) st = kDtmMaxStages;
+  P.stages = (int)st;
+  const int nblk = (ACH + 7) / 8;
+  int wq = nblk < 5 ? nblk : 5;
+  while (wq > 1 && (nblk + wq - 2) / (wq - 1) == (nblk + wq - 1) / wq) --wq;
+  P.wq = wq;
+  const size_t smem = (st + 2) * tile_bytes;
+  PQ_CUDA(cudaFuncSetAttribute(decode_levels_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = P.ntiles < sms ? P.ntiles : sms;
+  decode_levels_tma_kernel<<<grid, (4 + 4 * wq) * 32, smem, stream>>>(P, maps);
+  PQ_LAUNCH_CHECK();
+  return 1;
+}
+
+}  // namespace
 
 extern "C" int pqdet_decode_levels(int n_levels, const float* const* raw, const int* H, const int* W,
                                    const float* stride, float* out, int B, int A, int C, int device, void* stream) {
@@ -351,6 +535,10 @@ extern "C" int pqdet_decode_levels(int n_levels, const float* const* raw, const 
   L.n_levels = n_levels;
   PQ_ENTER(device);
   const int ch = 5 + C;
+  if (!getenv("PQDET_DECODE_GENERAL")) {
+    const int rc = try_decode_levels_tma(n_levels, raw, H, W, stride, out, B, A, C, rows, device, (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : PQDET_OK;
+  }
   const size_t smem = (size_t)kTileCells * ((A * ch) | 1) * sizeof(float);
   if (smem > 48 * 1024)
     PQ_CUDA(cudaFuncSetAttribute(decode_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -20,7 +20,6 @@
 // type 1) through an mbarrier ring, warp 1 issues the MMAs into one of two TMEM accumulators, and 4*wq epilogue warps
 // decode the other accumulator and hand the finished (128 cells x A x (5+C)) tile - one contiguous run of the output -
 // to a TMA bulk store.  `head_conv_decode_kernel` is the general kernel (any shape; cp.async staging).
-#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -265,27 +264,10 @@ struct HeadConvWsParams {
   int tile_bufs;       // 1 or 2 staging tiles for the output
   int buf_cols;        // TMEM column stride between the two accumulators
   int tiles_per_img, ntiles;
+  uint32_t magic_w;    // ceil(2^32 / W): cell / W by multiply-high (0 when W == 1)
   float stride;
   int64_t rows_total, row_off;
 };
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
-}
-// One lane of a converged warp; the surrounding loop stays warp-uniform so that descriptors and addresses live in
-// uniform registers (a loop run by `lane == 0` alone pays register -> uniform-register moves in front of every MMA).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void epi_bar_sync(int nthreads) {
-  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
 
 template <bool WANT_RAW>
 __global__ void __launch_bounds__(768, 1)
@@ -413,13 +395,22 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
     const int etid = tid - 128;
     const int r = q * 32 + lane;
     const int nblk = (ACH + 7) / 8;
+    const int k_first = (jq * 8) % ch;                      // channel-within-anchor of this warp's first block
+    const int k_step = (P.wq * 8) % ch;
     uint32_t tl = 0;
+    // per-tile bookkeeping without divisions: (image, tile within image) advance by gridDim.x with carries
+    int b = blockIdx.x / P.tiles_per_img, ti = blockIdx.x - b * P.tiles_per_img;
+    const int step_b = gridDim.x / P.tiles_per_img, step_t = gridDim.x - step_b * P.tiles_per_img;
     for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++tl) {
       const uint32_t buf = tl & 1u;
-      const int b = t / P.tiles_per_img, cell0 = (t - b * P.tiles_per_img) * kHcM;
+      const int cell0 = ti * kHcM;
       const int cell = cell0 + r;
-      const int cy = cell / P.Wd, cx = cell - cy * P.Wd;
+      const int cy = P.magic_w ? (int)__umulhi((uint32_t)cell, P.magic_w) : cell, cx = cell - cy * P.Wd;
       const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
+      float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch;
+      const size_t raw_base = (size_t)b * ACH * P.HW + cell;
+      ti += step_t; b += step_b;
+      if (ti >= P.tiles_per_img) { ti -= P.tiles_per_img; ++b; }
       mbar_wait(&acc_full[buf], (tl >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // the bulk store that last used this staging tile must have read it before it is overwritten
@@ -428,6 +419,7 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
         if (P.tile_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
       }
       epi_bar_sync(n_epi);
+      int k0 = k_first;
       for (int blk = jq; blk < nblk; blk += P.wq) {
         const int c0 = blk * 8;
         uint32_t v[8];
@@ -436,7 +428,6 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                      : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int k0 = c0 % ch;
         const float* bs = sbias + c0;
         float* trow = tile + r * ACH + c0;
         float raw[8];
@@ -445,58 +436,11 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
         if (WANT_RAW) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (c0 + i < ACH) P.out_raw[((size_t)b * ACH + c0 + i) * P.HW + cell] = raw[i];
+            if (c0 + i < ACH) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
         }
-        // 1 / (1 + e) through rcp_rn_core (pq_math.cuh) so that the 8 chains interleave instead of being serialised
-        // by __frcp_rn's per-call range check; x >= 2^126 (raw < -87: a denormal sigmoid) and NaN redo the block
-        // with __frcp_rn itself.
-        float e[8], rr[8];
-        bool slow = false;
-        if (k0 >= 4 && k0 + 8 <= ch && c0 + 8 <= ACH) {
-          // the common block: 8 objectness / class columns of one anchor -> 8 independent sigmoid chains
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = PQ_ADD(1.0f, expf(-raw[i]));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            rr[i] = rcp_rn_core(e[i]);
-            slow |= !(e[i] < kRcpCoreMax);
-          }
-          if (slow) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = __frcp_rn(e[i]);                          // sigmoidf_
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) trow[i] = rr[i];
-        } else {
-          // a block that straddles the box channels of an anchor (or the padding): same chains, the kind of each
-          // column selected at the end
-          int kk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {            // 5 + C >= 5, so k0 + i < 3 * (5 + C): two conditional wraps
-            int k = k0 + i;
-            if (k >= ch) k -= ch;
-            if (k >= ch) k -= ch;
-            kk[i] = k;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = expf(kk[i] < 4 ? raw[i] : -raw[i]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x = PQ_ADD(1.0f, e[i]);
-            rr[i] = rcp_rn_core(x);
-            slow |= (kk[i] >= 4) && !(x < kRcpCoreMax);
-          }
-          if (slow) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = __frcp_rn(PQ_ADD(1.0f, e[i]));           // sigmoidf_
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float g = (kk[i] & 1) ? gy : gx;
-            const float oc = PQ_MUL((kk[i] < 2) ? PQ_SUB(g, e[i]) : PQ_ADD(g, e[i]), P.stride);   // decode_coord
-            if (c0 + i < ACH) trow[i] = kk[i] < 4 ? oc : rr[i];
-          }
-        }
+        decode_block8(raw, k0, c0, ACH, ch, gx, gy, P.stride, trow);      // pq_math.cuh: 8 interleaved chains
+        k0 += k_step;
+        if (k0 >= ch) k0 -= ch;
       }
       // this warp no longer needs the accumulator: the MMA warp may start the tile after next in it
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -506,7 +450,6 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
         fence_async_smem();
         epi_bar_sync(n_epi);
         if (etid == 0) {
-          float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch;
           tma_store_1d(dst, tile, (uint32_t)(kHcM * ACH * sizeof(float)));
           tma_store_commit();
         }
@@ -526,22 +469,6 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
 
 namespace {
 
-typedef CUresult (*PqEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PqEncodeTiledFn encode_tiled_fn() {
-  static PqEncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
-        qr != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return (PqEncodeTiledFn)p;
-  }();
-  return fn;
-}
-
 // Launches the persistent kernel when the shape qualifies; returns 1 if it did, 0 if the general kernel must run,
 // < 0 on error.
 int try_head_conv_ws(const float* x, const float* weight, const float* bias, float* out_decoded, float* out_raw,
@@ -556,7 +483,7 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
     if ((reinterpret_cast<uintptr_t>(out_decoded) & 15) || (img_bytes & 15) || (off_bytes & 15)) return 0;
   }
   if ((int64_t)B * Cin > 0x7fffffff || (int64_t)B * (HW / kHcM) > 0x7fffffff) return 0;
-  PqEncodeTiledFn enc = encode_tiled_fn();
+  PqEncodeTiledFn enc = pq::encode_tiled_fn();
   if (!enc) return 0;
   HeadConvWsParams P;
   memset(&P, 0, sizeof(P));
@@ -608,6 +535,8 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
   P.buf_cols = 32;
   while (P.buf_cols < N) P.buf_cols <<= 1;
   P.tiles_per_img = HW / kHcM;
+  P.magic_w = W == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
+  if ((int64_t)HW * W >= 0x100000000ll) return 0;              // multiply-high exact for cell < 2^32 / W
   P.ntiles = B * P.tiles_per_img;
   P.stride = stride; P.rows_total = rows_total; P.row_off = row_off;
   CUtensorMap tmap;

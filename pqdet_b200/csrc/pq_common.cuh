@@ -1,6 +1,7 @@
 // Launch plumbing and block/warp primitives shared by the sm_100a kernels.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -139,5 +140,40 @@ __device__ __forceinline__ void tma_store_wait_read() {
 }
 // generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// One lane of a converged warp; the surrounding loop stays warp-uniform so that descriptors and addresses live in
+// uniform registers (a loop run by `lane == 0` alone pays register -> uniform-register moves in front of every MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+
+// ---- host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda) ---------
+typedef CUresult (*PqEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PqEncodeTiledFn encode_tiled_fn() {
+  static PqEncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (PqEncodeTiledFn)p;
+  }();
+  return fn;
+}
 
 }  // namespace pq
