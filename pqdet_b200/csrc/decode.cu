@@ -432,30 +432,12 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
 
 }  // namespace pq
 
-extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int C, int H, int W, float stride,
-                                int64_t out_rows_total, int64_t out_row_offset, int device, void* stream) {
-  if (B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
-  if (out_row_offset < 0 || out_row_offset + (int64_t)H * W * A > out_rows_total) return PQDET_ERR_INVALID_ARG;
-  if (B == 0) return PQDET_OK;                       // empty batch: tensors without storage are fine
-  if (!raw || !out) return PQDET_ERR_INVALID_ARG;
-  if (B > 65535) return PQDET_ERR_UNSUPPORTED;
-  PQ_ENTER(device);
-  const int ch = 5 + C;
-  const size_t smem = (size_t)pq::kTileCells * ((A * ch) | 1) * sizeof(float);
-  if (smem > 48 * 1024)
-    PQ_CUDA(cudaFuncSetAttribute(pq::decode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((H * W + pq::kTileCells - 1) / pq::kTileCells, B);
-  pq::decode_fwd_kernel<<<grid, pq::kDecodeThreads, smem, (cudaStream_t)stream>>>(
-      raw, out, A, ch, H, W, stride, out_rows_total, out_row_offset);
-  PQ_LAUNCH_CHECK();
-  return PQDET_OK;
-}
-
 namespace {
 
 // Launches the persistent TMA kernel when every level qualifies; 1 = launched, 0 = use the general kernel, < 0 = error.
 int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, const int* W, const float* stride,
-                          float* out, int B, int A, int C, int64_t rows, int device, cudaStream_t stream) {
+                          float* out, int B, int A, int C, int64_t rows, int64_t base_row_off, int device,
+                          cudaStream_t stream) {
   using namespace pq;
   const int ch = 5 + C, ACH = A * ch;
   if (ACH > 256) return 0;
@@ -467,7 +449,7 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   memset(&P, 0, sizeof(P));
   memset(&maps, 0, sizeof(maps));
   int tiles = 0;
-  int64_t row_off = 0;
+  int64_t row_off = base_row_off;
   for (int l = 0; l < n_levels; ++l) {
     const int HW = H[l] * W[l];
     if (HW % kDtmCells != 0 || (reinterpret_cast<uintptr_t>(raw[l]) & 15)) return 0;
@@ -512,6 +494,31 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
 
 }  // namespace
 
+extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int C, int H, int W, float stride,
+                                int64_t out_rows_total, int64_t out_row_offset, int device, void* stream) {
+  if (B < 0 || A <= 0 || C < 0 || H <= 0 || W <= 0) return PQDET_ERR_INVALID_ARG;
+  if (out_row_offset < 0 || out_row_offset + (int64_t)H * W * A > out_rows_total) return PQDET_ERR_INVALID_ARG;
+  if (B == 0) return PQDET_OK;                       // empty batch: tensors without storage are fine
+  if (!raw || !out) return PQDET_ERR_INVALID_ARG;
+  if (B > 65535) return PQDET_ERR_UNSUPPORTED;
+  PQ_ENTER(device);
+  const int ch = 5 + C;
+  if (!getenv("PQDET_DECODE_GENERAL")) {
+    const int rc = try_decode_levels_tma(1, &raw, &H, &W, &stride, out, B, A, C, out_rows_total, out_row_offset, device,
+                                         (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : PQDET_OK;
+  }
+  const size_t smem = (size_t)pq::kTileCells * ((A * ch) | 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    PQ_CUDA(cudaFuncSetAttribute(pq::decode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((H * W + pq::kTileCells - 1) / pq::kTileCells, B);
+  pq::decode_fwd_kernel<<<grid, pq::kDecodeThreads, smem, (cudaStream_t)stream>>>(
+      raw, out, A, ch, H, W, stride, out_rows_total, out_row_offset);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
+
 extern "C" int pqdet_decode_levels(int n_levels, const float* const* raw, const int* H, const int* W,
                                    const float* stride, float* out, int B, int A, int C, int device, void* stream) {
   using namespace pq;
@@ -536,7 +543,7 @@ extern "C" int pqdet_decode_levels(int n_levels, const float* const* raw, const 
   PQ_ENTER(device);
   const int ch = 5 + C;
   if (!getenv("PQDET_DECODE_GENERAL")) {
-    const int rc = try_decode_levels_tma(n_levels, raw, H, W, stride, out, B, A, C, rows, device, (cudaStream_t)stream);
+    const int rc = try_decode_levels_tma(n_levels, raw, H, W, stride, out, B, A, C, rows, 0, device, (cudaStream_t)stream);
     if (rc != 0) return rc < 0 ? rc : PQDET_OK;
   }
   const size_t smem = (size_t)kTileCells * ((A * ch) | 1) * sizeof(float);

@@ -181,6 +181,30 @@ def test_eval_concat_tma_pipeline_equals_general_kernel(B, C, size, monkeypatch)
     assert torch.equal(torch.cat(rows, 1).view(torch.int32), got.view(torch.int32))
 
 
+def test_single_level_decode_into_a_row_range(monkeypatch):
+    """pqdet_decode_fwd with out_rows_total / out_row_offset (the C ABI's own way to build the eval concat) through the
+    TMA pipeline and through the general kernel."""
+    from pqdet_b200 import _ops
+    B, C = 3, 20
+    g = torch.Generator(device="cuda").manual_seed(11)
+    raws = [torch.randn((B, 75, 512 // s, 512 // s), device="cuda", generator=g) for s in (32, 16, 8)]
+    N = sum(r.shape[2] * r.shape[3] * 3 for r in raws)
+    outs = []
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv("PQDET_DECODE_GENERAL", "1")
+        out = torch.full((B, N, 5 + C), -7.0, device="cuda")
+        off = 0
+        for r, s in zip(raws, (32, 16, 8)):
+            _ops.decode_fwd(r, C, s, out=out, rows_total=N, row_offset=off)
+            off += r.shape[2] * r.shape[3] * 3
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    monkeypatch.delenv("PQDET_DECODE_GENERAL")
+    assert torch.equal(outs[0], _ops.decode_levels(raws, C, (32, 16, 8)))
+
+
 def test_sigmoid_reciprocal_out_of_range_logits(monkeypatch):
     """The decode kernels interleave several 1/(1+e) chains with the range check of __frcp_rn hoisted out
     (pq_math.cuh rcp_rn_core); logits below -87 (1+e >= 2^126: denormal / zero sigmoid), +-inf-producing values and
