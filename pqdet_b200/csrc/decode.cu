@@ -374,9 +374,10 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
     const int q = warp & 3, jq = (warp - 4) >> 2;
     const int ctid = tid - 128;
     const int r = q * 32 + lane;
-    const int nblk = (ACH + 7) / 8;
-    const int k_first = (jq * 8) % ch;                      // channel-within-anchor of this warp's first block
-    const int k_step = (P.wq * 8) % ch;
+    // work units of one cell row: per anchor its 1 + C objectness / class channels in `grp` groups of `usz` <= 8
+    // (21 -> 3 x 7), numbered first, then the 4 box channels of every anchor (cheaper: no reciprocal); the wq warps of
+    // a quarter take the units round robin
+    const int ns = ch - 4, grp = (ns + 7) / 8, usz = (ns + grp - 1) / grp, nsig = P.A * grp, nunit = nsig + P.A;
     uint32_t s = 0, ph = 0, tl = 0;
     // per-tile bookkeeping without divisions: (image, tile within image) advance by gridDim.x with carries
     int b = blockIdx.x / P.tiles_img, t = blockIdx.x - b * P.tiles_img;
@@ -397,21 +398,36 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       epi_bar_sync(n_cmp);
       mbar_wait(&full_bar[s], ph);
       const float* src = reinterpret_cast<const float*>(dsm + (size_t)s * stage_bytes) + r;
-      int k0 = k_first;
-      for (int blk = jq; blk < nblk; blk += P.wq) {
-        const int c0 = blk * 8;
-        const float* sp = src + c0 * kDtmCells;
-        float raw[8];
-        if (c0 + 8 <= ACH) {
+      float* trow0 = tile + r * ACH;
+      for (int u = jq; u < nunit; u += P.wq) {
+        if (u >= nsig) {
+          const int a = u - nsig;
+          const float* sp = src + (a * ch) * kDtmCells;
+          float raw[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) raw[i] = sp[i * kDtmCells];
+          for (int i = 0; i < 4; ++i) raw[i] = sp[i * kDtmCells];
+          decode_box4(raw, gx, gy, stride, trow0 + a * ch);
         } else {
+          const int a = u / grp, j = u - a * grp;
+          const int k = 4 + j * usz, cnt = min(usz, ch - k), c0 = a * ch + k;
+          const float* sp = src + c0 * kDtmCells;
+          if (cnt == 8) {
+            float raw[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) raw[i] = (c0 + i < ACH) ? sp[i * kDtmCells] : 0.0f;
+            for (int i = 0; i < 8; ++i) raw[i] = sp[i * kDtmCells];
+            decode_sig<8>(raw, 8, trow0 + c0);
+          } else if (cnt == 7) {                                   // 1 + 20 classes = 3 x 7
+            float raw[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) raw[i] = sp[i * kDtmCells];
+            decode_sig<7>(raw, 7, trow0 + c0);
+          } else {
+            float raw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) raw[i] = (i < cnt) ? sp[i * kDtmCells] : 0.0f;
+            decode_sig<8>(raw, cnt, trow0 + c0);
+          }
         }
-        decode_block8(raw, k0, c0, ACH, ch, gx, gy, stride, tile + r * ACH + c0);
-        k0 += k_step;
-        if (k0 >= ch) k0 -= ch;
       }
       t += step_t; b += step_b;
       if (t >= P.tiles_img) { t -= P.tiles_img; ++b; }
@@ -471,21 +487,35 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   if ((int64_t)B * tiles > 0x7fffffff) return 0;
   P.out = out; P.A = A; P.ch = ch; P.n_levels = n_levels;
   P.tiles_img = tiles; P.ntiles = B * tiles; P.rows_total = rows;
-  int max_smem = 0, sms = 0;
-  PQ_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  PQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  DeviceLimits lim;
+  if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
+  const int max_smem = lim.max_smem_optin, sms = lim.sms;
   const size_t tile_bytes = (size_t)kDtmCells * ACH * 4;
   const size_t room = (size_t)max_smem - 1024;                      // static barriers
   if (room < 4 * tile_bytes) return 0;                              // 2 input stages + 2 staging tiles at least
   size_t st = room / tile_bytes - 2;
   if (st > (size_t)kDtmMaxStages) st = kDtmMaxStages;
   P.stages = (int)st;
-  const int nblk = (ACH + 7) / 8;
-  int wq = nblk < 5 ? nblk : 5;
-  while (wq > 1 && (nblk + wq - 2) / (wq - 1) == (nblk + wq - 1) / wq) --wq;
+  // compute warps per quarter: the count (<= 5) whose most loaded warp has the least work, units dealt round robin
+  // (cost model: a group of objectness / class channels ~ 2.5 x the 4 box channels of an anchor)
+  const int nsig = A * ((ch - 4 + 7) / 8), nunit = nsig + A;
+  int wq = 1, best_load = 1 << 30;
+  for (int w = 1; w <= 5 && w <= nunit; ++w) {
+    int worst = 0;
+    for (int j = 0; j < w; ++j) {
+      int load = 0;
+      for (int u = j; u < nunit; u += w) load += u < nsig ? 5 : 2;
+      worst = load > worst ? load : worst;
+    }
+    if (worst < best_load) { best_load = worst; wq = w; }
+  }
   P.wq = wq;
   const size_t smem = (st + 2) * tile_bytes;
-  PQ_CUDA(cudaFuncSetAttribute(decode_levels_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int smem_set[64];                    // the attribute sticks per device: raise it only when needed
+  if (device < 0 || device >= 64 || (int)smem > smem_set[device]) {
+    PQ_CUDA(cudaFuncSetAttribute(decode_levels_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (device >= 0 && device < 64) smem_set[device] = (int)smem;
+  }
   const int grid = P.ntiles < sms ? P.ntiles : sms;
   decode_levels_tma_kernel<<<grid, (4 + 4 * wq) * 32, smem, stream>>>(P, maps);
   PQ_LAUNCH_CHECK();

@@ -488,8 +488,9 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
   HeadConvWsParams P;
   memset(&P, 0, sizeof(P));
   const size_t w_bytes = (size_t)Cin * N * 4, tile_bytes = (size_t)kHcM * ACH * 4, bias_bytes = (size_t)(N + 8) * 4;
-  int max_smem = 0;
-  PQ_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  DeviceLimits lim;
+  if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
+  const int max_smem = lim.max_smem_optin, sms = lim.sms;
   // Stage = KC channels x 128 cells.  Every stage costs the MMA warp a fixed ~400 cycles of waits / fences / commit
   // (measured), so stages are as large as the budget allows: KC = the largest multiple of 8 that divides Cin with
   // at least 3 stages (>= 48 KB in flight) in what the resident weights and the output staging leave; two output
@@ -547,17 +548,21 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 0;
-  int sms = 0;
-  PQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const size_t smem = 1024 + (size_t)P.stages * stage_bytes + w_bytes + (size_t)P.tile_bufs * tile_bytes + bias_bytes;
   const int grid = P.ntiles < sms ? P.ntiles : sms;
-  if (out_raw) {
-    PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_conv_decode_ws_kernel<true><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
-  } else {
-    PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_conv_decode_ws_kernel<false><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
+  static int smem_set[2][64];                 // the attribute sticks per device: raise it only when needed
+  const int which = out_raw ? 1 : 0;
+  if (device < 0 || device >= 64 || (int)smem > smem_set[which][device]) {
+    if (out_raw)
+      PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (device >= 0 && device < 64) smem_set[which][device] = (int)smem;
   }
+  if (out_raw)
+    head_conv_decode_ws_kernel<true><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
+  else
+    head_conv_decode_ws_kernel<false><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
   PQ_LAUNCH_CHECK();
   return 1;
 }

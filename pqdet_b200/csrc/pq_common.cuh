@@ -176,4 +176,19 @@ inline PqEncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+
+// Device limits that the persistent kernels size themselves by, queried once per device.
+struct DeviceLimits { int max_smem_optin, sms; };
+inline bool device_limits(int device, DeviceLimits* out) {
+  static DeviceLimits cache[64];
+  static bool have[64];
+  if (device >= 0 && device < 64 && have[device]) { *out = cache[device]; return true; }
+  DeviceLimits d;
+  if (cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return false;
+  if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return false;
+  if (device >= 0 && device < 64) { cache[device] = d; have[device] = true; }
+  *out = d;
+  return true;
+}
+
 }  // namespace pq
