@@ -262,6 +262,7 @@ struct HeadConvWsParams {
   int stages;
   int wq;              // epilogue warps per TMEM lane quadrant
   int tile_bufs;       // 1 or 2 staging tiles for the output
+  int units;           // 1: anchor-aligned work units in the epilogue (needs ACH + 7 <= buf_cols), 0: 8-column blocks
   int buf_cols;        // TMEM column stride between the two accumulators
   int tiles_per_img, ntiles;
   uint32_t magic_w;    // ceil(2^32 / W): cell / W by multiply-high (0 when W == 1)
@@ -419,28 +420,79 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
         if (P.tile_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
       }
       epi_bar_sync(n_epi);
-      int k0 = k_first;
-      for (int blk = jq; blk < nblk; blk += P.wq) {
-        const int c0 = blk * 8;
-        uint32_t v[8];
-        const uint32_t taddr = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                     : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const float* bs = sbias + c0;
-        float* trow = tile + r * ACH + c0;
-        float raw[8];
+      const uint32_t tacc = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16);
+      float* trow0 = tile + r * ACH;
+      if (P.units) {
+        // anchor-aligned work units (see decode_levels_tma_kernel): per anchor its objectness / class channels in
+        // groups of usz <= 8, numbered first, then the 4 box channels of every anchor
+        const int ns = ch - 4, grp = (ns + 7) / 8, usz = (ns + grp - 1) / grp, nsig = P.A * grp, nunit = nsig + P.A;
+        for (int u = jq; u < nunit; u += P.wq) {
+          if (u >= nsig) {
+            const int c0 = (u - nsig) * ch;
+            uint32_t v[4];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(tacc + (uint32_t)c0) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float raw[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), bs[i]);       // bias 0 where there is none
-        if (WANT_RAW) {
+            for (int i = 0; i < 4; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
+            if (WANT_RAW) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (c0 + i < ACH) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
+              for (int i = 0; i < 4; ++i) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
+            }
+            decode_box4(raw, gx, gy, P.stride, trow0 + c0);
+          } else {
+            const int a = u / grp, j = u - a * grp;
+            const int k = 4 + j * usz, cnt = min(usz, ch - k), c0 = a * ch + k;
+            uint32_t v[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                         : "r"(tacc + (uint32_t)c0) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float raw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
+            if (WANT_RAW) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < cnt) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
+            }
+            if (cnt == 8) {
+              decode_sig<8>(raw, 8, trow0 + c0);
+            } else if (cnt == 7) {                                 // 1 + 20 classes = 3 x 7
+              float r7[7];
+#pragma unroll
+              for (int i = 0; i < 7; ++i) r7[i] = raw[i];
+              decode_sig<7>(r7, 7, trow0 + c0);
+            } else {
+              decode_sig<8>(raw, cnt, trow0 + c0);
+            }
+          }
         }
-        decode_block8(raw, k0, c0, ACH, ch, gx, gy, P.stride, trow);      // pq_math.cuh: 8 interleaved chains
-        k0 += k_step;
-        if (k0 >= ch) k0 -= ch;
+      } else {
+        int k0 = k_first;
+        for (int blk = jq; blk < nblk; blk += P.wq) {
+          const int c0 = blk * 8;
+          uint32_t v[8];
+          const uint32_t taddr = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(taddr) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const float* bs = sbias + c0;
+          float* trow = tile + r * ACH + c0;
+          float raw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), bs[i]);       // bias 0 where there is none
+          if (WANT_RAW) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (c0 + i < ACH) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
+          }
+          decode_block8(raw, k0, c0, ACH, ch, gx, gy, P.stride, trow);      // pq_math.cuh: 8 interleaved chains
+          k0 += k_step;
+          if (k0 >= ch) k0 -= ch;
+        }
       }
       // this warp no longer needs the accumulator: the MMA warp may start the tile after next in it
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -527,9 +579,29 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
   }
   const size_t stage_bytes = (size_t)P.KC * 512;
   const int nblk = (ACH + 7) / 8;
-  // epilogue warps per TMEM lane quadrant: up to 5, fewer when that does not lengthen the longest column-block list
-  int best = nblk < 5 ? nblk : 5;
-  while (best > 1 && (nblk + best - 2) / (best - 1) == (nblk + best - 1) / best) --best;
+  // epilogue warps per TMEM lane quadrant (<= 5).  With anchor-aligned units: the count whose most loaded warp has the
+  // least work, units dealt round robin (a group of objectness / class channels ~ 2.5 x the 4 box channels of an
+  // anchor); with 8-column blocks: fewer warps when that does not lengthen the longest block list.
+  int buf_cols = 32;
+  while (buf_cols < N) buf_cols <<= 1;
+  P.units = (ACH + 7 <= buf_cols) ? 1 : 0;          // a unit's 8-column read may run 7 columns past the last channel
+  int best = 1;
+  if (P.units) {
+    const int nsig = A * ((5 + C - 4 + 7) / 8), nunit = nsig + A;
+    int best_load = 1 << 30;
+    for (int w = 1; w <= 5 && w <= nunit; ++w) {
+      int worst = 0;
+      for (int j = 0; j < w; ++j) {
+        int load = 0;
+        for (int u = j; u < nunit; u += w) load += u < nsig ? 5 : 2;
+        worst = load > worst ? load : worst;
+      }
+      if (worst < best_load) { best_load = worst; best = w; }
+    }
+  } else {
+    best = nblk < 5 ? nblk : 5;
+    while (best > 1 && (nblk + best - 2) / (best - 1) == (nblk + best - 1) / best) --best;
+  }
   P.wq = best;
   P.w = weight; P.bias = bias; P.out_dec = out_decoded; P.out_raw = out_raw;
   P.B = B; P.Cin = Cin; P.HW = HW; P.Wd = W; P.A = A; P.C = C; P.N = N;
