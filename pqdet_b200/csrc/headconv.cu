@@ -2,24 +2,25 @@
 // activation = linear` convolution that feeds every [yolo] layer (model/cfg/regnetx-600m-fpn.cfg:646-651) is a
 // GEMM  raw[cell, o] = sum_c X[c, cell] * Wt[o, c] + bias[o]  and the only contraction on the path, so it runs on
 // the 5th-generation tensor cores: tcgen05.mma kind::tf32 (PyTorch's own convolutions use TF32 by default too),
-// 128 cells x N channels per CTA, accumulator in TMEM; the epilogue reads the accumulator back with tcgen05.ld,
+// 128 cells x N channels per tile, accumulator in TMEM; the epilogue reads the accumulator back with tcgen05.ld,
 // adds the bias, applies Decode (model/parser.py:206-235) and writes the rows of the (B, N, 5+C) prediction, so the
 // raw head never makes the round trip through HBM.
 //
-// Operand staging (cp.async; both operands use the un-swizzled "interleave" canonical layouts, in 16-byte units):
+// Two kernels.
+// `head_conv_decode_ws_kernel` (the fast path: H*W a multiple of 128, weights fit in shared memory) is persistent and
+// warp specialised: one CTA per SM keeps the whole weight matrix resident in shared memory, warp 0 streams X tiles
+// with TMA tensor-map loads (the NCHW planes are MN-major for this GEMM; tf32 takes an MN-major operand only in the
+// "128-byte swizzle, 32-byte atom" layout = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, UMMA layout type 1) through an
+// mbarrier ring, warp 1 issues the MMAs into one of two TMEM accumulators, and 4*wq epilogue warps decode the other
+// accumulator and hand the finished (128 cells x A x (5+C)) tile - one contiguous run of the output - to a TMA bulk
+// store.
+// `head_conv_decode_kernel` is the general kernel (any shape), one tile per CTA.  Operand staging with cp.async, both
+// operands in the un-swizzled "interleave" canonical layouts, in 16-byte units:
 //   A = X tile, K-major: unit(m, j = k/4) = 4 consecutive channels of cell m, at j*128 + m        (SBO 8, LBO 128)
 //   B = weights, K-major: unit(n, j = k/4) = 4 consecutive input channels of output n, at j*N + n (SBO 8, LBO N)
 // One tcgen05.mma consumes K = 8 tf32 values; the K loop runs in chunks of 32 channels through two smem stages: the
 // MMAs of a chunk (committed to that stage's mbarrier) run while the other stage is being filled.  The epilogue
 // tile reuses the stages; all 8 warps read the accumulator (warps w and w+4 share TMEM lane quadrant w%4).
-//
-// Two kernels.  `head_conv_decode_ws_kernel` (the fast path: H*W a multiple of 128, weights fit in shared memory) is
-// persistent and warp specialised: one CTA per SM keeps the whole weight matrix resident in shared memory, warp 0
-// streams X tiles with TMA tensor-map loads (the NCHW planes are MN-major for this GEMM; tf32 takes an MN-major
-// operand only in the "128-byte swizzle, 32-byte atom" layout = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, UMMA layout
-// type 1) through an mbarrier ring, warp 1 issues the MMAs into one of two TMEM accumulators, and 4*wq epilogue warps
-// decode the other accumulator and hand the finished (128 cells x A x (5+C)) tile - one contiguous run of the output -
-// to a TMA bulk store.  `head_conv_decode_kernel` is the general kernel (any shape; cp.async staging).
 #include <stdlib.h>
 #include <string.h>
 
