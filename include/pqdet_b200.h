@@ -287,6 +287,18 @@ int pqdet_head_conv_decode(const float* x, const float* weight, const float* bia
                            float* out_raw, int B, int Cin, int H, int W, int A, int C, float stride,
                            int64_t out_rows_total, int64_t out_row_offset, int device, void* stream);
 
+/* All levels of the head in ONE launch = the convolutions in front of the [yolo] layers + the eval branch of
+ * DetectionModel.forward (model/interpreter.py:72-76): level l's rows follow level l-1's in out_decoded
+ * (B, sum_l H_l*W_l*A, 5+C).  x[l] (B, Cin[l], H[l], W[l]), weight[l] (A*(5+C), Cin[l]), bias (array of pointers, NULL or
+ * with NULL entries = no bias).  The SMs are split between the levels in proportion to their cost.  Returns
+ * PQDET_ERR_UNSUPPORTED when a level does not qualify for the persistent kernel (H*W a multiple of 128, weights
+ * resident in shared memory) or when the batch is large enough for one launch per level to be faster (more than 32
+ * tiles of 128 cells per SM); the caller then runs pqdet_head_conv_decode per level. */
+int pqdet_head_conv_decode_levels(int n_levels, const float* const* x, const float* const* weight,
+                                  const float* const* bias, const int* Cin, const int* H, const int* W,
+                                  const float* stride, float* out_decoded, int B, int A, int C, int device,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,9 @@ BBOX_LOSS = {"l1": 0, "iou": 1, "giou": 2, "diou": 3}
 ST_CAND_OVERFLOW, ST_DET_TRUNCATED = 1, 2
 
 
+PQDET_ERR_UNSUPPORTED = -3      # include/pqdet_b200.h
+
+
 class PqdetError(RuntimeError):
     pass
 
@@ -98,6 +101,9 @@ SIGNATURES = {
                                           POINTER(c_float), c_void_p, c_void_p, c_int, c_void_p]),
     "pqdet_head_conv_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_float, c_int64, c_int64, c_int, c_void_p]),
+    "pqdet_head_conv_decode_levels": (c_int, [c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int),
+                                              POINTER(c_int), POINTER(c_float), c_void_p, c_int, c_int, c_int, c_int,
+                                              c_void_p]),
 }
 
 _LIB = None

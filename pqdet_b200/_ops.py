@@ -132,6 +132,36 @@ def head_conv_decode(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
     return (out, raw) if want_raw else out
 
 
+def head_conv_decode_levels(xs: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
+                            biases: Sequence[Optional[torch.Tensor]], num_classes: int, strides: Sequence[float],
+                            out: torch.Tensor) -> bool:
+    """All levels' head convolution + Decode in one launch into `out` (B, sum rows, 5+C)
+    (pqdet_head_conv_decode_levels).  Returns False when a level does not qualify for the persistent kernel (the
+    caller then runs head_conv_decode per level)."""
+    xs = [_req(x, "x") for x in xs]
+    ws = [_req(w.reshape(w.shape[0], -1), "weight") for w in weights]
+    bs = [None if b is None else _req(b, "bias") for b in biases]
+    L = len(xs)
+    ch = 5 + num_classes
+    B = xs[0].shape[0]
+    A = ws[0].shape[0] // ch
+    for x, w in zip(xs, ws):
+        if x.shape[0] != B or w.shape[0] != A * ch or w.shape[1] != x.shape[1] or x.device != xs[0].device:
+            raise ValueError("features / weights have inconsistent shapes or devices")
+    if out.shape != (B, sum(x.shape[2] * x.shape[3] * A for x in xs), ch) or not out.is_contiguous():
+        raise ValueError("out must be a contiguous (B, sum_l H_l*W_l*A, 5+C) tensor")
+    VP, IP, FP = ctypes.c_void_p * L, ctypes.c_int * L, ctypes.c_float * L
+    rc = _lib.load().pqdet_head_conv_decode_levels(
+        L, VP(*[x.data_ptr() for x in xs]), VP(*[w.data_ptr() for w in ws]),
+        VP(*[None if b is None else b.data_ptr() for b in bs]), IP(*[x.shape[1] for x in xs]),
+        IP(*[x.shape[2] for x in xs]), IP(*[x.shape[3] for x in xs]), FP(*[float(s) for s in strides]), _ptr(out), B, A,
+        num_classes, _dev(xs[0]), _stream(xs[0].device))
+    if rc == _lib.PQDET_ERR_UNSUPPORTED:
+        return False
+    _lib.check(rc, "pqdet_head_conv_decode_levels")
+    return True
+
+
 def decode_bwd(raw: torch.Tensor, grad_out: torch.Tensor, num_classes: int, stride: float) -> torch.Tensor:
     raw = _req(raw, "conv")
     grad_out = _req(grad_out, "grad_out")

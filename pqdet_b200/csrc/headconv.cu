@@ -271,9 +271,10 @@ struct HeadConvWsParams {
   int64_t rows_total, row_off;
 };
 
+// Body of the persistent kernel: this CTA is number `cta` of the `ncta` that share the level described by P.
 template <bool WANT_RAW>
-__global__ void __launch_bounds__(768, 1)
-head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __grid_constant__ CUtensorMap tmap_x) {
+__device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, const CUtensorMap* tmap_x, const int cta,
+                                                  const int ncta) {
   extern __shared__ __align__(1024) unsigned char hsm_ws[];
   __shared__ __align__(8) uint64_t full_bar[kWsMaxStages], empty_bar[kWsMaxStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -327,7 +328,7 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
     // ---- producer: one thread keeps the ring full -------------------------------------------------------------
     {
       uint32_t s = 0, ph = 0;
-      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x) {
+      for (int t = cta; t < P.ntiles; t += ncta) {
         const int b = t / P.tiles_per_img, cell0 = (t - b * P.tiles_per_img) * kHcM;
         for (int c = 0; c < nchunk; ++c) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -336,7 +337,7 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
             const uint32_t dst = sX + s * stage_bytes;
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              tma_load_2d(dst + (uint32_t)g * (uint32_t)KC * 128u, &tmap_x, cell0 + 32 * g, b * P.Cin + c * KC, &full_bar[s]);
+              tma_load_2d(dst + (uint32_t)g * (uint32_t)KC * 128u, tmap_x, cell0 + 32 * g, b * P.Cin + c * KC, &full_bar[s]);
           }
           __syncwarp();
           if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
@@ -358,7 +359,7 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
       const uint32_t stage_units = stage_bytes >> 4;
       const int kpc = KC / 8;
       uint32_t s = 0, ph = 0, a_stage = (uint32_t)da0, tl = 0;
-      for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++tl) {
+      for (int t = cta; t < P.ntiles; t += ncta, ++tl) {
         const uint32_t buf = tl & 1u;
         mbar_wait(&acc_empty[buf], ((tl >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -400,10 +401,10 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
     const int k_first = (jq * 8) % ch;                      // channel-within-anchor of this warp's first block
     const int k_step = (P.wq * 8) % ch;
     uint32_t tl = 0;
-    // per-tile bookkeeping without divisions: (image, tile within image) advance by gridDim.x with carries
-    int b = blockIdx.x / P.tiles_per_img, ti = blockIdx.x - b * P.tiles_per_img;
-    const int step_b = gridDim.x / P.tiles_per_img, step_t = gridDim.x - step_b * P.tiles_per_img;
-    for (int t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++tl) {
+    // per-tile bookkeeping without divisions: (image, tile within image) advance by ncta with carries
+    int b = cta / P.tiles_per_img, ti = cta - b * P.tiles_per_img;
+    const int step_b = ncta / P.tiles_per_img, step_t = ncta - step_b * P.tiles_per_img;
+    for (int t = cta; t < P.ntiles; t += ncta, ++tl) {
       const uint32_t buf = tl & 1u;
       const int cell0 = ti * kHcM;
       const int cell = cell0 + r;
@@ -518,15 +519,41 @@ head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __g
   }
 }
 
+
+template <bool WANT_RAW>
+__global__ void __launch_bounds__(768, 1)
+head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __grid_constant__ CUtensorMap tmap_x) {
+  head_conv_ws_body<WANT_RAW>(P, &tmap_x, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// All levels of the head in one launch: the CTAs are split between the levels in proportion to their estimated cost
+// (cta_lo), every CTA keeps the weights of its own level resident and runs the same body on that level's tiles.
+struct HeadConvLevelsParams {
+  HeadConvWsParams P[PQDET_MAX_LEVELS];
+  int cta_lo[PQDET_MAX_LEVELS + 1];
+  int n_levels;
+};
+struct HeadConvLevelsMaps {
+  CUtensorMap m[PQDET_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(768, 1)
+head_conv_decode_ws_levels_kernel(const __grid_constant__ HeadConvLevelsParams LP,
+                                  const __grid_constant__ HeadConvLevelsMaps maps) {
+  int l = 0;
+  while (l + 1 < LP.n_levels && (int)blockIdx.x >= LP.cta_lo[l + 1]) ++l;
+  head_conv_ws_body<false>(LP.P[l], &maps.m[l], (int)blockIdx.x - LP.cta_lo[l], LP.cta_lo[l + 1] - LP.cta_lo[l]);
+}
+
 }  // namespace pq
 
 namespace {
 
-// Launches the persistent kernel when the shape qualifies; returns 1 if it did, 0 if the general kernel must run,
-// < 0 on error.
-int try_head_conv_ws(const float* x, const float* weight, const float* bias, float* out_decoded, float* out_raw,
-                     int B, int Cin, int H, int W, int A, int C, float stride, int64_t rows_total, int64_t row_off,
-                     int device, cudaStream_t stream) {
+// Plans the persistent kernel for one level: 1 = P / tmap / smem are filled in, 0 = the shape does not qualify (the
+// general kernel must run), < 0 = error.
+int plan_head_conv_ws(const float* x, const float* weight, const float* bias, float* out_decoded, float* out_raw,
+                      int B, int Cin, int H, int W, int A, int C, float stride, int64_t rows_total, int64_t row_off,
+                      int device, pq::HeadConvWsParams* Pout, CUtensorMap* tmap_out, size_t* smem_out, int* sms_out) {
   using namespace pq;
   const int HW = H * W, ACH = A * (5 + C), N = (ACH + 15) / 16 * 16;
   if (HW % kHcM != 0 || Cin % 8 != 0 || N > 256) return 0;
@@ -621,7 +648,25 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 0;
-  const size_t smem = 1024 + (size_t)P.stages * stage_bytes + w_bytes + (size_t)P.tile_bufs * tile_bytes + bias_bytes;
+  *Pout = P;
+  *tmap_out = tmap;
+  *smem_out = 1024 + (size_t)P.stages * stage_bytes + w_bytes + (size_t)P.tile_bufs * tile_bytes + bias_bytes;
+  *sms_out = sms;
+  return 1;
+}
+
+// Launches the persistent kernel for one level when the shape qualifies; 1 = launched, 0 = general kernel, < 0 = error.
+int try_head_conv_ws(const float* x, const float* weight, const float* bias, float* out_decoded, float* out_raw,
+                     int B, int Cin, int H, int W, int A, int C, float stride, int64_t rows_total, int64_t row_off,
+                     int device, cudaStream_t stream) {
+  using namespace pq;
+  HeadConvWsParams P;
+  CUtensorMap tmap;
+  size_t smem = 0;
+  int sms = 0;
+  const int rc = plan_head_conv_ws(x, weight, bias, out_decoded, out_raw, B, Cin, H, W, A, C, stride, rows_total, row_off,
+                                   device, &P, &tmap, &smem, &sms);
+  if (rc != 1) return rc;
   const int grid = P.ntiles < sms ? P.ntiles : sms;
   static int smem_set[2][64];                 // the attribute sticks per device: raise it only when needed
   const int which = out_raw ? 1 : 0;
@@ -674,6 +719,100 @@ extern "C" int pqdet_head_conv_decode(const float* x, const float* weight, const
   PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((H * W + kHcM - 1) / kHcM, B);
   head_conv_decode_kernel<<<grid, kHcThreads, smem, (cudaStream_t)stream>>>(P);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
+// All levels of the head in one launch (DetectionHead.forward_from_features): level l's rows follow level l-1's in the
+// (B, sum_l H_l*W_l*A, 5+C) prediction.  PQDET_ERR_UNSUPPORTED when a level does not qualify for the persistent kernel
+// (the caller then runs pqdet_head_conv_decode per level).
+extern "C" int pqdet_head_conv_decode_levels(int n_levels, const float* const* x, const float* const* weight,
+                                             const float* const* bias, const int* Cin, const int* H, const int* W,
+                                             const float* stride, float* out_decoded, int B, int A, int C, int device,
+                                             void* stream) {
+  using namespace pq;
+  if (n_levels < 1 || n_levels > PQDET_MAX_LEVELS || !x || !weight || !Cin || !H || !W || !stride)
+    return PQDET_ERR_INVALID_ARG;
+  if (B < 0 || A < 1 || C < 0) return PQDET_ERR_INVALID_ARG;
+  if (B == 0) return PQDET_OK;
+  if (!out_decoded) return PQDET_ERR_INVALID_ARG;
+  if (getenv("PQDET_HEADCONV_GENERAL")) return PQDET_ERR_UNSUPPORTED;
+  int64_t rows_total = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!x[l] || !weight[l] || Cin[l] < 1 || H[l] < 1 || W[l] < 1) return PQDET_ERR_INVALID_ARG;
+    rows_total += (int64_t)H[l] * W[l] * A;
+  }
+  PQ_ENTER(device);
+  // Measured (VOC-512, B200): one launch wins while launch gaps and per-level tails matter (35 vs 55 us at 16 images,
+  // 71 vs 84 us at 64) and loses once every level fills the machine by itself (246 vs 218 us at 256 images, where the
+  // static split between the levels costs more than two launch gaps): decline above ~32 tiles per SM, before any
+  // planning work is spent.
+  {
+    DeviceLimits lim;
+    if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
+    int64_t all_tiles = 0;
+    for (int l = 0; l < n_levels; ++l) all_tiles += (int64_t)B * ((H[l] * W[l] + kHcM - 1) / kHcM);
+    if (all_tiles > (int64_t)32 * lim.sms) return PQDET_ERR_UNSUPPORTED;
+  }
+  HeadConvLevelsParams LP;
+  HeadConvLevelsMaps maps;
+  memset(&LP, 0, sizeof(LP));
+  memset(&maps, 0, sizeof(maps));
+  size_t smem = 0;
+  int sms = 0, threads = 0;
+  int64_t row_off = 0;
+  double cost[PQDET_MAX_LEVELS], total = 0.0;
+  for (int l = 0; l < n_levels; ++l) {
+    size_t sm_l = 0;
+    const int rc = plan_head_conv_ws(x[l], weight[l], bias ? bias[l] : nullptr, out_decoded, nullptr, B, Cin[l], H[l], W[l], A,
+                                     C, stride[l], rows_total, row_off, device, &LP.P[l], &maps.m[l], &sm_l, &sms);
+    if (rc < 0) return rc;
+    if (rc == 0) return PQDET_ERR_UNSUPPORTED;
+    smem = sm_l > smem ? sm_l : smem;
+    const int th = (4 + 4 * LP.P[l].wq) * 32;
+    if (threads && th != threads) return PQDET_ERR_UNSUPPORTED;
+    threads = th;
+    row_off += (int64_t)H[l] * W[l] * A;
+    // time of one tile: a fixed part (epilogue, hand-offs) + the features it streams (measured: 8.0 / 3.8 / 2.3 us per
+    // tile at Cin 352 / 176 / 80)
+    cost[l] = (double)LP.P[l].ntiles * (1.0 + 0.02 * Cin[l]);
+    total += cost[l];
+  }
+  if (sms < n_levels) return PQDET_ERR_UNSUPPORTED;
+  // CTAs per level in proportion to the cost, at least one, never more than the level has tiles
+  int given = 0, share[PQDET_MAX_LEVELS];
+  for (int l = 0; l < n_levels; ++l) {
+    int c = (int)(sms * cost[l] / total + 0.5);
+    c = c < 1 ? 1 : c;
+    c = c > LP.P[l].ntiles ? LP.P[l].ntiles : c;
+    share[l] = c;
+    given += c;
+  }
+  while (given > sms) {                       // rounding overshoot: take from the level with the most CTAs
+    int m = 0;
+    for (int l = 1; l < n_levels; ++l) m = share[l] > share[m] ? l : m;
+    if (share[m] <= 1) return PQDET_ERR_UNSUPPORTED;
+    --share[m]; --given;
+  }
+  for (bool grew = true; given < sms && grew;) {   // leftovers to the level with the most tiles per CTA
+    grew = false;
+    int m = -1;
+    double worst = 0.0;
+    for (int l = 0; l < n_levels; ++l) {
+      const double per = cost[l] / share[l];
+      if (share[l] < LP.P[l].ntiles && per > worst) { worst = per; m = l; }
+    }
+    if (m >= 0) { ++share[m]; ++given; grew = true; }
+  }
+  LP.n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) LP.cta_lo[l + 1] = LP.cta_lo[l] + share[l];
+  for (int l = n_levels; l < PQDET_MAX_LEVELS; ++l) LP.cta_lo[l + 1] = LP.cta_lo[n_levels];
+  static int smem_set[64];
+  if (device < 0 || device >= 64 || (int)smem > smem_set[device]) {
+    PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (device >= 0 && device < 64) smem_set[device] = (int)smem;
+  }
+  head_conv_decode_ws_levels_kernel<<<LP.cta_lo[n_levels], threads, smem, (cudaStream_t)stream>>>(LP, maps);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }

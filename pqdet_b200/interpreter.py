@@ -84,6 +84,16 @@ class _MultiLossSparseFn(torch.autograd.Function):
 _SCALE_SLOT = {8: 0, 16: 1, 32: 2}
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
 class DetectionHead(nn.Module):
     def __init__(self, opts: Sequence[dict], onnx: bool = False):
         """opts: one [yolo] option dict per level, in cfg order (FPN: strides 32, 16, 8)."""
@@ -149,6 +159,13 @@ class DetectionHead(nn.Module):
         rows = [f.shape[2] * f.shape[3] * (w.shape[0] // ch) for f, w in zip(features, weights)]
         N = sum(rows)
         out = torch.empty((B, N, ch), dtype=torch.float32, device=features[0].device)
+        # one launch for all levels when every level qualifies for the persistent kernel and the batch is small enough
+        # for the launch gaps to matter (the C side applies the same rule; checking here saves marshalling twice)
+        tiles = sum(B * ((f.shape[2] * f.shape[3] + 127) // 128) for f in features)
+        if (B and all((f.shape[2] * f.shape[3]) % 128 == 0 for f in features)
+                and tiles <= 32 * _sm_count(features[0].device)
+                and _ops.head_conv_decode_levels(features, weights, biases, C, [l.opt['stride'] for l in self.layers], out)):
+            return out
         off = 0
         for l, f, w, bi, r in zip(self.layers, features, weights, biases, rows):
             _ops.head_conv_decode(f, w, bi, C, l.opt['stride'], out=out, rows_total=N, row_offset=off)

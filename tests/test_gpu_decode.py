@@ -234,6 +234,35 @@ def test_sigmoid_reciprocal_out_of_range_logits(monkeypatch):
     assert torch.allclose(sig[ok].double(), ref[ok], rtol=1e-5, atol=1e-37)
 
 
+@pytest.mark.parametrize("B,C,size,cins", [(2, 20, 512, (352, 176, 80)), (37, 20, 512, (352, 176, 80)), (3, 10, 512, (64, 32, 16)),
+                                           (1, 20, 512, (352, 176, 80)), (5, 20, 1024, (48, 24)), (100, 20, 512, (80, 40, 16))])
+def test_head_conv_all_levels_in_one_launch(B, C, size, cins):
+    """pqdet_head_conv_decode_levels: the SMs are split between the levels, every CTA keeps its level's weights
+    resident; rows identical to one pqdet_head_conv_decode launch per level."""
+    from pqdet_b200 import _ops
+    g = torch.Generator(device="cuda").manual_seed(B + C)
+    ch = 5 + C
+    strides = (32, 16, 8)[:len(cins)]
+    feats = [torch.randn((B, c, size // s, size // s), device="cuda", generator=g) for c, s in zip(cins, strides)]
+    ws = [torch.randn((3 * ch, c, 1, 1), device="cuda", generator=g) * 0.04 for c in cins]
+    bs = [torch.randn((3 * ch,), device="cuda", generator=g) * 0.1 for _ in cins]
+    bs[-1] = None
+    N = sum(f.shape[2] * f.shape[3] * 3 for f in feats)
+    out = torch.full((B, N, ch), -3.0, device="cuda")
+    assert _ops.head_conv_decode_levels(feats, ws, bs, C, strides, out)
+    ref = torch.empty_like(out)
+    off = 0
+    for f, w, b, s in zip(feats, ws, bs, strides):
+        _ops.head_conv_decode(f, w, b, C, s, out=ref, rows_total=N, row_offset=off)
+        off += f.shape[2] * f.shape[3] * 3
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    # a level that does not qualify (8x8 = 64 cells) makes the call decline instead of computing something else
+    small = [torch.randn((B, 16, 8, 8), device="cuda")]
+    assert not _ops.head_conv_decode_levels(small, [torch.randn((3 * ch, 16), device="cuda")], [None], C, (32,),
+                                            torch.empty((B, 192, ch), device="cuda"))
+
+
 def test_forward_from_features_equals_conv_then_decode():
     from pqdet_b200 import _ops
     from pqdet_b200.interpreter import DetectionHead
