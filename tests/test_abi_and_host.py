@@ -41,6 +41,14 @@ def test_argument_validation_happens_before_any_cuda_call(lib):
     H = (ctypes.c_int * 3)(64, 32, 16)
     assert lib.pqdet_assign_workspace(2, H, H) >= 2 * (64 * 64 + 32 * 32 + 16 * 16) * 3 * 4
     assert lib.pqdet_loss_levels_workspace(3, 16, 3, H, H) > 0
+    # the section 8f entry points: same contract
+    assert lib.pqdet_head_conv_decode(None, None, None, None, None, 1, 8, 16, 16, 3, 20, ctypes.c_float(8), 768, 0, 0,
+                                      None) == -1
+    assert lib.pqdet_head_conv_decode(None, None, None, None, None, 0, 8, 16, 16, 3, 20, ctypes.c_float(8), 768, 0, 0,
+                                      None) == 0                      # empty batch: nothing to do, no pointer needed
+    assert lib.pqdet_head_conv_decode_levels(0, None, None, None, None, None, None, None, None, 1, 3, 20, 0, None) == -1
+    assert lib.pqdet_head_conv_decode_levels(5, None, None, None, None, None, None, None, None, 1, 3, 20, 0, None) == -1
+    assert lib.pqdet_decode_levels(0, None, None, None, None, None, 1, 3, 20, 0, None) == -1
 
 
 def test_product_never_imports_the_oracle():
