@@ -65,6 +65,55 @@ def install(strict: bool = False, patch_augment: bool = False) -> dict:
     return done
 
 
+def fuse_head_convs(model) -> int:
+    """SURVEY 8f-2 as a hook: let every `[yolo]` level of a reference DetectionModel (built after install(), weights
+    loaded) run its 1x1 head convolution + Decode as ONE tensor-core kernel in eval mode.
+
+    For each pqdet_b200.parser.YOLOLayer in `model.module_list` whose predecessor is the plain head convolution of the
+    cfgs (`filters=A*(5+C), size=1, stride=1, activation=linear`, no batch norm: an nn.Sequential holding only `conv`,
+    model/parser.py:385-410) and whose output no route / shortcut reads, the conv block's forward is overridden on
+    the instance: in eval mode on CUDA it hands its INPUT to the YOLOLayer together with its own parameters
+    (pqdet_head_conv_decode); in training mode, on CPU, for ONNX export or when a target is given it still convolves.
+    No module is added or renamed, so state_dict keys, pruning and checkpoint loading are unchanged.  Returns the
+    number of levels fused."""
+    import types
+
+    import torch
+
+    layers = list(model.module_list)
+    used = set()
+    for j, layer in enumerate(layers):              # who reads which cached output (model/interpreter.py:46-50)
+        t = getattr(layer, '_type', None)
+        refs = []
+        if t in ('shortcut', 'scale_channels'):
+            refs = [layer._from]
+        elif t == 'route':
+            refs = list(layer._layers)
+        for r in refs:
+            used.add(r if r >= 0 else j + r)
+    fused = 0
+    for i, layer in enumerate(layers):
+        if i == 0 or not isinstance(layer, parser.YOLOLayer) or getattr(model, 'quant', False):
+            continue
+        prev = layers[i - 1]
+        conv = getattr(prev, 'conv', None)
+        if getattr(prev, '_type', None) != 'convolutional' or not isinstance(conv, torch.nn.Conv2d) or len(prev) != 1:
+            continue
+        if (conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.padding != (0, 0) or conv.dilation != (1, 1)
+                or conv.groups != 1 or conv.out_channels % (5 + layer.opt['classes']) or (i - 1) in used):
+            continue
+
+        def forward(self, x, _yolo=layer, _plain=type(prev).forward):
+            if self.training or not x.is_cuda or _yolo.decode.onnx:
+                return _plain(self, x)
+            object.__setattr__(_yolo, '_pq_pending_conv', self.conv)      # not a submodule: state_dict unchanged
+            return x
+
+        prev.forward = types.MethodType(forward, prev)
+        fused += 1
+    return fused
+
+
 def _patch_evaluator():
     """Evaluator keeps its loop (eval/evaluator.py:44-62); its statistics go through DetectionAccumulator, so AP()
     runs the matching on the GPU and returns the same tools.AP tuple."""

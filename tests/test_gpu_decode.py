@@ -263,6 +263,75 @@ def test_head_conv_all_levels_in_one_launch(B, C, size, cins):
                                             torch.empty((B, 192, ch), device="cuda"))
 
 
+def test_fuse_head_convs_hook_on_a_reference_shaped_model():
+    """install.fuse_head_convs on a model laid out like the reference's DetectionModel (module_list of blocks with
+    `_type`, the 1x1 linear head conv in front of every [yolo], model/interpreter.py:40-63): eval output = Decode of the
+    convolution within TF32 precision, identical to pqdet_head_conv_decode; training mode, eval with a target, a head
+    conv whose output a route reads, and CPU tensors still run the convolution itself."""
+    from torch import nn
+    from pqdet_b200 import _ops, install, parser as pqp
+    C, ch = 20, 25
+
+    class Mock(nn.Module):
+        def __init__(self, routed):
+            super().__init__()
+            def block(mod, t, **kw):
+                for k, v in dict(_type=t, **kw).items():
+                    setattr(mod, k, v)
+                return mod
+            trunk = nn.Sequential()
+            trunk.add_module('conv', nn.Conv2d(3, 32, 3, padding=1))
+            trunk.add_module('act', nn.ReLU())
+            head = nn.Sequential()
+            head.add_module('conv', nn.Conv2d(32, 3 * ch, 1))
+            yolo = pqp.YOLOLayer(dict(classes=C, stride=8, bbox_loss='l1', ignore_thresh=0.5, l1_loss_gain=0.05))
+            mods = [block(trunk, 'convolutional'), block(head, 'convolutional'), block(yolo, 'yolo')]
+            if routed:
+                mods.append(block(nn.Identity(), 'route', _layers=[-2]))
+            self.module_list = nn.ModuleList(mods)
+
+        def forward(self, x, target=None):
+            cache = []
+            out = None
+            for layer in self.module_list:
+                if layer._type == 'yolo':
+                    x = layer(x, target)
+                    out = x
+                elif layer._type == 'route':
+                    x = cache[len(cache) + layer._layers[0]]
+                else:
+                    x = layer(x)
+                cache.append(x)
+            return out
+
+    torch.manual_seed(5)
+    m = Mock(False).cuda().eval()
+    img = torch.randn(2, 3, 32, 64, device="cuda")
+    label = torch.zeros((2, 32, 64, 3, 6 + C), device="cuda")            # the mock trunk keeps the resolution
+    label[..., 5] = 1.0                                                  # mix weight; no responsible cell
+    target = (label, torch.zeros((2, 1, 4), device="cuda"))
+    with torch.no_grad():
+        want = m(img)                                                    # conv (cuDNN, TF32 allowed) + our Decode
+        want_loss = m(img, target)
+        assert install.fuse_head_convs(m) == 1
+        got = m(img)
+        feats = m.module_list[0](img)
+        direct = _ops.head_conv_decode(feats, m.module_list[1].conv.weight, m.module_list[1].conv.bias, C, 8)
+        assert got.shape == want.shape and torch.equal(got, direct)
+        assert torch.allclose(got[..., 4:], want[..., 4:], rtol=0, atol=5e-3)
+        assert not hasattr(m.module_list[2], '_pq_pending_conv')
+        # eval with a target (validation loss): the YOLOLayer applies the convolution itself
+        got_loss = m(img, target)
+        for a_, b_ in zip(got_loss, want_loss):
+            assert torch.allclose(a_, b_, rtol=1e-4, atol=1e-6)
+        assert not hasattr(m.module_list[2], '_pq_pending_conv')
+        m.train()
+        assert m.module_list[1](feats).shape[1] == 3 * ch               # training mode: the block convolves
+        m.eval()
+    routed = Mock(True).cuda().eval()
+    assert install.fuse_head_convs(routed) == 0                         # someone else reads the raw head: left alone
+
+
 def test_forward_from_features_equals_conv_then_decode():
     from pqdet_b200 import _ops
     from pqdet_b200.interpreter import DetectionHead

@@ -43,6 +43,15 @@ def test_install_patches_the_reference_hook_points():
         ev._classes = ['a', 'b']
         ev.init_statics()
         assert type(ev._pq_acc).__name__ == 'DetectionAccumulator' and ev.detections_count == 0
+        # section 8f-2 hook: the three head convolutions hand their input to the YOLOLayer in CUDA eval mode; nothing
+        # about the module tree changes, and on CPU / in training mode the convolution still runs
+        import torch
+        keys = list(m.state_dict().keys())
+        assert inst.fuse_head_convs(m) == 3 and list(m.state_dict().keys()) == keys
+        head_conv = m.module_list[[i for i, l in enumerate(m.module_list) if l._type == 'yolo'][0] - 1]
+        probe = torch.randn(1, head_conv.conv.in_channels, 2, 2)
+        m.eval()
+        assert tuple(head_conv(probe).shape) == (1, 75, 2, 2) and not hasattr(yolo[0], '_pq_pending_conv')
         print('ok')
     """) % (ROOT, os.path.join(rh.REFERENCE_ROOT, "model", "cfg", "regnetx-600m-fpn.cfg"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=rh.REFERENCE_ROOT, timeout=300)
