@@ -84,6 +84,37 @@ class _MultiLossSparseFn(torch.autograd.Function):
 _SCALE_SLOT = {8: 0, 16: 1, 32: 2}
 
 
+
+def combine_eval(layers, outs: Sequence[torch.Tensor]) -> torch.Tensor:
+    """The eval branch of DetectionModel.forward (model/interpreter.py:72-76) on what the [yolo] layers RECEIVED: raw
+    heads, or - after install.fuse_head_convs - the inputs of the head convolutions, tagged with their nn.Conv2d.
+    Every level is decoded straight into its row range of the (B, N, 5+C) prediction: no per-level tensor, no cat."""
+    C = layers[0].opt['classes']
+    ch = 5 + C
+    strides = [l.opt['stride'] for l in layers]
+    convs = [getattr(o, '_pq_pending_conv', None) for o in outs]
+    if all(c is None for c in convs):
+        return _ops.decode_levels(list(outs), C, strides)
+    B = outs[0].shape[0]
+    A = [(o.shape[1] if c is None else c.out_channels) // ch for o, c in zip(outs, convs)]
+    rows = [o.shape[2] * o.shape[3] * a for o, a in zip(outs, A)]
+    N = sum(rows)
+    out = torch.empty((B, N, ch), dtype=torch.float32, device=outs[0].device)
+    if B and all(c is not None for c in convs):
+        tiles = sum(B * ((o.shape[2] * o.shape[3] + 127) // 128) for o in outs)
+        if (all((o.shape[2] * o.shape[3]) % 128 == 0 for o in outs) and tiles <= 32 * _sm_count(outs[0].device)
+                and _ops.head_conv_decode_levels(outs, [c.weight for c in convs], [c.bias for c in convs], C, strides, out)):
+            return out
+    off = 0
+    for o, c, s, r in zip(outs, convs, strides, rows):
+        if c is None:
+            _ops.decode_fwd(o, C, s, out=out, rows_total=N, row_offset=off)
+        else:
+            _ops.head_conv_decode(o, c.weight, c.bias, C, s, out=out, rows_total=N, row_offset=off)
+        off += r
+    return out
+
+
 _SM_COUNT = {}
 
 

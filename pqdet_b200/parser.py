@@ -62,10 +62,13 @@ class YOLOLayer(nn.Module):
         self.opt = opt
 
     def forward(self, x, target=None):
-        conv = self.__dict__.pop('_pq_pending_conv', None)
+        if target is None and self.__dict__.get('_pq_passthrough'):
+            return x                          # install.fuse_eval_concat: the model decodes all levels in one launch
+        conv = getattr(x, '_pq_pending_conv', None)
         if conv is not None:
             # install.fuse_head_convs: x is the INPUT of this level's 1x1 head convolution (the conv block passed its
-            # input through); eval runs convolution + Decode as one tensor-core kernel, anything else applies the conv
+            # input through, tagged); eval runs convolution + Decode as one tensor-core kernel, anything else applies
+            # the convolution first
             if target is None and not self.decode.onnx:
                 return _ops.head_conv_decode(x, conv.weight, conv.bias, self.opt['classes'], self.opt['stride'])
             x = torch.nn.functional.conv2d(x, conv.weight, conv.bias)

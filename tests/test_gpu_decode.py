@@ -319,17 +319,93 @@ def test_fuse_head_convs_hook_on_a_reference_shaped_model():
         direct = _ops.head_conv_decode(feats, m.module_list[1].conv.weight, m.module_list[1].conv.bias, C, 8)
         assert got.shape == want.shape and torch.equal(got, direct)
         assert torch.allclose(got[..., 4:], want[..., 4:], rtol=0, atol=5e-3)
-        assert not hasattr(m.module_list[2], '_pq_pending_conv')
         # eval with a target (validation loss): the YOLOLayer applies the convolution itself
         got_loss = m(img, target)
         for a_, b_ in zip(got_loss, want_loss):
             assert torch.allclose(a_, b_, rtol=1e-4, atol=1e-6)
-        assert not hasattr(m.module_list[2], '_pq_pending_conv')
+        # nn.DataParallel-style replicas (module __dict__ copies) carry no reference to the original modules
+        rep = m.module_list[1]._replicate_for_data_parallel()
+        assert type(rep).__name__ == '_FusedHeadConv' and not any(v is m.module_list[2] for v in rep.__dict__.values())
         m.train()
         assert m.module_list[1](feats).shape[1] == 3 * ch               # training mode: the block convolves
         m.eval()
     routed = Mock(True).cuda().eval()
     assert install.fuse_head_convs(routed) == 0                         # someone else reads the raw head: left alone
+
+
+def test_fuse_eval_concat_hook_on_a_reference_shaped_model():
+    """install.fuse_eval_concat on a model laid out like the reference's (AnyModel.forward = the layer loop returning
+    the [yolo] outputs, DetectionModel.forward = view + cat, model/interpreter.py:40-76): identical bits to the
+    per-level Decode + cat; with fuse_head_convs on top, identical to the head-conv kernel per level; training mode and
+    targets still take the reference's forward."""
+    from torch import nn
+    from pqdet_b200 import _ops, install, parser as pqp
+    C, ch = 20, 25
+
+    def block(mod, t, **kw):
+        for k, v in dict(_type=t, **kw).items():
+            setattr(mod, k, v)
+        return mod
+
+    class Loop(nn.Module):                       # AnyModel
+        def forward(self, x, target=None):
+            cache, outputs = [], []
+            for layer in self.module_list:
+                if layer._type == 'yolo':
+                    x = layer(x, target)
+                    outputs.append(x)
+                elif layer._type == 'route':
+                    x = cache[layer._layers[0]]
+                else:
+                    x = layer(x)
+                cache.append(x)
+            return outputs
+
+    class Model(Loop):                           # DetectionModel
+        def __init__(self):
+            super().__init__()
+            mods = []
+            def conv(cin, cout, k, act):
+                b = nn.Sequential()
+                b.add_module('conv', nn.Conv2d(cin, cout, k, padding=k // 2))
+                if act:
+                    b.add_module('act', nn.ReLU())
+                return block(b, 'convolutional')
+            mods.append(conv(3, 32, 3, True))                                               # 0 trunk
+            mods.append(conv(32, 3 * ch, 1, False))                                         # 1 head
+            mods.append(block(pqp.YOLOLayer(dict(classes=C, stride=32, bbox_loss='l1', ignore_thresh=0.5)), 'yolo'))
+            mods.append(block(nn.Identity(), 'route', _layers=[0]))                         # 3 back to the trunk
+            mods.append(block(nn.UpsamplingNearest2d(scale_factor=2), 'upsample'))          # 4
+            mods.append(conv(32, 16, 3, True))                                              # 5
+            mods.append(conv(16, 3 * ch, 1, False))                                         # 6 head
+            mods.append(block(pqp.YOLOLayer(dict(classes=C, stride=16, bbox_loss='l1', ignore_thresh=0.5)), 'yolo'))
+            self.module_list = nn.ModuleList(mods)
+
+        def forward(self, x, target=None):
+            outputs = super().forward(x, target)
+            if target is None:
+                return torch.cat([o.view((o.shape[0], -1, o.shape[-1])) for o in outputs], dim=1)
+            return outputs
+
+    torch.manual_seed(9)
+    m = Model().cuda().eval()
+    img = torch.randn(3, 3, 16, 32, device="cuda")
+    with torch.no_grad():
+        want = m(img)                                                     # Decode per level + view + cat
+        assert install.fuse_eval_concat(m) and install.fuse_eval_concat(m)
+        got = m(img)
+        assert got.shape == want.shape == (3, (16 * 32 + 32 * 64) * 3, ch) and torch.equal(got, want)
+        assert install.fuse_head_convs(m) == 2
+        fused = m(img)
+        f0 = m.module_list[0](img)
+        f1 = m.module_list[5](m.module_list[4](f0))
+        rows = [_ops.head_conv_decode(f, m.module_list[i].conv.weight, m.module_list[i].conv.bias, C, s).reshape(3, -1, ch)
+                for f, i, s in ((f0, 1, 32), (f1, 6, 16))]
+        assert torch.equal(fused, torch.cat(rows, 1))
+        assert torch.allclose(fused[..., 4:], want[..., 4:], rtol=0, atol=5e-3)
+        assert not any('_pq_passthrough' in l.__dict__ for l in m.module_list)
+    m.train()
+    assert isinstance(m(img, None), torch.Tensor)                        # training mode: the reference's own forward
 
 
 def test_forward_from_features_equals_conv_then_decode():

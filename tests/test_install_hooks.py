@@ -51,7 +51,12 @@ def test_install_patches_the_reference_hook_points():
         head_conv = m.module_list[[i for i, l in enumerate(m.module_list) if l._type == 'yolo'][0] - 1]
         probe = torch.randn(1, head_conv.conv.in_channels, 2, 2)
         m.eval()
-        assert tuple(head_conv(probe).shape) == (1, 75, 2, 2) and not hasattr(yolo[0], '_pq_pending_conv')
+        assert tuple(head_conv(probe).shape) == (1, 75, 2, 2) and type(head_conv).__name__ == '_FusedHeadConv'
+        import copy, pickle
+        assert pickle.loads(pickle.dumps(head_conv)).conv.weight.shape == head_conv.conv.weight.shape
+        # row a4 hook: the model's class gains a forward that combines the levels in one launch; module tree unchanged
+        assert inst.fuse_eval_concat(m) and list(m.state_dict().keys()) == keys
+        assert type(m).__mro__[1].__name__ == 'DetectionModel' and type(m).__mro__[2].__name__ == 'AnyModel'
         print('ok')
     """) % (ROOT, os.path.join(rh.REFERENCE_ROOT, "model", "cfg", "regnetx-600m-fpn.cfg"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=rh.REFERENCE_ROOT, timeout=300)
