@@ -323,6 +323,8 @@ struct DecodeTmaParams {
   float* out;
   int A, ch, n_levels;
   int Wd[PQDET_MAX_LEVELS];
+  int HW[PQDET_MAX_LEVELS];               // cells of a plane; the last tile of a level may be partial
+  int bulk[PQDET_MAX_LEVELS];             // 1: the level's row range is 16-byte aligned -> tiles leave as bulk stores
   uint32_t magic_w[PQDET_MAX_LEVELS];     // ceil(2^32 / W): cell / W by multiply-high (0 when W == 1)
   float stride[PQDET_MAX_LEVELS];
   int64_t row_off[PQDET_MAX_LEVELS];
@@ -387,6 +389,7 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       while (l + 1 < P.n_levels && t >= P.tile_off[l + 1]) ++l;
       const int cell0 = (t - P.tile_off[l]) * kDtmCells;
       const int cell = cell0 + r;
+      const int ncell = min(kDtmCells, P.HW[l] - cell0);     // < 128 on a level's last tile (TMA zero-fills the rest)
       const int Wd = P.Wd[l];
       const int cy = P.magic_w[l] ? (int)__umulhi((uint32_t)cell, P.magic_w[l]) : cell, cx = cell - cy * Wd;
       const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
@@ -399,7 +402,7 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       mbar_wait(&full_bar[s], ph);
       const float* src = reinterpret_cast<const float*>(dsm + (size_t)s * stage_bytes) + r;
       float* trow0 = tile + r * ACH;
-      for (int u = jq; u < nunit; u += P.wq) {
+      for (int u = jq; u < (r < ncell ? nunit : 0); u += P.wq) {
         if (u >= nsig) {
           const int a = u - nsig;
           const float* sp = src + (a * ch) * kDtmCells;
@@ -435,11 +438,19 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
       if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
-      fence_async_smem();
-      epi_bar_sync(n_cmp);
-      if (ctid == 0) {
-        tma_store_1d(dst, tile, (uint32_t)(kDtmCells * ACH * sizeof(float)));
-        tma_store_commit();
+      if (P.bulk[l]) {
+        fence_async_smem();
+        epi_bar_sync(n_cmp);
+        if (ctid == 0) {
+          tma_store_1d(dst, tile, (uint32_t)(ncell * ACH * sizeof(float)));
+          tma_store_commit();
+        }
+      } else {
+        // the level's rows do not start on a 16-byte boundary (e.g. behind a 19x19 level): cooperative stores; the
+        // barrier at the top of the tile after next orders them against the reuse of this staging tile
+        epi_bar_sync(n_cmp);
+        const int n = ncell * ACH;
+        for (int e = ctid; e < n; e += n_cmp) dst[e] = tile[e];
       }
     }
     if (ctid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -451,13 +462,18 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
 namespace {
 
 // Launches the persistent TMA kernel when every level qualifies; 1 = launched, 0 = use the general kernel, < 0 = error.
+// A level qualifies when a tensor map can address its planes: plane stride (H*W*4 bytes) a multiple of 16, base aligned.
+bool decode_level_tma_ok(const float* raw, int H, int W) {
+  return ((H * W) % 4 == 0) && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && (int64_t)H * W * W < 0x100000000ll;
+}
+
 int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, const int* W, const float* stride,
-                          float* out, int B, int A, int C, int64_t rows, int64_t base_row_off, int device,
+                          const int64_t* row_offs, float* out, int B, int A, int C, int64_t rows, int device,
                           cudaStream_t stream) {
   using namespace pq;
   const int ch = 5 + C, ACH = A * ch;
   if (ACH > 256) return 0;
-  if ((reinterpret_cast<uintptr_t>(out) & 15) || (((size_t)rows * ch * 4) & 15)) return 0;
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (((size_t)rows * ch * 4) & 15) == 0;
   PqEncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return 0;
   DecodeTmaParams P;
@@ -465,17 +481,15 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   memset(&P, 0, sizeof(P));
   memset(&maps, 0, sizeof(maps));
   int tiles = 0;
-  int64_t row_off = base_row_off;
   for (int l = 0; l < n_levels; ++l) {
     const int HW = H[l] * W[l];
-    if (HW % kDtmCells != 0 || (reinterpret_cast<uintptr_t>(raw[l]) & 15)) return 0;
+    if (!decode_level_tma_ok(raw[l], H[l], W[l])) return 0;
     if ((int64_t)B * ACH > 0x7fffffff) return 0;
-    if (((size_t)row_off * ch * 4) & 15) return 0;
-    P.Wd[l] = W[l]; P.stride[l] = stride[l]; P.row_off[l] = row_off; P.tile_off[l] = tiles;
+    const int64_t row_off = row_offs[l];
+    P.Wd[l] = W[l]; P.HW[l] = HW; P.stride[l] = stride[l]; P.row_off[l] = row_off; P.tile_off[l] = tiles;
+    P.bulk[l] = (out_aligned && (((size_t)row_off * ch * 4) & 15) == 0) ? 1 : 0;
     P.magic_w[l] = W[l] == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)W[l] - 1) / (uint64_t)W[l]);
-    if ((int64_t)HW * W[l] >= 0x100000000ll) return 0;          // multiply-high exact for cell < 2^32 / W
-    tiles += HW / kDtmCells;
-    row_off += (int64_t)HW * A;
+    tiles += (HW + kDtmCells - 1) / kDtmCells;
     cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)B * ACH}, strides[1] = {(cuuint64_t)HW * 4};
     cuuint32_t box[2] = {(cuuint32_t)kDtmCells, (cuuint32_t)ACH}, estr[2] = {1u, 1u};
     if (enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(raw[l]), dims, strides, box, estr,
@@ -534,7 +548,7 @@ extern "C" int pqdet_decode_fwd(const float* raw, float* out, int B, int A, int 
   PQ_ENTER(device);
   const int ch = 5 + C;
   if (!getenv("PQDET_DECODE_GENERAL")) {
-    const int rc = try_decode_levels_tma(1, &raw, &H, &W, &stride, out, B, A, C, out_rows_total, out_row_offset, device,
+    const int rc = try_decode_levels_tma(1, &raw, &H, &W, &stride, &out_row_offset, out, B, A, C, out_rows_total, device,
                                          (cudaStream_t)stream);
     if (rc != 0) return rc < 0 ? rc : PQDET_OK;
   }
@@ -557,25 +571,48 @@ extern "C" int pqdet_decode_levels(int n_levels, const float* const* raw, const 
   if (B == 0) return PQDET_OK;
   if (B > 65535) return PQDET_ERR_UNSUPPORTED;
   if (!out) return PQDET_ERR_INVALID_ARG;
-  DecodeLevels L;
-  memset(&L, 0, sizeof(L));
-  int64_t rows = 0;
-  int tiles = 0;
+  int64_t rows = 0, row_off[PQDET_MAX_LEVELS];
   for (int l = 0; l < n_levels; ++l) {
     if (!raw[l] || H[l] < 1 || W[l] < 1) return PQDET_ERR_INVALID_ARG;
-    L.raw[l] = raw[l]; L.H[l] = H[l]; L.W[l] = W[l]; L.stride[l] = stride[l];
-    L.row_off[l] = rows; L.tile_off[l] = tiles;
+    row_off[l] = rows;
     rows += (int64_t)H[l] * W[l] * A;
-    tiles += (H[l] * W[l] + kTileCells - 1) / kTileCells;
   }
-  for (int l = n_levels; l <= PQDET_MAX_LEVELS; ++l) L.tile_off[l] = tiles;
-  L.n_levels = n_levels;
   PQ_ENTER(device);
   const int ch = 5 + C;
+  // Levels a tensor map can address (plane stride a multiple of 16 bytes) go to the persistent TMA pipeline, the
+  // others (e.g. the 19x19 level of a 608 input) to the general kernel; both write their own row ranges of `out`.
+  bool on_tma[PQDET_MAX_LEVELS] = {false, false, false, false};
   if (!getenv("PQDET_DECODE_GENERAL")) {
-    const int rc = try_decode_levels_tma(n_levels, raw, H, W, stride, out, B, A, C, rows, 0, device, (cudaStream_t)stream);
-    if (rc != 0) return rc < 0 ? rc : PQDET_OK;
+    const float* t_raw[PQDET_MAX_LEVELS];
+    int t_H[PQDET_MAX_LEVELS], t_W[PQDET_MAX_LEVELS], idx[PQDET_MAX_LEVELS], nt = 0;
+    float t_stride[PQDET_MAX_LEVELS];
+    int64_t t_off[PQDET_MAX_LEVELS];
+    for (int l = 0; l < n_levels; ++l) {
+      if (!decode_level_tma_ok(raw[l], H[l], W[l])) continue;
+      t_raw[nt] = raw[l]; t_H[nt] = H[l]; t_W[nt] = W[l]; t_stride[nt] = stride[l]; t_off[nt] = row_off[l];
+      idx[nt++] = l;
+    }
+    if (nt > 0) {
+      const int rc = try_decode_levels_tma(nt, t_raw, t_H, t_W, t_stride, t_off, out, B, A, C, rows, device,
+                                           (cudaStream_t)stream);
+      if (rc < 0) return rc;
+      if (rc == 1)
+        for (int i = 0; i < nt; ++i) on_tma[idx[i]] = true;
+    }
   }
+  DecodeLevels L;
+  memset(&L, 0, sizeof(L));
+  int tiles = 0, ng = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (on_tma[l]) continue;
+    L.raw[ng] = raw[l]; L.H[ng] = H[l]; L.W[ng] = W[l]; L.stride[ng] = stride[l];
+    L.row_off[ng] = row_off[l]; L.tile_off[ng] = tiles;
+    tiles += (H[l] * W[l] + kTileCells - 1) / kTileCells;
+    ++ng;
+  }
+  if (ng == 0) return PQDET_OK;
+  for (int l = ng; l <= PQDET_MAX_LEVELS; ++l) L.tile_off[l] = tiles;
+  L.n_levels = ng;
   const size_t smem = (size_t)kTileCells * ((A * ch) | 1) * sizeof(float);
   if (smem > 48 * 1024)
     PQ_CUDA(cudaFuncSetAttribute(decode_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -160,24 +160,29 @@ def test_head_conv_persistent_kernel_equals_general_kernel(B, Cin, H, W, C, monk
     assert torch.equal(dec, dec_g) and torch.equal(dec_only, dec_g)
 
 
-@pytest.mark.parametrize("B,C,size", [(3, 20, 512), (37, 20, 512), (5, 10, 512), (2, 1, 512), (2, 80, 512), (9, 3, 1024)])
-def test_eval_concat_tma_pipeline_equals_general_kernel(B, C, size, monkeypatch):
-    """The eval concat of 128-cell-aligned levels runs as a persistent TMA pipeline (tensor-map loads -> decode -> bulk
-    store); PQDET_DECODE_GENERAL forces the general kernel.  Identical bits, more tiles than SMs included; C = 80
-    does not fit the pipeline's shared memory and must fall back by itself."""
+@pytest.mark.parametrize("B,C,size,strides", [(3, 20, 512, (32, 16, 8)), (37, 20, 512, (32, 16, 8)), (5, 10, 512, (32, 16, 8)),
+                                              (2, 1, 512, (32, 16, 8)), (2, 80, 512, (32, 16, 8)), (9, 3, 1024, (32, 16, 8)),
+                                              (3, 10, 608, (32, 16, 8)), (2, 20, 416, (32, 16, 8)), (2, 20, 320, (32, 16, 8)),
+                                              (3, 10, 608, (8, 16, 32)), (2, 20, 416, (8, 16, 32)), (40, 10, 608, (32, 16, 8))])
+def test_eval_concat_tma_pipeline_equals_general_kernel(B, C, size, strides, monkeypatch):
+    """The eval concat runs as a persistent TMA pipeline (tensor-map loads -> decode -> bulk store) for every level
+    whose plane stride a tensor map can address; PQDET_DECODE_GENERAL forces the general kernel.  Identical bits, more
+    tiles than SMs included.  C = 80 does not fit the pipeline's shared memory and falls back by itself; 608 / 416 /
+    320 inputs have a level the pipeline cannot take (19x19, 13x13: general kernel, same launch sequence), partial
+    last tiles, and - behind such a level - row ranges that are not 16-byte aligned (cooperative stores)."""
     from pqdet_b200 import _ops
     g = torch.Generator(device="cuda").manual_seed(B * 100 + C)
     ACH = 3 * (5 + C)
-    strides = (32, 16, 8)
     raws = [torch.randn((B, ACH, size // s, size // s), device="cuda", generator=g) * 1.5 for s in strides]
     raws[0][0, :, 0, 0] = -120.0                                     # the checked reciprocal path
     raws[1][-1, 4::5 + C, 1, 2] = float("nan")
     got = _ops.decode_levels(raws, C, strides)
+    got2 = _ops.decode_levels(raws, C, strides)                      # staging tiles / ring phases reused
     monkeypatch.setenv("PQDET_DECODE_GENERAL", "1")
     ref = _ops.decode_levels(raws, C, strides)
     torch.cuda.synchronize()
     assert got.shape == ref.shape
-    assert torch.equal(got.view(torch.int32), ref.view(torch.int32))
+    assert torch.equal(got.view(torch.int32), ref.view(torch.int32)) and torch.equal(got2.view(torch.int32), ref.view(torch.int32))
     rows = [_ops.decode_fwd(r, C, s).reshape(B, -1, 5 + C) for r, s in zip(raws, strides)]
     assert torch.equal(torch.cat(rows, 1).view(torch.int32), got.view(torch.int32))
 
