@@ -104,6 +104,26 @@ def detect(raws, num_classes: int, strides) -> np.ndarray:
     return np.concatenate([o.reshape(o.shape[0], -1, o.shape[-1]) for o in outs], axis=1)
 
 
+def head_conv(x: np.ndarray, weight: np.ndarray, bias) -> np.ndarray:
+    """The `filters = A*(5+C), size = 1, stride = 1, activation = linear` convolution in front of every [yolo] layer
+    (model/cfg/regnetx-600m-fpn.cfg:646-651; built as nn.Conv2d by model/parser.py:385-401): a per-cell matrix product,
+    accumulated in float64 (the reference's ATen kernel accumulates in fp32 on CPU and in TF32 products / fp32
+    accumulation on CUDA; both are compared to this within their precision).  x (B,Cin,H,W), weight (O,Cin[,1,1]),
+    bias (O,) or None -> raw (B,O,H,W) float64."""
+    w = np.asarray(weight, dtype=np.float64).reshape(weight.shape[0], -1)
+    raw = np.einsum("bchw,oc->bohw", np.asarray(x, dtype=np.float64), w, optimize=True)
+    if bias is not None:
+        raw = raw + np.asarray(bias, dtype=np.float64).reshape(1, -1, 1, 1)
+    return raw
+
+
+def head_conv_error_bound(x: np.ndarray, weight: np.ndarray, rel: float) -> np.ndarray:
+    """|error| allowed for a head convolution whose operands carry a relative error `rel` each (2^-10 for TF32
+    truncation, ~2^-24 for fp32 accumulation noise): 2 * rel * sum_c |x_c * w_c| + 1e-5."""
+    w = np.abs(np.asarray(weight, dtype=np.float64)).reshape(weight.shape[0], -1)
+    return 2.0 * rel * np.einsum("bchw,oc->bohw", np.abs(np.asarray(x, dtype=np.float64)), w, optimize=True) + 1e-5
+
+
 # --------------------------------------------------------------------------------------------
 # a5  recover  (dataset/base_sample.py:98-139, voc_sample.py:92-95, coco_sample.py:97-100,
 #               visdrone_sample.py:84-88)

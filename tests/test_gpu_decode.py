@@ -127,12 +127,16 @@ def test_head_conv_decode_tensor_cores(B, Cin, H, W, C, stride):
     w = torch.randn((ACH, Cin, 1, 1), device="cuda", generator=g) * 0.05
     bias = torch.randn((ACH,), device="cuda", generator=g) * 0.1
     dec, raw = _ops.head_conv_decode(x, w, bias, C, stride, want_raw=True)
-    ref = torch.einsum("bchw,oc->bohw", x.double(), w.view(ACH, Cin).double()) + bias.double().view(1, -1, 1, 1)
-    # |error| <= 2 * 2^-10 * sum_c |x_c * w_c| (the tensor core truncates both operands to TF32; measured worst
-    # ratio 1.4e-3) + fp32 accumulation noise
-    bound = 2.0 ** -9 * torch.einsum("bchw,oc->bohw", x.double().abs(), w.view(ACH, Cin).double().abs()) + 1e-5
-    assert bool(((raw.double() - ref).abs() <= bound).all())
+    # oracle: fp64 convolution; |error| <= 2 * 2^-10 * sum_c |x_c * w_c| (the tensor core truncates both operands to
+    # TF32; measured worst ratio 1.4e-3) + fp32 accumulation noise
+    from oracle import pqdet_oracle as po
+    xn, wn = x.cpu().numpy(), w.cpu().numpy()
+    ref = po.head_conv(xn, wn, bias.cpu().numpy())
+    assert np.all(np.abs(raw.cpu().numpy() - ref) <= po.head_conv_error_bound(xn, wn, 2.0 ** -10))
     assert torch.equal(dec, _ops.decode_fwd(raw, C, stride))
+    want = po.decode(raw.cpu().numpy(), C, stride)                       # oracle Decode of the kernel's own raw head
+    got = dec.cpu().numpy()
+    assert np.all(np.abs(got - want) <= 1e-5 * np.maximum(np.abs(want), max(H, W) * stride))
     no_bias = _ops.head_conv_decode(x, w, None, C, stride, want_raw=True)[1]
     assert torch.allclose(no_bias + bias.view(1, -1, 1, 1), raw, rtol=0, atol=1e-5)
 

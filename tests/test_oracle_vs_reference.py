@@ -40,6 +40,29 @@ def test_eval_chain_matches_reference(ref):
         assert np.array_equal(got, want)
 
 
+def test_head_conv_oracle_matches_the_reference_model_head():
+    """the oracle's head convolution + decode against the reference's own modules - the nn.Conv2d the cfg
+    parser builds in front of a [yolo] layer and its Decode - on CPU (fp32 accumulation)."""
+    import os
+    ref = rh.load()
+    from model.interpreter import DetectionModel
+    m = DetectionModel(os.path.join(rh.REFERENCE_ROOT, "model", "cfg", "regnetx-600m-fpn.cfg")).eval()
+    i = [k for k, l in enumerate(m.module_list) if l._type == "yolo"][0]
+    block, yolo = m.module_list[i - 1], m.module_list[i]
+    conv = block.conv
+    assert len(block) == 1 and conv.kernel_size == (1, 1) and conv.out_channels == 75      # the plain linear head conv
+    torch.manual_seed(3)
+    x = torch.randn(2, conv.in_channels, 4, 6)
+    with torch.no_grad():
+        raw_ref = block(x)
+        dec_ref = yolo(raw_ref)
+    raw = po.head_conv(x.numpy(), conv.weight.detach().numpy(), conv.bias.detach().numpy())
+    assert np.all(np.abs(raw - raw_ref.numpy()) <= po.head_conv_error_bound(x.numpy(), conv.weight.detach().numpy(), 2.0 ** -22))
+    dec = po.decode(raw.astype(np.float32), 20, yolo.opt["stride"] if hasattr(yolo, "opt") else 32)
+    assert rel_close(dec[..., :4], dec_ref.numpy()[..., :4], 1e-4, scale=float(32 * 6))
+    assert rel_close(dec[..., 4:], dec_ref.numpy()[..., 4:], 1e-4, scale=1e-30)
+
+
 def test_dense_nms_takes_vanilla_path_on_cpu(ref):
     C, size = 10, 608
     heads = synth.make_heads(1, C, size, "dense", seed=2)
