@@ -5,7 +5,8 @@ per-image tools.torch_nms) restated with the same libraries the reference itself
 ATen ops for the elementwise work and torchvision.ops.batched_nms for the NMS (falling back to
 oracle/nms_oracle.c where torchvision is absent).  The reference sources cannot travel to the GPU box
 (/root/reference does not exist there), so this "port" is what bench.py times as cpu_baseline and as
-`--impl reference`; tests/test_oracle_vs_reference.py checks it against the live reference here.
+`--impl reference`; tests/test_oracle_vs_reference.py::test_cpu_path_port_is_the_reference_sequence pins every stage
+and the end result bit for bit to the live reference here (all three affines, sequential / threads / processes).
 """
 from __future__ import annotations
 
@@ -30,9 +31,13 @@ def decode_t(conv: torch.Tensor, num_classes: int, stride: int) -> torch.Tensor:
     gx = (torch.arange(W, dtype=torch.float32) + 0.5).view(1, 1, W, 1, 1)
     gy = (torch.arange(H, dtype=torch.float32) + 0.5).view(1, H, 1, 1, 1)
     grid = torch.cat([gx.expand(1, H, W, 1, 1), gy.expand(1, H, W, 1, 1)], dim=-1)
-    xymin = (grid - torch.exp(x[..., 0:2])) * stride
-    xymax = (grid + torch.exp(x[..., 2:4])) * stride
-    return torch.cat([xymin, xymax, torch.sigmoid(x[..., 4:])], dim=-1)
+    # the same four views the reference splits off and one ATen call per view (model/parser.py:215-233): ATen's CPU
+    # exp / sigmoid pick their vectorised or scalar inner loop from the operand's shape and strides, and the two
+    # differ in the last ulp, so e.g. one sigmoid over [..., 4:] is NOT bit-identical to sigmoid(conf), sigmoid(prob)
+    d1, d2, conf, prob = torch.split(x, [2, 2, 1, num_classes], dim=-1)
+    xymin = (grid - torch.exp(d1)) * stride
+    xymax = (grid + torch.exp(d2)) * stride
+    return torch.cat((xymin, xymax, torch.sigmoid(conf), torch.sigmoid(prob)), -1)
 
 
 def recover_t(pred: torch.Tensor, input_size, orig: torch.Tensor, kind: str) -> torch.Tensor:
@@ -93,6 +98,64 @@ def eval_chain_image_parallel(heads, strides, num_classes, input_size, orig, kin
             return list(ex.map(one, range(B)))
     finally:
         torch.set_num_threads(old)
+
+
+# ---- process-parallel form: the "all host cores" figure.  Threads do not give one: the per-image chain is a
+# string of small ATen calls and Python glue, so a thread pool serialises on the GIL (round-1 measurement: the
+# thread pool was slower than the sequential chain).  Worker processes are forked AFTER the batch exists, so
+# every worker sees the heads copy-on-write (no pickling of the 1.6 MB/image inputs); each task is a contiguous
+# block of images and returns its (K,6) arrays.
+_PP_STATE = {}
+
+
+def _pp_init():
+    torch.set_num_threads(1)
+
+
+def _pp_task(args):
+    key, lo, hi = args
+    heads, strides, num_classes, input_size, orig, kind, thr, iou = _PP_STATE[key]
+    o = orig[lo:hi] if orig.shape[0] > 1 else orig
+    out = eval_chain([h[lo:hi] for h in heads], strides, num_classes, input_size, o, kind, thr, iou)
+    return [t.numpy() for t in out]
+
+
+class ProcessPool:
+    """A pool of forked workers bound to one batch; run() pushes the whole batch through the reference's CPU
+    sequence, `chunk` images per task, and returns the per-image results in image order."""
+
+    def __init__(self, heads, strides, num_classes, input_size, orig, kind, thr, iou, workers: int, chunk: int = 0):
+        import multiprocessing as mp
+        self.key = id(self)
+        self.B = heads[0].shape[0]
+        self.workers = max(1, min(workers, self.B))
+        self.chunk = chunk or max(1, min(8, -(-self.B // (4 * self.workers))))
+        _PP_STATE[self.key] = (heads, strides, num_classes, torch.as_tensor(input_size, dtype=torch.float32),
+                               orig.reshape(-1, 2), kind, thr, iou)
+        self.pool = mp.get_context("fork").Pool(self.workers, initializer=_pp_init)
+
+    def run(self):
+        tasks = [(self.key, lo, min(lo + self.chunk, self.B)) for lo in range(0, self.B, self.chunk)]
+        out = []
+        for part in self.pool.map(_pp_task, tasks, chunksize=1):
+            out.extend(torch.from_numpy(a) for a in part)
+        return out
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        _PP_STATE.pop(self.key, None)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def eval_chain_process_parallel(heads, strides, num_classes, input_size, orig, kind, thr, iou, workers: int):
+    with ProcessPool(heads, strides, num_classes, input_size, orig, kind, thr, iou, workers, chunk=1) as pool:
+        return pool.run()
 
 
 def host_cores() -> int:

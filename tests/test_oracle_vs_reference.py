@@ -149,3 +149,40 @@ def test_resize_oracle_is_bit_exact_against_cv2():
         r = min(T / sw, T / sh)
         dw, dh = max(round(r * sw), 1), max(round(r * sh), 1)
         assert np.array_equal(ao.resize_linear_u8(img, dw, dh), cv2.resize(img, dsize=(dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+@pytest.mark.parametrize("kind,C,size,dist", [("voc", 20, 512, "sparse"), ("coco", 80, 320, "sparse"),
+                                              ("visdrone", 10, 608, "dense")])
+def test_cpu_path_port_is_the_reference_sequence(ref, kind, C, size, dist):
+    """oracle/cpu_path.py is the denominator of every speed-up bench.py reports (`--impl reference`, cpu_baseline).
+    Pin it bit for bit to the live reference's predict.py:33-45 sequence: Decode per level -> cat
+    (model/interpreter.py:72-75) -> RECOVER_BBOXES_REGISTER[kind] -> tools.torch_nms per image, for all three
+    affines, sequential and image-parallel (threads and processes)."""
+    from oracle import cpu_path
+    B = 3 if dist == "sparse" else 2
+    heads = synth.make_heads(B, C, size, dist, seed=17)
+    strides = synth.FPN_STRIDES
+    inp = torch.tensor([float(size), float(size)])
+    orig = torch.tensor([[375.0, 500.0], [333.0, 500.0], [float(size), float(size)]])[:B]
+    with torch.no_grad():
+        outs = [ref.Decode(C, s)(h) for h, s in zip(heads, strides)]
+        pred = torch.cat([o.reshape(B, -1, 5 + C) for o in outs], dim=1)
+        # the port's decode / recover stages on their own, bit for bit
+        mine = torch.cat([cpu_path.decode_t(h, C, s).reshape(B, -1, 5 + C) for h, s in zip(heads, strides)], dim=1)
+        assert torch.equal(mine, pred)
+        rec = ref.RECOVER[kind](pred.clone(), inp, orig)
+        assert torch.equal(cpu_path.recover_t(pred, inp, orig, kind), rec)
+        want = [ref.tools.torch_nms(rec[b], 0.1, 0.45) for b in range(B)]
+    assert sum(w.shape[0] for w in want) > 0
+    runs = {
+        "sequential": cpu_path.eval_chain(heads, strides, C, inp, orig, kind, 0.1, 0.45),
+        "threads": cpu_path.eval_chain_image_parallel(heads, strides, C, inp, orig, kind, 0.1, 0.45, workers=2),
+    }
+    if hasattr(cpu_path, "eval_chain_process_parallel"):
+        runs["processes"] = cpu_path.eval_chain_process_parallel(heads, strides, C, inp, orig, kind, 0.1, 0.45,
+                                                                 workers=2)
+    for name, got in runs.items():
+        assert len(got) == B, name
+        for b in range(B):
+            assert got[b].shape == want[b].shape, (name, b)
+            assert torch.equal(got[b], want[b]), (name, b)
