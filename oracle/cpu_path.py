@@ -28,8 +28,8 @@ def decode_t(conv: torch.Tensor, num_classes: int, stride: int) -> torch.Tensor:
     B, CH, H, W = conv.shape
     ch = 5 + num_classes
     x = conv.permute(0, 2, 3, 1).reshape(B, H, W, CH // ch, ch)
-    gx = (torch.arange(W, dtype=torch.float32) + 0.5).view(1, 1, W, 1, 1)
-    gy = (torch.arange(H, dtype=torch.float32) + 0.5).view(1, H, 1, 1, 1)
+    gx = (torch.arange(W, dtype=torch.float32, device=conv.device) + 0.5).view(1, 1, W, 1, 1)
+    gy = (torch.arange(H, dtype=torch.float32, device=conv.device) + 0.5).view(1, H, 1, 1, 1)
     grid = torch.cat([gx.expand(1, H, W, 1, 1), gy.expand(1, H, W, 1, 1)], dim=-1)
     # the same four views the reference splits off and one ATen call per view (model/parser.py:215-233): ATen's CPU
     # exp / sigmoid pick their vectorised or scalar inner loop from the operand's shape and strides, and the two

@@ -11,10 +11,31 @@
 #define PQ_FULL 0xffffffffu
 
 // Every ABI call selects the device explicitly (the library has its own runtime instance and
-// nn.DataParallel-style callers use one thread per GPU) and reports launch errors as codes.
+// nn.DataParallel-style callers use one thread per GPU) and reports launch errors as codes.  The
+// selection is scoped: PyTorch reads the thread's current device from the same CUDA runtime, so the
+// caller's device is put back on every return path (including the PQ_CUDA / PQ_LAUNCH_CHECK early
+// returns) -- a call with device=1 from a thread sitting on device 0 must not move that thread.
+namespace pq {
+struct DeviceScope {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+    ok = (prev == device) || (cudaSetDevice(device) == cudaSuccess);
+    if (ok && prev == device) prev = -1;          // nothing to restore
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+}  // namespace pq
+
 #define PQ_ENTER(device)                                                   \
+  pq::DeviceScope pq_device_scope_(device);                                \
   do {                                                                     \
-    if (cudaSetDevice(device) != cudaSuccess) return PQDET_ERR_CUDA;       \
+    if (!pq_device_scope_.ok) return PQDET_ERR_CUDA;                       \
   } while (0)
 
 #define PQ_LAUNCH_CHECK()                                                  \

@@ -22,12 +22,17 @@ class Detections:
     def __init__(self, det, idx, meta, B):
         self.det, self.idx, self.meta, self.B = det, idx, meta, B
         self._spill_batch = None          # (det, idx, host meta, {image id: position}) of the general path
+        self.general_first = False        # the whole batch went straight to the general path
         self._host = None
 
     @property
     def _spill(self):
         """image ids that were resolved by the general path (overflowed the fused kernel)."""
         return self._spill_batch[3] if self._spill_batch else {}
+
+    @property
+    def images_via_general_path(self) -> int:
+        return self.B if self.general_first else len(self._spill)
 
     def host_meta(self) -> torch.Tensor:
         """(3,B) int32 on the host: counts, ncand, status.  The only device->host sync."""
@@ -80,7 +85,11 @@ class Detections:
         return out
 
 
-_DENSE_HINT = {}          # workload signature -> True when the last call mostly overflowed the fused kernel
+class StrategyHints(dict):
+    """Caller-held memory for strategy='auto' (workload signature -> True when the last call with that signature
+    mostly overflowed the fused kernel).  The library keeps no state of its own: pass one of these as `hints=` from
+    whatever owns the evaluation loop (the evaluator hook of install.py holds one per Evaluator); without it every
+    call starts on the fused kernel."""
 
 
 def _general(h, keep, ids, n_sel, return_index, by_position, cap, max_det):
@@ -106,15 +115,16 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
                batch_original_size, dataset: str = "voc", score_threshold: float = 0.1,
                iou_threshold: float = 0.45, return_index: bool = False, resolve_overflow: bool = True,
                nms_mode: Optional[str] = None, iou_round: Optional[str] = None,
-               strategy: str = "auto") -> Detections:
+               strategy: str = "auto", hints: Optional[StrategyHints] = None) -> Detections:
     """heads: raw [yolo] inputs (B, A*(5+C), H_l, W_l) in cfg order with their strides.
     input_size (h, w) -- pass a tuple/CPU tensor (a CUDA tensor costs a sync);
     batch_original_size (B,2) or (2,) (h, w).  dataset in {'voc','coco','visdrone'} picks the affine.
     With resolve_overflow (default) images whose candidates do not fit the on-chip lists are re-run
     through the general path, so the result is always complete (costs the host read of `status`).
     strategy: 'fused' (one-launch kernel + per-image fallback), 'general' (bucketed global-memory path for
-    every image: the right choice for dense scenes such as VisDrone), or 'auto' (fused first; remembers per
-    workload signature when most images overflowed and then goes straight to the general path)."""
+    every image: the right choice for dense scenes such as VisDrone), or 'auto' (fused first; with a caller-held
+    `hints` object it remembers per workload signature when most images overflowed and then goes straight to the
+    general path)."""
     m, r = config.nms_modes()
     nms_mode, iou_round = nms_mode or m, iou_round or r
     h, keep = _ops.make_heads(heads, strides, num_classes, input_size, batch_original_size, dataset,
@@ -126,11 +136,13 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
                           torch.empty((0, FUSED_MAX_DET), dtype=torch.int32, device=dev) if return_index else None,
                           torch.zeros((2,), dtype=torch.int32, device=dev), 0)
     sig = (tuple(tuple(t.shape[1:]) for t in heads), num_classes, float(score_threshold), dataset)
-    if B and (strategy == "general" or (strategy == "auto" and _DENSE_HINT.get(sig, False))):
+    if B and (strategy == "general" or (strategy == "auto" and hints is not None and hints.get(sig, False))):
         gdet, gidx, gmeta, hm = _general(h, keep, None, B, return_index, False, max(B * 32768, 1 << 16), 8192)
         res = Detections(gdet, gidx, gmeta, B)
         res._host = hm
-        _DENSE_HINT[sig] = bool(hm[1].max() > FUSED_MAX_DET or hm[1].float().mean() > FUSED_MAX_DET / 2)
+        res.general_first = True
+        if hints is not None:
+            hints[sig] = bool(hm[1].max() > FUSED_MAX_DET or hm[1].float().mean() > FUSED_MAX_DET / 2)
         return res
     det, idx, meta = _ops.decode_nms_fused(h, keep, FUSED_MAX_DET, return_index)
     res = Detections(det, idx, meta, B)
@@ -138,7 +150,8 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
         return res
     status = res.host_meta()[2]
     over = torch.nonzero(status & _lib.ST_CAND_OVERFLOW).reshape(-1)
-    _DENSE_HINT[sig] = bool(over.numel() * 2 > B)
+    if hints is not None:
+        hints[sig] = bool(over.numel() * 2 > B)
     if over.numel() == 0:
         return res
     ids = over.to(torch.int32).to(det.device)

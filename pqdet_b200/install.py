@@ -19,11 +19,13 @@ from torch import nn
 from . import base_sample, loss, parser, tools as pq_tools
 
 
-def install(strict: bool = False, patch_augment: bool = False) -> dict:
+def install(strict: bool = False, patch_augment: bool = False, patch_evaluate: bool = True) -> dict:
     """Patch every reference module that is importable; returns {attribute path: True/False}.
     patch_augment: also replace dataset.augment.Resize by the GPU letterbox.  Off by default: DataLoader worker
     processes (where the training pipeline calls Resize) must not touch CUDA; turn it on for single-process eval /
-    predict scripts, or call pqdet_b200.augment.letterbox_normalize on whole batches instead."""
+    predict scripts, or call pqdet_b200.augment.letterbox_normalize on whole batches instead.
+    patch_evaluate: replace Evaluator.evaluate's per-image loop (eval/evaluator.py:52-61) by one fused launch per batch
+    (see detect_batch); the model must have been prepared with fuse_eval_concat to take the raw-head route."""
     done = {}
 
     def patch(modname, attr, value):
@@ -56,7 +58,9 @@ def install(strict: bool = False, patch_augment: bool = False) -> dict:
             done["dataset.RECOVER_BBOXES_REGISTER[%s]" % ds] = False
     # the steps either side of the path: evaluator statistics and the eval letterbox
     try:
-        _patch_evaluator()
+        _patch_evaluator(patch_evaluate)
+        if patch_evaluate:
+            done["eval.evaluator.Evaluator.evaluate"] = True
         done["eval.evaluator.Evaluator.{init_statics,add_detections,add_labels,AP}"] = True
     except Exception:
         if strict:
@@ -77,6 +81,11 @@ class _FusedHeadConv(nn.Sequential):
     def forward(self, x):
         if self.training or not x.is_cuda or torch.onnx.is_in_onnx_export():
             return super().forward(x)
+        if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad
+                                        or (self.conv.bias is not None and self.conv.bias.requires_grad)):
+            return super().forward(x)         # someone differentiates through the prediction: keep autograd intact
+        if not (torch.backends.cudnn.allow_tf32 and torch.backends.cudnn.enabled):
+            return super().forward(x)         # the tensor-core kernel is TF32; the user asked for full fp32 convs
         y = x.view_as(x)                      # a new tensor object on the same storage: the tag stays private
         y._pq_pending_conv = self.conv
         return y
@@ -91,7 +100,10 @@ def fuse_head_convs(model) -> int:
     model/parser.py:385-410) and whose output no route / shortcut reads, the conv block's class is switched to
     _FusedHeadConv: in eval mode on CUDA it hands its INPUT to the YOLOLayer together with its own parameters
     (pqdet_head_conv_decode); in training mode, on CPU, for ONNX export or when a target is given the convolution
-    still runs.  No module is added or renamed, so state_dict keys, pruning and checkpoint loading are unchanged.
+    still runs - and also whenever autograd is recording through the level (grad mode on and the input or the conv's
+    parameters require grad: the fused kernel has no backward) or the user turned TF32 convolutions off
+    (torch.backends.cudnn.allow_tf32 = False; the tensor-core kernel multiplies in TF32 like cuDNN's default).
+    No module is added or renamed, so state_dict keys, pruning and checkpoint loading are unchanged.
     Returns the number of levels fused."""
     layers = list(model.module_list)
     used = set()
@@ -124,19 +136,16 @@ def fuse_head_convs(model) -> int:
     return fused
 
 
-def fuse_eval_concat(model) -> bool:
-    """SURVEY section 8 row a4 as a hook: the eval branch of DetectionModel.forward (model/interpreter.py:72-76: every
-    [yolo] level decoded, viewed as (B, -1, 5+C) and concatenated) becomes one launch that decodes all levels
-    straight into the (B, N, 5+C) prediction - no per-level tensor, no torch.cat (which alone moves as many bytes as
-    the decode).  Combined with fuse_head_convs the head convolutions run inside that launch too.
-
-    The model's class is switched to a subclass whose forward, in CUDA eval mode without a target, runs the parent
-    class's layer loop (AnyModel.forward) with the YOLOLayers passing their input through and then combines the
-    levels (interpreter.combine_eval).  Training, targets and CPU tensors take the reference's own forward.  Returns
-    False (model untouched) if a [yolo] layer is not ours or something reads a [yolo] output."""
+def _fuse_model_forward(model, eval_concat: bool, train_levels: bool) -> bool:
+    """Switch the model's class to a subclass whose forward runs the parent's layer loop (AnyModel.forward) with the
+    YOLOLayers passing their input through, and then combines the levels itself (interpreter.combine_eval /
+    combine_train).  Flags accumulate over calls.  Returns False (model untouched) if a [yolo] layer is not ours or
+    something reads a [yolo] output."""
     from . import interpreter as pq_interpreter
     cls = type(model)
-    if getattr(cls, '_pq_eval_concat', False):
+    if getattr(cls, '_pq_fused_forward', False):
+        cls._pq_eval_concat = cls._pq_eval_concat or eval_concat
+        cls._pq_train_levels = cls._pq_train_levels or train_levels
         return True
     layers = list(model.module_list)
     yolo_idx = [i for i, l in enumerate(layers) if getattr(l, '_type', None) == 'yolo']
@@ -155,28 +164,78 @@ def fuse_eval_concat(model) -> bool:
     if loop is None:
         return False
 
-    def forward(self, x, target=None):
-        if target is not None or self.training or not x.is_cuda or torch.onnx.is_in_onnx_export():
-            return cls.forward(self, x, target)
+    def collect(self, x, target=None):
+        """-> (YOLOLayers in cfg order, what each of them received)."""
         yolos = [l for l in self.module_list if isinstance(l, parser.YOLOLayer)]
         for l in yolos:
             object.__setattr__(l, '_pq_passthrough', True)
         try:
-            outs = loop(self, x, None)
+            outs = loop(self, x, target)
         finally:
             for l in yolos:
                 l.__dict__.pop('_pq_passthrough', None)
         if not isinstance(outs, (list, tuple)):
             outs = [outs]
-        return pq_interpreter.combine_eval(yolos, outs)
+        return yolos, list(outs)
 
-    model.__class__ = type(cls.__name__, (cls,), {'forward': forward, '_pq_eval_concat': True})
+    def forward(self, x, target=None):
+        me = type(self)
+        if not x.is_cuda or torch.onnx.is_in_onnx_export():
+            return cls.forward(self, x, target)
+        if target is None:
+            if not me._pq_eval_concat or self.training:
+                return cls.forward(self, x, None)
+            return pq_interpreter.combine_eval(*collect(self, x))
+        if not me._pq_train_levels:
+            return cls.forward(self, x, target)
+        yolos, outs = collect(self, x, target)
+        return pq_interpreter.combine_train(yolos, outs, target)
+
+    model.__class__ = type(cls.__name__, (cls,), {
+        'forward': forward, '_pq_collect': collect, '_pq_fused_forward': True,
+        '_pq_eval_concat': eval_concat, '_pq_train_levels': train_levels})
     return True
 
 
-def _patch_evaluator():
-    """Evaluator keeps its loop (eval/evaluator.py:44-62); its statistics go through DetectionAccumulator, so AP()
-    runs the matching on the GPU and returns the same tools.AP tuple."""
+def fuse_eval_concat(model) -> bool:
+    """SURVEY section 8 row a4 as a hook: the eval branch of DetectionModel.forward (model/interpreter.py:72-76: every
+    [yolo] level decoded, viewed as (B, -1, 5+C) and concatenated) becomes one launch that decodes all levels
+    straight into the (B, N, 5+C) prediction - no per-level tensor, no torch.cat (which alone moves as many bytes as
+    the decode).  Combined with fuse_head_convs the head convolutions run inside that launch too.
+
+    Training mode, CPU tensors and ONNX export take the reference's own forward; when autograd is recording through
+    the prediction (eval mode, grad enabled, inputs requiring grad) the levels go through the autograd-aware Decode
+    and torch.cat, so the result keeps its grad_fn."""
+    return _fuse_model_forward(model, True, False)
+
+
+def fuse_train_levels(model) -> bool:
+    """The training analogue: DetectionModel.forward(x, target) (model/interpreter.py:77-85: one YOLOLayer call per
+    level, then Python sums over the per-level tuples) becomes ONE launch of the multi-level decode + loss + gradient
+    kernel (pqdet_loss_levels) behind one autograd node; the dict it returns has the reference's keys and shapes.
+    Levels with different loss options fall back to one launch per level."""
+    return _fuse_model_forward(model, False, True)
+
+
+def raw_heads(model, x):
+    """Run a model prepared by fuse_eval_concat / fuse_train_levels up to its [yolo] layers.
+    -> (raw head tensors in cfg order, strides, num_classes).  Head convolutions deferred by fuse_head_convs are
+    applied here.  This is what the fused decode + NMS kernel consumes (fused.decode_nms)."""
+    cls = type(model)
+    if not getattr(cls, '_pq_fused_forward', False):
+        raise ValueError("call install.fuse_eval_concat(model) first")
+    yolos, outs = cls._pq_collect(model, x)
+    raws = []
+    for o in outs:
+        conv = getattr(o, '_pq_pending_conv', None)
+        raws.append(o if conv is None else torch.nn.functional.conv2d(o, conv.weight, conv.bias))
+    return raws, [l.opt['stride'] for l in yolos], yolos[0].opt['classes']
+
+
+def _patch_evaluator(patch_evaluate: bool = True):
+    """Evaluator's statistics go through DetectionAccumulator, so AP() runs the matching on the GPU and returns the
+    same tools.AP tuple; with patch_evaluate its per-batch body (eval/evaluator.py:47-61: predict, recover, then per
+    image torch_nms + .cpu() + add_detections) becomes one fused launch and one device->host copy per batch."""
     ev_mod = importlib.import_module("eval.evaluator")
     ref_tools = sys.modules.get("tools") or importlib.import_module("tools")
     from .evaluator import DetectionAccumulator
@@ -200,3 +259,58 @@ def _patch_evaluator():
     for name, fn in (("init_statics", init_statics), ("add_detections", add_detections),
                      ("add_labels", add_labels), ("AP", AP)):
         setattr(ev_mod.Evaluator, name, fn)
+    if patch_evaluate:
+        ev_mod.Evaluator.evaluate = _make_evaluate(getattr(ev_mod, "tqdm", None))
+        ev_mod.Evaluator.pq_detect_batch = detect_batch
+
+
+def _dataset_kind(recover_fn) -> str:
+    name = getattr(recover_fn, "__name__", "")
+    for kind in ("voc", "coco", "visdrone"):
+        if name.endswith("_" + kind):
+            return kind
+    return ""
+
+
+def detect_batch(self, batch_img, batch_img_shape):
+    """One batch of Evaluator.evaluate (eval/evaluator.py:50-60) -> list of (K,6) float32 numpy arrays, one per
+    image, identical to what the reference's per-image `tools.torch_nms(...).cpu().numpy()` produces on our decode.
+
+    Fast route (model prepared by fuse_eval_concat, CUDA): the raw heads go straight into the fused decode + recover
+    + threshold + NMS kernel - ONE launch for the batch, nothing of size B x N written - and the rows come back in ONE
+    device->host copy.  Otherwise: predict + recover as the reference does, then one batched NMS launch."""
+    from . import fused
+    model = self.model
+    inner = model.module if isinstance(model, nn.DataParallel) and len(model.device_ids) <= 1 else model
+    kind = _dataset_kind(self._recover_bboxes)
+    if getattr(type(inner), '_pq_fused_forward', False) and batch_img.is_cuda and kind and not inner.training:
+        with torch.no_grad():
+            raws, strides, C = raw_heads(inner, batch_img)
+        hints = self.__dict__.setdefault('_pq_hints', fused.StrategyHints())
+        dets = fused.decode_nms(raws, strides, C, tuple(float(v) for v in self._input_size),
+                                batch_img_shape.to(batch_img.device), kind, self._score_threshold,
+                                self._iou_threshold, hints=hints)
+        return dets.to_numpy_list()
+    batch_pred_bbox = self.predict(batch_img)
+    device = batch_pred_bbox.device
+    input_size = torch.FloatTensor(self._input_size).to(device)
+    rec = self._recover_bboxes(batch_pred_bbox, input_size, batch_img_shape.to(device))
+    if rec.is_cuda:
+        outs = pq_tools.batched_torch_nms(rec, self._score_threshold, self._iou_threshold)
+        return [o.cpu().numpy() for o in outs]
+    ref_tools = sys.modules.get("tools") or importlib.import_module("tools")
+    return [ref_tools.torch_nms(p, self._score_threshold, self._iou_threshold).cpu().numpy() for p in rec]
+
+
+def _make_evaluate(tqdm):
+    def evaluate(self):
+        it = tqdm(self.dataset) if tqdm is not None else self.dataset
+        for data in it:
+            batch_img, batch_file_name, batch_img_shape, batch_label, batch_diff = data
+            rows = detect_batch(self, batch_img, batch_img_shape)
+            for file_name, labels, diffs, bboxes in zip(batch_file_name, batch_label, batch_diff, rows):
+                # the reference hands add_detections an array of shape (0,) for an empty image
+                self.add_detections(file_name, bboxes if len(bboxes) else bboxes.reshape(0))
+                self.add_labels(file_name, labels, diffs)
+        return self.AP()
+    return evaluate

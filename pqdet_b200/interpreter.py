@@ -93,6 +93,12 @@ def combine_eval(layers, outs: Sequence[torch.Tensor]) -> torch.Tensor:
     ch = 5 + C
     strides = [l.opt['stride'] for l in layers]
     convs = [getattr(o, '_pq_pending_conv', None) for o in outs]
+    if torch.is_grad_enabled() and any(o.requires_grad for o in outs):
+        # someone differentiates through an eval-mode prediction (saliency maps, adversarial examples,
+        # distillation): the one-launch concat has no grad_fn, so take the per-level autograd-aware Decode
+        # (model/interpreter.py:72-76 as written).  _FusedHeadConv never tags its input in this situation.
+        dec = [l.decode(o) for l, o in zip(layers, outs)]
+        return torch.cat([d.view((d.shape[0], -1, d.shape[-1])) for d in dec], dim=1)
     if all(c is None for c in convs):
         return _ops.decode_levels(list(outs), C, strides)
     B = outs[0].shape[0]
@@ -115,6 +121,17 @@ def combine_eval(layers, outs: Sequence[torch.Tensor]) -> torch.Tensor:
     return out
 
 
+def combine_train(layers, outs: Sequence[torch.Tensor], target):
+    """The training branch of DetectionModel.forward (model/interpreter.py:77-85) on what the [yolo] layers RECEIVED
+    (raw heads): decode + loss + gradient of every level in ONE launch instead of one YOLOLayer call per level plus
+    the Python sums.  Same dict, same values (the per-level kernels and the multi-level kernel share their code)."""
+    raws = []
+    for o in outs:
+        conv = getattr(o, '_pq_pending_conv', None)        # eval-mode validation loss behind fuse_head_convs
+        raws.append(o if conv is None else torch.nn.functional.conv2d(o, conv.weight, conv.bias))
+    return multi_level_loss(layers, raws, target)
+
+
 _SM_COUNT = {}
 
 
@@ -123,6 +140,36 @@ def _sm_count(device: torch.device) -> int:
     if idx not in _SM_COUNT:
         _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
     return _SM_COUNT[idx]
+
+
+def multi_level_loss(layers, heads: Sequence[torch.Tensor], target):
+    """All levels' decode + loss (+ gradient) in one launch.  layers: the YOLOLayers in cfg order; heads: their raw
+    inputs; target: the reference's 6-tuple (model/interpreter.py:16-20) or a train_dataset.SparseTarget."""
+    L = len(layers)
+    opt0 = layers[0].opt
+    if isinstance(target, SparseTarget):
+        same_opts = all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
+                        and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in layers)
+        if not same_opts:
+            raise ValueError("sparse targets need the same loss options on every [yolo] level")
+        if opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
+            raise NotImplementedError
+        slots = [_SCALE_SLOT[l.opt['stride']] for l in layers]
+        out, flag = _MultiLossSparseFn.apply(L, target.num_classes, [l.opt['stride'] for l in layers],
+                                             opt0['bbox_loss'], opt0['ignore_thresh'],
+                                             opt0.get('l1_loss_gain', 0.1), *heads, target.gt,
+                                             *[target.owner[i] for i in slots], *[target.bboxes[i] for i in slots])
+        return DetectionHead._result(out, flag, L)
+    same = all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
+               and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in layers)
+    if not same or opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
+        return DetectionHead._forward_per_level(layers, heads, target)
+    pairs = [_TARGET_MAP[l.opt['stride']](target) for l in layers]
+    C = pairs[0][0].shape[-1] - 6
+    out, flag = _MultiLossFn.apply(L, C, [l.opt['stride'] for l in layers], opt0['bbox_loss'],
+                                   opt0['ignore_thresh'], opt0.get('l1_loss_gain', 0.1),
+                                   *heads, *[p[0] for p in pairs], *[p[1] for p in pairs])
+    return DetectionHead._result(out, flag, L)
 
 
 class DetectionHead(nn.Module):
@@ -152,31 +199,7 @@ class DetectionHead(nn.Module):
                 _ops.decode_fwd(h, C, l.opt['stride'], out=out, rows_total=N, row_offset=off)
                 off += r
             return out
-        L = len(self.layers)
-        opt0 = self.layers[0].opt
-        if isinstance(target, SparseTarget):
-            same_opts = all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
-                            and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in self.layers)
-            if not same_opts:
-                raise ValueError("sparse targets need the same loss options on every [yolo] level")
-            if opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
-                raise NotImplementedError
-            slots = [_SCALE_SLOT[l.opt['stride']] for l in self.layers]
-            out, flag = _MultiLossSparseFn.apply(L, target.num_classes, [l.opt['stride'] for l in self.layers],
-                                                 opt0['bbox_loss'], opt0['ignore_thresh'],
-                                                 opt0.get('l1_loss_gain', 0.1), *heads, target.gt,
-                                                 *[target.owner[i] for i in slots], *[target.bboxes[i] for i in slots])
-            return self._result(out, flag, L)
-        same = all(l.opt['bbox_loss'] == opt0['bbox_loss'] and l.opt['ignore_thresh'] == opt0['ignore_thresh']
-                   and l.opt.get('l1_loss_gain', 0.1) == opt0.get('l1_loss_gain', 0.1) for l in self.layers)
-        if not same or opt0['bbox_loss'] not in ('l1', 'giou', 'diou', 'iou', 'ciou'):
-            return self._forward_per_level(heads, target)
-        pairs = [_TARGET_MAP[l.opt['stride']](target) for l in self.layers]
-        C = pairs[0][0].shape[-1] - 6
-        out, flag = _MultiLossFn.apply(L, C, [l.opt['stride'] for l in self.layers], opt0['bbox_loss'],
-                                       opt0['ignore_thresh'], opt0.get('l1_loss_gain', 0.1),
-                                       *heads, *[p[0] for p in pairs], *[p[1] for p in pairs])
-        return self._result(out, flag, L)
+        return multi_level_loss(self.layers, heads, target)
 
     def forward_from_features(self, features: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
                               biases: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -251,13 +274,14 @@ class DetectionHead(nn.Module):
             res['loss'].pq_nan_flag = flag
         return res
 
-    def _forward_per_level(self, heads, target):
+    @staticmethod
+    def _forward_per_level(layers, heads, target):
         """One launch per level (levels with different loss options)."""
         mode = config.nan_check
         if mode == "sync":
             config.nan_check = "lazy"            # one host sync per step instead of one per level
         try:
-            outputs = [l(h, _TARGET_MAP[l.opt['stride']](target)) for l, h in zip(self.layers, heads)]
+            outputs = [l(h, _TARGET_MAP[l.opt['stride']](target)) for l, h in zip(layers, heads)]
         finally:
             config.nan_check = mode
         if mode == "sync":

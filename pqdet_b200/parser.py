@@ -62,8 +62,9 @@ class YOLOLayer(nn.Module):
         self.opt = opt
 
     def forward(self, x, target=None):
-        if target is None and self.__dict__.get('_pq_passthrough'):
-            return x                          # install.fuse_eval_concat: the model decodes all levels in one launch
+        if self.__dict__.get('_pq_passthrough'):
+            # install.fuse_eval_concat / fuse_train_levels: the model combines all levels in one launch
+            return x
         conv = getattr(x, '_pq_pending_conv', None)
         if conv is not None:
             # install.fuse_head_convs: x is the INPUT of this level's 1x1 head convolution (the conv block passed its

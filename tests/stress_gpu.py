@@ -36,7 +36,6 @@ def one_case(rng, i):
     B = int(rng.integers(1, 5))
     orig = np.stack([rng.integers(120, 900, 2).astype(np.float32) for _ in range(B)])
     config.nms_semantics = sem
-    fused._DENSE_HINT.clear()
     heads = synth.make_heads(B, C, size, profile, seed=int(rng.integers(0, 1 << 30)), strides=strides)
     dheads = [h.cuda() for h in heads]
     opts = [dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in strides]

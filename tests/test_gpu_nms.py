@@ -86,7 +86,7 @@ def _fused_vs_chain(B, C, size, profile, kind, thr, iou, sem, seed, orig=None, s
     from pqdet_b200 import config, fused, synth
     from pqdet_b200.interpreter import DetectionHead
     config.nms_semantics = sem
-    fused._DENSE_HINT.clear()                                     # every case starts on the fused kernel
+    hints = fused.StrategyHints()                                 # caller-held: every case starts on the fused kernel
     strides = strides or synth.FPN_STRIDES
     heads = synth.make_heads(B, C, size, profile, seed=seed, strides=strides)
     dheads = [h.cuda() for h in heads]
@@ -99,12 +99,15 @@ def _fused_vs_chain(B, C, size, profile, kind, thr, iou, sem, seed, orig=None, s
     kw = {}
     if mode:
         kw["nms_mode"] = mode
-    dets = fused.decode_nms(dheads, strides, C, (size, size), cuda(orig), kind, thr, iou, return_index=True, **kw)
+    dets = fused.decode_nms(dheads, strides, C, (size, size), cuda(orig), kind, thr, iou, return_index=True,
+                            hints=hints, **kw)
     # the general path for every image must give the same rows (strategy='general', and what 'auto' switches to
     # after a mostly-overflowing call)
     for strat in ("general", "auto"):
         alt = fused.decode_nms(dheads, strides, C, (size, size), cuda(orig), kind, thr, iou, return_index=True,
-                               strategy=strat, **kw)
+                               strategy=strat, hints=hints, **kw)
+        if strat == "auto" and len(dets._spill) * 2 > B:
+            assert alt.general_first and alt.images_via_general_path == B      # the hint routed the batch
         for b in range(B):
             assert torch.equal(alt[b], dets[b]) and torch.equal(alt.indices(b), dets.indices(b)), (strat, b)
     # decoded boxes themselves: within 1e-5 of the oracle's decode
@@ -215,7 +218,6 @@ def test_fused_rectangular_heads_and_single_level():
     from pqdet_b200 import config, fused
     from pqdet_b200.parser import Decode
     config.nms_semantics = "cuda"
-    fused._DENSE_HINT.clear()
     g = torch.Generator().manual_seed(77)
     C, B = 4, 3
     shapes = [(12, 20, 32), (24, 40, 16)]                         # (H, W, stride): 384 x 640 input

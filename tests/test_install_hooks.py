@@ -57,6 +57,32 @@ def test_install_patches_the_reference_hook_points():
         # row a4 hook: the model's class gains a forward that combines the levels in one launch; module tree unchanged
         assert inst.fuse_eval_concat(m) and list(m.state_dict().keys()) == keys
         assert type(m).__mro__[1].__name__ == 'DetectionModel' and type(m).__mro__[2].__name__ == 'AnyModel'
+        # training analogue: same subclass gains the one-launch loss route; on CPU the reference's own loop still runs
+        assert inst.fuse_train_levels(m) and type(m)._pq_train_levels and type(m)._pq_eval_concat
+        assert list(m.state_dict().keys()) == keys
+        # the reference's own affine callables are recognised (dataset/*_sample.py), anything else is refused
+        from dataset.voc_sample import _voc_affine_bboxes
+        from dataset.coco_sample import _coco_affine_bboxes
+        from dataset.visdrone_sample import _visdrone_affine_bboxes
+        assert [pqb.affine_kind(f) for f in (_voc_affine_bboxes, _coco_affine_bboxes, _visdrone_affine_bboxes)] == \
+            ['voc', 'coco', 'visdrone']
+        try:
+            pqb.affine_kind(lambda a, b: (a, b))
+            raise SystemExit('custom affine accepted')
+        except ValueError:
+            pass
+        # Evaluator.evaluate is replaced (one fused launch per batch); the loop keeps the reference's data protocol
+        assert eval.evaluator.Evaluator.evaluate.__qualname__.startswith('_make_evaluate')
+        assert done['eval.evaluator.Evaluator.evaluate']
+        ev._score_threshold, ev._iou_threshold, ev._input_size = 0.1, 0.45, (64, 64)
+        ev._recover_bboxes = dataset.RECOVER_BBOXES_REGISTER['voc']
+        ev.model, ev.dataset = m, []
+        assert inst._dataset_kind(ev._recover_bboxes) == 'voc'
+        try:
+            ev.evaluate()                                  # empty data set: the reference's AP() leaves `metrics` unbound
+            raise SystemExit('empty evaluation returned')
+        except UnboundLocalError:
+            pass
         print('ok')
     """) % (ROOT, os.path.join(rh.REFERENCE_ROOT, "model", "cfg", "regnetx-600m-fpn.cfg"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=rh.REFERENCE_ROOT, timeout=300)
