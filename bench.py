@@ -120,19 +120,21 @@ def dist_env():
 # CPU path (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
 def cpu_eval_rate(n_images: int, repeats: int = 1, seed: int = 1234):
-    """images/s of the reference's CPU sequence on `n_images` of the headline workload, all host cores."""
+    """images/s of the reference's CPU sequence on `n_images` of the headline workload, all host cores:
+    one worker PROCESS per core (oracle/cpu_path.ProcessPool; threads serialise on the GIL), each running the
+    reference's per-image sequence with one intra-op thread."""
     from oracle import cpu_path
     from pqdet_b200 import synth
     cores = cpu_path.host_cores()
     heads = synth.make_heads(n_images, C_VOC, SIZE, "sparse", seed=seed, device="cpu")
     orig = torch.tensor([[float(SIZE), float(SIZE)]])
+    with cpu_path.ProcessPool(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, cores) as pool:
+        pool.run()                                                                     # warm-up (page in, fork COW)
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            out = pool.run()
+        dt_par = (time.perf_counter() - t0) / repeats
     torch.set_num_threads(cores)
-    cpu_path.eval_chain_image_parallel([h[:min(8, n_images)] for h in heads], STRIDES, C_VOC, (SIZE, SIZE), orig,
-                                       "voc", THR, IOU, cores)                       # warm-up
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        out = cpu_path.eval_chain_image_parallel(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, cores)
-    dt_par = (time.perf_counter() - t0) / repeats
     n_seq = min(n_images, 32)
     t0 = time.perf_counter()
     cpu_path.eval_chain([h[:n_seq] for h in heads], STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU)
@@ -198,50 +200,55 @@ def cpu_model():
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU sequence (oracle/cpu_path.py, pinned bit for bit to the live reference by
+    tests/test_oracle_vs_reference.py) on the SAME workload and the same images per step as our arm, on every host
+    core (one worker process per core)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
-    sample = 64
     from oracle import cpu_path
     from pqdet_b200 import synth
     cores = cpu_path.host_cores()
-    heads = synth.make_heads(sample, C_VOC, SIZE, "sparse", seed=1234, device="cpu")
+    B = B_PER_GPU
+    heads = synth.make_heads(B, C_VOC, SIZE, "sparse", seed=0, device="cpu")
     orig = torch.tensor([[float(SIZE), float(SIZE)]])
-    torch.set_num_threads(cores)
-
-    def step():
-        return cpu_path.eval_chain_image_parallel(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, cores)
-    for _ in range(max(args.warmup, 1)):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    val = sample * args.steps / dt
+    with cpu_path.ProcessPool(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, cores) as pool:
+        for _ in range(max(min(args.warmup, 2), 1)):
+            pool.run()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = pool.run()
+        dt = time.perf_counter() - t0
+    val = B * args.steps / dt
     line = {
         "impl": "reference", "metric": "images/sec decode+NMS", "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(sample_note="CPU arm: each step = %d images of the same workload" % sample),
+        "config": workload_config(),
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
-                         "sample": "%d images/step, image-parallel thread pool (1 intra-op thread each), torch CPU "
-                                   "ops + torchvision.ops.batched_nms = the reference's own CPU stack; the "
-                                   "reference's Python cannot travel to the GPU box" % sample},
+                         "sample": "%d images/step (the same step as the GPU arm), %d worker processes x 1 intra-op "
+                                   "thread, torch CPU ops + torchvision.ops.batched_nms = the reference's own CPU "
+                                   "stack in the reference's call sequence (the reference's Python cannot travel to "
+                                   "the GPU box; the port is pinned bit for bit to it in tests/)" % (B, cores)},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "stats": {"kept_per_image": float(np.mean([o.shape[0] for o in out]))},
     }
     print(json.dumps(line))
 
 
-def workload_config(sample_note=None):
-    cfg = {"workload": "BASELINE config E: eval sweep, VOC-shaped heads C=20 512x512 FPN(32,16,8), PQ-SYNTH-v1 sparse, "
-                       "fused decode+recover+threshold+class-aware NMS",
-           "images_per_gpu": B_PER_GPU, "score_threshold": THR, "nms_iou": IOU,
-           "nms_semantics": "torchvision-CUDA (trick <= 25000 candidates, FMA IoU order)",
-           "l2_policy": "inputs (1.65 GB/step/GPU) larger than L2 (126 MB)"}
-    if sample_note:
-        cfg["note"] = sample_note
-    return cfg
+N_SETS = 4          # distinct input sets rotated through the timed loop (no step re-reads what the last one read)
+
+
+def workload_config():
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": "BASELINE config E: eval sweep, VOC-shaped heads C=20 512x512 FPN(32,16,8), PQ-SYNTH-v1 sparse, "
+                        "fused decode+recover+threshold+class-aware NMS",
+            "images_per_gpu": B_PER_GPU, "images_per_step": B_PER_GPU, "score_threshold": THR, "nms_iou": IOU,
+            "nms_semantics": "torchvision-CUDA (trick <= 25000 candidates, FMA IoU order)",
+            "l2_policy": "inputs larger than L2 AND rotated: %d distinct 1024-image sets (1.65 GB each; the set a step "
+                         "touches, ~0.2 GB, exceeds the 126 MB L2) take turns, so no step re-reads the previous "
+                         "step's lines" % N_SETS}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -650,14 +657,15 @@ def bench_other_configs(device, peak):
     heads = synth.make_heads(B, C, size, "dense", seed=0, device=device)
     orig = torch.tensor([480.0, 480.0], device=device)
     res = {}
+    hints = fused.StrategyHints()                 # caller-held: the second call goes straight to the general path
     def run_c():
-        res["d"] = fused.decode_nms(heads, STRIDES, C, (size, size), orig, "visdrone", THR, IOU)
+        res["d"] = fused.decode_nms(heads, STRIDES, C, (size, size), orig, "visdrone", THR, IOU, hints=hints)
     dt = wall(run_c, 3)
     hm = res["d"].host_meta()
     out["C_decode_nms"] = {"workload": "VisDrone-shaped C=10 608x608 bs=64 dense profile, fused + general path incl. host "
                                        "round trips", "images_per_s": B / dt, "ms": dt * 1e3,
                            "candidates_per_image": float(hm[1].float().mean()), "kept_per_image": float(hm[0].float().mean()),
-                           "images_via_general_path": len(res["d"]._spill),
+                           "images_via_general_path": res["d"].images_via_general_path,
                            "roofline_frac": raw_bytes(C, size) * B / dt / (peak * 1e9)}
     del heads
     old = pqcfg.nan_check
@@ -719,6 +727,124 @@ def bench_other_configs(device, peak):
     return out
 
 
+def collective_legs(device, rank, world, steps, warmup, peak):
+    """Timed legs that contain the path's two collectives (north_star; every rank takes part, also at N = 1 where the
+    collective degenerates to a local copy).  All timing: CUDA events on the launching stream, barrier + synchronize on
+    both sides, MAX over ranks; per-step microseconds with and without the collective, on rotating input sets.
+
+    D_train_step  BASELINE config D shard: COCO 80-class 608x608, 16 images per GPU (bs=128 over 8 GPUs): GT rows ->
+                  pqdet_assign_sparse -> multi-level GIoU loss + d loss/d head (one launch) -> dist.reduce_losses
+                  (one all_reduce of the kernel's 19-float result, model/loss.py:105-108 + trainer.py:233).
+    E_eval_gather BASELINE config E: the headline fused decode+NMS on 1024 images per GPU -> dist.gather_detections_fixed
+                  (one all_gather of [count | 256 rows] per image, eval/evaluator.py:49-61's gather to the evaluator)."""
+    import torch.distributed as dist
+    from pqdet_b200 import _ops, synth
+    from pqdet_b200 import dist as pqd
+    from pqdet_b200 import config as pqcfg
+    from pqdet_b200.interpreter import DetectionHead
+    from pqdet_b200.train_dataset import DEFAULT_ANCHORS, DEFAULT_STRIDES, assign_sparse, pack_gt
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_us(fn, n):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es.record()
+        for _ in range(n):
+            fn()
+        ee.record()
+        barrier()
+        ms = torch.tensor([es.elapsed_time(ee)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) * 1e3 / n
+
+    legs = {}
+    old = pqcfg.nan_check
+    pqcfg.nan_check = "off"
+    try:
+        # ---- D: assignment + loss + loss all-reduce
+        B, C, size = 16, 80, 608
+        out_sizes = np.array([[size // 8] * 2, [size // 16] * 2, [size // 32] * 2])
+        head = DetectionHead([dict(classes=C, stride=s, bbox_loss="giou", ignore_thresh=0.5, l1_loss_gain=0.05) for s in STRIDES])
+        sets = []
+        for i in range(N_SETS):
+            gts = synth.make_gt(B, C, size, 2, 38, seed=1000 * rank + i)
+            gt_d, cnt_d = pack_gt(gts, device)
+            sets.append((synth.make_train_heads(B, C, size, seed=1000 * rank + i, device=device), gt_d, cnt_d))
+        it = [0]
+        last = {}
+
+        def train_step(with_collective):
+            hs, gt_d, cnt_d = sets[it[0] % N_SETS]
+            it[0] += 1
+            tgt = assign_sparse(gt_d, cnt_d, out_sizes, C, DEFAULT_ANCHORS, DEFAULT_STRIDES, 0.3, trim=False)
+            o, grads = head.loss_and_grad(hs, tgt)
+            if with_collective:
+                o = pqd.reduce_losses(o, B, global_batch=B * world)
+            last["o"], last["g"] = o, grads
+        us_with = timed_us(lambda: train_step(True), steps)
+        us_without = timed_us(lambda: train_step(False), steps)
+        alg = (2 * raw_bytes(C, size) + 4 * 3 * cells(size)) * B
+        legs["D_train_step"] = {
+            "workload": "BASELINE config D shard: COCO C=80 608x608, 16 images/GPU (bs=%d over %d GPUs), GT 2-38/img: "
+                        "pqdet_assign_sparse + pqdet_loss_levels_sparse (GIoU, fwd + d loss/d head) + all_reduce of the "
+                        "19-float loss vector" % (16 * world, world),
+            "metric": "images/sec assignment+loss (global)", "value": world * B / (us_with * 1e-6), "unit": "images/s",
+            "us_per_step": us_with, "us_per_step_without_collective": us_without,
+            "collective": "all_reduce(AVG) of 19 floats over NCCL, inside the timed region",
+            "collective_share": max(0.0, (us_with - us_without) / us_with),
+            "global_loss": float(last["o"]["loss"]),
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_step_per_gpu": alg, "peak": peak,
+                         "frac": alg / (us_without * 1e-6) / (peak * 1e9),
+                         "note": "2R + 4 B/row (sparse targets) over the step without the collective; at 16 images "
+                                 "the step is launch/latency bound (3 launches)"},
+            "input_sets_rotated": N_SETS}
+        del sets, last
+        # ---- E: fused decode+NMS + gather of the detections
+        Bv = B_PER_GPU
+        K_CAP = 256
+        esets = []
+        for i in range(2):
+            hh = synth.make_heads(Bv, C_VOC, SIZE, "sparse", seed=7000 + 10 * rank + i, device=device)
+            h, keep = _ops.make_heads(hh, STRIDES, C_VOC, (SIZE, SIZE), torch.tensor([float(SIZE), float(SIZE)], device=device),
+                                      "voc", THR, IOU, "auto_cuda", "tv_cuda")
+            esets.append((hh, h, keep))
+        out = _ops.alloc_fused_outputs(Bv, 2048, False, device)
+        bufs = [None]
+        res = {}
+
+        def eval_step(with_collective):
+            _, h, keep = esets[it[0] % 2]
+            it[0] += 1
+            det, _, meta = _ops.decode_nms_fused(h, keep, 2048, False, out=out)
+            if with_collective:
+                res["all"] = pqd.gather_detections_fixed(det, meta[:Bv], K_CAP, out=bufs[0])
+                bufs[0] = res["all"][2]
+        us_with = timed_us(lambda: eval_step(True), steps)
+        us_without = timed_us(lambda: eval_step(False), steps)
+        all_det, all_counts, _ = res["all"]
+        legs["E_eval_gather"] = {
+            "workload": "BASELINE config E: fused decode+NMS on 1024 VOC-512 images/GPU, then one all_gather of "
+                        "[count | %d rows x 6] per image to every rank" % K_CAP,
+            "metric": "images/sec decode+NMS+gather (global)", "value": world * Bv / (us_with * 1e-6), "unit": "images/s",
+            "us_per_step": us_with, "us_per_step_without_collective": us_without,
+            "collective": "all_gather_into_tensor of %d bytes per rank over NCCL, inside the timed region"
+                          % (Bv * (1 + K_CAP * 6) * 4),
+            "collective_share": max(0.0, (us_with - us_without) / us_with),
+            "gathered_images": int(all_counts.numel()), "gathered_detections": int(all_counts.sum()),
+            "truncated_images": int((all_counts >= K_CAP).sum())}
+    finally:
+        pqcfg.nan_check = old
+    return legs
+
+
 def run_ours(args):
     rank, local_rank, world = dist_env()
     import torch.distributed as dist
@@ -731,14 +857,22 @@ def run_ours(args):
     import pqdet_b200
     pqdet_b200.load_library()
     B = B_PER_GPU
-    heads = synth.make_heads(B, C_VOC, SIZE, "sparse", seed=rank, device=device)
     orig = torch.tensor([float(SIZE), float(SIZE)], device=device)
-    h, keep = _ops.make_heads(heads, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, "auto_cuda", "tv_cuda")
     MAXDET = 2048
     out = _ops.alloc_fused_outputs(B, MAXDET, False, device)
+    # N_SETS distinct 1024-image batches take turns in the timed loop (rotate the inputs)
+    sets = []
+    for i in range(N_SETS):
+        hs = synth.make_heads(B, C_VOC, SIZE, "sparse", seed=N_SETS * rank + i, device=device)
+        h_i, keep_i = _ops.make_heads(hs, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, "auto_cuda", "tv_cuda")
+        sets.append((hs, h_i, keep_i))
+    heads = sets[0][0]
+    turn = [0]
 
     def step():
-        _ops.decode_nms_fused(h, keep, MAXDET, False, out=out)
+        _, h_i, keep_i = sets[turn[0] % N_SETS]
+        turn[0] += 1
+        _ops.decode_nms_fused(h_i, keep_i, MAXDET, False, out=out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -746,12 +880,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # per-set statistics (one untimed pass each): kept rows, candidates, overflow, rows above the objectness threshold
+    set_stats = []
+    for hs, h_i, keep_i in sets:
+        _ops.decode_nms_fused(h_i, keep_i, MAXDET, False, out=out)
+        meta = out[2][:3 * B].view(3, B).cpu()
+        n_hit = 0
+        for t in hs:
+            n_hit += int((torch.sigmoid(t.view(B, 3, 5 + C_VOC, -1)[:, :, 4]) > THR).sum())
+        set_stats.append({"kept": int(meta[0].sum()), "ncand": meta[1].clone(), "overflow": int((meta[2] != 0).sum()),
+                          "n_hit": n_hit, "counts": meta[0].clone()})
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    turn[0] = 0
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for _ in range(args.steps):                              # EXACTLY K steps, nothing else on the stream
@@ -763,25 +908,34 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms)
-    meta = out[2][:3 * B].view(3, B).cpu()
-    counts, ncand, status = meta[0], meta[1], meta[2]
-    overflow = int((status != 0).sum())
+    counts = set_stats[0]["counts"]
+    ncand = torch.cat([st["ncand"] for st in set_stats])
+    overflow = sum(st["overflow"] for st in set_stats)
 
     # ---- end to end, host buffers in -> host buffers out, every step (the reference-facing call:
     # fused.decode_nms_host -> pqdet_decode_nms_host).  The heads sit in pinned host memory; the kernel pulls the
     # objectness planes and the channels of rows above threshold straight over PCIe (no staging copy) and writes
     # counts + detection rows straight into pinned host memory; the step ends with a stream synchronise, after
     # which the caller owns the rows.  `staged` = the same result with a full H2D copy of the heads first, the
-    # device-resident kernel, then D2H of counts + rows (what this path cost before the zero-copy entry point).
-    host_heads = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in heads]
-    for hh, t in zip(host_heads, heads):
-        hh.copy_(t)
-    torch.cuda.synchronize()
-    hz, keepz = _ops.make_heads_host(host_heads, STRIDES, C_VOC, (SIZE, SIZE), torch.tensor([float(SIZE), float(SIZE)]),
-                                     "voc", THR, IOU, "auto_cuda", "tv_cuda")
+    # device-resident kernel, then D2H of counts + rows (what this path costs for inputs that are not sparse).
+    # Two host-resident sets take turns.
+    N_HOST = 2
+    hsets = []
+    for i in range(N_HOST):
+        hh = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in sets[i][0]]
+        for a, t in zip(hh, sets[i][0]):
+            a.copy_(t)
+        torch.cuda.synchronize()
+        hz, keepz = _ops.make_heads_host(hh, STRIDES, C_VOC, (SIZE, SIZE), torch.tensor([float(SIZE), float(SIZE)]),
+                                         "voc", THR, IOU, "auto_cuda", "tv_cuda")
+        hsets.append((hh, hz, keepz))
+    host_heads = hsets[0][0]
     hout = _ops.alloc_host_outputs(B, MAXDET, False, device)
+    eturn = [0]
 
     def e2e_step():
+        _, hz, keepz = hsets[eturn[0] % N_HOST]
+        eturn[0] += 1
         _ops.decode_nms_host(hz, keepz, MAXDET, False, device, out=hout)
         torch.cuda.synchronize()
         return hout
@@ -789,10 +943,13 @@ def run_ours(args):
     dev_in = [torch.empty_like(t) for t in heads]
     h2, keep2 = _ops.make_heads(dev_in, STRIDES, C_VOC, (SIZE, SIZE), orig, "voc", THR, IOU, "auto_cuda", "tv_cuda")
     host_meta = torch.empty((3 * B,), dtype=torch.int32, pin_memory=True)
+    sturn = [0]
 
     def staged_step():
-        for d, s in zip(dev_in, host_heads):
-            d.copy_(s, non_blocking=True)
+        src = hsets[sturn[0] % N_HOST][0]
+        sturn[0] += 1
+        for d, s_ in zip(dev_in, src):
+            d.copy_(s_, non_blocking=True)
         det, _, m = _ops.decode_nms_fused(h2, keep2, MAXDET, False, out=out)
         host_meta.copy_(m[:3 * B], non_blocking=True)
         torch.cuda.synchronize()
@@ -813,18 +970,27 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return world * B * n / (float(ms) * 1e-3)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 10))
     e2e_val = timed(e2e_step, e2e_steps)
-    staged_val = timed(staged_step, 3)
+    staged_val = timed(staged_step, 4)
+    eturn[0] = 0
+    e2e_step()                                               # set 0 again, for the comparison below
+    _ops.decode_nms_fused(sets[0][1], sets[0][2], MAXDET, False, out=out)
+    torch.cuda.synchronize()
     e2e_same = bool(torch.equal(hout[2][:B], counts.to(torch.int32)) and
                     all(torch.equal(hout[0][b, :int(counts[b])], out[0][b, :int(counts[b])].cpu()) for b in range(0, B, 61)))
     # bytes that cross PCIe per step: the objectness planes (read in full, 128-byte lines) + one 32-byte sector per
     # (hit row, box/class channel) as the upper bound of the gathers; results: 3 int32 per image + 24 B per row
-    n_hit = 0
-    for t in heads:
-        n_hit += int((torch.sigmoid(t.view(B, 3, 5 + C_VOC, -1)[:, :, 4]) > THR).sum())
-    h2d_pulled = sum(B * 3 * t.shape[2] * t.shape[3] * 4 for t in heads) + n_hit * (4 + C_VOC) * 32
-    d2h_bytes = [3 * B * 4 + int(counts.sum()) * 24]
+    plane_bytes = sum(B * 3 * t.shape[2] * t.shape[3] * 4 for t in heads)
+    n_hit_mean = float(np.mean([st["n_hit"] for st in set_stats]))
+    kept_mean = float(np.mean([st["kept"] for st in set_stats]))
+    h2d_pulled = int(plane_bytes + n_hit_mean * (4 + C_VOC) * 32)
+    d2h_bytes = int(3 * B * 4 + kept_mean * 24)
+    # the collective legs run on every rank (they are collectives); cheap: a few hundred launches
+    try:
+        legs = collective_legs(device, rank, world, max(args.steps, 10), 3, measured_peak()[0])
+    except Exception as e:
+        legs = {"error": repr(e)}
     # keep the GPU busy with the timed kernel for ~0.4 s more so that the 100 ms nvidia-smi sampler sees clocks
     # and throttle reasons under exactly this load (the timed region itself lasts only a few ms)
     t_busy = time.perf_counter()
@@ -841,10 +1007,14 @@ def run_ours(args):
         return
     peak, peak_src = measured_peak()
     ms_step = total_ms / args.steps
-    k_mean = float(counts.float().mean())
-    alg_bytes = raw_bytes(C_VOC, SIZE) * B + 24.0 * float(counts.sum())
+    k_mean = kept_mean / B
+    alg_bytes = raw_bytes(C_VOC, SIZE) * B + 24.0 * kept_mean
     kern_ms = float(np.mean(per_step))
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    achieved_alg = alg_bytes / (kern_ms * 1e-3) / 1e9
+    # what the kernel MUST move: every objectness plane, one 32-byte sector per (row above the objectness threshold,
+    # box/class channel) -- the channels of a row sit in different planes --, and the result rows + 3 words per image
+    must_move = plane_bytes + n_hit_mean * (4 + C_VOC) * 32 + 3 * 4 * B + 24.0 * kept_mean
+    achieved = must_move / (kern_ms * 1e-3) / 1e9
     traffic = ncu_traffic("decode_nms_fused_kernel")
     line = {
         "metric": "images/sec decode+NMS", "value": world * B * args.steps / (total_ms * 1e-3), "unit": "images/s",
@@ -854,43 +1024,70 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "pq::decode_nms_fused_kernel<0>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src,
+                     "bytes_per_launch": must_move,
+                     "bytes_breakdown": {"objectness_planes": plane_bytes,
+                                         "hit_row_sectors": n_hit_mean * (4 + C_VOC) * 32,
+                                         "output": 3 * 4 * B + 24.0 * kept_mean},
+                     "frac_algorithmic": achieved_alg / peak, "achieved_algorithmic": achieved_alg,
+                     "algorithmic_bytes_per_launch": alg_bytes,
                      "achieved_dram": (traffic / (kern_ms * 1e-3) / 1e9) if traffic else None,
-                     "note": "achieved = algorithmic bytes (R*B + 24*K, SURVEY 8d) / mean kernel time; the kernel "
-                             "reads only the objectness planes plus the box/class channels of rows with conf > thr "
-                             "(exact early-out), so DRAM traffic is far below the algorithmic bytes and frac can "
-                             "exceed 1; achieved_dram = measured ncu DRAM bytes / time"},
-        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_pulled, "d2h_bytes_per_step": d2h_bytes[0],
+                     "note": "frac = bytes the kernel must move (objectness planes in full + one 32-byte sector per "
+                             "(row with conf > thr, box/class channel) + output rows) / mean kernel time / peak. "
+                             "frac_algorithmic uses SURVEY 8d's R*B + 24*K, which the exact conf <= thr early-out "
+                             "never reads in full, so it exceeds 1 and is NOT a roofline fraction; traffic / "
+                             "achieved_dram = measured ncu DRAM bytes of the committed capture"},
+        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_pulled, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps, "host_input_bytes_per_step": h2d, "identical_to_resident_run": e2e_same,
-                "staged_full_copy_value": staged_val,
+                "staged_full_copy_value": staged_val, "host_sets_rotated": N_HOST,
                 "note": "fused.decode_nms_host / pqdet_decode_nms_host: heads in pinned host memory, detections in "
                         "pinned host memory, stream synchronised every step; the kernel reads host memory in place "
                         "over PCIe (objectness planes + channels of the rows above threshold = h2d_bytes_per_step, "
                         "of host_input_bytes_per_step) and writes counts + rows back; staged_full_copy_value = "
-                        "full H2D copy -> resident kernel -> D2H of counts + rows"},
+                        "full H2D copy -> resident kernel -> D2H of counts + rows (the figure for inputs that are "
+                        "not sparse)"},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "stats": {"kept_per_image": k_mean, "candidates_per_image": float(ncand.float().mean()),
                   "max_candidates": int(ncand.max()), "overflow_images": overflow,
+                  "rows_above_objectness_threshold_per_image": n_hit_mean / B, "input_sets_rotated": N_SETS,
                   "kernel_ms_mean": kern_ms, "kernel_ms_min": float(np.min(per_step))},
+        "legs": legs,
     }
+    del hsets, dev_in
     if world == 1 and args.cpu_sample > 0:
         try:
             r = cpu_eval_rate(args.cpu_sample)
             line["cpu_baseline"] = {
                 "value": r["par"], "unit": "images/s", "cores": r["cores"], "kind": "port", "cpu": cpu_model(),
                 "sequential_as_is": r["seq"],
-                "sample": "%d images of the same workload, image-parallel thread pool over all host cores; "
+                "sample": "%d images of the same workload, one worker process per host core (1 intra-op thread each); "
                           "sequential_as_is = the reference's per-image loop on %d images with intra-op threads; "
-                          "torch CPU ops + torchvision.ops.batched_nms (oracle/cpu_path.py)" % (r["n"], r["n_seq"])}
+                          "torch CPU ops + torchvision.ops.batched_nms (oracle/cpu_path.py, pinned bit for bit to the "
+                          "live reference in tests/)" % (r["n"], r["n_seq"])}
         except Exception as e:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     if world == 1 and not args.no_loss:
-        line["loss"] = bench_loss(device, max(args.steps, 10), 3, peak)
-    if world == 1 and not args.no_loss:
+        loss = bench_loss(device, max(args.steps, 10), 3, peak)
+        line["loss"] = loss
         try:
-            line["other_configs"] = bench_other_configs(device, peak)
+            other = bench_other_configs(device, peak)
         except Exception as e:
-            line["other_configs"] = {"error": repr(e)}
+            other = {"error": repr(e)}
+        line["other_configs"] = other
+        # the five BASELINE configs as named legs (DESIGN.md section 6 documents every field)
+        l1 = loss.get("by_bbox_loss", {}).get("l1", {})
+        legs["A_bs1_latency"] = other.get("A_bs1_latency")
+        legs["B_loss"] = {"workload": loss.get("workload"), "metric": "images/sec decode+loss fwd+bwd",
+                          "value": l1.get("images_per_s"), "unit": "images/s", "us_per_step": 1e3 * l1.get("ms_per_step", 0.0),
+                          "roofline": {"bound": "hbm", "frac": l1.get("roofline_frac"), "achieved": l1.get("achieved_gbs"),
+                                       "peak": peak, "unit": "GB/s",
+                                       "algorithmic_bytes_per_image": loss.get("algorithmic_bytes_per_image")},
+                          "steady_state": loss.get("steady_state", {}).get("dense_labels")}
+        legs["C_decode_nms"] = other.get("C_decode_nms")
+        legs["C_loss"] = other.get("C_loss")
+        legs["D_assign_loss"] = other.get("D_assign_loss")
+        legs["E_decode_nms"] = {"workload": workload_config()["workload"], "metric": line["metric"], "value": line["value"],
+                                "unit": "images/s", "us_per_step": 1e3 * ms_step, "roofline_frac": achieved / peak}
     if world == 1 and args.cpu_sample > 0:
         try:
             line["gpu_stock_baseline"] = gpu_stock_rate(device)

@@ -26,20 +26,67 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def reduce_losses(losses: dict, local_batch: int, group=None) -> dict:
+def reduce_losses(losses: dict, local_batch: int, group=None, global_batch: Optional[int] = None) -> dict:
     """losses: the dict DetectionHead.forward returns on this rank (batch means over local_batch).
-    -> the same dict with every entry replaced by the global-batch mean.  One 7-float all_reduce."""
+    -> the same dict with every entry replaced by the global-batch mean (the reference's mean of replica means,
+    model/loss.py:105-108 + trainer.py:233, for any shard sizes).
+
+    With `global_batch` given (the trainer knows it) this is ONE collective on the kernel's own output vector and at
+    most one scaling kernel: all_reduce(AVG) when the shards are equal, else the vector is pre-scaled by
+    local_batch / global_batch and summed.  Without it the batch size travels with the sums (7 + 1 floats)."""
     keys = ['loss', 'giou_loss', 'conf_loss', 'class_loss']
-    parts = [losses[k].reshape(-1)[:1] for k in keys] + [b.reshape(-1)[:1] for b in losses['loss_per_branch']]
     nb = len(losses['loss_per_branch'])
+    live = dist.is_available() and dist.is_initialized()
+    raw = getattr(losses['loss'], 'pq_out', None)          # DetectionHead's (4+5L,) result vector, if this is ours
+    if global_batch is not None and raw is not None:
+        vec = raw.detach().clone()
+        world = dist.get_world_size(group) if live else 1
+        if local_batch * world == global_batch and (not live or dist.get_backend(group) == "nccl"):
+            if live:
+                dist.all_reduce(vec, op=dist.ReduceOp.AVG, group=group)          # NCCL-only reduction op
+        else:
+            vec.mul_(float(local_batch) / float(global_batch))
+            if live:
+                dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+        L = nb
+        out = {k: vec[i:i + 1] for i, k in enumerate(keys)}
+        out['loss_per_branch'] = [vec[4 + 4 * L + i:5 + 4 * L + i] for i in range(L)]
+        return out
+    parts = [losses[k].reshape(-1)[:1] for k in keys] + [b.reshape(-1)[:1] for b in losses['loss_per_branch']]
     vec = torch.cat(parts).detach().to(torch.float32) * float(local_batch)
     vec = torch.cat([vec, vec.new_tensor([float(local_batch)])])
-    if dist.is_available() and dist.is_initialized():
+    if live:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
     vec = vec[:-1] / vec[-1]
     out = {k: vec[i:i + 1] for i, k in enumerate(keys)}
     out['loss_per_branch'] = [vec[4 + i:5 + i] for i in range(nb)]
     return out
+
+
+def gather_detections_fixed(det: torch.Tensor, counts: torch.Tensor, k_cap: int, group=None, out=None):
+    """Eval gather without a host round trip: every rank contributes the same shape, so ONE all_gather moves
+    everything.  det (B, K, 6) padded rows, counts (B) int32 (device) -> (all_det (world, B, k_cap, 6),
+    all_counts (world, B) int32) on every rank, rank-major = global image order for equal contiguous shards.
+    Rows beyond k_cap are dropped (counts are clamped); the packed record per image is [count | k_cap rows], the count
+    bit-cast into the float buffer.  `out` = a previous result's packed buffers to reuse."""
+    B = det.shape[0]
+    k = min(k_cap, det.shape[1])
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rec = 1 + k_cap * 6
+    if out is None:
+        send = torch.zeros((B, rec), dtype=torch.float32, device=det.device)
+        recv = torch.empty((world, B, rec), dtype=torch.float32, device=det.device)
+    else:
+        send, recv = out
+    send[:, 0] = counts.to(torch.int32).clamp(max=k_cap).view(torch.float32)
+    send[:, 1:1 + k * 6] = det[:, :k].reshape(B, k * 6)
+    if world > 1:
+        dist.all_gather_into_tensor(recv.view(world * B, rec), send, group=group)
+    else:
+        recv[0].copy_(send)
+    all_counts = recv[:, :, 0].contiguous().view(torch.int32)
+    all_det = recv[:, :, 1:].view(world, B, k_cap, 6)
+    return all_det, all_counts, (send, recv)
 
 
 def gather_detections(det: torch.Tensor, counts: torch.Tensor, group=None):

@@ -272,6 +272,7 @@ class DetectionHead(nn.Module):
         }
         if config.nan_check == "lazy":
             res['loss'].pq_nan_flag = flag
+        res['loss'].pq_out = out              # the whole result vector, for dist.reduce_losses (one collective)
         return res
 
     @staticmethod

@@ -41,6 +41,27 @@ def _worker(rank, world, port, q):
             det[j, :i % 4] = float(i)
         flat = pqd.flatten_gathered(pqd.gather_detections(det, counts))
         ok_det = len(flat) == total and all(t.shape[0] == i % 4 and bool((t == float(i)).all()) for i, t in enumerate(flat))
+        # the lean form: the kernel's own (4+5L,) result vector, global batch known -> one collective
+        L = 3
+        out_vec = torch.zeros((4 + 5 * L,))
+        out_vec[0:4] = local[:, 0:4].mean(dim=0)
+        out_vec[4 + 4 * L:4 + 5 * L] = local[:, 4:7].mean(dim=0)
+        mine = {k: out_vec[i:i + 1] for i, k in enumerate(['loss', 'giou_loss', 'conf_loss', 'class_loss'])}
+        mine['loss_per_branch'] = [out_vec[4 + 4 * L + i:5 + 4 * L + i] for i in range(L)]
+        mine['loss'].pq_out = out_vec
+        red2 = pqd.reduce_losses(mine, hi - lo, global_batch=total)
+        got2 = torch.cat([red2['loss'], red2['giou_loss'], red2['conf_loss'], red2['class_loss']] + red2['loss_per_branch'])
+        ok_loss = ok_loss and bool(torch.allclose(got2, want, rtol=1e-6, atol=1e-7))
+        # fixed-capacity gather (equal shards: 5 images each): one collective, no host round trip
+        all_det, all_counts, bufs = pqd.gather_detections_fixed(det, counts, 3)
+        ok_fix = tuple(all_det.shape) == (world, hi - lo, 3, 6) and all_counts.dtype == torch.int32
+        for r in range(world):
+            rl, rh = pqd.shard_range(total, r, world)
+            for j, i in enumerate(range(rl, rh)):
+                n = min(i % 4, 3)
+                ok_fix = ok_fix and int(all_counts[r, j]) == n and bool((all_det[r, j, :n] == float(i)).all())
+        all_det2, _, _ = pqd.gather_detections_fixed(det, counts, 3, out=bufs)        # buffer reuse
+        ok_det = ok_det and ok_fix and bool(torch.equal(all_det, all_det2))
         q.put((rank, ok_loss, ok_det))
     finally:
         dist.destroy_process_group()
