@@ -62,7 +62,7 @@ def main():
     for k in st:
         allst.update(st[k])
     print("stall mix:", ", ".join("%s %.1f%%" % (c.replace("stall_", ""), 100.0 * v / ts) for c, v in allst.most_common(8)))
-    for k, v in sorted(agg.items(), key=lambda x: -samp[x[0]])[:top]:
+    for k, v in sorted(agg.items(), key=lambda x: (-samp[x[0]] if os.environ.get("SORT", "samples") == "samples" else -x[1]))[:top]:
         tops = ", ".join("%s:%d" % (c.replace("stall_", ""), x) for c, x in st[k].most_common(3))
         print("%-34s inst %5.1f%%  samples %5.1f%%  %s" % (k, 100.0 * v / tot, 100.0 * samp[k] / ts, tops))
 

@@ -75,7 +75,7 @@ def test_eval_hooks_one_launch_and_same_rows():
     assert strides == [32, 16, 8] and C == 4 and [tuple(r.shape[2:]) for r in raws] == [(4, 5), (8, 10), (16, 20)]
     orig = torch.tensor([[100., 150.], [128., 160.], [90., 160.], [128., 100.]], device="cuda")
     with count_abi_calls() as calls:
-        dets = fused.decode_nms(raws, strides, C, (128, 160), orig, "voc", 0.2, 0.45)
+        dets = fused.decode_nms(raws, strides, C, (128, 160), orig, "voc", 0.7, 0.45)
         rows = dets.to_numpy_list()
     assert calls == {"pqdet_decode_nms": 1}
     dec = torch.cat([l.decode(r).view(4, -1, 5 + C) for l, r in
@@ -83,7 +83,7 @@ def test_eval_hooks_one_launch_and_same_rows():
     rec = base_sample.recover_bboxes_prediction_voc(dec, (128, 160), orig)
     assert sum(len(r) for r in rows) > 0
     for b in range(4):
-        w = tools.torch_nms(rec[b], 0.2, 0.45).cpu().numpy().reshape(-1, 6)
+        w = tools.torch_nms(rec[b], 0.7, 0.45).cpu().numpy().reshape(-1, 6)
         assert np.array_equal(rows[b].reshape(-1, 6), w)
 
 
