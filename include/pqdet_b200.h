@@ -25,9 +25,18 @@
 extern "C" {
 #endif
 
-#define PQDET_VERSION 100          /* 0.1.0 */
+#define PQDET_VERSION 110          /* 0.1.1: capacity_class on the fused entry points */
 #define PQDET_MAX_LEVELS 4
-#define PQDET_MAX_CLASSES 126      /* class id is a 7-bit field of the sort key */
+#define PQDET_MAX_CLASSES 126      /* class id is a 7-bit field of the 64-bit sort keys (class:7 | ~score:32 | row:25);
+                                      more classes (or >= 2^25 rows per image) return PQDET_ERR_UNSUPPORTED */
+
+/* On-chip list capacities of the fused kernels, per image (capacity_class argument):
+ *   PQDET_CAP_COMPACT  512 rows above the objectness threshold, 1280 candidates; 128-thread CTAs, 7 per SM -
+ *                      the right geometry for eval batches of natural images (VOC / COCO-like: ~130 / ~600);
+ *   PQDET_CAP_LARGE    1024 rows, 2048 candidates; 256-thread CTAs, 4 per SM.
+ * An image that exceeds the lists is flagged PQDET_ST_CAND_OVERFLOW (counts = 0) and must be re-run with the larger
+ * class or through pqdet_nms_general; the results of both classes are identical wherever both fit. */
+enum { PQDET_CAP_COMPACT = 0, PQDET_CAP_LARGE = 1 };
 
 enum {
   PQDET_OK = 0,
@@ -98,7 +107,10 @@ int pqdet_recover(const float* pred, float* out, int B, int64_t N, int C, int af
  * work_counter           int32[2] of scratch (dynamic image scheduler).  counter_armed = 0: the call zeroes it
  *                        first; = 1: the caller guarantees both words are 0 - true after every completed
  *                        call on the same stream, because the last CTA to leave re-arms them - so a
- *                        steady-state loop enqueues nothing but the kernel */
+ *                        steady-state loop enqueues nothing but the kernel
+ * capacity_class         PQDET_CAP_* (above)
+ * heads->score_threshold must be >= 0 (scores are products of sigmoids; the keys order non-negative floats):
+ *                        negative thresholds return PQDET_ERR_UNSUPPORTED - use pqdet_nms_general */
 typedef struct {
   const float* raw[PQDET_MAX_LEVELS];
   int H[PQDET_MAX_LEVELS], W[PQDET_MAX_LEVELS];
@@ -116,7 +128,7 @@ typedef struct {
 
 int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
-                     int counter_armed, int device, void* stream);
+                     int counter_armed, int capacity_class, int device, void* stream);
 
 /* Host-buffer form of pqdet_decode_nms: the call predict.py:33-45 / eval/evaluator.py:48-61 would make when the
  * head outputs and the detections live in HOST memory.  heads->raw[], heads->orig_hw, det, det_idx, counts, ncand
@@ -127,16 +139,16 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
  * Outputs are valid after `stream` is synchronised. */
 int pqdet_decode_nms_host(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                           int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
-                          int counter_armed, int device, void* stream);
+                          int counter_armed, int capacity_class, int device, void* stream);
 
 /* ---- a6: tools.torch_nms (tools.py:540-566) for a whole batch in ONE launch: bboxes (B, N, 4+C) recovered
  * boxes + class scores -> detections, same outputs / status bits / scheduler-word contract as
- * pqdet_decode_nms.  Images with more than 1024 hit rows or 2048 candidates are flagged
- * PQDET_ST_CAND_OVERFLOW and must be re-run through pqdet_nms_general(bboxes=...). */
+ * pqdet_decode_nms.  Images that exceed the capacity class' lists are flagged PQDET_ST_CAND_OVERFLOW and must be
+ * re-run through pqdet_nms_general(bboxes=...).  score_threshold must be >= 0 (else PQDET_ERR_UNSUPPORTED). */
 int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, double score_threshold,
                     double iou_threshold, int nms_mode, int iou_round, float* det, int32_t* det_idx,
                     int max_det, int32_t* counts, int32_t* ncand, int32_t* status,
-                    int32_t* work_counter, int counter_armed, int device, void* stream);
+                    int32_t* work_counter, int counter_armed, int capacity_class, int device, void* stream);
 
 /* General (any candidate count) path, same results as pqdet_decode_nms.  Works on the images
  * listed in image_ids (device int32[n_images]; NULL = images 0..n_images-1).  det/det_idx/counts/

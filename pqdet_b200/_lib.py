@@ -19,6 +19,9 @@ NMS_MODE = {"auto_cuda": 0, "auto_cpu": 1, "trick": 2, "vanilla": 3}
 IOU_ROUND = {"tv_cuda": 0, "tv_cpu": 1}
 BBOX_LOSS = {"l1": 0, "iou": 1, "giou": 2, "diou": 3}
 ST_CAND_OVERFLOW, ST_DET_TRUNCATED = 1, 2
+# capacity classes of the fused kernels (include/pqdet_b200.h): per-image (hit rows, candidates) kept on chip
+CAPACITY = {"compact": 0, "large": 1}
+CAPACITY_LIMITS = {"compact": (512, 1280), "large": (1024, 2048)}
 
 
 PQDET_ERR_UNSUPPORTED = -3      # include/pqdet_b200.h
@@ -58,11 +61,11 @@ SIGNATURES = {
     "pqdet_recover": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float, c_float,
                               c_void_p, c_int, c_int, c_void_p]),
     "pqdet_decode_nms": (c_int, [POINTER(HeadsT), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_int, c_int, c_void_p]),
+                                 c_void_p, c_int, c_int, c_int, c_void_p]),
     "pqdet_decode_nms_host": (c_int, [POINTER(HeadsT), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_int, c_int, c_void_p]),
+                                      c_void_p, c_int, c_int, c_int, c_void_p]),
     "pqdet_nms_fused": (c_int, [c_void_p, c_int, c_int64, c_int, c_double, c_double, c_int, c_int, c_void_p,
-                                c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pqdet_nms_general_workspace": (c_int64, [c_int, c_int64, c_int, c_int64, c_int]),
     "pqdet_nms_general": (c_int, [POINTER(HeadsT), c_void_p, c_int64, c_int, c_int, c_double, c_double,
                                   c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,

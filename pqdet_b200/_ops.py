@@ -230,10 +230,11 @@ def alloc_fused_outputs(B: int, max_det: int, want_index: bool, device):
 _FUSED_ARMED = set()
 
 
-def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool, out=None):
+def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool, out=None, capacity: str = "compact"):
     """-> det (B,max_det,6), idx (B,max_det)|None, meta int32 (3B+2): counts, ncand, status, scheduler words.
     `out` = buffers from alloc_fused_outputs to reuse across calls: no allocation in the hot loop, and from
-    the second call on nothing but the kernel is enqueued (the kernel re-arms its own scheduler words)."""
+    the second call on nothing but the kernel is enqueued (the kernel re-arms its own scheduler words).
+    capacity: 'compact' (512 hit rows / 1280 candidates per image on chip, 7 CTAs per SM) or 'large' (1024 / 2048)."""
     raws, _ = keep_alive
     device = raws[0].device
     B = heads_t.B
@@ -244,7 +245,8 @@ def decode_nms_fused(heads_t, keep_alive, max_det: int, want_index: bool, out=No
     _FUSED_ARMED.discard(key)                       # if the call raises, the next one zeroes the words again
     _lib.check(_lib.load().pqdet_decode_nms(ctypes.byref(heads_t), _ptr(det), _ptr(idx), int(max_det),
                                             _ptr(counts), _ptr(ncand), _ptr(status), _ptr(work), armed,
-                                            _dev(raws[0]), _stream(device)), "pqdet_decode_nms")
+                                            _lib.CAPACITY[capacity], _dev(raws[0]), _stream(device)),
+               "pqdet_decode_nms")
     if out is not None:
         _FUSED_ARMED.add(key)
     return det, idx, meta
@@ -313,7 +315,8 @@ def alloc_host_outputs(B: int, max_det: int, want_index: bool, device):
     return det, idx, meta, work
 
 
-def decode_nms_host(heads_t, keep_alive, max_det: int, want_index: bool, device, out=None):
+def decode_nms_host(heads_t, keep_alive, max_det: int, want_index: bool, device, out=None,
+                    capacity: str = "compact"):
     """Host buffers in, host buffers out (pqdet_decode_nms_host).  -> det, idx, meta (pinned host), work (device).
     Asynchronous on the current stream of `device`: synchronise before reading the outputs."""
     device = torch.device(device)
@@ -326,14 +329,15 @@ def decode_nms_host(heads_t, keep_alive, max_det: int, want_index: bool, device,
     dev_index = device.index if device.index is not None else torch.cuda.current_device()
     _lib.check(_lib.load().pqdet_decode_nms_host(ctypes.byref(heads_t), _ptr(det), _ptr(idx), int(max_det),
                                                  _ptr(counts), _ptr(ncand), _ptr(status), _ptr(work), armed,
-                                                 dev_index, _stream(device)), "pqdet_decode_nms_host")
+                                                 _lib.CAPACITY[capacity], dev_index, _stream(device)),
+               "pqdet_decode_nms_host")
     if out is not None:
         _FUSED_ARMED.add(key)
     return det, idx, meta, work
 
 
 def nms_fused(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float, nms_mode: str, iou_round: str,
-              max_det: int, want_index: bool, out=None):
+              max_det: int, want_index: bool, out=None, capacity: str = "compact"):
     """tools.torch_nms for a batch in one launch.  bboxes (B, N, 4+C) -> det, idx, meta (as decode_nms_fused)."""
     bboxes = _req(bboxes, "bboxes")
     if bboxes.dim() != 3:
@@ -348,7 +352,8 @@ def nms_fused(bboxes: torch.Tensor, score_threshold: float, iou_threshold: float
     _lib.check(_lib.load().pqdet_nms_fused(_ptr(bboxes), B, N, C, float(score_threshold), float(iou_threshold),
                                            _lib.NMS_MODE[nms_mode], _lib.IOU_ROUND[iou_round], _ptr(det),
                                            _ptr(idx), int(max_det), _ptr(counts), _ptr(ncand), _ptr(status),
-                                           _ptr(work), armed, _dev(bboxes), _stream(device)), "pqdet_nms_fused")
+                                           _ptr(work), armed, _lib.CAPACITY[capacity], _dev(bboxes), _stream(device)),
+               "pqdet_nms_fused")
     if out is not None:
         _FUSED_ARMED.add(key)
     return det, idx, meta

@@ -28,10 +28,6 @@
 
 namespace pq {
 
-constexpr int kFusedThreads = 256;
-constexpr int kFusedWarps = kFusedThreads / 32;
-constexpr int kCapH = 1024;   // hit rows staged on chip per image
-constexpr int kCapM = 2048;   // candidates staged on chip per image
 constexpr int kHitBits = 25;  // low key field: hit slot (fused) or row (general)
 constexpr uint64_t kHitMask = (1ull << kHitBits) - 1;
 
@@ -168,23 +164,33 @@ __device__ __forceinline__ int warp_nms_segment(int s, int e, float off, float i
 // ------------------------------------------------------------------------------------------------
 constexpr int kWarpSortMax = 256;   // classes up to this many candidates are rank-sorted by one warp
 constexpr int kRankOutMax = 256;    // kept lists up to this size are ordered by rank counting
+constexpr int kSelectMax = 128;     // classes up to this many candidates: selection NMS in registers, no sort
 
-struct FusedSmem {
-  uint64_t keys[kCapM];     // candidate keys in emission order; reused for the output keys
-  float4 hbox[kCapH];       // recovered box of every hit row
-  uint32_t hmeta[kCapH];    // level << 30 | anchor << 27 | cell
-  float hconf[kCapH];
-  uint16_t order[kCapM];    // per-class member lists (candidate slots), score-sorted in place
-  uint16_t klist[kCapM];    // per-class kept positions (also scratch of the multi-tile rank sort)
-  uint8_t keepflag[kCapM];  // by candidate slot
-  uint8_t hhas[kCapH];
+// Two capacity classes (include/pqdet_b200.h: capacity_class).  The compact one keeps the per-image lists small
+// enough for 7 CTAs of 4 warps per SM (one CTA per image, 1036 images in flight on 148 SMs): the phases of an
+// image are serial and separated by CTA barriers, so what hides one image's barrier and memory latency is the
+// other images resident on the SM.  The large one is the round-1 geometry for denser scenes.
+template <int CLS> struct FusedCfg;
+template <> struct FusedCfg<0> { static constexpr int kThreads = 128, kCapH = 512, kCapM = 1280, kMinCtas = 7; };
+template <> struct FusedCfg<1> { static constexpr int kThreads = 256, kCapH = 1024, kCapM = 2048, kMinCtas = 4; };
+
+template <int CAPH, int CAPM>
+struct FusedSmemT {
+  uint64_t keys[CAPM];      // hit records during the scan, then candidate keys in emission order, then output keys
+  float4 hbox[CAPH];        // recovered box of every hit row
+  uint32_t hmeta[CAPH];     // level << 30 | anchor << 27 | cell
+  float hconf[CAPH];        // | dead after the fetch / offset phases: the sorted fallback reuses the two arrays
+  uint8_t hhas[CAPH];       // | as its kept-position list (uint16 x CAPM)
+  uint16_t order[CAPM];     // per-class member lists (candidate slots)
+  uint8_t keepflag[CAPM];   // by candidate slot
   int cls_cnt[128];
   int cls_fill[128];
   int seg_start[128];
-  const float* pbase[PQDET_MAX_LEVELS * 8];   // objectness plane of (level, anchor) for this image
-  float red[kFusedWarps];
+  const float* lvbase[PQDET_MAX_LEVELS];      // objectness plane of anchor 0 of this image, per level
+  float red[8];
   int b, H, M, K, maxcnt, next_class, nrec;
-  // followed by: uint32_t hitw[G_tot*4*A]; uint32_t gbase[G_tot];
+  // followed by: uint32_t hitw[G_tot*4*A]; uint32_t gbase[G_tot]; uint32_t utab[G_tot*A];
+  __device__ __forceinline__ uint16_t* klist() { return reinterpret_cast<uint16_t*>(hconf); }
 };
 
 __device__ __forceinline__ uint32_t pack_meta(int level, int a, int cell) {
@@ -257,70 +263,155 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
   __syncwarp();
 }
 
-// Objectness scan of one image.  The cells of a level are cut into groups of 128; a unit = (group g,
-// anchor a): lane l reads cells g*128 + 4l .. 4l+3 of that anchor's objectness plane with one 128-bit load
-// (scalar loads when the planes are not 16-byte aligned, e.g. 19x19) and the warp emits four ballot words,
-// word k holding the cells 4l+k.  hitw layout: [group][a*4 + k].  AT == 3 (the only anchor count PQDet uses)
-// turns the unit divmod into a multiply-shift; AT == 0 is the run-time generic version.
-template <int AT>
-__device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int lane, int warp, uint32_t* hitw,
-                                                uint64_t* rec, int* nrec) {
-  constexpr int U = 4;
-  const int A = AT ? AT : P.A;
-  const int ch = P.ch;
-  for (int l = 0; l < P.n_levels; ++l) {
-    const LevelDev& L = P.lv[l];
-    const int HW = L.HW, nu = L.nchunk * A;
-    const bool vec = L.vec4 != 0;
-    const unsigned astride = (unsigned)(ch * HW);                    // anchor a -> a + 1, in floats
-    const float* p0 = L.raw + ((size_t)b * A * ch + 4) * HW;         // objectness plane of anchor 0
-    uint4* hw = reinterpret_cast<uint4*>(hitw) + L.group_off * A;    // one uint4 (4 words) per unit
-    for (int u0 = warp; u0 < nu; u0 += kFusedWarps * U) {
-      float4 x[U];
+// Greedy NMS of one class by ONE warp WITHOUT sorting it: the class' n <= 32*R members live in registers (R per
+// lane: ~score bits, hit index, trick-shifted box).  Every round picks the best member still alive - one
+// redux.sync min over the ~score bits, a second one over (hit, r) among the holders of that minimum, which is
+// the (score desc, hit asc) order of nonzero() + stable sort - keeps it, and tests the alive members against it.
+// Identical to the sorted greedy walk: that one also visits candidates in this order and skips the suppressed.
+// Work is proportional to kept x ceil(n/32); a class of 30 candidates keeping 6 costs ~300 warp instructions where
+// rank sort + walk cost ~500.
+template <int ROUND, int R, typename S_t>
+__device__ __forceinline__ void warp_select_nms(S_t& S, int s, int n, float off, float iou_f, double iou_d) {
+  const int lane = lane_id();
+  uint32_t ns[R], tag[R];            // ~score bits; hit << 16 | candidate slot
+  float x1[R], y1[R], x2[R], y2[R];
+  unsigned alive = 0;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int un = u0 + u * kFusedWarps;
-        const int g = un / A;
-        const int a = un - g * A;
-        const int cell = g * 128 + 4 * lane;
-        x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (un < nu && cell < HW) {
-          const float* p = p0 + (a * astride + (unsigned)cell);
-          if (vec) {
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(p));
-          } else {
-            x[u].x = ldg_stream(p);
-            if (cell + 1 < HW) x[u].y = ldg_stream(p + 1);
-            if (cell + 2 < HW) x[u].z = ldg_stream(p + 2);
-            if (cell + 3 < HW) x[u].w = ldg_stream(p + 3);
+  for (int r = 0; r < R; ++r) {
+    const int j = lane + 32 * r;
+    ns[r] = 0xffffffffu; tag[r] = 0xffffffffu;
+    x1[r] = y1[r] = x2[r] = y2[r] = 0.0f;
+    if (j < n) {
+      const uint32_t slot = S.order[s + j];
+      const uint64_t key = S.keys[slot];
+      const uint32_t hit = (uint32_t)(key & kHitMask);
+      ns[r] = (uint32_t)(key >> kHitBits);
+      tag[r] = (hit << 16) | slot;
+      const float4 bx = S.hbox[hit];
+      x1[r] = PQ_ADD(bx.x, off); y1[r] = PQ_ADD(bx.y, off); x2[r] = PQ_ADD(bx.z, off); y2[r] = PQ_ADD(bx.w, off);
+      alive |= 1u << r;
+    }
+  }
+  for (;;) {
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((alive >> r) & 1u) m = min(m, ns[r]);
+    const uint32_t best = __reduce_min_sync(PQ_FULL, m);
+    if (!__any_sync(PQ_FULL, alive != 0u)) break;
+    // among the alive holders of `best`: the smallest hit index (unique within a class)
+    uint32_t cand = 0xffffffffu;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (((alive >> r) & 1u) && ns[r] == best) cand = min(cand, (tag[r] & 0xffff0000u) | (uint32_t)r);
+    const uint32_t win = __reduce_min_sync(PQ_FULL, cand);
+    const int wl = __ffs(__ballot_sync(PQ_FULL, cand == win)) - 1;
+    const int wr = (int)(win & 0xffffu);
+    float ax1 = x1[0], ay1 = y1[0], ax2 = x2[0], ay2 = y2[0];
+    uint32_t wtag = tag[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r)
+      if (wr == r) { ax1 = x1[r]; ay1 = y1[r]; ax2 = x2[r]; ay2 = y2[r]; wtag = tag[r]; }
+    if (lane == wl) {
+      S.keepflag[wtag & 0xffffu] = 1;
+      alive &= ~(1u << wr);
+    }
+    ax1 = __shfl_sync(PQ_FULL, ax1, wl); ay1 = __shfl_sync(PQ_FULL, ay1, wl);
+    ax2 = __shfl_sync(PQ_FULL, ax2, wl); ay2 = __shfl_sync(PQ_FULL, ay2, wl);
+    const float Sa = box_area(ax1, ay1, ax2, ay2);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (((alive >> r) & 1u) &&
+          nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1[r], y1[r], x2[r], y2[r], iou_f, iou_d))
+        alive &= ~(1u << r);
+  }
+}
+
+// Scan table: one word per unit (128 cells of one anchor's objectness plane), in hitw order un = group * A + anchor:
+//   level << 30 | slow << 29 | element offset of the unit from the image's anchor-0 objectness plane of that level.
+// `slow` marks units that need the generic code: a partial last group or planes that are not 16-byte aligned.
+// The table depends only on the geometry, so a CTA builds it once and reuses it for every image it pulls.
+constexpr uint32_t kUnitSlow = 1u << 29;
+constexpr uint32_t kUnitOffMask = kUnitSlow - 1u;
+
+__device__ __forceinline__ void build_unit_table(const HeadsDev& P, uint32_t* utab, int tid, int nthreads) {
+  const int A = P.A, nu = P.G_tot * A;
+  for (int un = tid; un < nu; un += nthreads) {
+    const int g = un / A, a = un - g * A;
+    const int l = level_of_group(P, g);
+    const LevelDev& L = P.lv[l];
+    const int gl = g - L.group_off;
+    const uint32_t off = (uint32_t)a * (uint32_t)(P.ch * L.HW) + (uint32_t)gl * 128u;
+    const bool slow = !L.vec4 || (gl + 1) * 128 > L.HW || off > kUnitOffMask;
+    utab[un] = ((uint32_t)l << 30) | (slow ? kUnitSlow : 0u) | (off & kUnitOffMask);
+  }
+}
+
+// Objectness scan of one image.  The cells of a level are cut into groups of 128; a unit = (group g, anchor a):
+// lane l reads cells g*128 + 4l .. 4l+3 of that anchor's objectness plane with one 128-bit load (scalar loads on
+// the slow units) and the warp emits four ballot words, word k holding the cells 4l+k.  hitw layout:
+// [group][a*4 + k] = one uint4 per unit.  A hit leaves a record (objectness, position) in `rec`, so that the
+// plane is never read a second time.  NW warps, U units in flight per warp.
+template <int NW, int CAPH>
+__device__ __forceinline__ void scan_objectness(const HeadsDev& P, const float* const* lvbase, const uint32_t* utab,
+                                                int lane, int warp, uint32_t* hitw, uint64_t* rec, int* nrec) {
+  constexpr int U = 4;
+  const int A = P.A, nu = P.G_tot * A;
+  uint4* hw = reinterpret_cast<uint4*>(hitw);
+  for (int u0 = warp; u0 < nu; u0 += NW * U) {
+    float4 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int un = u0 + u * NW;
+      x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (un < nu) {
+        const uint32_t e = utab[un];
+        const float* p = lvbase[e >> 30] + ((e & kUnitOffMask) + 4u * (unsigned)lane);
+        if (!(e & kUnitSlow)) {
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(p));
+        } else {
+          const LevelDev& L = P.lv[e >> 30];
+          const int g = un / A;
+          const int cell = (g - L.group_off) * 128 + 4 * lane;
+          const float* q = lvbase[e >> 30] + ((size_t)(un - g * A) * (size_t)(P.ch * L.HW) + (size_t)cell);
+          if (cell < L.HW) {
+            if (L.vec4) {
+              asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(q));
+            } else {
+              x[u].x = ldg_stream(q);
+              if (cell + 1 < L.HW) x[u].y = ldg_stream(q + 1);
+              if (cell + 2 < L.HW) x[u].z = ldg_stream(q + 2);
+              if (cell + 3 < L.HW) x[u].w = ldg_stream(q + 3);
+            }
           }
         }
       }
+    }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int un = u0 + u * kFusedWarps;
-        bool p0b = x[u].x > P.logit_lo, p1b = x[u].y > P.logit_lo, p2b = x[u].z > P.logit_lo, p3b = x[u].w > P.logit_lo;
-        if (p0b | p1b | p2b | p3b) {                                   // rare: exact test of the survivors
-          // a hit leaves a record (objectness, position) so that the plane is never read a second time
-          const uint32_t pos = ((uint32_t)(L.group_off + un / A) << 10) | ((uint32_t)(un % A) << 7) | ((uint32_t)lane << 2);
-          auto test = [&](float xv, uint32_t k) -> bool {
-            const float conf = sigmoidf_(xv);
-            if (!(conf > P.thr_f)) return false;
-            const int r = atomicAdd(nrec, 1);
-            if (r < kCapH) rec[r] = ((uint64_t)__float_as_uint(conf) << 32) | (pos | k);
-            return true;
-          };
-          if (p0b) p0b = test(x[u].x, 0);
-          if (p1b) p1b = test(x[u].y, 1);
-          if (p2b) p2b = test(x[u].z, 2);
-          if (p3b) p3b = test(x[u].w, 3);
-        }
-        uint4 wd;
-        wd.x = __ballot_sync(PQ_FULL, p0b); wd.y = __ballot_sync(PQ_FULL, p1b);
-        wd.z = __ballot_sync(PQ_FULL, p2b); wd.w = __ballot_sync(PQ_FULL, p3b);
-        if (lane == 0 && un < nu) hw[un] = wd;
+    for (int u = 0; u < U; ++u) {
+      const int un = u0 + u * NW;
+      bool p0b = x[u].x > P.logit_lo, p1b = x[u].y > P.logit_lo, p2b = x[u].z > P.logit_lo, p3b = x[u].w > P.logit_lo;
+      if (p0b | p1b | p2b | p3b) {                                   // rare: exact test of the survivors
+        const int g = un / A;
+        const uint32_t pos = ((uint32_t)g << 10) | ((uint32_t)(un - g * A) << 7) | ((uint32_t)lane << 2);
+        auto test = [&](float xv, uint32_t k) -> bool {
+          const float conf = sigmoidf_(xv);
+          if (!(conf > P.thr_f)) return false;
+          const int r = atomicAdd(nrec, 1);
+          if (r < CAPH) rec[r] = ((uint64_t)__float_as_uint(conf) << 32) | (pos | k);
+          return true;
+        };
+        if (p0b) p0b = test(x[u].x, 0);
+        if (p1b) p1b = test(x[u].y, 1);
+        if (p2b) p2b = test(x[u].z, 2);
+        if (p3b) p3b = test(x[u].w, 3);
       }
+      uint4 wd;
+      wd.x = __ballot_sync(PQ_FULL, p0b); wd.y = __ballot_sync(PQ_FULL, p1b);
+      wd.z = __ballot_sync(PQ_FULL, p2b); wd.w = __ballot_sync(PQ_FULL, p3b);
+      if (lane == 0 && un < nu) hw[un] = wd;
     }
   }
 }
@@ -328,36 +419,39 @@ __device__ __forceinline__ void scan_objectness(const HeadsDev& P, int b, int la
 // SRC == 0: candidates come from the raw heads (decode + recover fused in).  SRC == 1: from a recovered
 // (B, N, 4+C) tensor, i.e. tools.torch_nms for a whole batch in one launch: the front end streams every row
 // once (no early-out is possible, the scores are already formed), the sort / NMS / output back end is shared.
-template <int ROUND, int SRC>
-__global__ void __launch_bounds__(kFusedThreads, 4)
+template <int ROUND, int SRC, int CLS>
+__global__ void __launch_bounds__(FusedCfg<CLS>::kThreads, FusedCfg<CLS>::kMinCtas)
 decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constant__ DetOut O, int32_t* work) {
+  constexpr int NT = FusedCfg<CLS>::kThreads, NW = NT / 32;
+  constexpr int CAPH = FusedCfg<CLS>::kCapH, CAPM = FusedCfg<CLS>::kCapM;
+  using Smem = FusedSmemT<CAPH, CAPM>;
+  static_assert(5 * CAPH >= 2 * CAPM, "klist aliases hconf + hhas");
+  static_assert(CAPH % NT == 0 && CAPM % NT == 0, "per-thread register tiles");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
-  uint32_t* hitw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(FusedSmem));
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  uint32_t* hitw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem));
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int A = P.A, C = P.C, ch = P.ch;
   const int WG = SRC ? 1 : 4 * A;          // ballot words per group (128 cells x A anchors | 32 rows)
   const int W_tot = P.G_tot * WG;
   uint32_t* gbase = hitw + W_tot;
+  uint32_t* utab = gbase + P.G_tot;
+  if (SRC == 0) build_unit_table(P, utab, tid, NT);
 
   for (;;) {
     if (tid == 0) S.b = atomicAdd(work, 1);
     __syncthreads();
     const int b = S.b;
     if (b >= P.B) break;
-    if (SRC == 0 && tid < P.n_levels * A) {
-      const int l = tid / A, a = tid - l * A;
-      S.pbase[tid] = P.lv[l].raw + ((size_t)(b * A + a) * ch + 4) * P.lv[l].HW;
-    }
-    if (tid < 128) { S.cls_cnt[tid] = 0; S.cls_fill[tid] = 0; }
+    if (SRC == 0 && tid < P.n_levels) S.lvbase[tid] = P.lv[tid].raw + ((size_t)b * A * ch + 4) * P.lv[tid].HW;
+    for (int i = tid; i < 128; i += NT) { S.cls_cnt[i] = 0; S.cls_fill[i] = 0; }
     if (tid == 0) S.nrec = 0;
     __syncthreads();
     const float* img = SRC ? P.bboxes + (size_t)b * P.N * P.bb_row : nullptr;
 
     // ---- 1. scan: one ballot word per (level, group, anchor, sub-cell) | per 32 rows ---------------
     if (SRC == 0) {
-      if (A == 3) scan_objectness<3>(P, b, lane, warp, hitw, S.keys, &S.nrec);
-      else scan_objectness<0>(P, b, lane, warp, hitw, S.keys, &S.nrec);
+      scan_objectness<NW, CAPH>(P, S.lvbase, utab, lane, warp, hitw, S.keys, &S.nrec);
     } else {
       // a row is a hit iff any of its C scores exceeds thr (tools.py:551); 128-bit loads when rows are aligned
       const bool vec = ((P.bb_row & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.bboxes) & 15) == 0);
@@ -365,23 +459,23 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         // The image is one contiguous run of N * n4 128-bit words (n4 per row): consecutive threads read consecutive
         // words, so every byte crosses L2 once, fully coalesced; a word with a score above thr sets its row's bit.
         const int n4 = P.bb_row >> 2;
-        for (int w = tid; w < W_tot; w += kFusedThreads) hitw[w] = 0u;
+        for (int w = tid; w < W_tot; w += NT) hitw[w] = 0u;
         __syncthreads();
         const float4* img4 = reinterpret_cast<const float4*>(img);
         const int total4 = P.N * n4;
         constexpr int U = 4;
-        for (int e0 = tid; e0 < total4; e0 += kFusedThreads * U) {
+        for (int e0 = tid; e0 < total4; e0 += NT * U) {
           float4 v[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * kFusedThreads;
+            const int e = e0 + u * NT;
             if (e < total4)
               asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                            : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(img4 + e));
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * kFusedThreads;
+            const int e = e0 + u * NT;
             if (e >= total4) continue;
             const int row = (int)__umulhi((unsigned)e, P.magic_n4);           // e / n4
             if (e == row * n4) continue;                                       // word 0 of a row = the box
@@ -390,7 +484,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
           }
         }
       } else
-      for (int w = warp; w < W_tot; w += kFusedWarps) {
+      for (int w = warp; w < W_tot; w += NW) {
         const int row = w * 32 + lane;
         bool pass = false;
         if (row < P.N) {
@@ -432,13 +526,13 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     }
     __syncthreads();
     const int H = S.H;
-    if (H > kCapH) {
+    if (H > CAPH) {
       if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = -1; }
       __syncthreads();
       continue;
     }
     if (SRC == 1) {
-      for (int w = tid; w < W_tot; w += kFusedThreads) {    // word w = rows 32w .. 32w+31, already in row order
+      for (int w = tid; w < W_tot; w += NT) {    // word w = rows 32w .. 32w+31, already in row order
         unsigned word = hitw[w];
         int h = gbase[w];
         while (word) {
@@ -451,11 +545,11 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       }
     } else {
       // one hit record per thread: word a*4 + k of group g holds the cells 4*lane + k of anchor a
-      uint32_t pos[kCapH / kFusedThreads];
-      float cf[kCapH / kFusedThreads];
+      uint32_t pos[CAPH / NT];
+      float cf[CAPH / NT];
 #pragma unroll
-      for (int r = 0; r < kCapH / kFusedThreads; ++r) {
-        const int i = tid + r * kFusedThreads;
+      for (int r = 0; r < CAPH / NT; ++r) {
+        const int i = tid + r * NT;
         if (i < H) {
           const uint64_t rc = S.keys[i];
           pos[r] = (uint32_t)rc;
@@ -463,8 +557,8 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         }
       }
 #pragma unroll
-      for (int r = 0; r < kCapH / kFusedThreads; ++r) {
-        const int i = tid + r * kFusedThreads;
+      for (int r = 0; r < CAPH / NT; ++r) {
+        const int i = tid + r * NT;
         if (i >= H) continue;
         const int g = pos[r] >> 10, a = (pos[r] >> 7) & 7, j = (pos[r] >> 2) & 31, k = pos[r] & 3;
         const int l = level_of_group(P, g);
@@ -485,11 +579,11 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     }
     __syncthreads();
 
-    // ---- 3. box + class channels of the hit rows only: 8 lanes per row, 4 rows per warp step ------
+    // ---- 3. box + class channels of the hit rows only -------------------------------------------
     if (SRC == 1) {
       const int CK = 4 + C;
       const int sub = lane >> 3, k0 = lane & 7;
-      for (int h = warp * 4 + sub; h < H; h += kFusedWarps * 4) {
+      for (int h = warp * 4 + sub; h < H; h += NW * 4) {
         const float* r = img + (size_t)S.hmeta[h] * P.bb_row;
         for (int k = k0; k < CK; k += 8) {
           const float v = r[k];
@@ -502,7 +596,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
             if (lane == leader) base = atomicAdd(&S.M, __popc(peers));
             base = __shfl_sync(peers, base, leader);
             const int slot = base + __popc(peers & ((1u << lane) - 1u));
-            if (slot < kCapM) S.keys[slot] = cand_key(k - 4, v, (uint32_t)h);
+            if (slot < CAPM) S.keys[slot] = cand_key(k - 4, v, (uint32_t)h);
             atomicAdd(&S.cls_cnt[k - 4], 1);
             S.hhas[h] = 1;
           }
@@ -519,14 +613,15 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       constexpr int V = 8;
       const int ncg = (CK + V - 1) / V;
       const int nunit = ((H + 31) >> 5) * ncg;
-      for (int unit = warp; unit < nunit; unit += kFusedWarps) {
+      for (int unit = warp; unit < nunit; unit += NW) {
         const int chunk = unit / ncg, k_lo = (unit - chunk * ncg) * V;
         const int h = chunk * 32 + lane;
         if (h >= H) continue;
         const uint32_t meta = S.hmeta[h];
         const int l = meta >> 30, a = (meta >> 27) & 7, cell = meta & 0x7ffffff;
         const LevelDev& L = P.lv[l];
-        const float* base = S.pbase[l * A + a] + cell - (size_t)4 * L.HW;   // channel 0 of this row
+        // channel 0 of this row: the anchor's objectness plane minus four planes
+        const float* base = S.lvbase[l] + ((size_t)a * ch - 4) * L.HW + cell;
         const float conf = S.hconf[h];
         float v[V];
 #pragma unroll
@@ -548,11 +643,11 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
               // one shared-memory atomic per warp instead of one per candidate
               const unsigned peers = __activemask();
               const int leader = __ffs(peers) - 1;
-              int base = 0;
-              if (lane == leader) base = atomicAdd(&S.M, __popc(peers));
-              base = __shfl_sync(peers, base, leader);
-              const int slot = base + __popc(peers & ((1u << lane) - 1u));
-              if (slot < kCapM) S.keys[slot] = cand_key(k - 4, sc, (uint32_t)h);
+              int base2 = 0;
+              if (lane == leader) base2 = atomicAdd(&S.M, __popc(peers));
+              base2 = __shfl_sync(peers, base2, leader);
+              const int slot = base2 + __popc(peers & ((1u << lane) - 1u));
+              if (slot < CAPM) S.keys[slot] = cand_key(k - 4, sc, (uint32_t)h);
               atomicAdd(&S.cls_cnt[k - 4], 1);
               S.hhas[h] = 1;
             }
@@ -562,7 +657,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     }
     __syncthreads();
     const int M = S.M;
-    if (M > kCapM || M == 0) {
+    if (M > CAPM || M == 0) {
       if (tid == 0) {
         O.status[b] = M ? PQDET_ST_CAND_OVERFLOW : PQDET_ST_OK;
         O.counts[b] = 0;
@@ -578,14 +673,14 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     {
       float mx = -INFINITY;
       if (trick)
-        for (int h = tid; h < H; h += kFusedThreads)
+        for (int h = tid; h < H; h += NT)
           if (S.hhas[h]) {
             const float4 bx = S.hbox[h];
             mx = fmaxf(fmaxf(mx, fmaxf(bx.x, bx.y)), fmaxf(bx.z, bx.w));
           }
       mx = warp_max(mx);
       if (lane == 0) S.red[warp] = mx;
-      if (warp == 1) {                                     // exclusive prefix of the class counts
+      if (warp == NW - 1) {                                // exclusive prefix of the class counts
         int running = 0, mc = 0;
         for (int c0 = 0; c0 < C; c0 += 32) {
           const int c = c0 + lane;
@@ -602,29 +697,35 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       __syncthreads();
       mx = S.red[0];
 #pragma unroll
-      for (int i = 1; i < kFusedWarps; ++i) mx = fmaxf(mx, S.red[i]);
+      for (int i = 1; i < NW; ++i) mx = fmaxf(mx, S.red[i]);
       m1 = PQ_ADD(mx, 1.0f);
     }
 
-    // ---- 5. per-class member lists, score-sorted ------------------------------------------------
-    const bool warp_sort = S.maxcnt <= kWarpSortMax;
-    if (warp_sort) {
-      for (int i = tid; i < M; i += kFusedThreads) {
+    // ---- 5. per-class member lists --------------------------------------------------------------
+    const int maxcnt = S.maxcnt;
+    const bool lists = maxcnt <= kWarpSortMax;
+    if (!lists && next_pow2(M) > CAPM) {                   // one huge class and no room to sort the padded list
+      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = M; }
+      __syncthreads();
+      continue;
+    }
+    if (lists) {
+      for (int i = tid; i < M; i += NT) {
         const int c = (int)(S.keys[i] >> 57);
         S.order[S.seg_start[c] + atomicAdd(&S.cls_fill[c], 1)] = (uint16_t)i;
         S.keepflag[i] = 0;
       }
     } else {                                               // one huge class: block bitonic sort instead
       const int P2 = next_pow2(M);
-      for (int i = M + tid; i < P2; i += kFusedThreads) S.keys[i] = ~0ull;
+      for (int i = M + tid; i < P2; i += NT) S.keys[i] = ~0ull;
       __syncthreads();
       bitonic_sort_block(S.keys, P2);                      // class-major keys: segments are contiguous
-      for (int i = tid; i < M; i += kFusedThreads) { S.order[i] = (uint16_t)i; S.keepflag[i] = 0; }
+      for (int i = tid; i < M; i += NT) { S.order[i] = (uint16_t)i; S.keepflag[i] = 0; }
     }
     __syncthreads();
 
-    // ---- 6. per-class sort + greedy NMS, one warp per class -------------------------------------
-    for (;;) {                                             // warps pull classes dynamically (uneven sizes)
+    // ---- 6. greedy NMS, one warp per class (classes pulled dynamically: uneven sizes) ------------
+    for (;;) {
       int c = 0;
       if (lane == 0) c = atomicAdd(&S.next_class, 1);
       c = __shfl_sync(PQ_FULL, c, 0);
@@ -632,27 +733,36 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       const int n = S.cls_cnt[c];
       if (n == 0) continue;
       const int s = S.seg_start[c];
-      if (warp_sort) warp_rank_sort(S.keys, S.order, S.klist, s, n);
       const float off = trick ? PQ_MUL((float)c, m1) : 0.0f;
-      warp_nms_segment<ROUND>(
-          s, s + n, off, P.iou_f, P.iou_d,
-          [&](int pos) { return S.hbox[S.keys[S.order[pos]] & kHitMask]; },
-          [&](int slot, int pos) -> int {
-            if (pos >= 0) S.klist[slot] = (uint16_t)pos;
-            return S.klist[slot];
-          },
-          [&](int pos) { S.keepflag[S.order[pos]] = 1; });
+      if (lists && n <= 32) {
+        warp_select_nms<ROUND, 1>(S, s, n, off, P.iou_f, P.iou_d);
+      } else if (lists && n <= 64) {
+        warp_select_nms<ROUND, 2>(S, s, n, off, P.iou_f, P.iou_d);
+      } else if (lists && n <= kSelectMax) {
+        warp_select_nms<ROUND, 4>(S, s, n, off, P.iou_f, P.iou_d);
+      } else {
+        uint16_t* kl = S.klist();
+        if (lists) warp_rank_sort(S.keys, S.order, kl, s, n);
+        warp_nms_segment<ROUND>(
+            s, s + n, off, P.iou_f, P.iou_d,
+            [&](int pos) { return S.hbox[S.keys[S.order[pos]] & kHitMask]; },
+            [&](int slot, int pos) -> int {
+              if (pos >= 0) kl[slot] = (uint16_t)pos;
+              return kl[slot];
+            },
+            [&](int pos) { S.keepflag[S.order[pos]] = 1; });
+      }
     }
     __syncthreads();
 
     // ---- 7. kept keys -> (score desc, row, class) order -> output -------------------------------
     {
-      constexpr int R = kCapM / kFusedThreads;
+      constexpr int R = CAPM / NT;
       uint64_t loc[R];
       unsigned vmask = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int i = tid + r * kFusedThreads;
+        const int i = tid + r * NT;
         loc[r] = 0;
         if (i < M && S.keepflag[i]) { loc[r] = out_key(S.keys[i]); vmask |= 1u << r; }
       }
@@ -675,20 +785,20 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       }
       write_det(O, b, j, S.hbox[h], score, c, row, C);
     };
-    if (K <= kRankOutMax) {                                // position = number of smaller keys
-      if (tid < K) {
-        const uint64_t mine = S.keys[tid];
+    if (K <= kRankOutMax || next_pow2(K) > CAPM) {         // position = number of smaller keys
+      for (int i = tid; i < K; i += NT) {
+        const uint64_t mine = S.keys[i];
         int rank = 0;
         for (int j = 0; j < K; ++j) rank += (S.keys[j] < mine) ? 1 : 0;
         if (rank < O.max_det) emit(rank, mine);
       }
     } else {
       const int P3 = next_pow2(K);
-      for (int i = K + tid; i < P3; i += kFusedThreads) S.keys[i] = ~0ull;
+      for (int i = K + tid; i < P3; i += NT) S.keys[i] = ~0ull;
       __syncthreads();
       bitonic_sort_block(S.keys, P3);
       const int nout = min(K, O.max_det);
-      for (int j = tid; j < nout; j += kFusedThreads) emit(j, S.keys[j]);
+      for (int j = tid; j < nout; j += NT) emit(j, S.keys[j]);
     }
     if (tid == 0) {
       O.counts[b] = K;
@@ -864,7 +974,8 @@ gen_select_kernel(const __grid_constant__ GenParams G) {
       m &= m - 1;
       const float sc = score_of(c);                        // same expression as above: bit-identical
       const unsigned slot = s_base[c] + atomicAdd(&s_cnt[c], 1u);
-      G.keys[G.seg_off[(size_t)ii * C + c] + slot] = ((uint64_t)(~__float_as_uint(sc)) << 32) | (uint32_t)row;
+      // total-order transform: the general path also serves tools.torch_nms on arbitrary (possibly negative) scores
+      G.keys[G.seg_off[(size_t)ii * C + c] + slot] = ((uint64_t)(~float_to_ordered(sc)) << 32) | (uint32_t)row;
     }
   }
   if (G.from_heads) G.rbox[(size_t)ii * G.N + row] = make_float4(box[0], box[1], box[2], box[3]);
@@ -1152,7 +1263,7 @@ gen_finalize_kernel(const __grid_constant__ GenParams G, const __grid_constant__
   const float* bb = G.from_heads ? nullptr : G.bboxes + (size_t)b * G.N * (4 + C);
   for (int j = tid; j < nout; j += kFinThreads) {
     const uint64_t k2 = keys[j];
-    const float score = __uint_as_float(~(uint32_t)(k2 >> 32));
+    const float score = ordered_to_float(~(uint32_t)(k2 >> 32));
     const uint32_t low = (uint32_t)k2;
     const uint32_t row = low >> 7;
     const int c = low & 127;
@@ -1222,11 +1333,18 @@ static int fill_heads(const pqdet_heads_t* h, HeadsDev* P) {
 
 namespace pq {
 
-// Shared launcher of the fused kernel (both sources, both rounding orders).
+// Shared launcher of the fused kernel (both sources, both rounding orders, both capacity classes).
 static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counter, int counter_armed,
-                        int iou_round, int src, int device, cudaStream_t st) {
+                        int iou_round, int src, int cap_class, int device, cudaStream_t st) {
+  if (cap_class != PQDET_CAP_COMPACT && cap_class != PQDET_CAP_LARGE) return PQDET_ERR_INVALID_ARG;
+  if (!(P.thr_f >= 0.0f)) return PQDET_ERR_UNSUPPORTED;     // ~score keys order non-negative floats only
   const int WG = src ? 1 : 4 * P.A;
-  const size_t smem = sizeof(FusedSmem) + (size_t)P.G_tot * (WG + 1) * sizeof(uint32_t);
+  const size_t lists = cap_class == PQDET_CAP_COMPACT
+                           ? sizeof(FusedSmemT<FusedCfg<0>::kCapH, FusedCfg<0>::kCapM>)
+                           : sizeof(FusedSmemT<FusedCfg<1>::kCapH, FusedCfg<1>::kCapM>);
+  const int threads = cap_class == PQDET_CAP_COMPACT ? FusedCfg<0>::kThreads : FusedCfg<1>::kThreads;
+  // hitw + gbase + (heads source) the scan's unit table
+  const size_t smem = lists + ((size_t)P.G_tot * (WG + 1) + (src ? 0 : (size_t)P.G_tot * P.A)) * sizeof(uint32_t);
   if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
   // work_counter = int32[2].  counter_armed != 0: the caller guarantees both words are zero (they are after
   // every completed call: the kernel re-arms them), so no memset is enqueued.
@@ -1234,7 +1352,7 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
   auto launch = [&](auto kern, int which) -> int {
     // Launch geometry is a pure function of (device, kernel, smem); remember the last one per device as a
     // single 64-bit word (smem << 32 | grid) so concurrent callers can only ever see a consistent pair.
-    static std::atomic<uint64_t> cache[4][16];
+    static std::atomic<uint64_t> cache[8][16];
     int per_sm_grid = 0;
     if (device < 16) {
       const uint64_t c = cache[which][device].load(std::memory_order_relaxed);
@@ -1243,7 +1361,7 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
     if (per_sm_grid == 0) {
       PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = 1, sm_count = 148;
-      PQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem));
+      PQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
       if (per_sm < 1) per_sm = 1;
       per_sm_grid = sm_count * per_sm;                      // persistent: one resident wave
@@ -1251,23 +1369,28 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
     }
     int grid = per_sm_grid;
     if (grid > P.B) grid = P.B;
-    kern<<<grid, kFusedThreads, smem, st>>>(P, O, work_counter);
+    kern<<<grid, threads, smem, st>>>(P, O, work_counter);
     PQ_LAUNCH_CHECK();
     return PQDET_OK;
   };
-  if (src == 0) {
-    if (iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0, 0>, 0);
-    return launch(decode_nms_fused_kernel<1, 0>, 1);
+  const int r = iou_round == PQDET_IOU_TV_CUDA ? 0 : 1;
+  switch (cap_class * 4 + src * 2 + r) {
+    case 0: return launch(decode_nms_fused_kernel<0, 0, 0>, 0);
+    case 1: return launch(decode_nms_fused_kernel<1, 0, 0>, 1);
+    case 2: return launch(decode_nms_fused_kernel<0, 1, 0>, 2);
+    case 3: return launch(decode_nms_fused_kernel<1, 1, 0>, 3);
+    case 4: return launch(decode_nms_fused_kernel<0, 0, 1>, 4);
+    case 5: return launch(decode_nms_fused_kernel<1, 0, 1>, 5);
+    case 6: return launch(decode_nms_fused_kernel<0, 1, 1>, 6);
+    default: return launch(decode_nms_fused_kernel<1, 1, 1>, 7);
   }
-  if (iou_round == PQDET_IOU_TV_CUDA) return launch(decode_nms_fused_kernel<0, 1>, 2);
-  return launch(decode_nms_fused_kernel<1, 1>, 3);
 }
 
 }  // namespace pq
 
 extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                                 int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
-                                int counter_armed, int device, void* stream) {
+                                int counter_armed, int capacity_class, int device, void* stream) {
   using namespace pq;
   HeadsDev P;
   memset(&P, 0, sizeof(P));
@@ -1277,7 +1400,7 @@ extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t*
   if (P.B == 0) return PQDET_OK;
   PQ_ENTER(device);
   DetOut O{det, det_idx, max_det, counts, ncand, status};
-  return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 0, device, (cudaStream_t)stream);
+  return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 0, capacity_class, device, (cudaStream_t)stream);
 }
 
 // Host-buffer entry: every pointer may be page-locked host memory; it is translated to its device alias and the
@@ -1296,7 +1419,7 @@ static int device_alias(T** p, int allow_null) {
 
 extern "C" int pqdet_decode_nms_host(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
-                                     int counter_armed, int device, void* stream) {
+                                     int counter_armed, int capacity_class, int device, void* stream) {
   using namespace pq;
   if (!heads) return PQDET_ERR_INVALID_ARG;
   PQ_ENTER(device);
@@ -1315,13 +1438,15 @@ extern "C" int pqdet_decode_nms_host(const pqdet_heads_t* heads, float* det, int
     cudaGetLastError();
     return PQDET_ERR_INVALID_ARG;
   }
-  return pqdet_decode_nms(&h, det, det_idx, max_det, counts, ncand, status, work_counter, counter_armed, device, stream);
+  return pqdet_decode_nms(&h, det, det_idx, max_det, counts, ncand, status, work_counter, counter_armed, capacity_class,
+                          device, stream);
 }
 
 extern "C" int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, double score_threshold,
                                double iou_threshold, int nms_mode, int iou_round, float* det, int32_t* det_idx,
                                int max_det, int32_t* counts, int32_t* ncand, int32_t* status,
-                               int32_t* work_counter, int counter_armed, int device, void* stream) {
+                               int32_t* work_counter, int counter_armed, int capacity_class, int device,
+                               void* stream) {
   using namespace pq;
   if (!bboxes || !det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
   if (B < 0 || N < 0 || C < 1) return PQDET_ERR_INVALID_ARG;
@@ -1353,7 +1478,7 @@ extern "C" int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, dou
     P.magic_n4 = (uint32_t)(((1ull << 32) + (uint64_t)((4 + C) >> 2) - 1) / (uint64_t)((4 + C) >> 2));
   PQ_ENTER(device);
   DetOut O{det, det_idx, max_det, counts, ncand, status};
-  return launch_fused(P, O, work_counter, counter_armed, iou_round, 1, device, (cudaStream_t)stream);
+  return launch_fused(P, O, work_counter, counter_armed, iou_round, 1, capacity_class, device, (cudaStream_t)stream);
 }
 
 namespace pq {

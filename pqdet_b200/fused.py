@@ -13,7 +13,7 @@ import torch
 
 from . import _lib, _ops, config
 
-FUSED_MAX_DET = 2048          # == kCapM of csrc/nms.cu: a fused image never keeps more than its candidates
+FUSED_MAX_DET = 2048          # the larger capacity class' candidate list: a fused image never keeps more than that
 
 
 class Detections:
@@ -86,10 +86,22 @@ class Detections:
 
 
 class StrategyHints(dict):
-    """Caller-held memory for strategy='auto' (workload signature -> True when the last call with that signature
-    mostly overflowed the fused kernel).  The library keeps no state of its own: pass one of these as `hints=` from
-    whatever owns the evaluation loop (the evaluator hook of install.py holds one per Evaluator); without it every
-    call starts on the fused kernel."""
+    """Caller-held memory for strategy='auto': workload signature -> 'compact' | 'large' | 'general', the route the
+    last call with that signature suggests for the next one (compact / large = the fused kernel's capacity classes,
+    general = the bucketed path for dense scenes).  The library keeps no state of its own: pass one of these as
+    `hints=` from whatever owns the evaluation loop (the evaluator hook of install.py holds one per Evaluator);
+    without it every call starts on the compact fused kernel."""
+
+
+def _next_route(ncand_max: int, ncand_mean: float) -> str:
+    """Route for a workload whose images have this many candidates (what a complete run reports)."""
+    _, m_small = _lib.CAPACITY_LIMITS["compact"]
+    _, m_large = _lib.CAPACITY_LIMITS["large"]
+    if ncand_max <= m_small:
+        return "compact"
+    if ncand_max <= m_large and ncand_mean <= m_large / 2:
+        return "large"
+    return "general"
 
 
 def _general(h, keep, ids, n_sel, return_index, by_position, cap, max_det):
@@ -121,10 +133,10 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
     batch_original_size (B,2) or (2,) (h, w).  dataset in {'voc','coco','visdrone'} picks the affine.
     With resolve_overflow (default) images whose candidates do not fit the on-chip lists are re-run
     through the general path, so the result is always complete (costs the host read of `status`).
-    strategy: 'fused' (one-launch kernel + per-image fallback), 'general' (bucketed global-memory path for
-    every image: the right choice for dense scenes such as VisDrone), or 'auto' (fused first; with a caller-held
-    `hints` object it remembers per workload signature when most images overflowed and then goes straight to the
-    general path)."""
+    strategy: 'compact' / 'large' (the one-launch kernel with that capacity class + per-image fallback; 'fused' =
+    'compact'), 'general' (bucketed global-memory path for every image: the right choice for dense scenes such as
+    VisDrone), or 'auto' (compact first; with a caller-held `hints` object it remembers per workload signature
+    what the last call suggested - the large lists, or straight to the general path when most images overflowed)."""
     m, r = config.nms_modes()
     nms_mode, iou_round = nms_mode or m, iou_round or r
     h, keep = _ops.make_heads(heads, strides, num_classes, input_size, batch_original_size, dataset,
@@ -136,22 +148,33 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
                           torch.empty((0, FUSED_MAX_DET), dtype=torch.int32, device=dev) if return_index else None,
                           torch.zeros((2,), dtype=torch.int32, device=dev), 0)
     sig = (tuple(tuple(t.shape[1:]) for t in heads), num_classes, float(score_threshold), dataset)
-    if B and (strategy == "general" or (strategy == "auto" and hints is not None and hints.get(sig, False))):
+    route = hints.get(sig, "compact") if (strategy == "auto" and hints is not None) else "compact"
+    if strategy in ("compact", "large"):
+        route = strategy
+    if score_threshold < 0:
+        route = "general"                     # the fused kernels' keys order non-negative scores only
+    if B and (strategy == "general" or route == "general"):
         gdet, gidx, gmeta, hm = _general(h, keep, None, B, return_index, False, max(B * 32768, 1 << 16), 8192)
         res = Detections(gdet, gidx, gmeta, B)
         res._host = hm
         res.general_first = True
         if hints is not None:
-            hints[sig] = bool(hm[1].max() > FUSED_MAX_DET or hm[1].float().mean() > FUSED_MAX_DET / 2)
+            hints[sig] = _next_route(int(hm[1].max()), float(hm[1].float().mean()))
         return res
-    det, idx, meta = _ops.decode_nms_fused(h, keep, FUSED_MAX_DET, return_index)
+    det, idx, meta = _ops.decode_nms_fused(h, keep, FUSED_MAX_DET, return_index, capacity=route)
     res = Detections(det, idx, meta, B)
+    res.capacity = route
     if not resolve_overflow or B == 0:
         return res
     status = res.host_meta()[2]
     over = torch.nonzero(status & _lib.ST_CAND_OVERFLOW).reshape(-1)
     if hints is not None:
-        hints[sig] = bool(over.numel() * 2 > B)
+        if over.numel() == 0:
+            hints[sig] = route
+        elif route == "compact" and over.numel() * 2 <= B:
+            hints[sig] = "large"                  # some images outgrew the compact lists: try the large ones next
+        else:
+            hints[sig] = "general" if over.numel() * 2 > B else route
     if over.numel() == 0:
         return res
     ids = over.to(torch.int32).to(det.device)
@@ -199,7 +222,8 @@ class HostDetections:
 def decode_nms_host(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classes: int, input_size,
                     batch_original_size, dataset: str = "voc", score_threshold: float = 0.1,
                     iou_threshold: float = 0.45, return_index: bool = False, device=None, out=None,
-                    nms_mode: Optional[str] = None, iou_round: Optional[str] = None) -> HostDetections:
+                    nms_mode: Optional[str] = None, iou_round: Optional[str] = None,
+                    capacity: str = "compact") -> HostDetections:
     """decode_nms for head tensors in PINNED HOST memory; the detections come back in pinned host memory.
     The GPU reads only what the kernel touches (objectness planes + the channels of rows above threshold) straight
     over PCIe and writes the rows back, so there is no staging copy of the heads in either direction.  Images that
@@ -211,7 +235,7 @@ def decode_nms_host(heads: Sequence[torch.Tensor], strides: Sequence[int], num_c
     h, keep = _ops.make_heads_host(heads, strides, num_classes, input_size, batch_original_size, dataset,
                                    score_threshold, iou_threshold, nms_mode, iou_round)
     B = h.B
-    det, idx, meta, work = _ops.decode_nms_host(h, keep, FUSED_MAX_DET, return_index, device, out=out)
+    det, idx, meta, work = _ops.decode_nms_host(h, keep, FUSED_MAX_DET, return_index, device, out=out, capacity=capacity)
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(device))
     res = HostDetections(det, idx, meta, B, ev)

@@ -15,7 +15,7 @@ from . import _lib, _ops, config
 # ------------------------------------------------------------------------------------------------
 # a6: tools.py:540-566
 # ------------------------------------------------------------------------------------------------
-_FUSED_MAX_DET = 2048            # == kCapM of csrc/nms.cu
+_FUSED_MAX_DET = 2048            # the larger capacity class' candidate list (csrc/nms.cu FusedCfg<1>)
 
 
 def _general_nms(bboxes, ids, n_sel, score_threshold, iou_threshold, nms_mode, iou_round, return_index, by_position):
@@ -46,7 +46,8 @@ def batched_torch_nms(bboxes: torch.Tensor, score_threshold: float, iou_threshol
     """Batched form of torch_nms: bboxes (B, N, 4+C) -> list of B tensors (K_b, 6)
     (and, if return_index, a list of int64 tensors row*C+class).  One kernel launch and one host read for the
     whole batch (csrc/nms.cu, scores source); images whose candidates do not fit the on-chip lists are re-run
-    through the general path.  strategy='general' forces the general path for every image."""
+    through the general path.  strategy='general' forces the general path for every image (it is also taken for a
+    negative score_threshold), 'large' picks the fused kernel's larger capacity class."""
     if bboxes.dim() != 3:
         raise ValueError("bboxes must be (B, N, 4+C)")
     B, N, _ = bboxes.shape
@@ -58,13 +59,13 @@ def batched_torch_nms(bboxes: torch.Tensor, score_threshold: float, iou_threshol
         e = [empty for _ in range(B)]
         return (e, [torch.zeros((0,), dtype=torch.int64, device=bboxes.device) for _ in range(B)]) \
             if return_index else e
-    if strategy == "general":
+    if strategy == "general" or score_threshold < 0:      # the fused kernel's keys order non-negative scores only
         det, idx, hm = _general_nms(bboxes, None, B, score_threshold, iou_threshold, nms_mode, iou_round,
                                     return_index, False)
         outs = [det[b, :int(hm[0, b])] for b in range(B)]
         return (outs, [idx[b, :int(hm[0, b])].to(torch.int64) for b in range(B)]) if return_index else outs
     det, idx, meta = _ops.nms_fused(bboxes, score_threshold, iou_threshold, nms_mode, iou_round, _FUSED_MAX_DET,
-                                    return_index)
+                                    return_index, capacity="large" if strategy == "large" else "compact")
     hm = meta[:3 * B].view(3, B).cpu()                                # the one device->host read
     outs = [det[b, :int(hm[0, b])] for b in range(B)]
     idxs = [idx[b, :int(hm[0, b])].to(torch.int64) for b in range(B)] if return_index else None

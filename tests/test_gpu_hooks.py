@@ -101,7 +101,7 @@ def test_evaluate_hook_runs_one_fused_launch_per_batch():
 
         def __init__(self, model, dataset):
             self.model, self.dataset = model, dataset
-            self._score_threshold, self._iou_threshold, self._input_size = 0.2, 0.45, (128, 128)
+            self._score_threshold, self._iou_threshold, self._input_size = 0.7, 0.45, (128, 128)
             self._recover_bboxes = base_sample.RECOVER_BBOXES_REGISTER['coco']
             self.acc = DetectionAccumulator(['a', 'b', 'c', 'd'])
             self.seen = []
@@ -135,7 +135,7 @@ def test_evaluate_hook_runs_one_fused_launch_per_batch():
         for k, (imgs, names, shapes, _, _) in enumerate(batches):
             rec = ev._recover_bboxes(m(imgs), torch.tensor([128., 128.]).cuda(), shapes.cuda())
             for i in range(3):
-                w = tools.torch_nms(rec[i], 0.2, 0.45).cpu().numpy()
+                w = tools.torch_nms(rec[i], 0.7, 0.45).cpu().numpy()
                 got = ev.seen[3 * k + i][1]
                 assert got.shape == w.shape and np.array_equal(got, w), (k, i)
     # a model without the hook takes predict -> recover -> ONE batched NMS launch
