@@ -265,8 +265,9 @@ __device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* o
 
 // Greedy NMS of one class by ONE warp WITHOUT sorting it: the class' n <= 32*R members live in registers (R per
 // lane: ~score bits, hit index, trick-shifted box).  Every round picks the best member still alive - one
-// redux.sync min over the ~score bits, a second one over (hit, r) among the holders of that minimum, which is
-// the (score desc, hit asc) order of nonzero() + stable sort - keeps it, and tests the alive members against it.
+// redux.sync min over the ~score bits; if several lanes hold that minimum (an exact score tie) a second one over
+// the hit indices, which is the (score desc, hit asc) order of nonzero() + stable sort - keeps it, and tests the
+// alive members against it.
 // Identical to the sorted greedy walk: that one also visits candidates in this order and skips the suppressed.
 // Work is proportional to kept x ceil(n/32); a class of 30 candidates keeping 6 costs ~300 warp instructions where
 // rank sort + walk cost ~500.
@@ -298,15 +299,23 @@ __device__ __forceinline__ void warp_select_nms(S_t& S, int s, int n, float off,
     for (int r = 0; r < R; ++r)
       if ((alive >> r) & 1u) m = min(m, ns[r]);
     const uint32_t best = __reduce_min_sync(PQ_FULL, m);
-    if (!__any_sync(PQ_FULL, alive != 0u)) break;
-    // among the alive holders of `best`: the smallest hit index (unique within a class)
+    if (best == 0xffffffffu) break;                        // nobody left (a live score is > thr >= 0: ~bits < 2^32 - 1)
+    // the alive holders of `best`: normally one lane with one register; on an exact score tie the smallest hit
+    // index wins (unique within a class) - (score desc, hit asc) is the order of nonzero() + stable sort
     uint32_t cand = 0xffffffffu;
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (((alive >> r) & 1u) && ns[r] == best) cand = min(cand, (tag[r] & 0xffff0000u) | (uint32_t)r);
-    const uint32_t win = __reduce_min_sync(PQ_FULL, cand);
-    const int wl = __ffs(__ballot_sync(PQ_FULL, cand == win)) - 1;
-    const int wr = (int)(win & 0xffffu);
+    const unsigned holders = __ballot_sync(PQ_FULL, cand != 0xffffffffu);
+    int wl = __ffs(holders) - 1;
+    uint32_t win = 0u;
+    if (holders & (holders - 1u)) {                        // several lanes hold it: rare
+      win = __reduce_min_sync(PQ_FULL, cand);
+      wl = __ffs(__ballot_sync(PQ_FULL, cand == win)) - 1;
+    } else if (R > 1) {
+      win = __shfl_sync(PQ_FULL, cand, wl);
+    }
+    const int wr = (R > 1) ? (int)(win & 0xffffu) : 0;
     float ax1 = x1[0], ay1 = y1[0], ax2 = x2[0], ay2 = y2[0];
     uint32_t wtag = tag[0];
 #pragma unroll
@@ -326,6 +335,14 @@ __device__ __forceinline__ void warp_select_nms(S_t& S, int s, int n, float off,
         alive &= ~(1u << r);
   }
 }
+
+#ifdef PQ_PHASE_TIMING
+// debug builds only (profiles/tools/fused_phases.py): cycles per phase, summed over the CTAs' thread 0
+__device__ unsigned long long pq_phase_cycles[16];
+#define PQ_PHASE(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&pq_phase_cycles[i], (unsigned long long)(t_ - pq_t0)); pq_t0 = t_; } } while (0)
+#else
+#define PQ_PHASE(i) do { } while (0)
+#endif
 
 // Scan table: one word per unit (128 cells of one anchor's objectness plane), in hitw order un = group * A + anchor:
 //   level << 30 | slow << 29 | element offset of the unit from the image's anchor-0 objectness plane of that level.
@@ -347,6 +364,28 @@ __device__ __forceinline__ void build_unit_table(const HeadsDev& P, uint32_t* ut
   }
 }
 
+// The generic unit load of the scan (partial last group of a level, planes that are not 16-byte aligned such as
+// 19x19): kept out of line, the unrolled scan loop only carries the one-instruction fast path.
+__device__ __noinline__ float4 scan_load_slow(const HeadsDev& P, const float* lvbase_l, int l, int un, int lane) {
+  float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  const LevelDev& L = P.lv[l];
+  const int g = un / P.A;
+  const int cell = (g - L.group_off) * 128 + 4 * lane;
+  const float* q = lvbase_l + ((size_t)(un - g * P.A) * (size_t)(P.ch * L.HW) + (size_t)cell);
+  if (cell < L.HW) {
+    if (L.vec4) {
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(q));
+    } else {
+      x.x = ldg_stream(q);
+      if (cell + 1 < L.HW) x.y = ldg_stream(q + 1);
+      if (cell + 2 < L.HW) x.z = ldg_stream(q + 2);
+      if (cell + 3 < L.HW) x.w = ldg_stream(q + 3);
+    }
+  }
+  return x;
+}
+
 // Objectness scan of one image.  The cells of a level are cut into groups of 128; a unit = (group g, anchor a):
 // lane l reads cells g*128 + 4l .. 4l+3 of that anchor's objectness plane with one 128-bit load (scalar loads on
 // the slow units) and the warp emits four ballot words, word k holding the cells 4l+k.  hitw layout:
@@ -355,7 +394,10 @@ __device__ __forceinline__ void build_unit_table(const HeadsDev& P, uint32_t* ut
 template <int NW, int CAPH>
 __device__ __forceinline__ void scan_objectness(const HeadsDev& P, const float* const* lvbase, const uint32_t* utab,
                                                 int lane, int warp, uint32_t* hitw, uint64_t* rec, int* nrec) {
-  constexpr int U = 4;
+#ifndef PQ_SCAN_U
+#define PQ_SCAN_U 4
+#endif
+  constexpr int U = PQ_SCAN_U;
   const int A = P.A, nu = P.G_tot * A;
   uint4* hw = reinterpret_cast<uint4*>(hitw);
   for (int u0 = warp; u0 < nu; u0 += NW * U) {
@@ -371,47 +413,41 @@ __device__ __forceinline__ void scan_objectness(const HeadsDev& P, const float* 
           asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(p));
         } else {
-          const LevelDev& L = P.lv[e >> 30];
-          const int g = un / A;
-          const int cell = (g - L.group_off) * 128 + 4 * lane;
-          const float* q = lvbase[e >> 30] + ((size_t)(un - g * A) * (size_t)(P.ch * L.HW) + (size_t)cell);
-          if (cell < L.HW) {
-            if (L.vec4) {
-              asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                           : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w) : "l"(q));
-            } else {
-              x[u].x = ldg_stream(q);
-              if (cell + 1 < L.HW) x[u].y = ldg_stream(q + 1);
-              if (cell + 2 < L.HW) x[u].z = ldg_stream(q + 2);
-              if (cell + 3 < L.HW) x[u].w = ldg_stream(q + 3);
-            }
-          }
+          x[u] = scan_load_slow(P, lvbase[e >> 30], (int)(e >> 30), un, lane);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int un = u0 + u * NW;
-      bool p0b = x[u].x > P.logit_lo, p1b = x[u].y > P.logit_lo, p2b = x[u].z > P.logit_lo, p3b = x[u].w > P.logit_lo;
-      if (p0b | p1b | p2b | p3b) {                                   // rare: exact test of the survivors
-        const int g = un / A;
-        const uint32_t pos = ((uint32_t)g << 10) | ((uint32_t)(un - g * A) << 7) | ((uint32_t)lane << 2);
-        auto test = [&](float xv, uint32_t k) -> bool {
-          const float conf = sigmoidf_(xv);
-          if (!(conf > P.thr_f)) return false;
-          const int r = atomicAdd(nrec, 1);
-          if (r < CAPH) rec[r] = ((uint64_t)__float_as_uint(conf) << 32) | (pos | k);
-          return true;
-        };
-        if (p0b) p0b = test(x[u].x, 0);
-        if (p1b) p1b = test(x[u].y, 1);
-        if (p2b) p2b = test(x[u].z, 2);
-        if (p3b) p3b = test(x[u].w, 3);
-      }
+      // conservative logit-space prefilter only; the exact conf > thr test runs later, once per surviving row and
+      // in parallel (phase 2b).  A row that passes here but fails there (|x - logit(thr)| < 1e-3) merely occupies
+      // a hit slot: its confidence is forced to 0, so it can never yield a candidate.
+      const bool p0b = x[u].x > P.logit_lo, p1b = x[u].y > P.logit_lo, p2b = x[u].z > P.logit_lo, p3b = x[u].w > P.logit_lo;
       uint4 wd;
       wd.x = __ballot_sync(PQ_FULL, p0b); wd.y = __ballot_sync(PQ_FULL, p1b);
       wd.z = __ballot_sync(PQ_FULL, p2b); wd.w = __ballot_sync(PQ_FULL, p3b);
-      if (lane == 0 && un < nu) hw[un] = wd;
+      if (un < nu) {
+        if (lane == 0) hw[un] = wd;
+        if (wd.x | wd.y | wd.z | wd.w) {                               // warp-uniform, ~1 unit in 3 on natural images
+          // the rows leave a record (objectness logit, position): ONE shared-memory atomic per unit reserves the
+          // unit's records, every lane derives its own offsets from the ballot words
+          const int n0 = __popc(wd.x), n1 = __popc(wd.y), n2 = __popc(wd.z);
+          int base = 0;
+          if (lane == 0) base = atomicAdd(nrec, n0 + n1 + n2 + __popc(wd.w));
+          base = __shfl_sync(PQ_FULL, base, 0);
+          const unsigned lt = (1u << lane) - 1u;
+          const int g = un / A;
+          const uint32_t pos = ((uint32_t)g << 10) | ((uint32_t)(un - g * A) << 7) | ((uint32_t)lane << 2);
+          auto put = [&](bool hit, float xv, int at, uint32_t k) {
+            if (hit && at < CAPH) rec[at] = ((uint64_t)__float_as_uint(xv) << 32) | (pos | k);
+          };
+          put(p0b, x[u].x, base + __popc(wd.x & lt), 0);
+          put(p1b, x[u].y, base + n0 + __popc(wd.y & lt), 1);
+          put(p2b, x[u].z, base + n0 + n1 + __popc(wd.z & lt), 2);
+          put(p3b, x[u].w, base + n0 + n1 + n2 + __popc(wd.w & lt), 3);
+        }
+      }
     }
   }
 }
@@ -438,11 +474,15 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
   uint32_t* utab = gbase + P.G_tot;
   if (SRC == 0) build_unit_table(P, utab, tid, NT);
 
+#ifdef PQ_PHASE_TIMING
+  long long pq_t0 = clock64();
+#endif
   for (;;) {
     if (tid == 0) S.b = atomicAdd(work, 1);
     __syncthreads();
     const int b = S.b;
     if (b >= P.B) break;
+    PQ_PHASE(0);
     if (SRC == 0 && tid < P.n_levels) S.lvbase[tid] = P.lv[tid].raw + ((size_t)b * A * ch + 4) * P.lv[tid].HW;
     for (int i = tid; i < 128; i += NT) { S.cls_cnt[i] = 0; S.cls_fill[i] = 0; }
     if (tid == 0) S.nrec = 0;
@@ -509,6 +549,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       }
     }
     __syncthreads();
+    PQ_PHASE(1);
 
     // ---- 2. deterministic slots: exclusive prefix of the per-group hit counts --------------------
     if (warp == 0) {
@@ -525,6 +566,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       if (lane == 0) { S.H = running; S.M = 0; S.K = 0; S.maxcnt = 0; S.next_class = 0; }
     }
     __syncthreads();
+    PQ_PHASE(2);
     const int H = S.H;
     if (H > CAPH) {
       if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = -1; }
@@ -553,7 +595,10 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         if (i < H) {
           const uint64_t rc = S.keys[i];
           pos[r] = (uint32_t)rc;
-          cf[r] = __uint_as_float((uint32_t)(rc >> 32));
+          // exact objectness test (model/parser.py:230 + tools.py:551: score = prob*conf <= conf): a row the
+          // logit-space prefilter let through by its margin gets confidence 0 and can never yield a candidate
+          const float conf = sigmoidf_(__uint_as_float((uint32_t)(rc >> 32)));
+          cf[r] = (conf > P.thr_f) ? conf : 0.0f;
         }
       }
 #pragma unroll
@@ -578,6 +623,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       }
     }
     __syncthreads();
+    PQ_PHASE(3);
 
     // ---- 3. box + class channels of the hit rows only -------------------------------------------
     if (SRC == 1) {
@@ -608,54 +654,103 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       // neighbouring cells, so the rows of one instruction fall into few 32-byte sectors of that channel plane
       // (fewer memory requests; this is what bounds the kernel when the heads live in pinned host memory and
       // every distinct sector is one PCIe read).  8 loads are in flight per lane.
+      // A unit = (32 consecutive hit rows, 8 consecutive channels): lane = row, so one load instruction asks for
+      // the SAME channel of 32 rows.  Hit rows are in (cell, anchor) order and real objects light up runs of
+      // neighbouring cells, so the rows of one instruction fall into few 32-byte sectors of that channel plane
+      // (fewer memory requests; this is what bounds the kernel when the heads live in pinned host memory and
+      // every distinct sector is one PCIe read).  8 x UP loads are in flight per lane.  The candidates of a unit are
+      // appended with ONE reservation (a warp prefix sum + one shared-memory atomic) and the class counters are bumped
+      // by fire-and-forget atomics: nothing in the loop waits for an atomic's return value per channel.
       const Affine af = image_affine(P, b);
       const int CK = 4 + C;
-      constexpr int V = 8;
+#ifndef PQ_FETCH_UP
+#define PQ_FETCH_UP 1
+#endif
+#ifndef PQ_FETCH_V
+#define PQ_FETCH_V 8
+#endif
+      constexpr int V = PQ_FETCH_V, UP = PQ_FETCH_UP;
       const int ncg = (CK + V - 1) / V;
       const int nunit = ((H + 31) >> 5) * ncg;
-      for (int unit = warp; unit < nunit; unit += NW) {
-        const int chunk = unit / ncg, k_lo = (unit - chunk * ncg) * V;
-        const int h = chunk * 32 + lane;
-        if (h >= H) continue;
-        const uint32_t meta = S.hmeta[h];
-        const int l = meta >> 30, a = (meta >> 27) & 7, cell = meta & 0x7ffffff;
-        const LevelDev& L = P.lv[l];
-        // channel 0 of this row: the anchor's objectness plane minus four planes
-        const float* base = S.lvbase[l] + ((size_t)a * ch - 4) * L.HW + cell;
-        const float conf = S.hconf[h];
-        float v[V];
+      for (int unit0 = warp; unit0 < nunit; unit0 += NW * UP) {
+        float v[UP][V];
+        int klo[UP], hrow[UP];
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-          const int k = k_lo + u;
-          if (k < CK) v[u] = ldg_stream(base + (size_t)((k < 4) ? k : k + 1) * L.HW);
-        }
-        int cx = 0, cy = 0;
-        if (k_lo == 0) { cy = cell / L.W; cx = cell - cy * L.W; }
+        for (int q = 0; q < UP; ++q) {
+          const int unit = unit0 + q * NW;
+          const int chunk = unit / ncg;
+          klo[q] = (unit - chunk * ncg) * V;
+          const int h = chunk * 32 + lane;
+          hrow[q] = (unit < nunit && h < H) ? h : -1;
+          if (hrow[q] >= 0) {
+            const uint32_t meta = S.hmeta[h];
+            const int l = meta >> 30, a = (meta >> 27) & 7, cell = meta & 0x7ffffff;
+            const int HW = P.lv[l].HW;
+            // channel 0 of this row: the anchor's objectness plane minus four planes
+            const float* base = S.lvbase[l] + ((size_t)a * ch - 4) * HW + cell;
 #pragma unroll
-        for (int u = 0; u < V; ++u) {
-          const int k = k_lo + u;
-          if (k >= CK) continue;
-          if (k < 4) {
-            reinterpret_cast<float*>(&S.hbox[h])[k] = recover_coord(k, decode_coord(k, v[u], cx, cy, L.stride), af);
-          } else {
-            const float sc = PQ_MUL(sigmoidf_(v[u]), conf);
-            if (sc > P.thr_f) {
-              // one shared-memory atomic per warp instead of one per candidate
-              const unsigned peers = __activemask();
-              const int leader = __ffs(peers) - 1;
-              int base2 = 0;
-              if (lane == leader) base2 = atomicAdd(&S.M, __popc(peers));
-              base2 = __shfl_sync(peers, base2, leader);
-              const int slot = base2 + __popc(peers & ((1u << lane) - 1u));
-              if (slot < CAPM) S.keys[slot] = cand_key(k - 4, sc, (uint32_t)h);
-              atomicAdd(&S.cls_cnt[k - 4], 1);
-              S.hhas[h] = 1;
+            for (int u = 0; u < V; ++u) {
+              const int k = klo[q] + u;
+              if (k < CK) v[q][u] = ldg_stream(base + (size_t)((k < 4) ? k : k + 1) * HW);
             }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < UP; ++q) {
+          if (unit0 + q * NW >= nunit) break;                 // warp-uniform
+          const int h = hrow[q];
+          const bool valid = h >= 0;
+          unsigned pass = 0;                                  // bit u: channel klo + u is a candidate of this row
+          if (valid) {
+            const float conf = S.hconf[h];
+            if (klo[q] == 0) {
+              const uint32_t meta = S.hmeta[h];               // re-read: cheaper than carrying it across the loads
+              const LevelDev& L = P.lv[meta >> 30];
+              const int cell = meta & 0x7ffffff;
+              const int cy = cell / L.W, cx = cell - cy * L.W;
+              float4 bx;
+              bx.x = recover_coord(0, decode_coord(0, v[q][0], cx, cy, L.stride), af);
+              bx.y = recover_coord(1, decode_coord(1, v[q][1], cx, cy, L.stride), af);
+              bx.z = recover_coord(2, decode_coord(2, v[q][2], cx, cy, L.stride), af);
+              bx.w = recover_coord(3, decode_coord(3, v[q][3], cx, cy, L.stride), af);
+              S.hbox[h] = bx;
+            }
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+              const int k = klo[q] + u;
+              if (k >= 4 && k < CK) {
+                v[q][u] = PQ_MUL(sigmoidf_(v[q][u]), conf);
+                if (v[q][u] > P.thr_f) pass |= 1u << u;
+              }
+            }
+          }
+          // class counters: one fire-and-forget atomic per channel that has candidates
+#pragma unroll
+          for (int u = 0; u < V; ++u) {
+            const unsigned bal = __ballot_sync(PQ_FULL, (pass >> u) & 1u);
+            if (lane == u && bal) atomicAdd(&S.cls_cnt[klo[q] + u - 4], __popc(bal));
+          }
+          const int cnt = __popc(pass);
+          const int incl = warp_inclusive_sum(cnt);
+          const int total = __shfl_sync(PQ_FULL, incl, 31);
+          if (total) {                                        // warp-uniform
+            int base2 = 0;
+            if (lane == 0) base2 = atomicAdd(&S.M, total);
+            base2 = __shfl_sync(PQ_FULL, base2, 0);
+            int slot = base2 + incl - cnt;
+            if (cnt) S.hhas[h] = 1;
+#pragma unroll
+            for (int u = 0; u < V; ++u)
+              if ((pass >> u) & 1u) {
+                if (slot < CAPM) S.keys[slot] = cand_key(klo[q] + u - 4, v[q][u], (uint32_t)h);
+                ++slot;
+              }
           }
         }
       }
     }
     __syncthreads();
+    PQ_PHASE(4);
     const int M = S.M;
     if (M > CAPM || M == 0) {
       if (tid == 0) {
@@ -701,6 +796,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       m1 = PQ_ADD(mx, 1.0f);
     }
 
+    PQ_PHASE(5);
     // ---- 5. per-class member lists --------------------------------------------------------------
     const int maxcnt = S.maxcnt;
     const bool lists = maxcnt <= kWarpSortMax;
@@ -723,39 +819,55 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       for (int i = tid; i < M; i += NT) { S.order[i] = (uint16_t)i; S.keepflag[i] = 0; }
     }
     __syncthreads();
+    PQ_PHASE(6);
 
     // ---- 6. greedy NMS, one warp per class (classes pulled dynamically: uneven sizes) ------------
-    for (;;) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&S.next_class, 1);
-      c = __shfl_sync(PQ_FULL, c, 0);
-      if (c >= C) break;
-      const int n = S.cls_cnt[c];
-      if (n == 0) continue;
-      const int s = S.seg_start[c];
-      const float off = trick ? PQ_MUL((float)c, m1) : 0.0f;
-      if (lists && n <= 32) {
-        warp_select_nms<ROUND, 1>(S, s, n, off, P.iou_f, P.iou_d);
-      } else if (lists && n <= 64) {
-        warp_select_nms<ROUND, 2>(S, s, n, off, P.iou_f, P.iou_d);
-      } else if (lists && n <= kSelectMax) {
-        warp_select_nms<ROUND, 4>(S, s, n, off, P.iou_f, P.iou_d);
-      } else {
-        uint16_t* kl = S.klist();
-        if (lists) warp_rank_sort(S.keys, S.order, kl, s, n);
-        warp_nms_segment<ROUND>(
-            s, s + n, off, P.iou_f, P.iou_d,
-            [&](int pos) { return S.hbox[S.keys[S.order[pos]] & kHitMask]; },
-            [&](int slot, int pos) -> int {
-              if (pos >= 0) kl[slot] = (uint16_t)pos;
-              return kl[slot];
-            },
-            [&](int pos) { S.keepflag[S.order[pos]] = 1; });
+    {
+      auto pull = [&]() -> int {                              // next class that has candidates, or C
+        for (;;) {
+          int c = 0;
+          if (lane == 0) c = atomicAdd(&S.next_class, 1);
+          c = __shfl_sync(PQ_FULL, c, 0);
+          if (c >= C || S.cls_cnt[c] > 0) return c;
+        }
+      };
+      auto single = [&](int c) {
+        const int n = S.cls_cnt[c];
+        const int s = S.seg_start[c];
+        const float off = trick ? PQ_MUL((float)c, m1) : 0.0f;
+        if (lists && n <= 32) {
+          warp_select_nms<ROUND, 1>(S, s, n, off, P.iou_f, P.iou_d);
+        } else if (lists && n <= 64) {
+          warp_select_nms<ROUND, 2>(S, s, n, off, P.iou_f, P.iou_d);
+        } else if (lists && n <= kSelectMax) {
+          warp_select_nms<ROUND, 4>(S, s, n, off, P.iou_f, P.iou_d);
+        } else {
+          uint16_t* kl = S.klist();
+          if (lists) warp_rank_sort(S.keys, S.order, kl, s, n);
+          warp_nms_segment<ROUND>(
+              s, s + n, off, P.iou_f, P.iou_d,
+              [&](int pos) { return S.hbox[S.keys[S.order[pos]] & kHitMask]; },
+              [&](int slot, int pos) -> int {
+                if (pos >= 0) kl[slot] = (uint16_t)pos;
+                return kl[slot];
+              },
+              [&](int pos) { S.keepflag[S.order[pos]] = 1; });
+        }
+      };
+      for (;;) {
+        const int c = pull();
+        if (c >= C) break;
+        single(c);
       }
     }
     __syncthreads();
+    PQ_PHASE(7);
 
     // ---- 7. kept keys -> (score desc, row, class) order -> output -------------------------------
+    // order[] and keepflag[] are dead from here on: order[] takes the high (~score) words of the kept keys,
+    // keepflag[] the rank -> key permutation used to detect exact score ties.
+    uint32_t* hi32 = reinterpret_cast<uint32_t*>(S.order);         // CAPM / 2 words
+    uint16_t* perm = reinterpret_cast<uint16_t*>(S.keepflag);      // CAPM / 2 entries
     {
       constexpr int R = CAPM / NT;
       uint64_t loc[R];
@@ -767,12 +879,18 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         if (i < M && S.keepflag[i]) { loc[r] = out_key(S.keys[i]); vmask |= 1u << r; }
       }
       __syncthreads();
+      if (tid == 0) S.next_class = 0;                      // reused as the tie flag below
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (vmask & (1u << r)) S.keys[atomicAdd(&S.K, 1)] = loc[r];
+        if (vmask & (1u << r)) {
+          const int pos = atomicAdd(&S.K, 1);
+          S.keys[pos] = loc[r];
+          if (pos < CAPM / 2) hi32[pos] = (uint32_t)(loc[r] >> 32);
+        }
       __syncthreads();
     }
     const int K = S.K;
+    PQ_PHASE(8);
     auto emit = [&](int j, uint64_t k2) {
       const float score = __uint_as_float(~(uint32_t)(k2 >> 32));
       const uint32_t low = (uint32_t)k2;
@@ -785,7 +903,53 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       }
       write_det(O, b, j, S.hbox[h], score, c, row, C);
     };
-    if (K <= kRankOutMax || next_pow2(K) > CAPM) {         // position = number of smaller keys
+#ifndef PQ_RANK32
+#define PQ_RANK32 1
+#endif
+    if (PQ_RANK32 && K <= kRankOutMax && K <= CAPM / 2) {
+      // position = number of smaller keys.  Counted on the 32-bit ~score words, four per shared-memory load; the
+      // ranks are a permutation unless two kept detections share a score exactly (then redone on the full keys).
+      constexpr int RR = (kRankOutMax + NT - 1) / NT;
+      int rk[RR];
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        const int i = tid + r * NT;
+        rk[r] = -1;
+        if (i < K) {
+          const uint32_t mh = hi32[i];
+          int rank = 0;
+          const int K4 = K & ~3;
+          for (int j = 0; j < K4; j += 4) {
+            const uint4 o = *reinterpret_cast<const uint4*>(hi32 + j);
+            rank += (o.x < mh) ? 1 : 0;
+            rank += (o.y < mh) ? 1 : 0;
+            rank += (o.z < mh) ? 1 : 0;
+            rank += (o.w < mh) ? 1 : 0;
+          }
+          for (int j = K4; j < K; ++j) rank += (hi32[j] < mh) ? 1 : 0;
+          rk[r] = rank;
+          perm[rank] = (uint16_t)i;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < RR; ++r)
+        if (rk[r] >= 0 && perm[rk[r]] != (uint16_t)(tid + r * NT)) S.next_class = 1;
+      __syncthreads();
+      const bool tie = S.next_class != 0;
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        const int i = tid + r * NT;
+        if (i >= K) continue;
+        const uint64_t mine = S.keys[i];
+        int rank = rk[r];
+        if (tie) {
+          rank = 0;
+          for (int j = 0; j < K; ++j) rank += (S.keys[j] < mine) ? 1 : 0;
+        }
+        if (rank < O.max_det) emit(rank, mine);
+      }
+    } else if (next_pow2(K) > CAPM) {                       // no room to pad for the bitonic network
       for (int i = tid; i < K; i += NT) {
         const uint64_t mine = S.keys[i];
         int rank = 0;
@@ -806,6 +970,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       O.status[b] = (K > O.max_det) ? PQDET_ST_DET_TRUNCATED : PQDET_ST_OK;
     }
     __syncthreads();
+    PQ_PHASE(9);
   }
   // re-arm the scheduler for the next launch on this stream: the last CTA to leave zeroes both words
   // (work[0] = next image, work[1] = CTAs that have finished), so steady-state calls need no memset
@@ -1387,6 +1552,17 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
 }
 
 }  // namespace pq
+
+#ifdef PQ_PHASE_TIMING
+extern "C" int pqdet_debug_phase_cycles(unsigned long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, pq::pq_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(pq::pq_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif
 
 extern "C" int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                                 int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,

@@ -42,7 +42,7 @@ def _model(seed=0, **kw):
     m = MiniDetectionModel(**kw).cuda()
     for mod in m.modules():                       # spread the logits a little so that some boxes pass the threshold
         if isinstance(mod, torch.nn.Conv2d) and mod.bias is not None:
-            torch.nn.init.normal_(mod.bias, 0.0, 1.5)
+            torch.nn.init.normal_(mod.bias, 0.5, 1.5)
     return m
 
 
