@@ -169,9 +169,22 @@ int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes, int64_t N
                       int32_t* status, void* workspace, int64_t workspace_bytes, int64_t cand_capacity,
                       int64_t* needed, int device, void* stream);
 
+/* ---- a13: tools.nms (tools.py:507-538; no callers in the reference): per-class selection loop with hard NMS or the
+ * soft-NMS decay exp(-iou^2 / sigma), the reference's semantics in full (first pick of a class is not thresholded,
+ * iou_calc1's clamped union, scores decay in place).  The n boxes are grouped by class by the caller: class c owns
+ * rows [seg_off[c], seg_off[c+1]) of boxes (n,4) / scores (n) (scores is overwritten with the decayed values).
+ * out_idx / out_score (n): for class c the picks in order at [seg_off[c], seg_off[c] + out_count[c]).
+ * alive_scratch: n bytes. */
+int pqdet_classwise_nms(const float* boxes, float* scores, const int32_t* seg_off, int n_classes, int64_t n,
+                        int soft, double sigma, double score_threshold, double iou_threshold,
+                        int32_t* out_idx, float* out_score, int32_t* out_count, uint8_t* alive_scratch,
+                        int device, void* stream);
+
 /* ---- a7/a8: tools.py:357-437 iou_calc3 / giou / diou / ciou, elementwise over n box pairs
- * (broadcasting is done by the caller).  kind: 0 iou, 1 giou, 2 diou, 3 ciou.
- * grad_b1/grad_b2 (may be NULL): d out / d boxes times grad_out (kinds 0..2). */
+ * (broadcasting is done by the caller).  kind: 0 iou, 1 giou, 2 diou, 3 ciou, 4 iou with the union clamped at 1e-14
+ * (tools.iou_calc1, tools.py:335-355; forward only).
+ * grad_b1/grad_b2 (may be NULL): d out / d boxes times grad_out (kinds 0..3; ciou's alpha is a constant of the
+ * differentiation, as under the reference's torch.no_grad()). */
 int pqdet_iou_pairwise(const float* b1, const float* b2, float* out, int64_t n, int kind,
                        int device, void* stream);
 int pqdet_iou_pairwise_bwd(const float* b1, const float* b2, const float* grad_out, float* grad_b1,

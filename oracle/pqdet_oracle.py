@@ -399,3 +399,38 @@ def create_label_batch(batch_bboxes, output_sizes, num_classes, anchors, strides
     labels = [np.stack([p[i] for p in per], axis=0) for i in range(3)]
     gts = [collate_gt_lists([p[3 + i] for p in per]) for i in range(3)]
     return labels, gts
+
+
+def iou_calc1(boxes1: np.ndarray, boxes2: np.ndarray) -> np.ndarray:
+    """tools.py:335-355 (numpy, dtype of the inputs, union clamped at 1e-14)."""
+    a1 = (boxes1[..., 2] - boxes1[..., 0]) * (boxes1[..., 3] - boxes1[..., 1])
+    a2 = (boxes2[..., 2] - boxes2[..., 0]) * (boxes2[..., 3] - boxes2[..., 1])
+    lu = np.maximum(boxes1[..., :2], boxes2[..., :2])
+    rd = np.minimum(boxes1[..., 2:], boxes2[..., 2:])
+    sec = np.maximum(rd - lu, 0.0)
+    inter = sec[..., 0] * sec[..., 1]
+    return inter / np.maximum(a1 + a2 - inter, 1e-14)
+
+
+def numpy_nms(bboxes: np.ndarray, score_threshold: float, iou_threshold: float, sigma: float = 0.3,
+              method: str = "nms") -> np.ndarray:
+    """tools.py:507-538, class by class in ASCENDING class order (the reference iterates a Python set, whose order is
+    unspecified): selection loop, hard NMS or soft-NMS decay, the first pick of a class not thresholded."""
+    assert method in ("nms", "soft-nms")
+    out = []
+    for cls in sorted(set(bboxes[:, 5].tolist())):
+        rows = bboxes[bboxes[:, 5] == cls].copy()
+        while len(rows) > 0:
+            m = int(np.argmax(rows[:, 4]))
+            best = rows[m]
+            out.append(best)
+            rows = np.concatenate([rows[:m], rows[m + 1:]])
+            iou = iou_calc1(best[np.newaxis, :4], rows[:, :4])
+            weight = np.ones((len(iou),), dtype=np.float32)
+            if method == "nms":
+                weight[iou > iou_threshold] = 0.0
+            else:
+                weight = np.exp(-(1.0 * iou ** 2 / sigma))
+            rows[:, 4] = rows[:, 4] * weight
+            rows = rows[rows[:, 4] > score_threshold]
+    return np.array(out)

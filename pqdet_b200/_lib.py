@@ -70,6 +70,8 @@ SIGNATURES = {
     "pqdet_nms_general": (c_int, [POINTER(HeadsT), c_void_p, c_int64, c_int, c_int, c_double, c_double,
                                   c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "pqdet_classwise_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_double, c_double, c_double,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pqdet_iou_pairwise": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "pqdet_iou_pairwise_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                        c_int, c_void_p]),

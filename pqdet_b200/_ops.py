@@ -630,3 +630,21 @@ def loss_levels_sparse(raws, owners, gt6: torch.Tensor, gts, num_classes: int, s
         _lib.BBOX_LOSS[bbox_loss], float(ignore_thresh), float(l1_loss_gain), _ptr(out), _ptr(flag), _ptr(ws),
         1, _dev(raws[0]), _stream(device)), "pqdet_loss_levels_sparse")
     return out, flag, grads
+
+
+def classwise_nms(boxes: torch.Tensor, scores: torch.Tensor, seg_off: torch.Tensor, soft: bool, sigma: float,
+                  score_threshold: float, iou_threshold: float):
+    """tools.nms on class-grouped rows (pqdet_classwise_nms).  -> picked indices (n), their scores (n), counts (C)."""
+    boxes, scores = _req(boxes, "boxes"), _req(scores, "scores").clone()
+    n, n_classes = boxes.shape[0], seg_off.numel() - 1
+    dev = boxes.device
+    seg_off = seg_off.to(device=dev, dtype=torch.int32).contiguous()
+    out_idx = torch.zeros((max(n, 1),), dtype=torch.int32, device=dev)
+    out_score = torch.zeros((max(n, 1),), dtype=torch.float32, device=dev)
+    out_count = torch.zeros((max(n_classes, 1),), dtype=torch.int32, device=dev)
+    alive = torch.empty((max(n, 1),), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.load().pqdet_classwise_nms(_ptr(boxes), _ptr(scores), _ptr(seg_off), int(n_classes), int(n),
+                                               1 if soft else 0, float(sigma), float(score_threshold),
+                                               float(iou_threshold), _ptr(out_idx), _ptr(out_score), _ptr(out_count),
+                                               _ptr(alive), _dev(boxes), _stream(dev)), "pqdet_classwise_nms")
+    return out_idx[:n], out_score[:n], out_count[:n_classes]

@@ -39,7 +39,7 @@ static unsigned grid_for(int64_t n) {
 
 extern "C" int pqdet_iou_pairwise(const float* b1, const float* b2, float* out, int64_t n, int kind,
                                   int device, void* stream) {
-  if (!b1 || !b2 || !out || n < 0 || kind < 0 || kind > 3) return PQDET_ERR_INVALID_ARG;
+  if (!b1 || !b2 || !out || n < 0 || kind < 0 || kind > 4) return PQDET_ERR_INVALID_ARG;
   if (((uintptr_t)b1 | (uintptr_t)b2) & 15) return PQDET_ERR_INVALID_ARG;
   if (n == 0) return PQDET_OK;
   PQ_ENTER(device);
@@ -51,7 +51,7 @@ extern "C" int pqdet_iou_pairwise(const float* b1, const float* b2, float* out, 
 
 extern "C" int pqdet_iou_pairwise_bwd(const float* b1, const float* b2, const float* grad_out, float* grad_b1,
                                       float* grad_b2, int64_t n, int kind, int device, void* stream) {
-  if (!b1 || !b2 || !grad_out || n < 0 || kind < 0 || kind > 2) return PQDET_ERR_INVALID_ARG;
+  if (!b1 || !b2 || !grad_out || n < 0 || kind < 0 || kind > 3) return PQDET_ERR_INVALID_ARG;
   if (((uintptr_t)b1 | (uintptr_t)b2 | (uintptr_t)grad_b1 | (uintptr_t)grad_b2) & 15) return PQDET_ERR_INVALID_ARG;
   if (n == 0) return PQDET_OK;
   PQ_ENTER(device);

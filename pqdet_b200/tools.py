@@ -107,8 +107,6 @@ class _IouFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         b1, b2 = ctx.saved_tensors
-        if ctx.kind == 3:
-            raise NotImplementedError("ciou backward: the reference's ciou loss always raises 'NaN in loss'")
         g1, g2 = _ops.iou_pairwise_bwd(b1, b2, g.contiguous(), ctx.kind)
 
         def unbroadcast(gr, shape):
@@ -155,14 +153,9 @@ def _np_to_cuda(a):
 
 
 def iou_calc1(boxes1: np.ndarray, boxes2: np.ndarray):
-    """tools.py:335-355: numpy xyxy IoU with the union clamped at 1e-14.  fp32 on the GPU; the clamp
-    only matters for degenerate unions, where IoU is forced to inter/1e-14 like the reference."""
+    """tools.py:335-355: numpy xyxy IoU with the union clamped at 1e-14 (fp32 on the GPU, same operation order)."""
     b1, b2 = np.asarray(boxes1), np.asarray(boxes2)
-    out = _ops.iou_pairwise(_np_to_cuda(b1), _np_to_cuda(b2), 0).cpu().numpy()
-    bad = ~np.isfinite(out)
-    if bad.any():
-        out = np.where(bad, 0.0, out)
-    return out
+    return _ops.iou_pairwise(_np_to_cuda(b1), _np_to_cuda(b2), 4).cpu().numpy()
 
 
 def iou_xywh_numpy(boxes1: np.ndarray, boxes2: np.ndarray):
@@ -175,27 +168,28 @@ def iou_xywh_numpy(boxes1: np.ndarray, boxes2: np.ndarray):
 
 
 def nms(bboxes, score_threshold, iou_threshold, sigma=0.3, method='nms'):
-    """tools.py:507-538 (no callers in the reference).  bboxes (N,6) [x1,y1,x2,y2,score,class].
-    Hard NMS only; rows come back grouped by class like the reference's per-class loop.  Boxes with
-    score <= score_threshold are dropped up front (the reference drops them after the first pick)."""
+    """tools.py:507-538 (no callers in the reference).  bboxes (N,6) [x1,y1,x2,y2,score,class] -> the picked rows,
+    class by class, each with the score it had when it was picked (soft-NMS decays scores in place).  Hard NMS
+    ('nms') and 'soft-nms' with the reference's semantics: the first pick of a class is not compared with
+    score_threshold, iou_calc1's clamped union, ties go to the earlier row.  fp32 arithmetic (the reference
+    computes in the dtype of `bboxes`).  Classes come out in ascending order (the reference iterates a Python set)."""
     assert method in ['nms', 'soft-nms']
-    if method == 'soft-nms':
-        raise NotImplementedError("soft-nms is dead code in the reference and is not part of the hot path")
     bboxes = np.asarray(bboxes, dtype=np.float32)
     if len(bboxes) == 0:
         return np.array([])
-    classes = sorted(set(bboxes[:, 5].tolist()))
-    cmap = {c: i for i, c in enumerate(classes)}
-    C = len(classes)
-    if C > _lib.MAX_CLASSES:
-        raise _lib.PqdetError("more than %d distinct classes" % _lib.MAX_CLASSES)
-    dense = np.full((len(bboxes), 4 + C), -np.inf, dtype=np.float32)
-    dense[:, :4] = bboxes[:, :4]
-    for r, c in enumerate(bboxes[:, 5].tolist()):
-        dense[r, 4 + cmap[c]] = bboxes[r, 4]
-    outs, idx = batched_torch_nms(_np_to_cuda(dense)[None], score_threshold, iou_threshold, return_index=True,
-                                  nms_mode="vanilla", iou_round="tv_cpu", strategy="general")
-    rows = (idx[0] // C).cpu().numpy()
-    kept = bboxes[rows]
-    order = np.argsort([cmap[c] for c in kept[:, 5].tolist()], kind="stable")
-    return kept[order]
+    classes = np.unique(bboxes[:, 5])
+    order = np.argsort(bboxes[:, 5], kind="stable")                   # group by class, keep the row order inside
+    grouped = bboxes[order]
+    seg = np.searchsorted(grouped[:, 5], classes, side="left").astype(np.int32)
+    seg = np.concatenate([seg, np.array([len(grouped)], np.int32)])
+    idx, score, count = _ops.classwise_nms(_np_to_cuda(grouped[:, :4]), _np_to_cuda(grouped[:, 4]),
+                                           torch.from_numpy(seg).cuda(), method == 'soft-nms', float(sigma),
+                                           float(score_threshold), float(iou_threshold))
+    idx, score, count = idx.cpu().numpy(), score.cpu().numpy(), count.cpu().numpy()
+    out = []
+    for ci in range(len(classes)):
+        sel = idx[seg[ci]:seg[ci] + count[ci]]
+        rows = grouped[sel].copy()
+        rows[:, 4] = score[seg[ci]:seg[ci] + count[ci]]
+        out.append(rows)
+    return np.concatenate(out, axis=0)

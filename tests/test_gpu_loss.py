@@ -214,15 +214,50 @@ def test_iou_family_golden_and_backward():
         assert rel_close(qc.grad.cpu().numpy(), q.grad.numpy(), 1e-4, scale=float(q.grad.abs().max()))
 
 
-def test_numpy_nms_wrapper():
+def test_numpy_nms_hard_and_soft_vs_oracle():
+    """Row a13: tools.nms (tools.py:507-538) with the reference's semantics - hard NMS bit-exact, soft-NMS within
+    fp32 exp rounding (numpy's exp vs libdevice expf: same picks, scores within 1e-6)."""
     from pqdet_b200 import tools
-    g = load_golden("nms")
-    bb = g["small_in"]
-    boxes, scores, cls, _ = po.select_candidates(bb, 0.1)
-    rows = np.concatenate([boxes, scores[:, None], cls[:, None].astype(np.float32)], axis=1)
-    out = tools.nms(rows, 0.1, 0.45)
-    want = po.torch_nms(bb, 0.1, 0.45, device="cpu", mode="vanilla")
-    assert sorted(map(bytes, out.astype(np.float32))) == sorted(map(bytes, want))
+    rng = np.random.default_rng(12)
+    for n, ncls in ((150, 4), (1, 1), (700, 9)):
+        c = rng.random((n, 2)) * 120
+        wh = rng.random((n, 2)) * 40 + 4
+        bb = np.concatenate([c - wh / 2, c + wh / 2, rng.random((n, 1)), rng.integers(0, ncls, (n, 1))],
+                            axis=1).astype(np.float32)
+        for thr in (0.3, 0.95):                                      # 0.95: most classes only yield their unthresholded first pick
+            want = po.numpy_nms(bb.copy(), thr, 0.45, method="nms")
+            got = tools.nms(bb.copy(), thr, 0.45, method="nms")
+            assert got.shape == want.shape and np.array_equal(got, want), (n, thr)
+        for thr, sigma in ((0.3, 0.3), (0.05, 0.5)):
+            want = po.numpy_nms(bb.copy(), thr, 0.45, sigma=sigma, method="soft-nms")
+            got = tools.nms(bb.copy(), thr, 0.45, sigma=sigma, method="soft-nms")
+            assert got.shape == want.shape, (n, thr, got.shape, want.shape)
+            assert np.array_equal(got[:, [0, 1, 2, 3, 5]], want[:, [0, 1, 2, 3, 5]])
+            assert rel_close(got[:, 4], want[:, 4], 1e-5, scale=1e-30)
+    assert tools.nms(np.zeros((0, 6), np.float32), 0.1, 0.45).size == 0
+    # iou_calc1 incl. the clamped union of degenerate boxes
+    b1 = np.array([[0, 0, 10, 10], [5, 5, 5, 5], [0, 0, 1, 1]], np.float32)
+    b2 = np.array([[5, 5, 15, 15], [5, 5, 5, 5], [2, 2, 3, 3]], np.float32)
+    assert np.array_equal(tools.iou_calc1(b1, b2), po.iou_calc1(b1, b2))
+
+
+def test_ciou_value_and_backward_vs_oracle():
+    """tools.ciou (tools.py:439-477) forward and gradient (alpha constant, as under the reference's no_grad)."""
+    from pqdet_b200 import tools
+    g = torch.Generator().manual_seed(4)
+    p = torch.rand((200, 2), generator=g) * 50
+    p = torch.cat([p, p + torch.rand((200, 2), generator=g) * 30 + 1], dim=1)
+    q = torch.rand((200, 2), generator=g) * 50
+    q = torch.cat([q, q + torch.rand((200, 2), generator=g) * 30 + 1], dim=1)
+    p1, q1 = p.clone().requires_grad_(True), q.clone().requires_grad_(True)
+    want = loss_ref.ciou_t(p1, q1)
+    want.sum().backward()
+    p2, q2 = p.cuda().requires_grad_(True), q.cuda().requires_grad_(True)
+    got = tools.ciou(p2, q2)
+    got.sum().backward()
+    assert rel_close(got.detach().cpu().numpy(), want.detach().numpy(), 1e-5, scale=1.0)
+    assert rel_close(p2.grad.cpu().numpy(), p1.grad.numpy(), 1e-4, scale=float(p1.grad.abs().max()))
+    assert rel_close(q2.grad.cpu().numpy(), q1.grad.numpy(), 1e-4, scale=float(q1.grad.abs().max()))
 
 
 def test_loss_and_assignment_full_size_configs():

@@ -186,3 +186,34 @@ def test_cpu_path_port_is_the_reference_sequence(ref, kind, C, size, dist):
         for b in range(B):
             assert got[b].shape == want[b].shape, (name, b)
             assert torch.equal(got[b], want[b]), (name, b)
+
+
+def test_numpy_nms_and_ciou_oracles_match_the_reference(ref):
+    """Row a13 / a8: the oracle's restatements of tools.nms (hard and soft, tools.py:507-538), tools.iou_calc1 and
+    tools.ciou (value and autograd gradient) against the live reference."""
+    rng = np.random.default_rng(8)
+    n = 120
+    c = rng.random((n, 2)) * 100
+    wh = rng.random((n, 2)) * 40 + 4
+    bb = np.concatenate([c - wh / 2, c + wh / 2, rng.random((n, 1)), rng.integers(0, 4, (n, 1))], axis=1).astype(np.float32)
+    assert np.array_equal(po.iou_calc1(bb[:50, None, :4], bb[None, 50:90, :4]), ref.tools.iou_calc1(bb[:50, None, :4], bb[None, 50:90, :4]))
+    for method, thr in (("nms", 0.3), ("soft-nms", 0.3), ("soft-nms", 0.05), ("nms", 0.95)):
+        want = ref.tools.nms(bb.copy(), thr, 0.45, sigma=0.3, method=method)
+        got = po.numpy_nms(bb.copy(), thr, 0.45, sigma=0.3, method=method)
+        assert want.shape == got.shape and len(want) > 0
+        # the reference walks the classes in set order: compare class by class
+        for cls in np.unique(bb[:, 5]):
+            assert np.array_equal(got[got[:, 5] == cls], want[want[:, 5] == cls]), (method, cls)
+    g = torch.Generator().manual_seed(4)
+    p = (torch.rand((64, 2), generator=g) * 50)
+    p = torch.cat([p, p + torch.rand((64, 2), generator=g) * 30 + 1], dim=1).requires_grad_(True)
+    q = (torch.rand((64, 2), generator=g) * 50)
+    q = torch.cat([q, q + torch.rand((64, 2), generator=g) * 30 + 1], dim=1).requires_grad_(True)
+    a = ref.tools.ciou(p, q)
+    a.sum().backward()
+    p2, q2 = p.detach().clone().requires_grad_(True), q.detach().clone().requires_grad_(True)
+    b = loss_ref.ciou_t(p2, q2)
+    b.sum().backward()
+    assert torch.equal(a, b)
+    # same formula, differently shaped autograd graph: the accumulation order of the gradient terms differs
+    assert torch.allclose(p.grad, p2.grad, rtol=1e-5, atol=1e-8) and torch.allclose(q.grad, q2.grad, rtol=1e-5, atol=1e-8)
