@@ -130,6 +130,27 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
                      int counter_armed, int capacity_class, int device, void* stream);
 
+/* ---- 8f-2 (second half): the eval path starting at the INPUT of the head convolutions, with nothing of size
+ * B x N ever written (model/cfg/regnetx-600m-fpn.cfg:646-651 + model/parser.py:206-235 + tools.py:540-566).
+ * pqdet_head_conv_hits  one level: 1x1 head convolution on the tensor cores (tcgen05, TF32 like PyTorch's default);
+ *                       the epilogue reads back only the objectness column of every anchor and appends one record
+ *                       [row, objectness, 4 box, C class raw values] (6 + C floats; row = its index in the
+ *                       concatenated prediction, stored as int bits) per row whose objectness can exceed
+ *                       score_threshold.  rec (B, rec_cap, 6 + C); rec_count (B) int32, zeroed by the caller before
+ *                       the first level, counts appended records of all levels (> rec_cap: the image overflowed).
+ *                       Returns PQDET_ERR_UNSUPPORTED for shapes outside the persistent kernel (H*W not a multiple
+ *                       of 128, weights beyond shared memory): use pqdet_head_conv_decode(out_raw) + pqdet_decode_nms.
+ * pqdet_records_nms     the fused kernel's back end on those records: exact conf > thr test, decode + recover of the
+ *                       boxes, scores, class-aware NMS, output - same outputs / status / scheduler-word contract as
+ *                       pqdet_decode_nms; heads supplies the geometry (raw[] is ignored).  Results are identical to
+ *                       pqdet_decode_nms on the raw heads this convolution would have written. */
+int pqdet_head_conv_hits(const float* x, const float* weight, const float* bias, int B, int Cin, int H, int W,
+                         int A, int C, double score_threshold, int64_t row_offset, float* rec, int32_t* rec_count,
+                         int rec_cap, int device, void* stream);
+int pqdet_records_nms(const pqdet_heads_t* heads, const float* rec, const int32_t* rec_count, int rec_cap,
+                      float* det, int32_t* det_idx, int max_det, int32_t* counts, int32_t* ncand, int32_t* status,
+                      int32_t* work_counter, int counter_armed, int capacity_class, int device, void* stream);
+
 /* Host-buffer form of pqdet_decode_nms: the call predict.py:33-45 / eval/evaluator.py:48-61 would make when the
  * head outputs and the detections live in HOST memory.  heads->raw[], heads->orig_hw, det, det_idx, counts, ncand
  * and status may each be PAGE-LOCKED host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) or device

@@ -108,10 +108,10 @@ def decode_levels(raws: Sequence[torch.Tensor], num_classes: int, strides: Seque
 
 def head_conv_decode(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], num_classes: int,
                      stride: float, out: Optional[torch.Tensor] = None, rows_total: Optional[int] = None,
-                     row_offset: int = 0, want_raw: bool = False):
+                     row_offset: int = 0, want_raw: bool = False, want_decoded: bool = True):
     """1x1 head convolution + Decode on the tensor cores (pqdet_head_conv_decode).
     x (B,Cin,H,W), weight (A*(5+C), Cin[,1,1]), bias (A*(5+C))|None -> decoded (B,H,W,A,5+C) [or rows of `out`],
-    raw (B, A*(5+C), H, W) if want_raw."""
+    raw (B, A*(5+C), H, W) if want_raw; want_decoded=False (with want_raw): only the raw head."""
     x = _req(x, "x")
     weight = _req(weight.reshape(weight.shape[0], -1), "weight")
     if bias is not None:
@@ -122,13 +122,19 @@ def head_conv_decode(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
     if ACH % ch or weight.shape[1] != Cin:
         raise ValueError("weight %s does not match Cin=%d / 5+classes=%d" % (tuple(weight.shape), Cin, ch))
     A = ACH // ch
-    if out is None:
+    if not want_decoded:
+        if not want_raw:
+            raise ValueError("nothing to compute")
+        out, rows_total, row_offset = None, H * W * A, 0
+    elif out is None:
         out = torch.empty((B, H, W, A, ch), dtype=torch.float32, device=x.device)
         rows_total, row_offset = H * W * A, 0
     raw = torch.empty((B, ACH, H, W), dtype=torch.float32, device=x.device) if want_raw else None
     _lib.check(_lib.load().pqdet_head_conv_decode(_ptr(x), _ptr(weight), _ptr(bias), _ptr(out), _ptr(raw), B, Cin, H, W,
                                                   A, num_classes, float(stride), int(rows_total), int(row_offset),
                                                   _dev(x), _stream(x.device)), "pqdet_head_conv_decode")
+    if not want_decoded:
+        return raw
     return (out, raw) if want_raw else out
 
 
@@ -648,3 +654,64 @@ def classwise_nms(boxes: torch.Tensor, scores: torch.Tensor, seg_off: torch.Tens
                                                float(iou_threshold), _ptr(out_idx), _ptr(out_score), _ptr(out_count),
                                                _ptr(alive), _dev(boxes), _stream(dev)), "pqdet_classwise_nms")
     return out_idx[:n], out_score[:n], out_count[:n_classes]
+
+
+def make_geometry(B: int, A: int, shapes: Sequence[Tuple[int, int]], strides: Sequence[float], num_classes: int,
+                  input_size, original_size, kind: str, score_threshold: float, iou_threshold: float,
+                  nms_mode: str, iou_round: str, device):
+    """pqdet_heads_t without raw tensors (pqdet_records_nms only needs the level geometry)."""
+    if not 1 <= len(shapes) <= _lib.MAX_LEVELS or len(shapes) != len(strides):
+        raise ValueError("need 1..%d levels with matching strides" % _lib.MAX_LEVELS)
+    h = _lib.HeadsT()
+    for i, ((H, W), s) in enumerate(zip(shapes, strides)):
+        h.raw[i] = None
+        h.H[i], h.W[i] = int(H), int(W)
+        h.stride[i] = float(s)
+    h.n_levels = len(shapes)
+    h.B, h.A, h.C = B, A, num_classes
+    h.affine_kind = _lib.AFFINE[kind]
+    h.in_h, h.in_w = _hw_pair(input_size, "input_size")
+    orig, per = _orig(original_size, B, device)
+    h.orig_hw = orig.data_ptr()
+    h.orig_per_image = per
+    h.score_threshold = float(score_threshold)
+    h.iou_threshold = float(iou_threshold)
+    h.nms_mode = _lib.NMS_MODE[nms_mode]
+    h.iou_round = _lib.IOU_ROUND[iou_round]
+    return h, (orig,)
+
+
+def head_conv_hits(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], num_classes: int,
+                   score_threshold: float, row_offset: int, rec: torch.Tensor, rec_count: torch.Tensor) -> bool:
+    """One level of pqdet_head_conv_hits: appends the level's hit records to rec (B, cap, 6+C) / rec_count (B).
+    -> False when the shape is outside the persistent tensor-core kernel (the caller takes the raw-head route)."""
+    x = _req(x, "x")
+    weight = _req(weight.reshape(weight.shape[0], -1), "weight")
+    if bias is not None:
+        bias = _req(bias, "bias")
+    B, Cin, H, W = x.shape
+    ch = 5 + num_classes
+    if weight.shape[0] % ch or weight.shape[1] != Cin:
+        raise ValueError("weight must be (A*(5+C), Cin)")
+    A = weight.shape[0] // ch
+    code = _lib.load().pqdet_head_conv_hits(_ptr(x), _ptr(weight), _ptr(bias), B, Cin, H, W, A, num_classes,
+                                            float(score_threshold), int(row_offset), _ptr(rec), _ptr(rec_count),
+                                            int(rec.shape[1]), _dev(x), _stream(x.device))
+    if code == _lib.PQDET_ERR_UNSUPPORTED:
+        return False
+    _lib.check(code, "pqdet_head_conv_hits")
+    return True
+
+
+def records_nms(heads_t, keep_alive, rec: torch.Tensor, rec_count: torch.Tensor, max_det: int, want_index: bool,
+                capacity: str = "compact"):
+    """The fused kernel's back end on hit records (pqdet_records_nms).  -> det, idx, meta as decode_nms_fused."""
+    device = rec.device
+    B = heads_t.B
+    det, idx, meta = alloc_fused_outputs(B, max_det, want_index, device)
+    counts, ncand, status, work = meta[0:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:]
+    _lib.check(_lib.load().pqdet_records_nms(ctypes.byref(heads_t), _ptr(rec), _ptr(rec_count), int(rec.shape[1]),
+                                             _ptr(det), _ptr(idx), int(max_det), _ptr(counts), _ptr(ncand),
+                                             _ptr(status), _ptr(work), 0, _lib.CAPACITY[capacity], _dev(rec),
+                                             _stream(device)), "pqdet_records_nms")
+    return det, idx, meta

@@ -269,10 +269,16 @@ struct HeadConvWsParams {
   uint32_t magic_w;    // ceil(2^32 / W): cell / W by multiply-high (0 when W == 1)
   float stride;
   int64_t rows_total, row_off;
+  // HITS mode (pqdet_head_conv_hits): instead of the decoded tile the epilogue appends one record per row whose
+  // objectness logit passes the conservative prefilter: [row (int bits), objectness, 4 box, C class raw values]
+  float* rec;          // (B, rec_cap, 6 + C)
+  int32_t* rec_count;  // (B) appended records (may exceed rec_cap: the image then overflowed)
+  int rec_cap;
+  float logit_lo;
 };
 
 // Body of the persistent kernel: this CTA is number `cta` of the `ncta` that share the level described by P.
-template <bool WANT_RAW>
+template <bool WANT_RAW, bool HITS = false>
 __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, const CUtensorMap* tmap_x, const int cta,
                                                   const int ncta) {
   extern __shared__ __align__(1024) unsigned char hsm_ws[];
@@ -416,6 +422,64 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
       if (ti >= P.tiles_per_img) { ti -= P.tiles_per_img; ++b; }
       mbar_wait(&acc_full[buf], (tl >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (HITS) {
+        // Threshold in the epilogue (second half): only the objectness column of every anchor is read
+        // back; a warp fetches the anchor's other 4 + C columns only when one of its 32 cells passes the prefilter,
+        // and only those cells leave a record.  Nothing of size B x N is written.
+        const uint32_t tacc = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16);
+        const int img = t / P.tiles_per_img;                 // (b was already advanced to the next tile above)
+        for (int a = jq; a < P.A; a += P.wq) {
+          const int c0 = a * ch;
+          uint32_t vo;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(vo) : "r"(tacc + (uint32_t)(c0 + 4)) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const float xo = PQ_ADD(__uint_as_float(vo), sbias[c0 + 4]);
+          const bool pass = xo > P.logit_lo;
+          const unsigned pm = __ballot_sync(PQ_FULL, pass);
+          if (pm == 0u) continue;                            // warp-uniform
+          int slot0 = 0;
+          if (lane == 0) slot0 = atomicAdd(P.rec_count + img, __popc(pm));
+          slot0 = __shfl_sync(PQ_FULL, slot0, 0);
+          const int slot = slot0 + __popc(pm & ((1u << lane) - 1u));
+          const bool store = pass && slot < P.rec_cap;
+          float* rc = P.rec + ((size_t)img * P.rec_cap + (store ? slot : 0)) * (size_t)(6 + P.C);
+          uint32_t v4[4];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v4[0]), "=r"(v4[1]), "=r"(v4[2]), "=r"(v4[3]) : "r"(tacc + (uint32_t)c0) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (store) {
+            rc[0] = __int_as_float((int)(P.row_off + (int64_t)cell * P.A + a));
+            rc[1] = xo;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rc[2 + i] = PQ_ADD(__uint_as_float(v4[i]), sbias[c0 + i]);
+          }
+          for (int k = 5; k < ch; k += 8) {                  // class columns, 8 at a time (reads may run past the anchor)
+            if (c0 + k + 8 <= P.buf_cols) {
+              uint32_t v[8];
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                           : "r"(tacc + (uint32_t)(c0 + k)) : "memory");
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              if (store) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (k + i < ch) rc[1 + k + i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + k + i]);
+              }
+            } else {                                           // the last columns of a 256-column accumulator (COCO)
+              for (int i = 0; i < 8 && k + i < ch; ++i) {
+                uint32_t v1;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v1) : "r"(tacc + (uint32_t)(c0 + k + i)) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (store) rc[1 + k + i] = PQ_ADD(__uint_as_float(v1), sbias[c0 + k + i]);
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
       // the bulk store that last used this staging tile must have read it before it is overwritten
       float* tile = tile0 + (P.tile_bufs == 2 ? (int)buf * kHcM * ACH : 0);
       if (etid == 0) {
@@ -524,6 +588,11 @@ template <bool WANT_RAW>
 __global__ void __launch_bounds__(768, 1)
 head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __grid_constant__ CUtensorMap tmap_x) {
   head_conv_ws_body<WANT_RAW>(P, &tmap_x, (int)blockIdx.x, (int)gridDim.x);
+}
+
+__global__ void __launch_bounds__(768, 1)
+head_conv_hits_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __grid_constant__ CUtensorMap tmap_x) {
+  head_conv_ws_body<false, true>(P, &tmap_x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // All levels of the head in one launch: the CTAs are split between the levels in proportion to their estimated cost
@@ -686,6 +755,40 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
 }
 
 }  // namespace
+
+extern "C" int pqdet_head_conv_hits(const float* x, const float* weight, const float* bias, int B, int Cin, int H, int W,
+                                    int A, int C, double score_threshold, int64_t row_offset, float* rec,
+                                    int32_t* rec_count, int rec_cap, int device, void* stream) {
+  using namespace pq;
+  if (B < 0 || Cin < 1 || H < 1 || W < 1 || A < 1 || C < 1 || rec_cap < 1 || row_offset < 0) return PQDET_ERR_INVALID_ARG;
+  if (B == 0) return PQDET_OK;
+  if (!x || !weight || !rec || !rec_count) return PQDET_ERR_INVALID_ARG;
+  if (A * (5 + C) > 256 || B > 65535) return PQDET_ERR_UNSUPPORTED;
+  if (row_offset + (int64_t)H * W * A >= (1ll << 31)) return PQDET_ERR_UNSUPPORTED;
+  PQ_ENTER(device);
+  HeadConvWsParams P;
+  CUtensorMap tmap;
+  size_t smem = 0;
+  int sms = 0;
+  const int rc = plan_head_conv_ws(x, weight, bias, nullptr, nullptr, B, Cin, H, W, A, C, 1.0f, (int64_t)H * W * A, 0,
+                                   device, &P, &tmap, &smem, &sms);
+  if (rc < 0) return rc;
+  if (rc == 0) return PQDET_ERR_UNSUPPORTED;                 // shape outside the persistent kernel: caller falls back
+  P.rec = rec; P.rec_count = rec_count; P.rec_cap = rec_cap;
+  P.row_off = row_offset;
+  P.logit_lo = logit_lo_for((float)score_threshold);
+  // three anchors' objectness columns per quadrant: more than A epilogue warps per quadrant would idle
+  if (P.wq > A) P.wq = A;
+  const int grid = P.ntiles < sms ? P.ntiles : sms;
+  static int smem_set[64];
+  if (device < 0 || device >= 64 || (int)smem > smem_set[device]) {
+    PQ_CUDA(cudaFuncSetAttribute(head_conv_hits_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (device >= 0 && device < 64) smem_set[device] = (int)smem;
+  }
+  head_conv_hits_ws_kernel<<<grid, (4 + 4 * P.wq) * 32, smem, (cudaStream_t)stream>>>(P, tmap);
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
 
 extern "C" int pqdet_head_conv_decode(const float* x, const float* weight, const float* bias, float* out_decoded,
                                       float* out_raw, int B, int Cin, int H, int W, int A, int C, float stride,

@@ -60,6 +60,11 @@ struct HeadsDev {
   const float* bboxes;
   int bb_row;
   uint32_t magic_n4;   // ceil(2^32 / (bb_row / 4)): word index -> row by multiply-high
+  // SRC == 2 (hit records written by the head convolution's epilogue, pqdet_head_conv_hits): per image up to
+  // rec_cap records [row (int bits), objectness logit, 4 box, C class raw values], in arrival order
+  const float* rec;
+  const int32_t* rec_count;
+  int rec_cap;
 };
 
 struct DetOut {
@@ -468,7 +473,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
   uint32_t* hitw = reinterpret_cast<uint32_t*>(smem_raw + sizeof(Smem));
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int A = P.A, C = P.C, ch = P.ch;
-  const int WG = SRC ? 1 : 4 * A;          // ballot words per group (128 cells x A anchors | 32 rows)
+  const int WG = (SRC == 1) ? 1 : 4 * A;   // ballot words per group (128 cells x A anchors | 32 rows)
   const int W_tot = P.G_tot * WG;
   uint32_t* gbase = hitw + W_tot;
   uint32_t* utab = gbase + P.G_tot;
@@ -487,11 +492,13 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     for (int i = tid; i < 128; i += NT) { S.cls_cnt[i] = 0; S.cls_fill[i] = 0; }
     if (tid == 0) S.nrec = 0;
     __syncthreads();
-    const float* img = SRC ? P.bboxes + (size_t)b * P.N * P.bb_row : nullptr;
+    const float* img = (SRC == 1) ? P.bboxes + (size_t)b * P.N * P.bb_row : nullptr;
 
     // ---- 1. scan: one ballot word per (level, group, anchor, sub-cell) | per 32 rows ---------------
     if (SRC == 0) {
       scan_objectness<NW, CAPH>(P, S.lvbase, utab, lane, warp, hitw, S.keys, &S.nrec);
+    } else if (SRC == 2) {
+      // the scan already happened in the head convolution's epilogue: the image's hit records sit in global memory
     } else {
       // a row is a hit iff any of its C scores exceeds thr (tools.py:551); 128-bit loads when rows are aligned
       const bool vec = ((P.bb_row & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.bboxes) & 15) == 0);
@@ -552,7 +559,9 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     PQ_PHASE(1);
 
     // ---- 2. deterministic slots: exclusive prefix of the per-group hit counts --------------------
-    if (warp == 0) {
+    if (SRC == 2) {
+      if (tid == 0) { S.H = P.rec_count[b]; S.M = 0; S.K = 0; S.maxcnt = 0; S.next_class = 0; }
+    } else if (warp == 0) {
       int running = 0;
       for (int g0 = 0; g0 < P.G_tot; g0 += 32) {
         const int g = g0 + lane;
@@ -568,12 +577,33 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     __syncthreads();
     PQ_PHASE(2);
     const int H = S.H;
-    if (H > CAPH) {
+    if (H > CAPH || (SRC == 2 && H > P.rec_cap)) {
       if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = -1; }
       __syncthreads();
       continue;
     }
-    if (SRC == 1) {
+    if (SRC == 2) {
+      // Records arrive in the order the epilogue warps appended them; the hit slot of a row is its rank among the
+      // image's rows (row order = nonzero() order, which is what breaks score ties).  order[] (free until step 5)
+      // keeps slot -> record for the fetch below.
+      const float* recs = P.rec + (size_t)b * P.rec_cap * (size_t)(6 + C);
+      uint32_t* srow = reinterpret_cast<uint32_t*>(S.keys);
+      for (int i = tid; i < H; i += NT) srow[i] = (uint32_t)__float_as_int(recs[(size_t)i * (6 + C)]);
+      __syncthreads();
+      for (int i = tid; i < H; i += NT) {
+        const uint32_t row = srow[i];
+        int rank = 0;
+        for (int j = 0; j < H; ++j) rank += (srow[j] < row) ? 1 : 0;
+        const int l = level_of_row(P, (int)row);
+        const int il = (int)row - P.lv[l].row_off;
+        const int cell = il / A;
+        S.hmeta[rank] = pack_meta(l, il - cell * A, cell);
+        const float conf = sigmoidf_(recs[(size_t)i * (6 + C) + 1]);
+        S.hconf[rank] = (conf > P.thr_f) ? conf : 0.0f;
+        S.hhas[rank] = 0;
+        S.order[rank] = (uint16_t)i;
+      }
+    } else if (SRC == 1) {
       for (int w = tid; w < W_tot; w += NT) {    // word w = rows 32w .. 32w+31, already in row order
         unsigned word = hitw[w];
         int h = gbase[w];
@@ -686,12 +716,22 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
             const uint32_t meta = S.hmeta[h];
             const int l = meta >> 30, a = (meta >> 27) & 7, cell = meta & 0x7ffffff;
             const int HW = P.lv[l].HW;
-            // channel 0 of this row: the anchor's objectness plane minus four planes
-            const float* base = S.lvbase[l] + ((size_t)a * ch - 4) * HW + cell;
+            if (SRC == 2) {
+              // the row's raw values from its hit record: [row, objectness, 4 box, C class]
+              const float* rr = P.rec + ((size_t)b * P.rec_cap + S.order[h]) * (size_t)(6 + C) + 2;
 #pragma unroll
-            for (int u = 0; u < V; ++u) {
-              const int k = klo[q] + u;
-              if (k < CK) v[q][u] = ldg_stream(base + (size_t)((k < 4) ? k : k + 1) * HW);
+              for (int u = 0; u < V; ++u) {
+                const int k = klo[q] + u;
+                if (k < CK) v[q][u] = __ldg(rr + k);
+              }
+            } else {
+              // channel 0 of this row: the anchor's objectness plane minus four planes
+              const float* base = S.lvbase[l] + ((size_t)a * ch - 4) * HW + cell;
+#pragma unroll
+              for (int u = 0; u < V; ++u) {
+                const int k = klo[q] + u;
+                if (k < CK) v[q][u] = ldg_stream(base + (size_t)((k < 4) ? k : k + 1) * HW);
+              }
             }
           }
         }
@@ -897,7 +937,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       const int h = low >> 7, c = low & 127;
       const uint32_t meta = S.hmeta[h];
       int64_t row = meta;
-      if (SRC == 0) {
+      if (SRC != 1) {
         const LevelDev& L = P.lv[meta >> 30];
         row = L.row_off + (int64_t)(meta & 0x7ffffff) * A + ((meta >> 27) & 7);
       }
@@ -1479,15 +1519,7 @@ static int fill_heads(const pqdet_heads_t* h, HeadsDev* P) {
   P->kind = h->affine_kind; P->in_h = h->in_h; P->in_w = h->in_w;
   P->orig = h->orig_hw; P->orig_per_image = h->orig_per_image;
   P->thr_f = (float)h->score_threshold;
-  // conf > thr needs sigmoid(x) > thr; x <= logit(thr) - margin can never pass (the margin is
-  // ~1e3 times the worst-case error of the fp32 sigmoid).  thr <= 0 or >= 1: no prefilter / nothing passes.
-  const double t = (double)P->thr_f;
-  if (!(t > 0.0)) P->logit_lo = -INFINITY;
-  else if (t >= 1.0) P->logit_lo = INFINITY;
-  else {
-    const double lg = log(t / (1.0 - t));
-    P->logit_lo = (float)(lg - 1e-3 * (1.0 + fabs(lg)));
-  }
+  P->logit_lo = logit_lo_for(P->thr_f);
   P->iou_f = (float)h->iou_threshold;
   P->iou_d = h->iou_threshold;
   P->nms_mode = h->nms_mode;
@@ -1503,13 +1535,13 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
                         int iou_round, int src, int cap_class, int device, cudaStream_t st) {
   if (cap_class != PQDET_CAP_COMPACT && cap_class != PQDET_CAP_LARGE) return PQDET_ERR_INVALID_ARG;
   if (!(P.thr_f >= 0.0f)) return PQDET_ERR_UNSUPPORTED;     // ~score keys order non-negative floats only
-  const int WG = src ? 1 : 4 * P.A;
+  const int WG = (src == 1) ? 1 : 4 * P.A;
   const size_t lists = cap_class == PQDET_CAP_COMPACT
                            ? sizeof(FusedSmemT<FusedCfg<0>::kCapH, FusedCfg<0>::kCapM>)
                            : sizeof(FusedSmemT<FusedCfg<1>::kCapH, FusedCfg<1>::kCapM>);
   const int threads = cap_class == PQDET_CAP_COMPACT ? FusedCfg<0>::kThreads : FusedCfg<1>::kThreads;
   // hitw + gbase + (heads source) the scan's unit table
-  const size_t smem = lists + ((size_t)P.G_tot * (WG + 1) + (src ? 0 : (size_t)P.G_tot * P.A)) * sizeof(uint32_t);
+  const size_t smem = lists + ((size_t)P.G_tot * (WG + 1) + (src == 0 ? (size_t)P.G_tot * P.A : 0)) * sizeof(uint32_t);
   if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
   // work_counter = int32[2].  counter_armed != 0: the caller guarantees both words are zero (they are after
   // every completed call: the kernel re-arms them), so no memset is enqueued.
@@ -1517,7 +1549,7 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
   auto launch = [&](auto kern, int which) -> int {
     // Launch geometry is a pure function of (device, kernel, smem); remember the last one per device as a
     // single 64-bit word (smem << 32 | grid) so concurrent callers can only ever see a consistent pair.
-    static std::atomic<uint64_t> cache[8][16];
+    static std::atomic<uint64_t> cache[12][16];
     int per_sm_grid = 0;
     if (device < 16) {
       const uint64_t c = cache[which][device].load(std::memory_order_relaxed);
@@ -1539,7 +1571,7 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
     return PQDET_OK;
   };
   const int r = iou_round == PQDET_IOU_TV_CUDA ? 0 : 1;
-  switch (cap_class * 4 + src * 2 + r) {
+  switch (src == 2 ? 8 + cap_class * 4 + r : cap_class * 4 + src * 2 + r) {
     case 0: return launch(decode_nms_fused_kernel<0, 0, 0>, 0);
     case 1: return launch(decode_nms_fused_kernel<1, 0, 0>, 1);
     case 2: return launch(decode_nms_fused_kernel<0, 1, 0>, 2);
@@ -1547,7 +1579,11 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
     case 4: return launch(decode_nms_fused_kernel<0, 0, 1>, 4);
     case 5: return launch(decode_nms_fused_kernel<1, 0, 1>, 5);
     case 6: return launch(decode_nms_fused_kernel<0, 1, 1>, 6);
-    default: return launch(decode_nms_fused_kernel<1, 1, 1>, 7);
+    case 7: return launch(decode_nms_fused_kernel<1, 1, 1>, 7);
+    case 8: return launch(decode_nms_fused_kernel<0, 2, 0>, 8);      // src 2: cap_class * 4 + 4 + r
+    case 9: return launch(decode_nms_fused_kernel<1, 2, 0>, 9);
+    case 12: return launch(decode_nms_fused_kernel<0, 2, 1>, 10);
+    default: return launch(decode_nms_fused_kernel<1, 2, 1>, 11);
   }
 }
 
@@ -1592,6 +1628,28 @@ static int device_alias(T** p, int allow_null) {
   return PQDET_ERR_INVALID_ARG;          // pageable host memory: the device cannot read it
 }
 }  // namespace pq
+
+extern "C" int pqdet_records_nms(const pqdet_heads_t* heads, const float* rec, const int32_t* rec_count, int rec_cap,
+                                 float* det, int32_t* det_idx, int max_det, int32_t* counts, int32_t* ncand,
+                                 int32_t* status, int32_t* work_counter, int counter_armed, int capacity_class,
+                                 int device, void* stream) {
+  using namespace pq;
+  if (!heads) return PQDET_ERR_INVALID_ARG;
+  pqdet_heads_t h = *heads;
+  for (int l = 0; l < PQDET_MAX_LEVELS; ++l) h.raw[l] = rec;     // geometry only: the raw heads were never written
+  HeadsDev P;
+  memset(&P, 0, sizeof(P));
+  int rc = fill_heads(&h, &P);
+  if (rc != PQDET_OK) return rc;
+  if (!rec || !rec_count || rec_cap < 1) return PQDET_ERR_INVALID_ARG;
+  if (!det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
+  if (P.B == 0) return PQDET_OK;
+  for (int l = 0; l < PQDET_MAX_LEVELS; ++l) P.lv[l].raw = nullptr;
+  P.rec = rec; P.rec_count = rec_count; P.rec_cap = rec_cap;
+  PQ_ENTER(device);
+  DetOut O{det, det_idx, max_det, counts, ncand, status};
+  return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 2, capacity_class, device, (cudaStream_t)stream);
+}
 
 extern "C" int pqdet_decode_nms_host(const pqdet_heads_t* heads, float* det, int32_t* det_idx, int max_det,
                                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,

@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/pqdet_b200.h"
@@ -47,6 +48,16 @@ struct DeviceScope {
   do {                                                                     \
     if ((call) != cudaSuccess) return PQDET_ERR_CUDA;                      \
   } while (0)
+
+// conf > thr needs sigmoid(x) > thr; x <= logit(thr) - margin can never pass (the margin is ~1e3 times the
+// worst-case error of the fp32 sigmoid).  thr <= 0: no prefilter; thr >= 1: nothing passes.
+static inline float logit_lo_for(float thr_f) {
+  const double t = (double)thr_f;
+  if (!(t > 0.0)) return -INFINITY;
+  if (t >= 1.0) return INFINITY;
+  const double lg = log(t / (1.0 - t));
+  return (float)(lg - 1e-3 * (1.0 + fabs(lg)));
+}
 
 namespace pq {
 

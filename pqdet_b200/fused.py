@@ -187,6 +187,65 @@ def decode_nms(heads: Sequence[torch.Tensor], strides: Sequence[int], num_classe
     return res
 
 
+def features_nms(features: Sequence[torch.Tensor], weights: Sequence[torch.Tensor], biases, strides: Sequence[int],
+                 num_classes: int, input_size, batch_original_size, dataset: str = "voc",
+                 score_threshold: float = 0.1, iou_threshold: float = 0.45, return_index: bool = False,
+                 nms_mode: Optional[str] = None, iou_round: Optional[str] = None, capacity: str = "compact",
+                 hints: Optional[StrategyHints] = None) -> Detections:
+    """The eval path starting one layer earlier: features[l] = the INPUT of level l's 1x1 head
+    convolution, weights / biases = its parameters -> detections, identical to decode_nms on the raw heads that
+    convolution produces.  The convolution runs on the tensor cores (TF32, like PyTorch's default) and its epilogue
+    keeps only the rows whose objectness can pass the threshold (a few hundred of the 16 128 rows of a VOC image), so
+    neither the raw heads nor the decoded prediction are ever written: the bound is reading the features.
+    Levels whose shape the persistent kernel cannot take (H*W not a multiple of 128) make the whole call take the
+    raw-head route: head convolution with the raw output materialised, then decode_nms."""
+    m, r = config.nms_modes()
+    nms_mode, iou_round = nms_mode or m, iou_round or r
+    C = num_classes
+    B = features[0].shape[0]
+    dev = features[0].device
+    biases = list(biases) if biases is not None else [None] * len(features)
+    A = weights[0].shape[0] // (5 + C)
+
+    def raw_route():
+        raws = [_ops.head_conv_decode(f, w, bi, C, float(s), want_raw=True, want_decoded=False)
+                for f, w, bi, s in zip(features, weights, biases, strides)]
+        return decode_nms(raws, strides, C, input_size, batch_original_size, dataset, score_threshold, iou_threshold,
+                          return_index, True, nms_mode, iou_round, hints=hints)
+    if B == 0 or score_threshold < 0:
+        return raw_route()
+    cap_h = _lib.CAPACITY_LIMITS[capacity][0]
+    rec = torch.empty((B, cap_h, 6 + C), dtype=torch.float32, device=dev)
+    rec_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    row_off = 0
+    for f, w, bi in zip(features, weights, biases):
+        if not _ops.head_conv_hits(f, w, bi, C, score_threshold, row_off, rec, rec_count):
+            return raw_route()
+        row_off += f.shape[2] * f.shape[3] * A
+    h, keep = _ops.make_geometry(B, A, [tuple(f.shape[2:]) for f in features], strides, C, input_size,
+                                 batch_original_size, dataset, score_threshold, iou_threshold, nms_mode, iou_round, dev)
+    det, idx, meta = _ops.records_nms(h, keep, rec, rec_count, FUSED_MAX_DET, return_index, capacity)
+    res = Detections(det, idx, meta, B)
+    res.capacity = capacity
+    over = torch.nonzero(res.host_meta()[2] & _lib.ST_CAND_OVERFLOW).reshape(-1)
+    if over.numel():
+        # dense images: materialise the raw heads of just those and resolve them through the general path
+        sub = over.to(dev)
+        raws = [_ops.head_conv_decode(f[sub].contiguous(), w, bi, C, float(s), want_raw=True, want_decoded=False)
+                for f, w, bi, s in zip(features, weights, biases, strides)]
+        orig = batch_original_size if isinstance(batch_original_size, torch.Tensor) else torch.tensor(batch_original_size)
+        orig = orig.to(device=dev, dtype=torch.float32)
+        o_sub = orig[sub] if orig.dim() == 2 else orig
+        d = decode_nms(raws, strides, C, input_size, o_sub, dataset, score_threshold, iou_threshold, return_index,
+                       True, nms_mode, iou_round, strategy="general")
+        hm = res.host_meta()
+        ghm = d.host_meta()
+        res._spill_batch = (d.det, d.idx, ghm, {int(b): i for i, b in enumerate(over.tolist())})
+        for i, b in enumerate(over.tolist()):
+            hm[0, b], hm[1, b], hm[2, b] = ghm[0, i], ghm[1, i], 0
+    return res
+
+
 class HostDetections:
     """Result of decode_nms_host: everything already sits in pinned host memory (numpy views, no copies)."""
 

@@ -446,3 +446,62 @@ def test_recover_small_class_counts(C):
     for kind in ("voc", "visdrone"):
         got = base_sample.RECOVER_BBOXES_REGISTER[kind](cuda(pred), (256, 256), cuda(orig)).cpu().numpy()
         assert np.array_equal(got, po.recover(pred, (256, 256), orig, kind)), (C, kind)
+
+
+@pytest.mark.parametrize("C,size,B,cins,thr", [(20, 512, 6, (352, 176, 80), 0.1), (80, 512, 3, (64, 48, 32), 0.05),
+                                               (3, 256, 5, (40, 24, 16), 0.3)])
+def test_features_to_detections_equals_raw_head_route(C, size, B, cins, thr):
+    """SURVEY 8f-2, second half: head convolution whose epilogue thresholds + the fused kernel's back end on the hit
+    records (pqdet_head_conv_hits -> pqdet_records_nms) against the raw-head route on the SAME convolution's raw
+    output (pqdet_head_conv_decode(out_raw) -> pqdet_decode_nms): identical rows and indices, and no launch that
+    writes a B x N tensor."""
+    from pqdet_b200 import _ops, fused, synth
+    torch.manual_seed(C + size)
+    strides = synth.FPN_STRIDES
+    ch = 3 * (5 + C)
+    feats = [torch.randn((B, cin, size // s, size // s), device="cuda") for cin, s in zip(cins, strides)]
+    ws = [torch.randn((ch, cin), device="cuda") * (1.5 / cin ** 0.5) for cin in cins]
+    bs = [torch.randn((ch,), device="cuda") * 0.3 for _ in cins]
+    for b_ in bs:
+        b_[4::(5 + C)] -= 3.5                                   # objectness logits: a few percent of the rows pass
+    orig = torch.tensor([[375., 500.], [333., 500.], [float(size)] * 2, [500., 281.], [480., 640.], [300., 400.]])[:B].cuda()
+    raws = [_ops.head_conv_decode(f, w, b_, C, float(s), want_raw=True, want_decoded=False)
+            for f, w, b_, s in zip(feats, ws, bs, strides)]
+    want = fused.decode_nms(raws, strides, C, (size, size), orig, "voc", thr, 0.45, return_index=True)
+    got = fused.features_nms(feats, ws, bs, strides, C, (size, size), orig, "voc", thr, 0.45, return_index=True)
+    assert int(want.counts.sum()) > 0
+    assert torch.equal(got.host_meta()[0], want.host_meta()[0]) and torch.equal(got.host_meta()[1], want.host_meta()[1])
+    for b in range(B):
+        assert torch.equal(got[b], want[b]), b
+        assert torch.equal(got.indices(b), want.indices(b)), b
+    assert len(got._spill) == len(want._spill)
+
+
+def test_features_to_detections_falls_back_on_unaligned_levels_and_dense_images():
+    from pqdet_b200 import _ops, fused, synth
+    torch.manual_seed(5)
+    C, size, B = 4, 608, 2                                      # 19x19 / 38x38 / 76x76: outside the persistent kernel
+    strides = synth.FPN_STRIDES
+    ch = 3 * (5 + C)
+    cins = (32, 24, 16)
+    feats = [torch.randn((B, cin, size // s, size // s), device="cuda") for cin, s in zip(cins, strides)]
+    ws = [torch.randn((ch, cin), device="cuda") * 0.2 for cin in cins]
+    bs = [torch.randn((ch,), device="cuda") * 0.3 - 1.0 for _ in cins]
+    orig = torch.tensor([float(size), float(size)]).cuda()
+    raws = [_ops.head_conv_decode(f, w, b_, C, float(s), want_raw=True, want_decoded=False)
+            for f, w, b_, s in zip(feats, ws, bs, strides)]
+    want = fused.decode_nms(raws, strides, C, (size, size), orig, "coco", 0.1, 0.45)
+    got = fused.features_nms(feats, ws, bs, strides, C, (size, size), orig, "coco", 0.1, 0.45)
+    for b in range(B):
+        assert torch.equal(got[b], want[b])
+    # aligned levels, but every row is a hit: the records overflow and the images are resolved through the general path
+    size = 256
+    feats = [torch.randn((B, cin, size // s, size // s), device="cuda") for cin, s in zip(cins, strides)]
+    bs2 = [b_ + 6.0 for b_ in bs]
+    raws = [_ops.head_conv_decode(f, w, b_, C, float(s), want_raw=True, want_decoded=False)
+            for f, w, b_, s in zip(feats, ws, bs2, strides)]
+    want = fused.decode_nms(raws, strides, C, (size, size), orig, "coco", 0.1, 0.45)
+    got = fused.features_nms(feats, ws, bs2, strides, C, (size, size), orig, "coco", 0.1, 0.45)
+    assert len(got._spill) == B
+    for b in range(B):
+        assert torch.equal(got[b], want[b])
