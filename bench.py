@@ -628,6 +628,49 @@ def bench_other_configs(device, peak):
                                         "fused_gbs": (xb + ob) / (t_fused_q * 1e-3) / 1e9,
                                         "frac_of_hbm_peak": (xb + ob) / (t_fused_q * 1e-3) / 1e9 / measured_peak()[0]}}
             del feats
+        # features -> detections (second half): the same convolutions with the thresholding epilogue +
+        # the fused kernel's back end on the hit records, against the raw-head route (convolution with the raw head
+        # materialised, then the fused decode+NMS kernel) and the materialise-everything route
+        try:
+            from pqdet_b200 import fused as pqfused, base_sample as pqbs, tools as pqtools
+            nB = 256
+            ws1 = [torch.randn((75, c), device=device) / c ** 0.5 for c in cins]           # unit-variance logits
+            bs1 = [torch.randn((75,), device=device) * 0.1 for _ in cins]
+            for b_ in bs1:
+                b_[4::25] -= 4.6                                                          # ~0.8 % of the rows pass conf > 0.1
+                b_[5:25] -= 2.0; b_[30:50] -= 2.0; b_[55:75] -= 2.0
+            feats = [torch.randn((nB, c, SIZE // s, SIZE // s), device=device) for c, s in zip(cins, STRIDES)]
+            origF = torch.tensor([float(SIZE), float(SIZE)], device=device)
+            with torch.no_grad():
+                def fused_route():
+                    return pqfused.features_nms(feats, ws1, bs1, STRIDES, C_VOC, (SIZE, SIZE), origF, "voc", THR, IOU)
+                def raw_route():
+                    raws = [_ops.head_conv_decode(f, w, b_, C_VOC, float(s_), want_raw=True, want_decoded=False)
+                            for f, w, b_, s_ in zip(feats, ws1, bs1, STRIDES)]
+                    return pqfused.decode_nms(raws, STRIDES, C_VOC, (SIZE, SIZE), origF, "voc", THR, IOU)
+                def stock_route():
+                    rec = pqbs.recover_bboxes_prediction_voc(
+                        headF([torch.nn.functional.conv2d(f, w.view(75, -1, 1, 1), b_) for f, w, b_ in zip(feats, ws1, bs1)]),
+                        (SIZE, SIZE), origF)
+                    return pqtools.batched_torch_nms(rec, THR, IOU)
+                d1 = fused_route(); d2 = raw_route(); stock_route()
+                same = all(torch.equal(d1[b], d2[b]) for b in range(0, nB, 17))
+                t1 = float(np.median([time_steps(fused_route, 1)[0] for _ in range(7)]))
+                t2 = float(np.median([time_steps(raw_route, 1)[0] for _ in range(7)]))
+                t3 = float(np.median([time_steps(stock_route, 1)[0] for _ in range(5)]))
+            xb = sum(f.numel() for f in feats) * 4
+            entry["features_to_detections_bs256"] = {
+                "what": "conv inputs -> detections incl. the host read of counts/status: pqdet_head_conv_hits x3 + "
+                        "pqdet_records_nms; raw_head_route = pqdet_head_conv_decode(out_raw) x3 + pqdet_decode_nms; "
+                        "materialising_route = cuDNN conv x3 + one-launch decode + recover + batched torch_nms",
+                "ms": t1, "images_per_s": nB / (t1 * 1e-3), "raw_head_route_ms": t2, "materialising_route_ms": t3,
+                "identical_rows_to_raw_head_route": bool(same),
+                "kept_per_image": float(d1.counts.float().mean()), "candidates_per_image": float(d1.host_meta()[1].float().mean()),
+                "feature_bytes": xb, "features_read_gbs": xb / (t1 * 1e-3) / 1e9,
+                "frac_of_hbm_peak": xb / (t1 * 1e-3) / 1e9 / measured_peak()[0]}
+            del feats
+        except Exception as e:
+            entry["features_to_detections_bs256"] = {"error": repr(e)}
         out["head_conv_decode"] = entry
     except Exception as e:
         out["head_conv_decode"] = {"error": repr(e)}

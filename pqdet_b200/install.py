@@ -284,12 +284,22 @@ def detect_batch(self, batch_img, batch_img_shape):
     inner = model.module if isinstance(model, nn.DataParallel) and len(model.device_ids) <= 1 else model
     kind = _dataset_kind(self._recover_bboxes)
     if getattr(type(inner), '_pq_fused_forward', False) and batch_img.is_cuda and kind and not inner.training:
-        with torch.no_grad():
-            raws, strides, C = raw_heads(inner, batch_img)
         hints = self.__dict__.setdefault('_pq_hints', fused.StrategyHints())
-        dets = fused.decode_nms(raws, strides, C, tuple(float(v) for v in self._input_size),
-                                batch_img_shape.to(batch_img.device), kind, self._score_threshold,
-                                self._iou_threshold, hints=hints)
+        size = tuple(float(v) for v in self._input_size)
+        shapes = batch_img_shape.to(batch_img.device)
+        with torch.no_grad():
+            yolos, outs = type(inner)._pq_collect(inner, batch_img)
+            convs = [getattr(o, '_pq_pending_conv', None) for o in outs]
+            strides, C = [l.opt['stride'] for l in yolos], yolos[0].opt['classes']
+            if all(c is not None for c in convs):
+                # fuse_head_convs is in place: the head convolutions run inside the detection kernels too
+                # (features -> detections, nothing of size B x N is written)
+                dets = fused.features_nms(outs, [c.weight for c in convs], [c.bias for c in convs], strides, C, size,
+                                          shapes, kind, self._score_threshold, self._iou_threshold, hints=hints)
+            else:
+                raws = [o if c is None else torch.nn.functional.conv2d(o, c.weight, c.bias) for o, c in zip(outs, convs)]
+                dets = fused.decode_nms(raws, strides, C, size, shapes, kind, self._score_threshold,
+                                        self._iou_threshold, hints=hints)
         return dets.to_numpy_list()
     batch_pred_bbox = self.predict(batch_img)
     device = batch_pred_bbox.device

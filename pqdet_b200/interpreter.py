@@ -226,6 +226,17 @@ class DetectionHead(nn.Module):
             off += r
         return out
 
+    def detect_from_features(self, features: Sequence[torch.Tensor], weights: Sequence[torch.Tensor], biases,
+                             input_size, batch_original_size, dataset: str = "voc", score_threshold: float = 0.1,
+                             iou_threshold: float = 0.45, **kw):
+        """The whole eval post-process from the inputs of the head convolutions: convolution on the
+        tensor cores whose epilogue thresholds, then decode + recover + class-aware NMS on the surviving rows
+        (fused.features_nms).  -> fused.Detections, identical to fused.decode_nms on the raw heads."""
+        from . import fused
+        return fused.features_nms(features, weights, biases, [l.opt['stride'] for l in self.layers],
+                                  self.layers[0].opt['classes'], input_size, batch_original_size, dataset,
+                                  score_threshold, iou_threshold, **kw)
+
     def loss_and_grad(self, heads: Sequence[torch.Tensor], target):
         """The training branch without autograd glue: ONE kernel launch gives the loss dict of forward(heads,
         target) and d loss.mean() / d head for every level (the kernel always computes both).  A trainer continues

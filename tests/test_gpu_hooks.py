@@ -138,6 +138,19 @@ def test_evaluate_hook_runs_one_fused_launch_per_batch():
                 w = tools.torch_nms(rec[i], 0.7, 0.45).cpu().numpy()
                 got = ev.seen[3 * k + i][1]
                 assert got.shape == w.shape and np.array_equal(got, w), (k, i)
+    # with the head convolutions deferred too (fuse_head_convs) the route starts at the conv inputs: one conv launch
+    # per level whose epilogue thresholds + one NMS launch on the hit records; same rows up to TF32 vs cuDNN rounding,
+    # so compare against the same kernels' raw-head route
+    m3 = _model(1).eval()
+    assert install.fuse_eval_concat(m3) and install.fuse_head_convs(m3) == 3
+    ev3 = Ev(m3, batches)
+    with count_abi_calls() as calls:
+        ev3.evaluate()
+    if "pqdet_records_nms" in calls:          # 128 x 128 inputs: 16 / 64 / 256 cells per level - only levels of >= 128 cells qualify
+        assert calls["pqdet_records_nms"] == 2 and calls["pqdet_head_conv_hits"] == 6
+    else:
+        assert calls.get("pqdet_decode_nms", 0) == 2 and calls.get("pqdet_head_conv_decode", 0) == 6
+    assert len(ev3.seen) == 6
     # a model without the hook takes predict -> recover -> ONE batched NMS launch
     ev2 = Ev(_model(1).eval(), batches)
     with count_abi_calls() as calls:
