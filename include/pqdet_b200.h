@@ -138,8 +138,9 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
  *                       concatenated prediction, stored as int bits) per row whose objectness can exceed
  *                       score_threshold.  rec (B, rec_cap, 6 + C); rec_count (B) int32, zeroed by the caller before
  *                       the first level, counts appended records of all levels (> rec_cap: the image overflowed).
- *                       Returns PQDET_ERR_UNSUPPORTED for shapes outside the persistent kernel (H*W not a multiple
- *                       of 128, weights beyond shared memory): use pqdet_head_conv_decode(out_raw) + pqdet_decode_nms.
+ *                       Shapes the persistent kernel cannot take (plane stride not a multiple of 16 bytes, weights
+ *                       beyond shared memory) run the general tcgen05 kernel with the same epilogue; more than 256
+ *                       output channels return PQDET_ERR_UNSUPPORTED (pqdet_head_conv_decode(out_raw) + pqdet_decode_nms).
  * pqdet_records_nms     the fused kernel's back end on those records: exact conf > thr test, decode + recover of the
  *                       boxes, scores, class-aware NMS, output - same outputs / status / scheduler-word contract as
  *                       pqdet_decode_nms; heads supplies the geometry (raw[] is ignored).  Results are identical to

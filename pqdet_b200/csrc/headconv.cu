@@ -43,6 +43,11 @@ struct HeadConvParams {
   int tmem_cols;       // power of two >= max(N, 32)
   float stride;
   int64_t rows_total, row_off;
+  // HITS mode (see HeadConvWsParams)
+  float* rec;
+  int32_t* rec_count;
+  int rec_cap;
+  float logit_lo;
 };
 
 __device__ __forceinline__ uint64_t hc_smem_desc(uint32_t smem_addr, uint32_t lbo_units, uint32_t sbo_units) {
@@ -66,6 +71,62 @@ __device__ __forceinline__ void hc_mma_tf32(uint32_t d_tmem, uint32_t a_lo, uint
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// The thresholding epilogue shared by both kernels (pqdet_head_conv_hits): for anchor `a` of this warp's 32 cells read
+// back only the objectness column, and - only when one of the cells passes the logit-space prefilter - the anchor's
+// 4 box + C class columns; the passing cells append a record [row, objectness, 4 box, C class raw values].
+// tacc = TMEM address of the warp's lane quadrant, column 0; col_limit = allocated accumulator columns.
+template <typename BiasFn>
+__device__ __forceinline__ void hc_emit_hits(uint32_t tacc, int a, int ch, int C, int col_limit, BiasFn bias_at,
+                                             bool in_level, int lane, int64_t row, int img, float* rec,
+                                             int32_t* rec_count, int rec_cap, float logit_lo) {
+  const int c0 = a * ch;
+  uint32_t vo;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(vo) : "r"(tacc + (uint32_t)(c0 + 4)) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const float xo = PQ_ADD(__uint_as_float(vo), bias_at(c0 + 4));
+  const bool pass = in_level && xo > logit_lo;
+  const unsigned pm = __ballot_sync(PQ_FULL, pass);
+  if (pm == 0u) return;                                      // warp-uniform
+  int slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(rec_count + img, __popc(pm));
+  slot0 = __shfl_sync(PQ_FULL, slot0, 0);
+  const int slot = slot0 + __popc(pm & ((1u << lane) - 1u));
+  const bool store = pass && slot < rec_cap;
+  float* rc = rec + ((size_t)img * rec_cap + (store ? slot : 0)) * (size_t)(6 + C);
+  uint32_t v4[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v4[0]), "=r"(v4[1]), "=r"(v4[2]), "=r"(v4[3]) : "r"(tacc + (uint32_t)c0) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (store) {
+    rc[0] = __int_as_float((int)row);
+    rc[1] = xo;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rc[2 + i] = PQ_ADD(__uint_as_float(v4[i]), bias_at(c0 + i));
+  }
+  for (int k = 5; k < ch; k += 8) {                          // class columns, 8 at a time (reads may run past the anchor)
+    if (c0 + k + 8 <= col_limit) {
+      uint32_t v[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(tacc + (uint32_t)(c0 + k)) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (store) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (k + i < ch) rc[1 + k + i] = PQ_ADD(__uint_as_float(v[i]), bias_at(c0 + k + i));
+      }
+    } else {                                                 // the last columns of a 256-column accumulator (COCO)
+      for (int i = 0; i < 8 && k + i < ch; ++i) {
+        uint32_t v1;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v1) : "r"(tacc + (uint32_t)(c0 + k + i)) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (store) rc[1 + k + i] = PQ_ADD(__uint_as_float(v1), bias_at(c0 + k + i));
+      }
+    }
+  }
+}
+
+template <bool HITS>
 __global__ void __launch_bounds__(kHcThreads)
 head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
   extern __shared__ __align__(128) unsigned char hsm[];
@@ -182,7 +243,14 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
   // ---- epilogue: accumulator row = cell, column = output channel; warps w and w+4 share TMEM lane quadrant
   // w%4 and split the columns ------------------------------------------------------------------------------
   const int ST = ACH | 1;
-  {
+  if (HITS) {
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int a = half; a < P.A; a += 2)
+      hc_emit_hits(tacc, a, ch, P.C, P.tmem_cols, [&](int c) { return P.bias ? __ldg(P.bias + c) : 0.0f; }, r < ncell,
+                   lane, P.row_off + (int64_t)(cell0 + r) * P.A + a, b, P.rec, P.rec_count, P.rec_cap, P.logit_lo);
+  } else {
     const int q = warp & 3, half = warp >> 2;
     const int r = q * 32 + lane;                          // TMEM lane == row of the tile
     const int cell = cell0 + r;
@@ -263,6 +331,7 @@ struct HeadConvWsParams {
   int stages;
   int wq;              // epilogue warps per TMEM lane quadrant
   int tile_bufs;       // 1 or 2 staging tiles for the output
+  int all_bulk;        // every output tile is full and 16-byte aligned: all of them leave as bulk stores
   int units;           // 1: anchor-aligned work units in the epilogue (needs ACH + 7 <= buf_cols), 0: 8-column blocks
   int buf_cols;        // TMEM column stride between the two accumulators
   int tiles_per_img, ntiles;
@@ -414,6 +483,8 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
       const uint32_t buf = tl & 1u;
       const int cell0 = ti * kHcM;
       const int cell = cell0 + r;
+      const int ncell = min(kHcM, P.HW - cell0);          // the last tile of a level may be partial (TMA zero-fills)
+      const bool in_level = r < ncell;
       const int cy = P.magic_w ? (int)__umulhi((uint32_t)cell, P.magic_w) : cell, cx = cell - cy * P.Wd;
       const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
       float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch;
@@ -428,53 +499,9 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
         // and only those cells leave a record.  Nothing of size B x N is written.
         const uint32_t tacc = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16);
         const int img = t / P.tiles_per_img;                 // (b was already advanced to the next tile above)
-        for (int a = jq; a < P.A; a += P.wq) {
-          const int c0 = a * ch;
-          uint32_t vo;
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(vo) : "r"(tacc + (uint32_t)(c0 + 4)) : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const float xo = PQ_ADD(__uint_as_float(vo), sbias[c0 + 4]);
-          const bool pass = xo > P.logit_lo;
-          const unsigned pm = __ballot_sync(PQ_FULL, pass);
-          if (pm == 0u) continue;                            // warp-uniform
-          int slot0 = 0;
-          if (lane == 0) slot0 = atomicAdd(P.rec_count + img, __popc(pm));
-          slot0 = __shfl_sync(PQ_FULL, slot0, 0);
-          const int slot = slot0 + __popc(pm & ((1u << lane) - 1u));
-          const bool store = pass && slot < P.rec_cap;
-          float* rc = P.rec + ((size_t)img * P.rec_cap + (store ? slot : 0)) * (size_t)(6 + P.C);
-          uint32_t v4[4];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(v4[0]), "=r"(v4[1]), "=r"(v4[2]), "=r"(v4[3]) : "r"(tacc + (uint32_t)c0) : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (store) {
-            rc[0] = __int_as_float((int)(P.row_off + (int64_t)cell * P.A + a));
-            rc[1] = xo;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rc[2 + i] = PQ_ADD(__uint_as_float(v4[i]), sbias[c0 + i]);
-          }
-          for (int k = 5; k < ch; k += 8) {                  // class columns, 8 at a time (reads may run past the anchor)
-            if (c0 + k + 8 <= P.buf_cols) {
-              uint32_t v[8];
-              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                           : "r"(tacc + (uint32_t)(c0 + k)) : "memory");
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-              if (store) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (k + i < ch) rc[1 + k + i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + k + i]);
-              }
-            } else {                                           // the last columns of a 256-column accumulator (COCO)
-              for (int i = 0; i < 8 && k + i < ch; ++i) {
-                uint32_t v1;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v1) : "r"(tacc + (uint32_t)(c0 + k + i)) : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (store) rc[1 + k + i] = PQ_ADD(__uint_as_float(v1), sbias[c0 + k + i]);
-              }
-            }
-          }
-        }
+        for (int a = jq; a < P.A; a += P.wq)
+          hc_emit_hits(tacc, a, ch, P.C, P.buf_cols, [&](int c) { return sbias[c]; }, in_level, lane,
+                       P.row_off + (int64_t)cell * P.A + a, img, P.rec, P.rec_count, P.rec_cap, P.logit_lo);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -483,7 +510,9 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
       // the bulk store that last used this staging tile must have read it before it is overwritten
       float* tile = tile0 + (P.tile_bufs == 2 ? (int)buf * kHcM * ACH : 0);
       if (etid == 0) {
-        if (P.tile_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        // with two staging tiles one bulk store may still be reading the OTHER tile - but only if every tile leaves
+        // as a bulk store (otherwise the group count no longer tells which tile a pending group reads)
+        if (P.tile_bufs == 2 && P.all_bulk) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
       }
       epi_bar_sync(n_epi);
       const uint32_t tacc = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16);
@@ -502,7 +531,7 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
             float raw[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
-            if (WANT_RAW) {
+            if (WANT_RAW && in_level) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
             }
@@ -518,7 +547,7 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
             float raw[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
-            if (WANT_RAW) {
+            if (WANT_RAW && in_level) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (i < cnt) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
@@ -550,7 +579,7 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
           float raw[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), bs[i]);       // bias 0 where there is none
-          if (WANT_RAW) {
+          if (WANT_RAW && in_level) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               if (c0 + i < ACH) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
@@ -565,11 +594,20 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       if (P.out_dec) {
-        fence_async_smem();
+        // a full tile whose rows start on a 16-byte boundary leaves as ONE bulk store; a partial last tile, or a level
+        // whose row range is not 16-byte aligned in the concatenated prediction (608 x 608: 22743 rows per image),
+        // leaves through coalesced stores of all epilogue threads
+        const bool bulk = (ncell == kHcM) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+        if (bulk) fence_async_smem();
         epi_bar_sync(n_epi);
-        if (etid == 0) {
-          tma_store_1d(dst, tile, (uint32_t)(kHcM * ACH * sizeof(float)));
-          tma_store_commit();
+        if (bulk) {
+          if (etid == 0) {
+            tma_store_1d(dst, tile, (uint32_t)(kHcM * ACH * sizeof(float)));
+            tma_store_commit();
+          }
+        } else {
+          const int nval = ncell * ACH;
+          for (int i = etid; i < nval; i += n_epi) dst[i] = tile[i];
         }
       }
     }
@@ -625,13 +663,14 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
                       int device, pq::HeadConvWsParams* Pout, CUtensorMap* tmap_out, size_t* smem_out, int* sms_out) {
   using namespace pq;
   const int HW = H * W, ACH = A * (5 + C), N = (ACH + 15) / 16 * 16;
-  if (HW % kHcM != 0 || Cin % 8 != 0 || N > 256) return 0;
+  // the planes must be addressable by a tensor map (plane stride a multiple of 16 bytes); the last tile of a level
+  // may be partial (38 x 38, 76 x 76), the output need not be 16-byte aligned (decided per tile in the epilogue)
+  if (HW % 4 != 0 || Cin % 8 != 0 || N > 256) return 0;
+  if (getenv("PQDET_HEADCONV_ALIGNED_ONLY") && HW % kHcM != 0) return 0;     // A/B switch: round-1 eligibility
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15)) return 0;
-  if (out_decoded) {
-    const size_t img_bytes = (size_t)rows_total * (5 + C) * 4, off_bytes = (size_t)row_off * (5 + C) * 4;
-    if ((reinterpret_cast<uintptr_t>(out_decoded) & 15) || (img_bytes & 15) || (off_bytes & 15)) return 0;
-  }
-  if ((int64_t)B * Cin > 0x7fffffff || (int64_t)B * (HW / kHcM) > 0x7fffffff) return 0;
+  if (out_decoded && (reinterpret_cast<uintptr_t>(out_decoded) & 3)) return 0;
+  const int tiles_img = (HW + kHcM - 1) / kHcM;
+  if ((int64_t)B * Cin > 0x7fffffff || (int64_t)B * tiles_img > 0x7fffffff) return 0;
   PqEncodeTiledFn enc = pq::encode_tiled_fn();
   if (!enc) return 0;
   HeadConvWsParams P;
@@ -704,7 +743,12 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   P.B = B; P.Cin = Cin; P.HW = HW; P.Wd = W; P.A = A; P.C = C; P.N = N;
   P.buf_cols = 32;
   while (P.buf_cols < N) P.buf_cols <<= 1;
-  P.tiles_per_img = HW / kHcM;
+  P.tiles_per_img = tiles_img;
+  {
+    const size_t img_bytes = (size_t)rows_total * (5 + C) * 4, off_bytes = (size_t)row_off * (5 + C) * 4;
+    P.all_bulk = (HW % kHcM == 0) && !(reinterpret_cast<uintptr_t>(out_decoded) & 15) && !(img_bytes & 15) &&
+                 !(off_bytes & 15);
+  }
   P.magic_w = W == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
   if ((int64_t)HW * W >= 0x100000000ll) return 0;              // multiply-high exact for cell < 2^32 / W
   P.ntiles = B * P.tiles_per_img;
@@ -770,10 +814,32 @@ extern "C" int pqdet_head_conv_hits(const float* x, const float* weight, const f
   CUtensorMap tmap;
   size_t smem = 0;
   int sms = 0;
-  const int rc = plan_head_conv_ws(x, weight, bias, nullptr, nullptr, B, Cin, H, W, A, C, 1.0f, (int64_t)H * W * A, 0,
+  const int rc = getenv("PQDET_HEADCONV_GENERAL") ? 0 :
+                 plan_head_conv_ws(x, weight, bias, nullptr, nullptr, B, Cin, H, W, A, C, 1.0f, (int64_t)H * W * A, 0,
                                    device, &P, &tmap, &smem, &sms);
   if (rc < 0) return rc;
-  if (rc == 0) return PQDET_ERR_UNSUPPORTED;                 // shape outside the persistent kernel: caller falls back
+  if (rc == 0) {
+    // shape outside the persistent kernel (19 x 19: plane stride not a multiple of 16 bytes; weights beyond shared
+    // memory): the general tcgen05 kernel with the same thresholding epilogue
+    HeadConvParams G;
+    memset(&G, 0, sizeof(G));
+    G.x = x; G.w = weight; G.bias = bias;
+    G.B = B; G.Cin = Cin; G.H = H; G.W = W; G.A = A; G.C = C;
+    const int ACH = A * (5 + C);
+    G.N = (ACH + 15) / 16 * 16;
+    G.tmem_cols = 32;
+    while (G.tmem_cols < G.N) G.tmem_cols <<= 1;
+    G.row_off = row_offset;
+    G.rec = rec; G.rec_count = rec_count; G.rec_cap = rec_cap;
+    G.logit_lo = logit_lo_for((float)score_threshold);
+    const size_t gsmem = 2 * ((size_t)(kHcKC / 4) * kHcM * 16 + (size_t)(kHcKC / 4) * G.N * 16);
+    if (gsmem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
+    PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    dim3 ggrid((H * W + kHcM - 1) / kHcM, B);
+    head_conv_decode_kernel<true><<<ggrid, kHcThreads, gsmem, (cudaStream_t)stream>>>(G);
+    PQ_LAUNCH_CHECK();
+    return PQDET_OK;
+  }
   P.rec = rec; P.rec_count = rec_count; P.rec_cap = rec_cap;
   P.row_off = row_offset;
   P.logit_lo = logit_lo_for((float)score_threshold);
@@ -819,9 +885,9 @@ extern "C" int pqdet_head_conv_decode(const float* x, const float* weight, const
   const size_t tile_bytes = (size_t)kHcM * (ACH | 1) * sizeof(float);
   const size_t smem = stages > tile_bytes ? stages : tile_bytes;
   if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
-  PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((H * W + kHcM - 1) / kHcM, B);
-  head_conv_decode_kernel<<<grid, kHcThreads, smem, (cudaStream_t)stream>>>(P);
+  head_conv_decode_kernel<false><<<grid, kHcThreads, smem, (cudaStream_t)stream>>>(P);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }

@@ -67,7 +67,7 @@ def headconv_case(rng):
     ACH = 3 * (5 + C)
     Cin = int(rng.choice([8, 16, 24, 40, 80, 96, 176, 352, 30, 7, 512]))
     if rng.random() < 0.7:
-        H, W = [(8, 16), (16, 16), (16, 32), (32, 32), (64, 64), (4, 32)][int(rng.integers(0, 6))]
+        H, W = [(8, 16), (16, 16), (16, 32), (32, 32), (64, 64), (4, 32), (38, 38), (76, 76), (19, 19), (20, 26)][int(rng.integers(0, 10))]
     else:
         H, W = int(rng.integers(1, 40)), int(rng.integers(1, 40))
     B = int(rng.choice([1, 2, 5, 40]))

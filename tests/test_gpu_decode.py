@@ -266,10 +266,22 @@ def test_head_conv_all_levels_in_one_launch(B, C, size, cins):
         off += f.shape[2] * f.shape[3] * 3
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
-    # a level that does not qualify (8x8 = 64 cells) makes the call decline instead of computing something else
-    small = [torch.randn((B, 16, 8, 8), device="cuda")]
-    assert not _ops.head_conv_decode_levels(small, [torch.randn((3 * ch, 16), device="cuda")], [None], C, (32,),
-                                            torch.empty((B, 192, ch), device="cuda"))
+    # a level the persistent kernel cannot take (19x19: plane stride not a multiple of 16 bytes) makes the call
+    # decline instead of computing something else; a partial-tile level (8x8 = 64 cells) is computed, identically to
+    # the general kernel
+    odd = [torch.randn((B, 16, 19, 19), device="cuda")]
+    assert not _ops.head_conv_decode_levels(odd, [torch.randn((3 * ch, 16), device="cuda")], [None], C, (32,),
+                                            torch.empty((B, 19 * 19 * 3, ch), device="cuda"))
+    small, wsm = [torch.randn((B, 16, 8, 8), device="cuda")], [torch.randn((3 * ch, 16), device="cuda")]
+    o1 = torch.empty((B, 192, ch), device="cuda")
+    if _ops.head_conv_decode_levels(small, wsm, [None], C, (32,), o1):
+        import os
+        os.environ["PQDET_HEADCONV_GENERAL"] = "1"
+        try:
+            o2 = _ops.head_conv_decode(small[0], wsm[0], None, C, 32.0).reshape(B, 192, ch)
+        finally:
+            del os.environ["PQDET_HEADCONV_GENERAL"]
+        assert torch.equal(o1, o2)
 
 
 def test_fuse_head_convs_hook_on_a_reference_shaped_model():
@@ -505,3 +517,43 @@ def test_features_to_detections_falls_back_on_unaligned_levels_and_dense_images(
     assert len(got._spill) == B
     for b in range(B):
         assert torch.equal(got[b], want[b])
+
+
+@pytest.mark.parametrize("C,cins", [(10, (352, 176, 80)), (80, (64, 48, 32))])
+def test_head_conv_608_levels_persistent_vs_general(C, cins, monkeypatch):
+    """608 x 608 inputs (BASELINE configs C / D): 38 x 38 and 76 x 76 levels now take the persistent kernel (partial
+    last tile through TMA zero fill, rows of the concatenated prediction not 16-byte aligned -> cooperative stores);
+    19 x 19 (plane stride 1444 B) stays on the general kernel.  Both kernels must agree bit for bit, per level and
+    through forward_from_features (the unaligned row offsets), and the HITS epilogue of both must give the same
+    detections."""
+    from pqdet_b200 import _ops, fused, synth
+    from pqdet_b200.interpreter import DetectionHead
+    torch.manual_seed(C)
+    B, size = 3, 608
+    strides = synth.FPN_STRIDES
+    ch = 3 * (5 + C)
+    feats = [torch.randn((B, cin, size // s, size // s), device="cuda") for cin, s in zip(cins, strides)]
+    ws = [torch.randn((ch, cin), device="cuda") / cin ** 0.5 for cin in cins]
+    bs = [torch.randn((ch,), device="cuda") * 0.3 for _ in cins]
+    for b_ in bs:
+        b_[4::(5 + C)] -= 3.0
+    head = DetectionHead([dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in strides])
+    orig = torch.tensor([[480., 480.], [360., 640.], [608., 608.]]).cuda()
+    got_levels = [_ops.head_conv_decode(f, w, b_, C, float(s), want_raw=True) for f, w, b_, s in zip(feats, ws, bs, strides)]
+    got_cat = head.forward_from_features(feats, ws, bs)
+    got_det = fused.features_nms(feats, ws, bs, strides, C, (size, size), orig, "coco", 0.1, 0.45, return_index=True)
+    monkeypatch.setenv("PQDET_HEADCONV_GENERAL", "1")
+    ref_levels = [_ops.head_conv_decode(f, w, b_, C, float(s), want_raw=True) for f, w, b_, s in zip(feats, ws, bs, strides)]
+    ref_cat = head.forward_from_features(feats, ws, bs)
+    ref_det = fused.features_nms(feats, ws, bs, strides, C, (size, size), orig, "coco", 0.1, 0.45, return_index=True)
+    monkeypatch.delenv("PQDET_HEADCONV_GENERAL")
+    torch.cuda.synchronize()
+    for (gd, gr), (rd, rr) in zip(got_levels, ref_levels):
+        assert torch.equal(gr.view(torch.int32), rr.view(torch.int32)) and torch.equal(gd.view(torch.int32), rd.view(torch.int32))
+    assert torch.equal(got_cat.view(torch.int32), ref_cat.view(torch.int32))
+    raws = [r for _, r in got_levels]
+    want = fused.decode_nms(raws, strides, C, (size, size), orig, "coco", 0.1, 0.45, return_index=True)
+    assert int(want.counts.sum()) > 0
+    for b in range(B):
+        assert torch.equal(got_det[b], want[b]) and torch.equal(ref_det[b], want[b]), b
+        assert torch.equal(got_det.indices(b), want.indices(b))
