@@ -363,7 +363,8 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
   const uint32_t sX = base;
   const uint32_t sW = base + (uint32_t)S * stage_bytes;
   float* tile0 = reinterpret_cast<float*>(aligned + (size_t)S * stage_bytes + (size_t)P.Cin * N * 4);
-  float* sbias = tile0 + P.tile_bufs * kHcM * ACH;          // N + 8 floats, zero beyond ACH or without a bias
+  const int tile_stride = kHcM * ACH + 4;                   // + 16 bytes: a tile is written at the output's 16-byte phase
+  float* sbias = tile0 + P.tile_bufs * tile_stride;         // N + 8 floats, zero beyond ACH or without a bias
   const int n_epi = 4 * P.wq * 32;
 
   if (warp == 1) {
@@ -508,11 +509,16 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
         continue;
       }
       // the bulk store that last used this staging tile must have read it before it is overwritten
-      float* tile = tile0 + (P.tile_bufs == 2 ? (int)buf * kHcM * ACH : 0);
+      // the staging tile starts at the same offset inside a 16-byte unit as its destination, so that everything
+      // but at most 3 floats at either end can leave as one bulk store even when the rows of this image are not
+      // 16-byte aligned in the concatenated prediction (608 x 608: 22743 rows per image)
+      const int mis = (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
+      float* tile = tile0 + (P.tile_bufs == 2 ? (int)buf * tile_stride : 0) + mis;
       if (etid == 0) {
         // with two staging tiles one bulk store may still be reading the OTHER tile - but only if every tile leaves
         // as a bulk store (otherwise the group count no longer tells which tile a pending group reads)
         if (P.tile_bufs == 2 && P.all_bulk) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        // (all_bulk: every tile commits exactly one group, so "at most one pending" = the other tile's)
       }
       epi_bar_sync(n_epi);
       const uint32_t tacc = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16);
@@ -597,16 +603,19 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
         // a full tile whose rows start on a 16-byte boundary leaves as ONE bulk store; a partial last tile, or a level
         // whose row range is not 16-byte aligned in the concatenated prediction (608 x 608: 22743 rows per image),
         // leaves through coalesced stores of all epilogue threads
-        const bool bulk = (ncell == kHcM) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-        if (bulk) fence_async_smem();
+        const int nval = ncell * ACH;
+        const int i0 = (4 - mis) & 3;                       // first element on a 16-byte boundary (global and shared)
+        const int i1 = nval - ((mis + nval) & 3);           // end of the last whole 16-byte unit
+        fence_async_smem();
         epi_bar_sync(n_epi);
-        if (bulk) {
+        if (i1 > i0) {
           if (etid == 0) {
-            tma_store_1d(dst, tile, (uint32_t)(kHcM * ACH * sizeof(float)));
+            tma_store_1d(dst + i0, tile + i0, (uint32_t)((i1 - i0) * sizeof(float)));
             tma_store_commit();
           }
+          if (etid >= 32 && etid < 32 + i0) dst[etid - 32] = tile[etid - 32];
+          if (etid >= 64 && etid < 64 + (nval - i1)) dst[i1 + etid - 64] = tile[i1 + etid - 64];
         } else {
-          const int nval = ncell * ACH;
           for (int i = etid; i < nval; i += n_epi) dst[i] = tile[i];
         }
       }
@@ -675,7 +684,7 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   if (!enc) return 0;
   HeadConvWsParams P;
   memset(&P, 0, sizeof(P));
-  const size_t w_bytes = (size_t)Cin * N * 4, tile_bytes = (size_t)kHcM * ACH * 4, bias_bytes = (size_t)(N + 8) * 4;
+  const size_t w_bytes = (size_t)Cin * N * 4, tile_bytes = (size_t)(kHcM * ACH + 4) * 4, bias_bytes = (size_t)(N + 8) * 4;
   DeviceLimits lim;
   if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
   const int max_smem = lim.max_smem_optin, sms = lim.sms;
@@ -746,8 +755,10 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   P.tiles_per_img = tiles_img;
   {
     const size_t img_bytes = (size_t)rows_total * (5 + C) * 4, off_bytes = (size_t)row_off * (5 + C) * 4;
-    P.all_bulk = (HW % kHcM == 0) && !(reinterpret_cast<uintptr_t>(out_decoded) & 15) && !(img_bytes & 15) &&
-                 !(off_bytes & 15);
+    (void)img_bytes; (void)off_bytes;
+    // every tile commits exactly one bulk group as soon as it holds a whole 16-byte unit at any phase (>= 7 values)
+    const int last_cells = HW % kHcM ? HW % kHcM : kHcM;
+    P.all_bulk = (last_cells * ACH >= 7) ? 1 : 0;
   }
   P.magic_w = W == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)W - 1) / (uint64_t)W);
   if ((int64_t)HW * W >= 0x100000000ll) return 0;              // multiply-high exact for cell < 2^32 / W
