@@ -394,8 +394,12 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       const int cy = P.magic_w[l] ? (int)__umulhi((uint32_t)cell, P.magic_w[l]) : cell, cx = cell - cy * Wd;
       const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
       const float stride = P.stride[l];
-      float* tile = tile0 + (size_t)(tl & 1u) * kDtmCells * ACH;
       float* dst = P.out + ((size_t)b * P.rows_total + P.row_off[l] + (size_t)cell0 * P.A) * ch;
+      // the staging tile starts at the same offset inside a 16-byte unit as its destination: everything but at most
+      // 3 floats at either end leaves as one bulk store even when this image's rows are not 16-byte aligned in the
+      // prediction (608 x 608: 22743 rows per image; a level behind a 19 x 19 level)
+      const int mis = (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
+      float* tile = tile0 + (size_t)(tl & 1u) * (kDtmCells * ACH + 4) + mis;
       // the bulk store that last used this staging tile must have read it before it is overwritten
       if (ctid == 0) tma_store_wait_read<1>();
       epi_bar_sync(n_cmp);
@@ -438,19 +442,23 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
       if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
-      if (P.bulk[l]) {
+      {
+        const int n = ncell * ACH;
+        const int i0 = (4 - mis) & 3;                       // first element on a 16-byte boundary (global and shared)
+        const int i1 = n - ((mis + n) & 3);                 // end of the last whole 16-byte unit
         fence_async_smem();
         epi_bar_sync(n_cmp);
+        // every tile commits exactly one bulk group (so "at most one pending" above = the other staging tile's)
         if (ctid == 0) {
-          tma_store_1d(dst, tile, (uint32_t)(ncell * ACH * sizeof(float)));
+          if (i1 > i0) tma_store_1d(dst + i0, tile + i0, (uint32_t)((i1 - i0) * sizeof(float)));
           tma_store_commit();
         }
-      } else {
-        // the level's rows do not start on a 16-byte boundary (e.g. behind a 19x19 level): cooperative stores; the
-        // barrier at the top of the tile after next orders them against the reuse of this staging tile
-        epi_bar_sync(n_cmp);
-        const int n = ncell * ACH;
-        for (int e = ctid; e < n; e += n_cmp) dst[e] = tile[e];
+        if (i1 > i0) {
+          if (ctid >= 32 && ctid < 32 + i0) dst[ctid - 32] = tile[ctid - 32];
+          if (ctid >= 64 && ctid < 64 + (n - i1)) dst[i1 + ctid - 64] = tile[i1 + ctid - 64];
+        } else {
+          for (int e = ctid; e < n; e += n_cmp) dst[e] = tile[e];
+        }
       }
     }
     if (ctid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -505,7 +513,7 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
   const int max_smem = lim.max_smem_optin, sms = lim.sms;
   const size_t tile_bytes = (size_t)kDtmCells * ACH * 4;
-  const size_t room = (size_t)max_smem - 1024;                      // static barriers
+  const size_t room = (size_t)max_smem - 1024 - 32;                 // static barriers, 16 bytes of phase room per staging tile
   if (room < 4 * tile_bytes) return 0;                              // 2 input stages + 2 staging tiles at least
   size_t st = room / tile_bytes - 2;
   if (st > (size_t)kDtmMaxStages) st = kDtmMaxStages;
@@ -524,7 +532,7 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
     if (worst < best_load) { best_load = worst; wq = w; }
   }
   P.wq = wq;
-  const size_t smem = (st + 2) * tile_bytes;
+  const size_t smem = (st + 2) * tile_bytes + 32;
   static int smem_set[64];                    // the attribute sticks per device: raise it only when needed
   if (device < 0 || device >= 64 || (int)smem > smem_set[device]) {
     PQ_CUDA(cudaFuncSetAttribute(decode_levels_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
