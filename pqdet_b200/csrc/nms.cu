@@ -20,6 +20,7 @@
 // Images whose hit rows / candidates do not fit the on-chip lists are flagged
 // (PQDET_ST_CAND_OVERFLOW) and handled by the general path below: global-memory candidate
 // lists bucketed by (image, class), one CTA per bucket.
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -1052,6 +1053,10 @@ struct GenParams {
   uint64_t* kkeys;           // [cand_capacity] kept keys per image
   uint32_t* klist;           // [cand_capacity] kept positions per bucket
   float4* rbox;              // [n_images][N]   recovered boxes of hit rows (from_heads only)
+  // single-pass select: candidates are first appended, in arrival order and with their class in the key, to a
+  // per-image stage of `stage_quota` keys (aliased onto kkeys, which is not needed before the bucket kernels)
+  uint32_t* stage_fill;      // [n_images]
+  int64_t stage_quota;
   int64_t cand_capacity;
   int64_t* needed;
   int32_t* ok;               // 1 when the workspace is large enough
@@ -1083,6 +1088,9 @@ __device__ __forceinline__ bool gen_row_from_index(const HeadsDev& P, int64_t i,
 }
 
 // pass 0: count candidates per (image, class) + max picked coordinate; pass 1: scatter keys into the buckets.
+// pass 2 = passes 0 and 1 in ONE read of the heads: counts as pass 0, and the keys - with the class in bits 25..31 -
+// are appended to the image's stage (one global atomic per CTA); gen_bucketize_kernel moves them into the buckets
+// once gen_plan_kernel has laid those out.  (Pass 1 re-evaluates every row: 85 us per 64 dense 608 x 608 images.)
 // Every thread evaluates one row and remembers which classes pass as a 128-bit mask.  Counts and slot
 // reservations go through a per-CTA shared-memory histogram, so the global counters see one atomic per
 // (CTA, class) instead of one per candidate (dense scenes: ~12k candidates per image on C counters).
@@ -1152,6 +1160,50 @@ gen_select_kernel(const __grid_constant__ GenParams G) {
     }
   }
   const bool any = (m0 | m1) != 0;
+  if (PASS == 2) {
+    __shared__ unsigned s_wsum[8];
+    __shared__ unsigned s_stage_base;
+    const int lane = lane_id(), warp = warp_id();
+    const unsigned mine = (unsigned)(__popcll(m0) + __popcll(m1));
+    unsigned inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned o = __shfl_up_sync(PQ_FULL, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    unsigned mo = any ? float_to_ordered(fmaxf(fmaxf(box[0], box[1]), fmaxf(box[2], box[3]))) : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mo = max(mo, __shfl_xor_sync(PQ_FULL, mo, d));
+    if (lane == 0 && mo) atomicMax(&s_max, mo);
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) before += s_wsum[w];
+      total += s_wsum[w];
+    }
+    if (tid == 0) s_stage_base = total ? atomicAdd(&G.stage_fill[ii], total) : 0u;
+    if (tid < C && s_cnt[tid]) atomicAdd(&G.cls_count[(size_t)ii * C + tid], s_cnt[tid]);
+    if (tid == 0 && s_max) atomicMax(&G.max_ord[ii], s_max);
+    __syncthreads();
+    if (!any) return;
+    uint64_t slot = (uint64_t)s_stage_base + before + inc - mine;
+    uint64_t* stage = G.kkeys + (size_t)ii * (size_t)G.stage_quota;
+    for (int h = 0; h < 2; ++h) {
+      uint64_t m = h ? m1 : m0;
+      while (m) {
+        const int c = __ffsll((long long)m) - 1 + 64 * h;
+        m &= m - 1;
+        const float sc = score_of(c);
+        if (slot < (uint64_t)G.stage_quota)
+          stage[slot] = ((uint64_t)(~float_to_ordered(sc)) << 32) | ((uint64_t)c << kHitBits) | (uint32_t)row;
+        ++slot;
+      }
+    }
+    if (G.from_heads) G.rbox[(size_t)ii * G.N + row] = make_float4(box[0], box[1], box[2], box[3]);
+    return;
+  }
   if (PASS == 0) {
     // max picked coordinate of the image: warp max, one shared atomic per warp, one global atomic per CTA
     unsigned mo = any ? float_to_ordered(fmaxf(fmaxf(box[0], box[1]), fmaxf(box[2], box[3]))) : 0u;
@@ -1184,6 +1236,40 @@ gen_select_kernel(const __grid_constant__ GenParams G) {
     }
   }
   if (G.from_heads) G.rbox[(size_t)ii * G.N + row] = make_float4(box[0], box[1], box[2], box[3]);
+}
+
+// Single-pass select, second half: the staged keys of an image (arrival order, class in bits 25..31) go to their
+// (image, class) buckets.  Same per-CTA histogram trick as pass 1, but on 8 bytes per candidate instead of a
+// re-evaluation of the heads.
+__global__ void __launch_bounds__(256)
+gen_bucketize_kernel(const __grid_constant__ GenParams G) {
+  if (*G.ok == 0) return;
+  __shared__ unsigned s_cnt[128];
+  __shared__ unsigned s_base[128];
+  const int ii = blockIdx.y;
+  const int C = G.C;
+  const int tid = threadIdx.x;
+  const uint32_t M = G.stage_fill[ii];
+  if ((uint64_t)blockIdx.x * 256 >= M) return;
+  if (tid < 128) s_cnt[tid] = 0;
+  __syncthreads();
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + tid;
+  uint64_t key = 0;
+  int c = -1;
+  unsigned local = 0;
+  if (i < M) {
+    key = G.kkeys[(size_t)ii * (size_t)G.stage_quota + i];
+    c = (int)((key >> kHitBits) & 127u);
+    local = atomicAdd(&s_cnt[c], 1u);
+  }
+  __syncthreads();
+  if (tid < C) {
+    const unsigned n = s_cnt[tid];
+    s_base[tid] = n ? atomicAdd(&G.cls_fill[(size_t)ii * C + tid], n) : 0u;
+  }
+  __syncthreads();
+  if (c >= 0)
+    G.keys[G.seg_off[(size_t)ii * C + c] + s_base[c] + local] = (key & 0xffffffff00000000ull) | (key & kHitMask);
 }
 
 // Block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix
@@ -1254,8 +1340,23 @@ gen_plan_kernel(const __grid_constant__ GenParams G, const __grid_constant__ Det
     base_img += s_tot_b;
     __syncthreads();
   }
-  const unsigned long long need = base_seg > base_img ? base_seg : base_img;
-  const bool ok = need <= (unsigned long long)G.cand_capacity;
+  unsigned long long need = base_seg > base_img ? base_seg : base_img;
+  bool ok = need <= (unsigned long long)G.cand_capacity;
+  if (G.stage_quota > 0) {
+    // single-pass select: every image's candidates had to fit its stage; if not, ask for n_images x the largest
+    __shared__ unsigned s_maxm;
+    if (threadIdx.x == 0) s_maxm = 0;
+    __syncthreads();
+    for (int ii = threadIdx.x; ii < G.n_images; ii += 1024) atomicMax(&s_maxm, G.stage_fill[ii]);
+    __syncthreads();
+    const unsigned long long maxm = s_maxm;
+    if (maxm > (unsigned long long)G.stage_quota) {
+      ok = false;
+      const unsigned long long want = maxm * (unsigned long long)G.n_images;
+      if (want > need) need = want;
+      if (need <= (unsigned long long)G.cand_capacity) need = (unsigned long long)G.cand_capacity + 1;
+    }
+  }
   if (threadIdx.x == 0) {
     *G.needed = (int64_t)need;
     *G.ok = ok ? 1 : 0;
@@ -1299,20 +1400,30 @@ __device__ __forceinline__ int bucket_greedy(uint32_t n, float iou_f, double iou
     }
     const unsigned dm = __ballot_sync(PQ_FULL, dead);
     if (lane == 0) s_dead[warp] = dm;
-    for (int i = warp; i < 32; i += kSegWarps) {           // B: row i of the step's suppression matrix
-      const float ax1 = __shfl_sync(PQ_FULL, me.x, i), ay1 = __shfl_sync(PQ_FULL, me.y, i);
-      const float ax2 = __shfl_sync(PQ_FULL, me.z, i), ay2 = __shfl_sync(PQ_FULL, me.w, i);
-      const float Sa = box_area(ax1, ay1, ax2, ay2);
-      const bool sup = (lane > i) && valid &&
-                       nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, me.x, me.y, me.z, me.w, iou_f, iou_d);
-      const unsigned row = __ballot_sync(PQ_FULL, sup);
-      if (lane == 0) s_rows[i] = row;
+    __syncthreads();
+    // B: rows of the step's suppression matrix - only for the candidates that survived A (typically a fifth of the
+    // step in dense scenes), dealt round robin to the warps
+    unsigned alldead = 0;
+#pragma unroll
+    for (int q = 0; q < kSegWarps; ++q) alldead |= s_dead[q];
+    {
+      unsigned todo = ~alldead;
+      int nth = 0;
+      while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if ((nth++ % kSegWarps) != warp) continue;
+        const float ax1 = __shfl_sync(PQ_FULL, me.x, i), ay1 = __shfl_sync(PQ_FULL, me.y, i);
+        const float ax2 = __shfl_sync(PQ_FULL, me.z, i), ay2 = __shfl_sync(PQ_FULL, me.w, i);
+        const float Sa = box_area(ax1, ay1, ax2, ay2);
+        const bool sup = (lane > i) && valid &&
+                         nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, me.x, me.y, me.z, me.w, iou_f, iou_d);
+        const unsigned row = __ballot_sync(PQ_FULL, sup);
+        if (lane == 0) s_rows[i] = row;
+      }
     }
     __syncthreads();
     if (warp == 0) {                                       // C
-      unsigned alldead = 0;
-#pragma unroll
-      for (int q = 0; q < kSegWarps; ++q) alldead |= s_dead[q];
       const unsigned myrow = s_rows[lane];
       unsigned alive = ~alldead, kept = 0;
       while (alive) {
@@ -1717,8 +1828,8 @@ extern "C" int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, dou
 
 namespace pq {
 struct GenLayout {
-  size_t cls_count, cls_fill, seg_off, seg_cap, max_ord, img_off, img_cap, kept_count, needed_ok, keys, kkeys,
-      klist, rbox, total;
+  size_t cls_count, cls_fill, seg_off, seg_cap, max_ord, stage_fill, img_off, img_cap, kept_count, needed_ok, keys,
+      kkeys, klist, rbox, total;
 };
 static GenLayout gen_layout(int n_images, int64_t N, int C, int64_t cap, int from_heads) {
   GenLayout L;
@@ -1729,6 +1840,7 @@ static GenLayout gen_layout(int n_images, int64_t N, int C, int64_t cap, int fro
   L.cls_fill = take(nc * 4);
   L.kept_count = take((size_t)n_images * 4);
   L.max_ord = take((size_t)n_images * 4);
+  L.stage_fill = take((size_t)n_images * 4);
   L.needed_ok = take(16);
   L.seg_off = take(nc * 8);
   L.seg_cap = take(nc * 4);
@@ -1791,6 +1903,7 @@ extern "C" int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes
   G.cls_fill = (uint32_t*)(ws + L.cls_fill);
   G.kept_count = (uint32_t*)(ws + L.kept_count);
   G.max_ord = (uint32_t*)(ws + L.max_ord);
+  G.stage_fill = (uint32_t*)(ws + L.stage_fill);
   G.needed = needed ? needed : (int64_t*)(ws + L.needed_ok);
   G.ok = (int32_t*)(ws + L.needed_ok + 8);
   G.seg_off = (int64_t*)(ws + L.seg_off);
@@ -1806,12 +1919,26 @@ extern "C" int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes
   // the counters are the first four (contiguous) regions of the layout
   PQ_CUDA(cudaMemsetAsync(ws, 0, L.seg_off, st));
   dim3 sel_grid((unsigned)((G.N + 255) / 256), n_images);
-  gen_select_kernel<0><<<sel_grid, 256, 0, st>>>(G);
-  PQ_LAUNCH_CHECK();
-  gen_plan_kernel<<<1, 1024, 0, st>>>(G, O);
-  PQ_LAUNCH_CHECK();
-  gen_select_kernel<1><<<sel_grid, 256, 0, st>>>(G);
-  PQ_LAUNCH_CHECK();
+  // PQDET_GEN_SELECT=twopass: count, plan, re-evaluate + scatter (round 1); default: one read of the heads
+  const char* ssel = getenv("PQDET_GEN_SELECT");
+  const bool single = !(ssel && ssel[0] == 't') && cand_capacity / n_images >= 256;
+  G.stage_quota = single ? cand_capacity / n_images : 0;
+  if (single) {
+    gen_select_kernel<2><<<sel_grid, 256, 0, st>>>(G);
+    PQ_LAUNCH_CHECK();
+    gen_plan_kernel<<<1, 1024, 0, st>>>(G, O);
+    PQ_LAUNCH_CHECK();
+    dim3 bgrid((unsigned)((G.stage_quota + 255) / 256), n_images);
+    gen_bucketize_kernel<<<bgrid, 256, 0, st>>>(G);
+    PQ_LAUNCH_CHECK();
+  } else {
+    gen_select_kernel<0><<<sel_grid, 256, 0, st>>>(G);
+    PQ_LAUNCH_CHECK();
+    gen_plan_kernel<<<1, 1024, 0, st>>>(G, O);
+    PQ_LAUNCH_CHECK();
+    gen_select_kernel<1><<<sel_grid, 256, 0, st>>>(G);
+    PQ_LAUNCH_CHECK();
+  }
   dim3 seg_grid(G.C, n_images);
   auto launch_buckets = [&](auto small, auto big) -> int {
     const size_t sb = kSegBytesPerKey * kSegSmallKeys, bb = kSegBytesPerKey * kSegBigKeys;

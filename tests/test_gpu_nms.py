@@ -306,3 +306,30 @@ def test_empty_batch_empty_rows_and_truncation():
     assert m[0].tolist() == full.counts.tolist() and all(int(s) & _lib.ST_DET_TRUNCATED for s in m[2])
     for b in range(3):
         assert torch.equal(det[b], full[b][:16])
+
+
+@pytest.mark.parametrize("profile,C,size,kind", [("dense", 10, 608, "visdrone"), ("gauss", 20, 256, "voc")])
+def test_single_pass_select_equals_two_pass(profile, C, size, kind, monkeypatch):
+    """General path: candidates staged per image in one read of the heads + gen_bucketize_kernel (default) against
+    round 1's count / plan / re-evaluate route (PQDET_GEN_SELECT=twopass): identical rows and indices, also when the
+    first capacity guess is too small (the retry loop of fused._general) and through the tools.torch_nms drop-in."""
+    from pqdet_b200 import base_sample, config, fused, synth, tools
+    from pqdet_b200.interpreter import DetectionHead
+    config.nms_semantics = "cuda"
+    B = 3
+    heads = [h.cuda() for h in synth.make_heads(B, C, size, profile, seed=77)]
+    orig = torch.tensor([[480., 480.], [360., 640.], [float(size)] * 2]).cuda()
+    kw = dict(return_index=True, strategy="general")
+    one = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, kind, 0.1, 0.45, **kw)
+    opts = [dict(classes=C, stride=s, bbox_loss="l1", ignore_thresh=0.5, l1_loss_gain=0.05) for s in synth.FPN_STRIDES]
+    rec = base_sample.RECOVER_BBOXES_REGISTER[kind](DetectionHead(opts)(heads), (size, size), orig)
+    drop1, didx1 = tools.batched_torch_nms(rec, 0.1, 0.45, return_index=True, strategy="general")
+    monkeypatch.setenv("PQDET_GEN_SELECT", "twopass")
+    two = fused.decode_nms(heads, synth.FPN_STRIDES, C, (size, size), orig, kind, 0.1, 0.45, **kw)
+    drop2, didx2 = tools.batched_torch_nms(rec, 0.1, 0.45, return_index=True, strategy="general")
+    monkeypatch.delenv("PQDET_GEN_SELECT")
+    assert int(one.counts.sum()) > 100
+    for b in range(B):
+        assert torch.equal(one[b], two[b]) and torch.equal(one.indices(b), two.indices(b)), b
+        assert torch.equal(drop1[b], drop2[b]) and torch.equal(didx1[b], didx2[b]), b
+        assert torch.equal(drop1[b], one[b])
