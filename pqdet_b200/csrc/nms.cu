@@ -123,54 +123,10 @@ __device__ __forceinline__ void write_det(const DetOut& O, int b, int j, float4 
   if (O.det_idx) O.det_idx[(size_t)b * O.max_det + j] = (int32_t)(row * C + c);
 }
 
-// Greedy NMS of one class segment [s, e) of the sorted key list by ONE warp.
-// getbox(pos) returns the (recovered, unshifted) box of sorted position pos.
-template <int ROUND, typename GetBox, typename KList, typename Mark>
-__device__ __forceinline__ int warp_nms_segment(int s, int e, float off, float iou_f, double iou_d,
-                                                GetBox getbox, KList klist, Mark mark) {
-  const int lane = lane_id();
-  int k = 0;
-  for (int base = s; base < e; base += 32) {
-    const int p = base + lane;
-    const bool valid = p < e;
-    float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-    if (valid) {
-      float4 bx = getbox(p);
-      x1 = PQ_ADD(bx.x, off); y1 = PQ_ADD(bx.y, off); x2 = PQ_ADD(bx.z, off); y2 = PQ_ADD(bx.w, off);
-    }
-    bool dead = !valid;
-    for (int q = 0; q < k; ++q) {                       // against boxes kept in earlier steps
-      float4 a = getbox(klist(s + q, -1));
-      float ax1 = PQ_ADD(a.x, off), ay1 = PQ_ADD(a.y, off), ax2 = PQ_ADD(a.z, off), ay2 = PQ_ADD(a.w, off);
-      float Sa = box_area(ax1, ay1, ax2, ay2);
-      if (!dead && nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, iou_f, iou_d)) dead = true;
-      if (!__any_sync(PQ_FULL, !dead)) break;
-    }
-    unsigned alive = __ballot_sync(PQ_FULL, !dead);
-    while (alive) {                                     // inside the step: next survivor is kept
-      const int i = __ffs(alive) - 1;
-      alive &= alive - 1;
-      float ax1 = __shfl_sync(PQ_FULL, x1, i), ay1 = __shfl_sync(PQ_FULL, y1, i);
-      float ax2 = __shfl_sync(PQ_FULL, x2, i), ay2 = __shfl_sync(PQ_FULL, y2, i);
-      float Sa = box_area(ax1, ay1, ax2, ay2);
-      if (lane == i) { klist(s + k, p); mark(p); }
-      ++k;
-      bool sup = (lane > i) && !dead &&
-                 nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1, y1, x2, y2, iou_f, iou_d);
-      dead |= sup;
-      alive &= ~__ballot_sync(PQ_FULL, sup);
-    }
-    __syncwarp();
-  }
-  return k;
-}
-
 // ------------------------------------------------------------------------------------------------
 // fused kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kWarpSortMax = 256;   // classes up to this many candidates are rank-sorted by one warp
-constexpr int kRankOutMax = 256;    // kept lists up to this size are ordered by rank counting
-constexpr int kSelectMax = 128;     // classes up to this many candidates: selection NMS in registers, no sort
+constexpr int kWarpClassMax = 128;  // classes up to this many candidates: one warp, members in registers (1, 2 or 4 per lane)
 
 // Two capacity classes (include/pqdet_b200.h: capacity_class).  The compact one keeps the per-image lists small
 // enough for 7 CTAs of 4 warps per SM (one CTA per image, 1036 images in flight on 148 SMs): the phases of an
@@ -182,91 +138,31 @@ template <> struct FusedCfg<1> { static constexpr int kThreads = 256, kCapH = 10
 
 template <int CAPH, int CAPM>
 struct FusedSmemT {
-  uint64_t keys[CAPM];      // hit records during the scan, then candidate keys in emission order, then output keys
+  uint64_t keys[CAPM];      // hit records during the scan, then candidate keys in emission order
   float4 hbox[CAPH];        // recovered box of every hit row
   uint32_t hmeta[CAPH];     // level << 30 | anchor << 27 | cell
-  float hconf[CAPH];        // | dead after the fetch / offset phases: the sorted fallback reuses the two arrays
-  uint8_t hhas[CAPH];       // | as its kept-position list (uint16 x CAPM)
+  float hconf[CAPH];        // | hconf and hhas are dead once the NMS starts; together with the pad they hold the
+  uint8_t hhas[CAPH];       // | output keys of the kept detections, appended by the selection rounds themselves
+  uint8_t okpad[CAPM];      // | (kOutCap of them: an image that keeps more is resolved by the general path)
   uint16_t order[CAPM];     // per-class member lists (candidate slots)
-  uint8_t keepflag[CAPM];   // by candidate slot
   int cls_cnt[128];
   int cls_fill[128];
   int seg_start[128];
   const float* lvbase[PQDET_MAX_LEVELS];      // objectness plane of anchor 0 of this image, per level
   float red[8];
-  int b, H, M, K, maxcnt, next_class, nrec;
+  uint32_t wbest[8];        // CTA-cooperative class walk: per-warp best ~score, winner tag, winner box
+  uint32_t win;
+  float4 wbox;
+  int big[128];             // classes that need the whole CTA
+  int nbig;
+  int b, H, M, K, next_class, nrec;
   // followed by: uint32_t hitw[G_tot*4*A]; uint32_t gbase[G_tot]; uint32_t utab[G_tot*A];
-  __device__ __forceinline__ uint16_t* klist() { return reinterpret_cast<uint16_t*>(hconf); }
+  static constexpr int kOutCap = (5 * CAPH + CAPM) / 8;
+  __device__ __forceinline__ uint64_t* okeys() { return reinterpret_cast<uint64_t*>(hconf); }
 };
 
 __device__ __forceinline__ uint32_t pack_meta(int level, int a, int cell) {
   return ((uint32_t)level << 30) | ((uint32_t)a << 27) | (uint32_t)cell;
-}
-
-// Rank sort of one class' member list by ONE warp: order[s..s+n) holds candidate slots in arbitrary
-// order; afterwards it holds them sorted by key (score desc, hit asc).  Keys are unique, so the rank
-// (number of smaller keys) is the final position.  n <= 32: pure register/shuffle; larger: tiles.
-__device__ __forceinline__ void warp_rank_sort(const uint64_t* keys, uint16_t* order, uint16_t* scratch,
-                                               int s, int n) {
-  const int lane = lane_id();
-  if (n <= 32) {
-    const int slot = (lane < n) ? order[s + lane] : 0;
-    const uint64_t mine = (lane < n) ? keys[slot] : ~0ull;
-    // same class => the order is decided by bits [56:25] (~score) and, only on exact score ties, by the
-    // hit index: count with one 32-bit shuffle per peer and redo in 64 bits in the (rare) tie case.
-    const uint32_t ms = (uint32_t)(mine >> kHitBits);
-    int rank = 0;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const uint32_t o = __shfl_sync(PQ_FULL, ms, j);
-      rank += (o < ms) ? 1 : 0;
-    }
-    // distinct scores <=> distinct ranks; a shared rank among the real entries means an exact score tie
-    const unsigned same = __match_any_sync(PQ_FULL, (lane < n) ? rank : 64 + lane);   // all lanes take part
-    const bool tie = (lane < n) && (__popc(same) > 1);
-    if (__any_sync(PQ_FULL, tie)) {
-      rank = 0;
-      for (int j = 0; j < 32; ++j) {
-        const uint64_t o = __shfl_sync(PQ_FULL, mine, j);
-        rank += (o < mine) ? 1 : 0;
-      }
-    }
-    __syncwarp();
-    if (lane < n) order[s + rank] = (uint16_t)slot;
-    __syncwarp();
-    return;
-  }
-  for (int t0 = 0; t0 < n; t0 += 32) {
-    const bool va = t0 + lane < n;
-    const int slot = va ? order[s + t0 + lane] : 0;
-    const uint64_t mine = va ? keys[slot] : ~0ull;
-    const uint32_t ms = (uint32_t)(mine >> kHitBits);
-    int rank = 0, eq = 0;
-    for (int t1 = 0; t1 < n; t1 += 32) {
-      const int op = t1 + lane;
-      const uint32_t other = (op < n) ? (uint32_t)(keys[order[s + op]] >> kHitBits) : 0xffffffffu;
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t o = __shfl_sync(PQ_FULL, other, j);
-        rank += (o < ms) ? 1 : 0;
-        eq += (o == ms) ? 1 : 0;
-      }
-    }
-    if (__any_sync(PQ_FULL, va && eq > 1)) {               // exact score tie somewhere: redo in 64 bits
-      rank = 0;
-      for (int t1 = 0; t1 < n; t1 += 32) {
-        const uint64_t other = (t1 + lane < n) ? keys[order[s + t1 + lane]] : ~0ull;
-        for (int j = 0; j < 32; ++j) {
-          const uint64_t o = __shfl_sync(PQ_FULL, other, j);
-          rank += (o < mine) ? 1 : 0;
-        }
-      }
-    }
-    if (va) scratch[s + rank] = (uint16_t)slot;
-  }
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) order[s + i] = scratch[s + i];
-  __syncwarp();
 }
 
 // Greedy NMS of one class by ONE warp WITHOUT sorting it: the class' n <= 32*R members live in registers (R per
@@ -282,7 +178,7 @@ __device__ __forceinline__ void warp_select_nms(S_t& S, int s, int n, float off,
   const int lane = lane_id();
   uint32_t ns[R], tag[R];            // ~score bits; hit << 16 | candidate slot
   float x1[R], y1[R], x2[R], y2[R];
-  unsigned alive = 0;
+  unsigned alive = 0, kept = 0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int j = lane + 32 * r;
@@ -328,7 +224,7 @@ __device__ __forceinline__ void warp_select_nms(S_t& S, int s, int n, float off,
     for (int r = 1; r < R; ++r)
       if (wr == r) { ax1 = x1[r]; ay1 = y1[r]; ax2 = x2[r]; ay2 = y2[r]; wtag = tag[r]; }
     if (lane == wl) {
-      S.keepflag[wtag & 0xffffu] = 1;
+      kept |= 1u << wr;
       alive &= ~(1u << wr);
     }
     ax1 = __shfl_sync(PQ_FULL, ax1, wl); ay1 = __shfl_sync(PQ_FULL, ay1, wl);
@@ -340,6 +236,105 @@ __device__ __forceinline__ void warp_select_nms(S_t& S, int s, int n, float off,
           nms_suppresses<ROUND>(ax1, ay1, ax2, ay2, Sa, x1[r], y1[r], x2[r], y2[r], iou_f, iou_d))
         alive &= ~(1u << r);
   }
+  // the class' kept detections append their output keys with ONE reservation (nothing in the rounds waits for an atomic)
+  int total = 0;
+  unsigned km[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    km[r] = __ballot_sync(PQ_FULL, (kept >> r) & 1u);
+    total += __popc(km[r]);
+  }
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&S.K, total);
+  base = __shfl_sync(PQ_FULL, base, 0);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pos = base + __popc(km[r] & ((1u << lane) - 1u));
+    if (((kept >> r) & 1u) && pos < S_t::kOutCap) S.okeys()[pos] = out_key(S.keys[tag[r] & 0xffffu]);
+    base += __popc(km[r]);
+  }
+}
+
+// The same selection walk for a class too large for one warp, by the whole CTA: thread t owns members t, t + NT, ...
+// (alive / kept bits in registers; the members themselves - ~score, hit, shifted box - are re-read from shared memory
+// every round, which only crowds of one class pay for).  A round = per-warp redux of the best alive ~score, the warp
+// results through shared memory, atomicMin over (hit, slot) among the holders of the best score (lowest hit index
+// wins a tie), the winner publishes its box, everybody tests its alive members.  Three barriers per round.
+// All threads of the CTA call it; n <= 32 * NT.
+template <int ROUND, int NT, typename S_t>
+__device__ __forceinline__ void cta_select_nms(S_t& S, int s, int n, float off, float iou_f, double iou_d) {
+  constexpr int NW = NT / 32;
+  const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const int T = (n - tid + NT - 1) / NT;                     // members of this thread (n > tid) or <= 0
+  unsigned alive = (T >= 32) ? 0xffffffffu : ((T > 0) ? ((1u << T) - 1u) : 0u), kept = 0;
+  auto member = [&](int t, uint32_t& nsv, uint32_t& tagv) {
+    const uint32_t slot = S.order[s + tid + NT * t];
+    const uint64_t key = S.keys[slot];
+    nsv = (uint32_t)(key >> kHitBits);
+    tagv = ((uint32_t)(key & kHitMask) << 16) | slot;
+  };
+  for (;;) {
+    uint32_t m = 0xffffffffu;
+    for (unsigned rem = alive; rem; rem &= rem - 1) {
+      uint32_t nsv, tagv;
+      member(__ffs(rem) - 1, nsv, tagv);
+      m = min(m, nsv);
+    }
+    const uint32_t wb = __reduce_min_sync(PQ_FULL, m);
+    if (lane == 0) S.wbest[warp] = wb;
+    if (tid == 0) S.win = 0xffffffffu;
+    __syncthreads();
+    uint32_t best = S.wbest[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) best = min(best, S.wbest[w]);
+    if (best == 0xffffffffu) break;                          // uniform: every thread read the same words
+    if (m == best)
+      for (unsigned rem = alive; rem; rem &= rem - 1) {
+        uint32_t nsv, tagv;
+        member(__ffs(rem) - 1, nsv, tagv);
+        if (nsv == best) atomicMin(&S.win, tagv);
+      }
+    __syncthreads();
+    const uint32_t win = S.win;
+    if (m == best)
+      for (unsigned rem = alive; rem; rem &= rem - 1) {
+        const int t = __ffs(rem) - 1;
+        uint32_t nsv, tagv;
+        member(t, nsv, tagv);
+        if (tagv == win) {
+          const float4 bx = S.hbox[win >> 16];
+          S.wbox = make_float4(PQ_ADD(bx.x, off), PQ_ADD(bx.y, off), PQ_ADD(bx.z, off), PQ_ADD(bx.w, off));
+          kept |= 1u << t;
+          alive &= ~(1u << t);
+        }
+      }
+    __syncthreads();
+    const float4 a = S.wbox;
+    const float Sa = box_area(a.x, a.y, a.z, a.w);
+    for (unsigned rem = alive; rem; rem &= rem - 1) {
+      const int t = __ffs(rem) - 1;
+      uint32_t nsv, tagv;
+      member(t, nsv, tagv);
+      const float4 bx = S.hbox[tagv >> 16];
+      if (nms_suppresses<ROUND>(a.x, a.y, a.z, a.w, Sa, PQ_ADD(bx.x, off), PQ_ADD(bx.y, off), PQ_ADD(bx.z, off),
+                                PQ_ADD(bx.w, off), iou_f, iou_d))
+        alive &= ~(1u << t);
+    }
+  }
+  // append: one reservation per warp
+  const int mine = __popc(kept);
+  const int incl = warp_inclusive_sum(mine);
+  const int total = __shfl_sync(PQ_FULL, incl, 31);
+  int base = 0;
+  if (lane == 0 && total) base = atomicAdd(&S.K, total);
+  base = __shfl_sync(PQ_FULL, base, 0) + incl - mine;
+  for (unsigned rem = kept; rem; rem &= rem - 1) {
+    uint32_t nsv, tagv;
+    member(__ffs(rem) - 1, nsv, tagv);
+    if (base < S_t::kOutCap) S.okeys()[base] = out_key(S.keys[tagv & 0xffffu]);
+    ++base;
+  }
+  __syncthreads();                                           // wbest / win are reused by the next class
 }
 
 #ifdef PQ_PHASE_TIMING
@@ -467,7 +462,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
   constexpr int NT = FusedCfg<CLS>::kThreads, NW = NT / 32;
   constexpr int CAPH = FusedCfg<CLS>::kCapH, CAPM = FusedCfg<CLS>::kCapM;
   using Smem = FusedSmemT<CAPH, CAPM>;
-  static_assert(5 * CAPH >= 2 * CAPM, "klist aliases hconf + hhas");
+  static_assert((8 * CAPM + 16 * CAPH + 4 * CAPH) % 16 == 0, "output keys are read two at a time");
   static_assert(CAPH % NT == 0 && CAPM % NT == 0, "per-thread register tiles");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -561,7 +556,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
 
     // ---- 2. deterministic slots: exclusive prefix of the per-group hit counts --------------------
     if (SRC == 2) {
-      if (tid == 0) { S.H = P.rec_count[b]; S.M = 0; S.K = 0; S.maxcnt = 0; S.next_class = 0; }
+      if (tid == 0) { S.H = P.rec_count[b]; S.M = 0; S.K = 0; S.nbig = 0; S.next_class = 0; }
     } else if (warp == 0) {
       int running = 0;
       for (int g0 = 0; g0 < P.G_tot; g0 += 32) {
@@ -573,7 +568,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         if (g < P.G_tot) gbase[g] = running + inc - c;
         running += __shfl_sync(PQ_FULL, inc, 31);
       }
-      if (lane == 0) { S.H = running; S.M = 0; S.K = 0; S.maxcnt = 0; S.next_class = 0; }
+      if (lane == 0) { S.H = running; S.M = 0; S.K = 0; S.nbig = 0; S.next_class = 0; }
     }
     __syncthreads();
     PQ_PHASE(2);
@@ -817,18 +812,14 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       mx = warp_max(mx);
       if (lane == 0) S.red[warp] = mx;
       if (warp == NW - 1) {                                // exclusive prefix of the class counts
-        int running = 0, mc = 0;
+        int running = 0;
         for (int c0 = 0; c0 < C; c0 += 32) {
           const int c = c0 + lane;
           const int n = (c < C) ? S.cls_cnt[c] : 0;
           const int inc = warp_inclusive_sum(n);
           if (c < C) S.seg_start[c] = running + inc - n;
           running += __shfl_sync(PQ_FULL, inc, 31);
-          mc = max(mc, n);
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mc = max(mc, __shfl_xor_sync(PQ_FULL, mc, d));
-        if (lane == 0) S.maxcnt = mc;
       }
       __syncthreads();
       mx = S.red[0];
@@ -839,171 +830,77 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
 
     PQ_PHASE(5);
     // ---- 5. per-class member lists --------------------------------------------------------------
-    const int maxcnt = S.maxcnt;
-    const bool lists = maxcnt <= kWarpSortMax;
-    if (!lists && next_pow2(M) > CAPM) {                   // one huge class and no room to sort the padded list
-      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = M; }
-      __syncthreads();
-      continue;
-    }
-    if (lists) {
-      for (int i = tid; i < M; i += NT) {
-        const int c = (int)(S.keys[i] >> 57);
-        S.order[S.seg_start[c] + atomicAdd(&S.cls_fill[c], 1)] = (uint16_t)i;
-        S.keepflag[i] = 0;
-      }
-    } else {                                               // one huge class: block bitonic sort instead
-      const int P2 = next_pow2(M);
-      for (int i = M + tid; i < P2; i += NT) S.keys[i] = ~0ull;
-      __syncthreads();
-      bitonic_sort_block(S.keys, P2);                      // class-major keys: segments are contiguous
-      for (int i = tid; i < M; i += NT) { S.order[i] = (uint16_t)i; S.keepflag[i] = 0; }
+    for (int i = tid; i < M; i += NT) {
+      const int c = (int)(S.keys[i] >> 57);
+      S.order[S.seg_start[c] + atomicAdd(&S.cls_fill[c], 1)] = (uint16_t)i;
     }
     __syncthreads();
     PQ_PHASE(6);
 
-    // ---- 6. greedy NMS, one warp per class (classes pulled dynamically: uneven sizes) ------------
+    // ---- 6. greedy NMS: one warp per class (classes pulled dynamically: uneven sizes), the whole CTA for the
+    // classes beyond kWarpClassMax candidates; kept detections append their output key themselves ----------------
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&S.next_class, 1);
+      c = __shfl_sync(PQ_FULL, c, 0);
+      if (c >= C) break;
+      const int n = S.cls_cnt[c];
+      if (n == 0) continue;
+      if (n > kWarpClassMax) {
+        if (lane == 0) S.big[atomicAdd(&S.nbig, 1)] = c;
+        continue;
+      }
+      const int s = S.seg_start[c];
+      const float off = trick ? PQ_MUL((float)c, m1) : 0.0f;
+      if (n <= 32) warp_select_nms<ROUND, 1>(S, s, n, off, P.iou_f, P.iou_d);
+      else if (n <= 64) warp_select_nms<ROUND, 2>(S, s, n, off, P.iou_f, P.iou_d);
+      else warp_select_nms<ROUND, 4>(S, s, n, off, P.iou_f, P.iou_d);
+    }
+    __syncthreads();
     {
-      auto pull = [&]() -> int {                              // next class that has candidates, or C
-        for (;;) {
-          int c = 0;
-          if (lane == 0) c = atomicAdd(&S.next_class, 1);
-          c = __shfl_sync(PQ_FULL, c, 0);
-          if (c >= C || S.cls_cnt[c] > 0) return c;
-        }
-      };
-      auto single = [&](int c) {
-        const int n = S.cls_cnt[c];
-        const int s = S.seg_start[c];
-        const float off = trick ? PQ_MUL((float)c, m1) : 0.0f;
-        if (lists && n <= 32) {
-          warp_select_nms<ROUND, 1>(S, s, n, off, P.iou_f, P.iou_d);
-        } else if (lists && n <= 64) {
-          warp_select_nms<ROUND, 2>(S, s, n, off, P.iou_f, P.iou_d);
-        } else if (lists && n <= kSelectMax) {
-          warp_select_nms<ROUND, 4>(S, s, n, off, P.iou_f, P.iou_d);
-        } else {
-          uint16_t* kl = S.klist();
-          if (lists) warp_rank_sort(S.keys, S.order, kl, s, n);
-          warp_nms_segment<ROUND>(
-              s, s + n, off, P.iou_f, P.iou_d,
-              [&](int pos) { return S.hbox[S.keys[S.order[pos]] & kHitMask]; },
-              [&](int slot, int pos) -> int {
-                if (pos >= 0) kl[slot] = (uint16_t)pos;
-                return kl[slot];
-              },
-              [&](int pos) { S.keepflag[S.order[pos]] = 1; });
-        }
-      };
-      for (;;) {
-        const int c = pull();
-        if (c >= C) break;
-        single(c);
+      const int nbig = S.nbig;
+      for (int i = 0; i < nbig; ++i) {
+        const int c = S.big[i];
+        cta_select_nms<ROUND, NT>(S, S.seg_start[c], S.cls_cnt[c], trick ? PQ_MUL((float)c, m1) : 0.0f, P.iou_f, P.iou_d);
       }
     }
     __syncthreads();
     PQ_PHASE(7);
 
     // ---- 7. kept keys -> (score desc, row, class) order -> output -------------------------------
-    // order[] and keepflag[] are dead from here on: order[] takes the high (~score) words of the kept keys,
-    // keepflag[] the rank -> key permutation used to detect exact score ties.
-    uint32_t* hi32 = reinterpret_cast<uint32_t*>(S.order);         // CAPM / 2 words
-    uint16_t* perm = reinterpret_cast<uint16_t*>(S.keepflag);      // CAPM / 2 entries
-    {
-      constexpr int R = CAPM / NT;
-      uint64_t loc[R];
-      unsigned vmask = 0;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = tid + r * NT;
-        loc[r] = 0;
-        if (i < M && S.keepflag[i]) { loc[r] = out_key(S.keys[i]); vmask |= 1u << r; }
-      }
-      __syncthreads();
-      if (tid == 0) S.next_class = 0;                      // reused as the tie flag below
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (vmask & (1u << r)) {
-          const int pos = atomicAdd(&S.K, 1);
-          S.keys[pos] = loc[r];
-          if (pos < CAPM / 2) hi32[pos] = (uint32_t)(loc[r] >> 32);
-        }
-      __syncthreads();
-    }
     const int K = S.K;
     PQ_PHASE(8);
-    auto emit = [&](int j, uint64_t k2) {
-      const float score = __uint_as_float(~(uint32_t)(k2 >> 32));
-      const uint32_t low = (uint32_t)k2;
-      const int h = low >> 7, c = low & 127;
-      const uint32_t meta = S.hmeta[h];
-      int64_t row = meta;
-      if (SRC != 1) {
-        const LevelDev& L = P.lv[meta >> 30];
-        row = L.row_off + (int64_t)(meta & 0x7ffffff) * A + ((meta >> 27) & 7);
-      }
-      write_det(O, b, j, S.hbox[h], score, c, row, C);
-    };
-#ifndef PQ_RANK32
-#define PQ_RANK32 1
-#endif
-    if (PQ_RANK32 && K <= kRankOutMax && K <= CAPM / 2) {
-      // position = number of smaller keys.  Counted on the 32-bit ~score words, four per shared-memory load; the
-      // ranks are a permutation unless two kept detections share a score exactly (then redone on the full keys).
-      constexpr int RR = (kRankOutMax + NT - 1) / NT;
-      int rk[RR];
-#pragma unroll
-      for (int r = 0; r < RR; ++r) {
-        const int i = tid + r * NT;
-        rk[r] = -1;
-        if (i < K) {
-          const uint32_t mh = hi32[i];
-          int rank = 0;
-          const int K4 = K & ~3;
-          for (int j = 0; j < K4; j += 4) {
-            const uint4 o = *reinterpret_cast<const uint4*>(hi32 + j);
-            rank += (o.x < mh) ? 1 : 0;
-            rank += (o.y < mh) ? 1 : 0;
-            rank += (o.z < mh) ? 1 : 0;
-            rank += (o.w < mh) ? 1 : 0;
-          }
-          for (int j = K4; j < K; ++j) rank += (hi32[j] < mh) ? 1 : 0;
-          rk[r] = rank;
-          perm[rank] = (uint16_t)i;
-        }
-      }
+    if (K > Smem::kOutCap) {                               // more kept detections than the output list holds
+      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = M; }
       __syncthreads();
-#pragma unroll
-      for (int r = 0; r < RR; ++r)
-        if (rk[r] >= 0 && perm[rk[r]] != (uint16_t)(tid + r * NT)) S.next_class = 1;
-      __syncthreads();
-      const bool tie = S.next_class != 0;
-#pragma unroll
-      for (int r = 0; r < RR; ++r) {
-        const int i = tid + r * NT;
-        if (i >= K) continue;
-        const uint64_t mine = S.keys[i];
-        int rank = rk[r];
-        if (tie) {
-          rank = 0;
-          for (int j = 0; j < K; ++j) rank += (S.keys[j] < mine) ? 1 : 0;
-        }
-        if (rank < O.max_det) emit(rank, mine);
-      }
-    } else if (next_pow2(K) > CAPM) {                       // no room to pad for the bitonic network
+      continue;
+    }
+    {
+      // position = number of smaller keys (the keys are unique); two keys per shared-memory load
+      const uint64_t* ok = S.okeys();
       for (int i = tid; i < K; i += NT) {
-        const uint64_t mine = S.keys[i];
+        const uint64_t mine = ok[i];
         int rank = 0;
-        for (int j = 0; j < K; ++j) rank += (S.keys[j] < mine) ? 1 : 0;
-        if (rank < O.max_det) emit(rank, mine);
+        const int K2 = K & ~1;
+        for (int j = 0; j < K2; j += 2) {
+          const ulonglong2 o = *reinterpret_cast<const ulonglong2*>(ok + j);
+          rank += (o.x < mine) ? 1 : 0;
+          rank += (o.y < mine) ? 1 : 0;
+        }
+        if (K2 < K) rank += (ok[K2] < mine) ? 1 : 0;
+        if (rank < O.max_det) {
+          const float score = __uint_as_float(~(uint32_t)(mine >> 32));
+          const uint32_t low = (uint32_t)mine;
+          const int h = low >> 7, c = low & 127;
+          const uint32_t meta = S.hmeta[h];
+          int64_t row = meta;
+          if (SRC != 1) {
+            const LevelDev& L = P.lv[meta >> 30];
+            row = L.row_off + (int64_t)(meta & 0x7ffffff) * A + ((meta >> 27) & 7);
+          }
+          write_det(O, b, rank, S.hbox[h], score, c, row, C);
+        }
       }
-    } else {
-      const int P3 = next_pow2(K);
-      for (int i = K + tid; i < P3; i += NT) S.keys[i] = ~0ull;
-      __syncthreads();
-      bitonic_sort_block(S.keys, P3);
-      const int nout = min(K, O.max_det);
-      for (int j = tid; j < nout; j += NT) emit(j, S.keys[j]);
     }
     if (tid == 0) {
       O.counts[b] = K;
