@@ -6,6 +6,13 @@ ground truth per detection).  Here the host keeps the bookkeeping - detections o
 (-score, insertion index) like tools.PriorityQueue, labels grouped per (image, class) with numpy's own argsort -
 and the final cumsum / precision / recall / AP arithmetic, which the reference already evaluates vectorised in
 numpy; the matching itself runs as one kernel launch (csrc/ap.cu, pqdet_ap_match).
+
+Promotion rules: parity is pinned to NumPy >= 2 (NEP 50; the goldens were generated with numpy 2.3 plus the np.bool /
+np.float shims of oracle/ref_harness.py): a float32 detection box keeps the detection's own area
+(bb2-bb0+1)*(bb3-bb1+1) in float32.  The unmodified reference needs numpy < 1.24 (it uses np.bool / np.float), where
+float32 scalar + Python float promotes to float64; under those legacy rules `uni` is rounded differently, and an IoU
+that sits exactly on one of the ten thresholds can flip between tp and fp.  The bit-identical (C,10) table claim holds
+for the NumPy 2 semantics the tests run under.
 """
 from __future__ import annotations
 
