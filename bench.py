@@ -873,6 +873,37 @@ def collective_legs(device, rank, world, steps, warmup, peak):
         us_with = timed_us(lambda: eval_step(True), steps)
         us_without = timed_us(lambda: eval_step(False), steps)
         all_det, all_counts, _ = res["all"]
+        # the same gather with NO collective: the kernel stores its rows into every rank's buffers over NVLink peer
+        # memory (pqdet_decode_nms_gather + a symmetric-memory barrier); needs an initialised process group
+        peer = None
+        if world > 1:
+            try:
+                pg = pqd.PeerGather(Bv, K_CAP, device)
+
+                def peer_step():
+                    _, h, keep = esets[it[0] % 2]
+                    it[0] += 1
+                    res["peer"] = pg.decode_nms(h, keep)
+                us_peer = timed_us(peer_step, steps)
+                pdet, pcnt = res["peer"][0], res["peer"][1]
+                _, h, keep = esets[0]
+                it[0] = 0
+                eval_step(True)
+                it[0] = 0
+                peer_step()                                   # both on input set 0
+                torch.cuda.synchronize()
+                pdet, pcnt = res["peer"][0], res["peer"][1]
+                a_det, a_cnt, _ = res["all"]
+                same = bool(torch.equal(pcnt, a_cnt)) and all(
+                    torch.equal(pdet[r, j, :int(pcnt[r, j])], a_det[r, j, :int(a_cnt[r, j])])
+                    for r in range(world) for j in range(0, Bv, 97))
+                peer = {"us_per_step": us_peer, "value": world * Bv / (us_peer * 1e-6), "unit": "images/s",
+                        "identical_to_nccl_gather": same,
+                        "what": "pqdet_decode_nms_gather: kept rows + counts stored into every rank's gathered buffers "
+                                "through NVLink peer memory from inside the kernel, then a symmetric-memory barrier; no "
+                                "collective in the step"}
+            except Exception as e:
+                peer = {"error": repr(e)[:200]}
         legs["E_eval_gather"] = {
             "workload": "BASELINE config E: fused decode+NMS on 1024 VOC-512 images/GPU, then one all_gather of "
                         "[count | %d rows x 6] per image to every rank" % K_CAP,
@@ -881,6 +912,7 @@ def collective_legs(device, rank, world, steps, warmup, peak):
             "collective": "all_gather_into_tensor of %d bytes per rank over NCCL, inside the timed region"
                           % (Bv * (1 + K_CAP * 6) * 4),
             "collective_share": max(0.0, (us_with - us_without) / us_with),
+            "peer_memory_gather": peer,
             "gathered_images": int(all_counts.numel()), "gathered_detections": int(all_counts.sum()),
             "truncated_images": int((all_counts >= K_CAP).sum())}
     finally:

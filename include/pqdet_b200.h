@@ -130,6 +130,19 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
                      int32_t* counts, int32_t* ncand, int32_t* status, int32_t* work_counter,
                      int counter_armed, int capacity_class, int device, void* stream);
 
+/* ---- multi-GPU eval without a collective (the gather of eval detections,
+ * eval/evaluator.py:49-61 under nn.DataParallel): pqdet_decode_nms whose output stage ALSO stores every kept row and
+ * every count into the gathered buffers of all ranks of the node, through peer memory mapped over NVLink / NVSwitch
+ * (e.g. torch.distributed._symmetric_memory: peer_det[p] / peer_counts[p] = rank p's buffer as mapped into this
+ * process; p = rank is the local one).  peer_det[p] (world, B, gather_cap, 6), peer_counts[p] (world, B): this call
+ * fills block `rank` of every buffer (counts clamped to gather_cap, rows beyond it dropped).  The buffers are complete
+ * on a rank once every rank's call has finished - a device-side barrier (symmetric-memory signal pads) after the
+ * launch, no data-path collective.  det / counts / ncand / status are the usual local outputs. */
+int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, int max_det, int32_t* counts, int32_t* ncand,
+                            int32_t* status, float* const* peer_det, int32_t* const* peer_counts, int n_peers,
+                            int rank, int gather_cap, int32_t* work_counter, int counter_armed, int capacity_class,
+                            int device, void* stream);
+
 /* ---- 8f-2 (second half): the eval path starting at the INPUT of the head convolutions, with nothing of size
  * B x N ever written (model/cfg/regnetx-600m-fpn.cfg:646-651 + model/parser.py:206-235 + tools.py:540-566).
  * pqdet_head_conv_hits  one level: 1x1 head convolution on the tensor cores (tcgen05, TF32 like PyTorch's default);

@@ -64,6 +64,9 @@ SIGNATURES = {
                                  c_void_p, c_int, c_int, c_int, c_void_p]),
     "pqdet_decode_nms_host": (c_int, [POINTER(HeadsT), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pqdet_decode_nms_gather": (c_int, [POINTER(HeadsT), c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                        POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int,
+                                        c_int, c_int, c_void_p]),
     "pqdet_head_conv_hits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
                                      c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pqdet_records_nms": (c_int, [POINTER(HeadsT), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,

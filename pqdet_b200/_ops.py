@@ -715,3 +715,25 @@ def records_nms(heads_t, keep_alive, rec: torch.Tensor, rec_count: torch.Tensor,
                                              _ptr(status), _ptr(work), 0, _lib.CAPACITY[capacity], _dev(rec),
                                              _stream(device)), "pqdet_records_nms")
     return det, idx, meta
+
+
+def decode_nms_gather(heads_t, keep_alive, max_det: int, out, det_ptrs: Sequence[int], cnt_ptrs: Sequence[int], rank: int,
+                      gather_cap: int, capacity: str = "compact"):
+    """pqdet_decode_nms_gather: the fused kernel that also stores its rows / counts into every rank's gathered buffers
+    (peer memory).  out = buffers of alloc_fused_outputs (reused across calls).  -> det, meta."""
+    raws, _ = keep_alive
+    device = raws[0].device
+    B = heads_t.B
+    det, _, meta = out
+    counts, ncand, status, work = meta[0:B], meta[B:2 * B], meta[2 * B:3 * B], meta[3 * B:]
+    key = (work.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+    armed = 1 if key in _FUSED_ARMED else 0
+    _FUSED_ARMED.discard(key)
+    n = len(det_ptrs)
+    VP = ctypes.c_void_p * n
+    _lib.check(_lib.load().pqdet_decode_nms_gather(ctypes.byref(heads_t), _ptr(det), int(max_det), _ptr(counts),
+                                                   _ptr(ncand), _ptr(status), VP(*det_ptrs), VP(*cnt_ptrs), n, int(rank),
+                                                   int(gather_cap), _ptr(work), armed, _lib.CAPACITY[capacity],
+                                                   _dev(raws[0]), _stream(device)), "pqdet_decode_nms_gather")
+    _FUSED_ARMED.add(key)
+    return det, meta

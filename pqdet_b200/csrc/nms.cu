@@ -75,7 +75,19 @@ struct DetOut {
   int32_t* counts;
   int32_t* ncand;
   int32_t* status;
+  // gather mode (pqdet_decode_nms_gather): every kept row and every count is ALSO stored into the gathered buffers
+  // of all ranks of the node - peer memory mapped over NVLink - at this rank's block, so the eval gather costs no
+  // collective: peer_det[p] (world, B, gather_cap, 6), peer_cnt[p] (world, B), img_off = rank * B
+  float* peer_det[8];
+  int32_t* peer_cnt[8];
+  int n_peers, gather_cap, img_off;
 };
+
+// the image's kept count, locally and - in gather mode - in every rank's gathered counts
+__device__ __forceinline__ void set_count(const DetOut& O, int b, int k) {
+  O.counts[b] = k;
+  for (int p = 0; p < O.n_peers; ++p) O.peer_cnt[p][O.img_off + b] = min(k, O.gather_cap);
+}
 
 __device__ __forceinline__ bool use_trick(int mode, int64_t M) {
   if (mode == PQDET_NMS_TRICK) return true;
@@ -121,6 +133,15 @@ __device__ __forceinline__ void write_det(const DetOut& O, int b, int j, float4 
   d[1] = make_float2(bx.z, bx.w);
   d[2] = make_float2(score, (float)c);
   if (O.det_idx) O.det_idx[(size_t)b * O.max_det + j] = (int32_t)(row * C + c);
+  if (O.n_peers && j < O.gather_cap) {
+    const size_t at = ((size_t)(O.img_off + b) * O.gather_cap + j) * 6;
+    for (int p = 0; p < O.n_peers; ++p) {                  // 24-byte rows: 8-byte aligned stores over NVLink
+      float2* g = reinterpret_cast<float2*>(O.peer_det[p] + at);
+      g[0] = make_float2(bx.x, bx.y);
+      g[1] = make_float2(bx.z, bx.w);
+      g[2] = make_float2(score, (float)c);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,7 +595,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     PQ_PHASE(2);
     const int H = S.H;
     if (H > CAPH || (SRC == 2 && H > P.rec_cap)) {
-      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = -1; }
+      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = -1; }
       __syncthreads();
       continue;
     }
@@ -791,7 +812,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     if (M > CAPM || M == 0) {
       if (tid == 0) {
         O.status[b] = M ? PQDET_ST_CAND_OVERFLOW : PQDET_ST_OK;
-        O.counts[b] = 0;
+        set_count(O, b, 0);
         O.ncand[b] = M;
       }
       __syncthreads();
@@ -871,7 +892,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     const int K = S.K;
     PQ_PHASE(8);
     if (K > Smem::kOutCap) {                               // more kept detections than the output list holds
-      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; O.counts[b] = 0; O.ncand[b] = M; }
+      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = M; }
       __syncthreads();
       continue;
     }
@@ -903,7 +924,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
       }
     }
     if (tid == 0) {
-      O.counts[b] = K;
+      set_count(O, b, K);
       O.ncand[b] = M;
       O.status[b] = (K > O.max_det) ? PQDET_ST_DET_TRUNCATED : PQDET_ST_OK;
     }
@@ -1636,6 +1657,31 @@ static int device_alias(T** p, int allow_null) {
   return PQDET_ERR_INVALID_ARG;          // pageable host memory: the device cannot read it
 }
 }  // namespace pq
+
+extern "C" int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, int max_det, int32_t* counts,
+                                       int32_t* ncand, int32_t* status, float* const* peer_det,
+                                       int32_t* const* peer_counts, int n_peers, int rank, int gather_cap,
+                                       int32_t* work_counter, int counter_armed, int capacity_class, int device,
+                                       void* stream) {
+  using namespace pq;
+  HeadsDev P;
+  memset(&P, 0, sizeof(P));
+  int rc = fill_heads(heads, &P);
+  if (rc != PQDET_OK) return rc;
+  if (!det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
+  if (!peer_det || !peer_counts || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers || gather_cap < 1)
+    return PQDET_ERR_INVALID_ARG;
+  if (P.B == 0) return PQDET_OK;
+  PQ_ENTER(device);
+  DetOut O{det, nullptr, max_det, counts, ncand, status};
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peer_det[p] || !peer_counts[p]) return PQDET_ERR_INVALID_ARG;
+    O.peer_det[p] = peer_det[p];
+    O.peer_cnt[p] = peer_counts[p];
+  }
+  O.n_peers = n_peers; O.gather_cap = gather_cap; O.img_off = rank * P.B;
+  return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 0, capacity_class, device, (cudaStream_t)stream);
+}
 
 extern "C" int pqdet_records_nms(const pqdet_heads_t* heads, const float* rec, const int32_t* rec_count, int rec_cap,
                                  float* det, int32_t* det_idx, int max_det, int32_t* counts, int32_t* ncand,

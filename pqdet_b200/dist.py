@@ -126,3 +126,46 @@ def flatten_gathered(gathered) -> List[torch.Tensor]:
         for b in range(det.shape[0]):
             res.append(det[b, :int(counts[b])])
     return res
+
+
+class PeerGather:
+    """Eval gather over peer memory instead of a collective (one node, NVLink / NVSwitch): every rank's fused
+    decode+NMS launch stores its kept rows and counts straight into the gathered buffers of ALL ranks
+    (pqdet_decode_nms_gather; the buffers are torch symmetric memory, mapped into every process), then a device-side
+    barrier on the symmetric-memory signal pads.  No data-path collective, no host round trip.
+
+        pg = PeerGather(B_local, k_cap, device)            # once (collective: rendezvous)
+        all_det, all_counts = pg.decode_nms(heads_t, keep)  # every step; (world, B, k_cap, 6), (world, B) int32
+
+    Raises RuntimeError where symmetric memory is unavailable (callers fall back to gather_detections_fixed)."""
+
+    def __init__(self, B: int, k_cap: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("PeerGather maps at most 8 peers (one node)")
+        self.B, self.k_cap, self.device = B, k_cap, torch.device(device)
+        n_det = self.world * B * k_cap * 6
+        # one symmetric allocation: [gathered rows | gathered counts (int32 bit patterns)]
+        self.buf = symm.empty(n_det + self.world * B, dtype=torch.float32, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.all_det = self.buf[:n_det].view(self.world, B, k_cap, 6)
+        self.all_counts = self.buf[n_det:].view(torch.int32).view(self.world, B)
+        self.all_counts.zero_()
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._det_ptrs = ptrs
+        self._cnt_ptrs = [p + n_det * 4 for p in ptrs]
+        self._out = None
+        self.hdl.barrier()
+
+    def decode_nms(self, heads_t, keep_alive, max_det: int = 2048, capacity: str = "compact"):
+        """Fused decode+NMS of this rank's images; returns the gathered (all_det, all_counts) views, complete on every
+        rank once the call's stream work is done, and the local (det, meta) buffers."""
+        from . import _ops
+        if self._out is None:
+            self._out = _ops.alloc_fused_outputs(self.B, max_det, False, self.device)
+        det, meta = _ops.decode_nms_gather(heads_t, keep_alive, max_det, self._out, self._det_ptrs, self._cnt_ptrs,
+                                           self.rank, self.k_cap, capacity)
+        self.hdl.barrier()                                    # every rank's rows have landed everywhere
+        return self.all_det, self.all_counts, det, meta
