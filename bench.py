@@ -834,6 +834,31 @@ def collective_legs(device, rank, world, steps, warmup, peak):
             last["o"], last["g"] = o, grads
         us_with = timed_us(lambda: train_step(True), steps)
         us_without = timed_us(lambda: train_step(False), steps)
+        # the same exchange over NVLink peer memory instead of NCCL (dist.PeerReduce)
+        peer_red = None
+        if world > 1:
+            try:
+                pr = pqd.PeerReduce(device)
+
+                def peer_train_step():
+                    hs, gt_d, cnt_d = sets[it[0] % N_SETS]
+                    it[0] += 1
+                    tgt = assign_sparse(gt_d, cnt_d, out_sizes, C, DEFAULT_ANCHORS, DEFAULT_STRIDES, 0.3, trim=False)
+                    o, grads = head.loss_and_grad(hs, tgt)
+                    last["p"] = pr.reduce_losses(o, B, B * world)
+                us_peer = timed_us(peer_train_step, steps)
+                it[0] = 0
+                train_step(True)
+                it[0] = 0
+                peer_train_step()
+                torch.cuda.synchronize()
+                peer_red = {"us_per_step": us_peer, "value": world * B / (us_peer * 1e-6), "unit": "images/s",
+                            "global_loss": float(last["p"]["loss"]),
+                            "rel_diff_to_nccl": abs(float(last["p"]["loss"]) - float(last["o"]["loss"])) / abs(float(last["o"]["loss"])),
+                            "what": "pqdet_peer_publish into every rank's symmetric buffer + signal-pad barriers + "
+                                    "pqdet_peer_sum_rows: no collective in the step"}
+            except Exception as e:
+                peer_red = {"error": repr(e)[:200]}
         alg = (2 * raw_bytes(C, size) + 4 * 3 * cells(size)) * B
         legs["D_train_step"] = {
             "workload": "BASELINE config D shard: COCO C=80 608x608, 16 images/GPU (bs=%d over %d GPUs), GT 2-38/img: "
@@ -844,6 +869,7 @@ def collective_legs(device, rank, world, steps, warmup, peak):
             "collective": "all_reduce(AVG) of 19 floats over NCCL, inside the timed region",
             "collective_share": max(0.0, (us_with - us_without) / us_with),
             "global_loss": float(last["o"]["loss"]),
+            "peer_memory_reduce": peer_red,
             "roofline": {"bound": "hbm", "algorithmic_bytes_per_step_per_gpu": alg, "peak": peak,
                          "frac": alg / (us_without * 1e-6) / (peak * 1e9),
                          "note": "2R + 4 B/row (sparse targets) over the step without the collective; at 16 images "

@@ -143,6 +143,14 @@ int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, int max_det,
                             int rank, int gather_cap, int32_t* work_counter, int counter_armed, int capacity_class,
                             int device, void* stream);
 
+/* The training path's per-step loss exchange over the same peer memory (model/loss.py:105-108 + trainer.py:233:
+ * the mean of the replicas' losses): pqdet_peer_publish stores src[0..n) * scale into row `rank` of every rank's
+ * symmetric buffer (peer_bufs[p] = rank p's (world, row_stride) buffer as mapped here); after a device-side barrier
+ * pqdet_peer_sum_rows adds the rows in rank order into out[0..n).  n <= 1024. */
+int pqdet_peer_publish(const float* src, int n, float scale, float* const* peer_bufs, int n_peers, int rank,
+                       int row_stride, int device, void* stream);
+int pqdet_peer_sum_rows(const float* rows, int n, int n_rows, int row_stride, float* out, int device, void* stream);
+
 /* ---- 8f-2 (second half): the eval path starting at the INPUT of the head convolutions, with nothing of size
  * B x N ever written (model/cfg/regnetx-600m-fpn.cfg:646-651 + model/parser.py:206-235 + tools.py:540-566).
  * pqdet_head_conv_hits  one level: 1x1 head convolution on the tensor cores (tcgen05, TF32 like PyTorch's default);

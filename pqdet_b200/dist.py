@@ -169,3 +169,56 @@ class PeerGather:
                                            self.rank, self.k_cap, capacity)
         self.hdl.barrier()                                    # every rank's rows have landed everywhere
         return self.all_det, self.all_counts, det, meta
+
+
+class PeerReduce:
+    """reduce_losses over peer memory instead of a collective: every rank stores its scaled (4+5L)-float loss vector
+    into its row of every rank's symmetric buffer (pqdet_peer_publish), a device-side barrier, a local sum over the rows
+    in rank order (pqdet_peer_sum_rows).  Deterministic, no host round trip; the fixed cost of the NCCL all_reduce
+    (~80 us through torch for 19 floats) drops to two tiny launches and a signal-pad barrier."""
+
+    ROW = 64
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("PeerReduce maps at most 8 peers (one node)")
+        self.device = torch.device(device)
+        # two row sets used alternately: a fast rank's step k+1 never touches rows a slow rank still sums for step k,
+        # and by the time it reaches step k+2 it has passed step k+1's barrier, which the slow rank only enters after
+        # its step-k sum (stream order) - one barrier per step suffices
+        self.buf = symm.empty(2 * self.world * self.ROW, dtype=torch.float32, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        self._ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._step = 0
+        self.hdl.barrier()
+
+    def reduce_losses(self, losses: dict, local_batch: int, global_batch: int) -> dict:
+        """Same result as dist.reduce_losses(losses, local_batch, global_batch=...): the global-batch means."""
+        import ctypes
+        from . import _lib
+        raw = getattr(losses['loss'], 'pq_out', None)
+        if raw is None:
+            raise ValueError("PeerReduce needs the loss dict DetectionHead returns (its result vector)")
+        n = raw.numel()
+        nb = len(losses['loss_per_branch'])
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        VP = ctypes.c_void_p * self.world
+        lib = _lib.load()
+        half = (self._step & 1) * self.world * self.ROW * 4          # byte offset of this step's row set
+        self._step += 1
+        _lib.check(lib.pqdet_peer_publish(ctypes.c_void_p(raw.data_ptr()), n, float(local_batch) / float(global_batch),
+                                          VP(*[p + half for p in self._ptrs]), self.world, self.rank, self.ROW,
+                                          dev_index, st), "pqdet_peer_publish")
+        self.hdl.barrier()
+        vec = torch.empty((n,), dtype=torch.float32, device=self.device)
+        _lib.check(lib.pqdet_peer_sum_rows(ctypes.c_void_p(self.buf.data_ptr() + half), n, self.world, self.ROW,
+                                           ctypes.c_void_p(vec.data_ptr()), dev_index, st), "pqdet_peer_sum_rows")
+        keys = ['loss', 'giou_loss', 'conf_loss', 'class_loss']
+        out = {k: vec[i:i + 1] for i, k in enumerate(keys)}
+        out['loss_per_branch'] = [vec[4 + 4 * nb + i:5 + 4 * nb + i] for i in range(nb)]
+        return out

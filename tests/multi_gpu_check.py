@@ -74,6 +74,17 @@ def main():
         assert abs(a - b) <= 1e-5 * abs(b), (k, a, b)
     for a, b in zip(red["loss_per_branch"], whole["loss_per_branch"]):
         assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
+    try:
+        pr = pqd.PeerReduce(dev)
+        for _ in range(3):
+            red2 = pr.reduce_losses(local_out, hi - lo, total)
+        for k in ("loss", "giou_loss", "conf_loss", "class_loss"):
+            assert abs(float(red2[k]) - float(whole[k])) <= 1e-5 * abs(float(whole[k])), (k, float(red2[k]), float(whole[k]))
+        for a, b in zip(red2["loss_per_branch"], whole["loss_per_branch"]):
+            assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
+        peer += ", peer-memory loss reduce ok"
+    except RuntimeError as e:
+        peer += ", peer-memory loss reduce unavailable: %s" % (str(e).splitlines()[0][:120],)
     dist.barrier()
     if rank == 0:
         print("multi_gpu_check ok: world=%d, %d images, sharded rows bit-identical, reduced loss %.6f == %.6f; %s"
