@@ -808,6 +808,20 @@ def collective_legs(device, rank, world, steps, warmup, peak):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) * 1e3 / n
 
+    def peer_memory_ok():
+        """All ranks agree (one tiny all_reduce) that symmetric memory can be allocated before any of them enters the
+        collective rendezvous: a rank that cannot must not leave the others waiting."""
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            symm.empty(16, dtype=torch.float32, device=device)
+        except Exception:
+            ok = 0
+        t = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+    peer_ok = world > 1 and peer_memory_ok()
+
     legs = {}
     old = pqcfg.nan_check
     pqcfg.nan_check = "off"
@@ -835,8 +849,8 @@ def collective_legs(device, rank, world, steps, warmup, peak):
         us_with = timed_us(lambda: train_step(True), steps)
         us_without = timed_us(lambda: train_step(False), steps)
         # the same exchange over NVLink peer memory instead of NCCL (dist.PeerReduce)
-        peer_red = None
-        if world > 1:
+        peer_red = None if world == 1 else {"unavailable": "torch symmetric memory cannot be allocated on every rank"}
+        if peer_ok:
             try:
                 pr = pqd.PeerReduce(device)
 
@@ -901,8 +915,8 @@ def collective_legs(device, rank, world, steps, warmup, peak):
         all_det, all_counts, _ = res["all"]
         # the same gather with NO collective: the kernel stores its rows into every rank's buffers over NVLink peer
         # memory (pqdet_decode_nms_gather + a symmetric-memory barrier); needs an initialised process group
-        peer = None
-        if world > 1:
+        peer = None if world == 1 else {"unavailable": "torch symmetric memory cannot be allocated on every rank"}
+        if peer_ok:
             try:
                 pg = pqd.PeerGather(Bv, K_CAP, device)
 
@@ -1208,6 +1222,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-loss", action="store_true")
     args = ap.parse_args()
+    # a hung rank (a collective that never completes) must not hold the box: give up loudly after 10 minutes
+    def _watchdog():
+        time.sleep(600)
+        sys.stderr.write("bench.py: watchdog fired after 600 s, aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=_watchdog, daemon=True).start()
     if args.impl == "reference":
         run_reference(args)
     else:
