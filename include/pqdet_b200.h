@@ -135,7 +135,8 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
  * every count into the gathered buffers of all ranks of the node, through peer memory mapped over NVLink / NVSwitch
  * (e.g. torch.distributed._symmetric_memory: peer_det[p] / peer_counts[p] = rank p's buffer as mapped into this
  * process; p = rank is the local one).  peer_det[p] (world, B, gather_cap, 6), peer_counts[p] (world, B): this call
- * fills block `rank` of every buffer (counts clamped to gather_cap, rows beyond it dropped).  The buffers are complete
+ * fills block `rank` of every buffer (counts clamped to gather_cap, rows beyond it dropped; gather_cap must be
+ * even: an image's rows are staged on chip and leave as coalesced 16-byte stores).  The buffers are complete
  * on a rank once every rank's call has finished - a device-side barrier (symmetric-memory signal pads) after the
  * launch, no data-path collective.  det / counts / ncand / status are the usual local outputs. */
 int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, int max_det, int32_t* counts, int32_t* ncand,

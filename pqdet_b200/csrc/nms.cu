@@ -133,15 +133,6 @@ __device__ __forceinline__ void write_det(const DetOut& O, int b, int j, float4 
   d[1] = make_float2(bx.z, bx.w);
   d[2] = make_float2(score, (float)c);
   if (O.det_idx) O.det_idx[(size_t)b * O.max_det + j] = (int32_t)(row * C + c);
-  if (O.n_peers && j < O.gather_cap) {
-    const size_t at = ((size_t)(O.img_off + b) * O.gather_cap + j) * 6;
-    for (int p = 0; p < O.n_peers; ++p) {                  // 24-byte rows: 8-byte aligned stores over NVLink
-      float2* g = reinterpret_cast<float2*>(O.peer_det[p] + at);
-      g[0] = make_float2(bx.x, bx.y);
-      g[1] = make_float2(bx.z, bx.w);
-      g[2] = make_float2(score, (float)c);
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -919,7 +910,40 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
             const LevelDev& L = P.lv[meta >> 30];
             row = L.row_off + (int64_t)(meta & 0x7ffffff) * A + ((meta >> 27) & 7);
           }
-          write_det(O, b, rank, S.hbox[h], score, c, row, C);
+          const float4 bx = S.hbox[h];
+          write_det(O, b, rank, bx, score, c, row, C);
+          if (O.n_peers && rank < O.gather_cap) {          // gather mode: the row is also staged for the peers
+            constexpr int kStageRows = (int)(sizeof(S.keys) / 24);          // keys[] is free once the NMS is done
+            if (rank < kStageRows) {
+              float2* st = reinterpret_cast<float2*>(S.keys) + 3 * rank;
+              st[0] = make_float2(bx.x, bx.y);
+              st[1] = make_float2(bx.z, bx.w);
+              st[2] = make_float2(score, (float)c);
+            } else {                                       // beyond the staging area (> 426 rows of one image): direct
+              const size_t at = ((size_t)(O.img_off + b) * O.gather_cap + rank) * 6;
+              for (int p = 0; p < O.n_peers; ++p) {
+                float2* g = reinterpret_cast<float2*>(O.peer_det[p] + at);
+                g[0] = make_float2(bx.x, bx.y);
+                g[1] = make_float2(bx.z, bx.w);
+                g[2] = make_float2(score, (float)c);
+              }
+            }
+          }
+        }
+      }
+      if (O.n_peers) {
+        // the image's rows are one contiguous run in every rank's gathered buffer: they cross NVLink as coalesced
+        // 16-byte stores (a handful of 128-byte packets per image and peer) instead of three 8-byte stores per row
+        __syncthreads();
+        const int nrow = min(K, min(O.gather_cap, (int)(sizeof(S.keys) / 24)));
+        const int n2 = nrow * 3, n4 = n2 >> 1;             // float2 / float4 units (gather_cap is even: aligned base)
+        const float4* src4 = reinterpret_cast<const float4*>(S.keys);
+        const size_t at = (size_t)(O.img_off + b) * O.gather_cap * 6;
+        for (int p = 0; p < O.n_peers; ++p) {
+          float4* dst4 = reinterpret_cast<float4*>(O.peer_det[p] + at);
+          for (int i = tid; i < n4; i += NT) dst4[i] = src4[i];
+          if ((n2 & 1) && tid == 0)
+            reinterpret_cast<float2*>(O.peer_det[p] + at)[n2 - 1] = reinterpret_cast<const float2*>(S.keys)[n2 - 1];
         }
       }
     }
@@ -1669,8 +1693,9 @@ extern "C" int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, i
   int rc = fill_heads(heads, &P);
   if (rc != PQDET_OK) return rc;
   if (!det || !counts || !ncand || !status || !work_counter || max_det < 1) return PQDET_ERR_INVALID_ARG;
-  if (!peer_det || !peer_counts || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers || gather_cap < 1)
+  if (!peer_det || !peer_counts || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers || gather_cap < 2)
     return PQDET_ERR_INVALID_ARG;
+  if (gather_cap & 1) return PQDET_ERR_UNSUPPORTED;       // 16-byte aligned image blocks (coalesced float4 stores)
   if (P.B == 0) return PQDET_OK;
   PQ_ENTER(device);
   DetOut O{det, nullptr, max_det, counts, ncand, status};
