@@ -15,6 +15,19 @@ from pqdet_b200 import _ops, synth  # noqa: E402
 cap = sys.argv[1] if len(sys.argv) > 1 else "compact"
 B, C, size = (int(sys.argv[2]) if len(sys.argv) > 2 else 1024), 20, 512
 dev = torch.device("cuda", 0)
+if os.environ.get("PQ_L2_FETCH"):
+    # cudaLimitMaxL2FetchGranularity (0x05): a hint for the L2's DRAM fetch size (default 64 bytes)
+    import ctypes
+    torch.cuda.init()
+    torch.zeros(1, device=dev)
+    rt = None
+    for line in open("/proc/self/maps"):
+        if "libcudart" in line:
+            rt = ctypes.CDLL(line.split()[-1]); break
+    val = ctypes.c_size_t(0)
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["PQ_L2_FETCH"])))
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+    print("cudaLimitMaxL2FetchGranularity: rc %d, now %d" % (rc, val.value))
 orig = torch.tensor([float(size), float(size)], device=dev)
 sets = []
 for i in range(2):
