@@ -317,7 +317,8 @@ recover_tma_kernel(const float* __restrict__ pred, float* __restrict__ out, int6
 // one bulk store; two staging tiles, so the decode of tile i+1 overlaps the store of tile i.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kDtmCells = 128;
-constexpr int kDtmMaxStages = 4;
+constexpr int kDtmMaxStages = 8;
+constexpr int kDtmMaxUnits = 64;     // work units of one cell row (ACH <= 256: at most 32 + A)
 
 struct DecodeTmaParams {
   float* out;
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(768, 1)
 decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid_constant__ DecodeTmaMaps maps) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ __align__(8) uint64_t full_bar[kDtmMaxStages], empty_bar[kDtmMaxStages];
+  __shared__ uint32_t utab[kDtmMaxUnits];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int ch = P.ch, ACH = P.A * ch, S = P.stages;
   const uint32_t stage_bytes = (uint32_t)ACH * kDtmCells * 4u;
@@ -380,6 +382,19 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
     // (21 -> 3 x 7), numbered first, then the 4 box channels of every anchor (cheaper: no reciprocal); the wq warps of
     // a quarter take the units round robin
     const int ns = ch - 4, grp = (ns + 7) / 8, usz = (ns + grp - 1) / grp, nsig = P.A * grp, nunit = nsig + P.A;
+    // the units are the same for every tile: (first channel of the head | channel count << 16; count 0 = the 4 box
+    // channels), worked out once into shared memory (no division in the tile loop)
+    for (int u = ctid; u < nunit; u += n_cmp) {
+      uint32_t e;
+      if (u >= nsig) {
+        e = (uint32_t)((u - nsig) * ch);
+      } else {
+        const int a = u / grp, j = u - a * grp, k = 4 + j * usz;
+        e = (uint32_t)(a * ch + k) | ((uint32_t)min(usz, ch - k) << 16);
+      }
+      utab[u] = e;
+    }
+    epi_bar_sync(n_cmp);
     uint32_t s = 0, ph = 0, tl = 0;
     // per-tile bookkeeping without divisions: (image, tile within image) advance by gridDim.x with carries
     int b = blockIdx.x / P.tiles_img, t = blockIdx.x - b * P.tiles_img;
@@ -406,36 +421,24 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       mbar_wait(&full_bar[s], ph);
       const float* src = reinterpret_cast<const float*>(dsm + (size_t)s * stage_bytes) + r;
       float* trow0 = tile + r * ACH;
-      for (int u = jq; u < (r < ncell ? nunit : 0); u += P.wq) {
-        if (u >= nsig) {
-          const int a = u - nsig;
-          const float* sp = src + (a * ch) * kDtmCells;
-          float raw[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) raw[i] = sp[i * kDtmCells];
-          decode_box4(raw, gx, gy, stride, trow0 + a * ch);
-        } else {
-          const int a = u / grp, j = u - a * grp;
-          const int k = 4 + j * usz, cnt = min(usz, ch - k), c0 = a * ch + k;
+#ifndef PQ_DTM_NOCOMPUTE
+      if (r < ncell) {
+#pragma unroll 1
+        for (int u = jq; u < nunit; u += P.wq) {
+          const uint32_t e = utab[u];
+          const int c0 = (int)(e & 0xffffu), cnt = (int)(e >> 16);
           const float* sp = src + c0 * kDtmCells;
-          if (cnt == 8) {
-            float raw[8];
+          if (cnt == 0) {
+            float raw[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) raw[i] = sp[i * kDtmCells];
-            decode_sig<8>(raw, 8, trow0 + c0);
-          } else if (cnt == 7) {                                   // 1 + 20 classes = 3 x 7
-            float raw[7];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) raw[i] = sp[i * kDtmCells];
-            decode_sig<7>(raw, 7, trow0 + c0);
+            for (int k = 0; k < 4; ++k) raw[k] = sp[k * kDtmCells];
+            decode_box4(raw, gx, gy, stride, trow0 + c0);
           } else {
-            float raw[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) raw[i] = (i < cnt) ? sp[i * kDtmCells] : 0.0f;
-            decode_sig<8>(raw, cnt, trow0 + c0);
+            decode_sig_n_strided(sp, kDtmCells, cnt, trow0 + c0);
           }
         }
       }
+#endif
       t += step_t; b += step_b;
       if (t >= P.tiles_img) { t -= P.tiles_img; ++b; }
       // this warp has read its part of the stage: the producer may refill it
@@ -450,7 +453,9 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
         epi_bar_sync(n_cmp);
         // every tile commits exactly one bulk group (so "at most one pending" above = the other staging tile's)
         if (ctid == 0) {
+#ifndef PQ_DTM_NOSTORE
           if (i1 > i0) tma_store_1d(dst + i0, tile + i0, (uint32_t)((i1 - i0) * sizeof(float)));
+#endif
           tma_store_commit();
         }
         if (i1 > i0) {
@@ -480,7 +485,7 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
                           cudaStream_t stream) {
   using namespace pq;
   const int ch = 5 + C, ACH = A * ch;
-  if (ACH > 256) return 0;
+  if (ACH > 256 || A * ((ch - 4 + 7) / 8) + A > kDtmMaxUnits) return 0;
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (((size_t)rows * ch * 4) & 15) == 0;
   PqEncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return 0;
@@ -517,6 +522,10 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   if (room < 4 * tile_bytes) return 0;                              // 2 input stages + 2 staging tiles at least
   size_t st = room / tile_bytes - 2;
   if (st > (size_t)kDtmMaxStages) st = kDtmMaxStages;
+  if (const char* e = getenv("PQDET_DECODE_STAGES")) {                // A/B switch: cap the input ring
+    const size_t cap = (size_t)atoi(e);
+    if (cap >= 2 && cap < st) st = cap;
+  }
   P.stages = (int)st;
   // compute warps per quarter: the count (<= 5) whose most loaded warp has the least work, units dealt round robin
   // (cost model: a group of objectness / class channels ~ 2.5 x the 4 box channels of an anchor)

@@ -353,6 +353,7 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
   extern __shared__ __align__(1024) unsigned char hsm_ws[];
   __shared__ __align__(8) uint64_t full_bar[kWsMaxStages], empty_bar[kWsMaxStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t utab[64];        // work units of one cell row: first channel | channel count << 16 (0 = box)
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int ACH = P.A * (5 + P.C), ch = 5 + P.C, N = P.N, KC = P.KC, S = P.stages;
   const int nchunk = P.Cin / KC;
@@ -477,6 +478,23 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
     const int k_first = (jq * 8) % ch;                      // channel-within-anchor of this warp's first block
     const int k_step = (P.wq * 8) % ch;
     uint32_t tl = 0;
+    // anchor-aligned work units (see decode_levels_tma_kernel): per anchor its objectness / class channels in groups
+    // of usz <= 8, numbered first, then the 4 box channels of every anchor; the same for every tile, so the table is
+    // worked out once (no division in the tile loop)
+    const int ns = ch - 4, grp = (ns + 7) / 8, usz = (ns + grp - 1) / grp, nsig = P.A * grp, nunit = nsig + P.A;
+    if (P.units && !HITS) {
+      for (int u = etid; u < nunit; u += 4 * P.wq * 32) {
+        uint32_t e;
+        if (u >= nsig) {
+          e = (uint32_t)((u - nsig) * ch);
+        } else {
+          const int a = u / grp, j = u - a * grp, k = 4 + j * usz;
+          e = (uint32_t)(a * ch + k) | ((uint32_t)min(usz, ch - k) << 16);
+        }
+        utab[u] = e;
+      }
+      epi_bar_sync(4 * P.wq * 32);
+    }
     // per-tile bookkeeping without divisions: (image, tile within image) advance by ncta with carries
     int b = cta / P.tiles_per_img, ti = cta - b * P.tiles_per_img;
     const int step_b = ncta / P.tiles_per_img, step_t = ncta - step_b * P.tiles_per_img;
@@ -524,12 +542,11 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
       const uint32_t tacc = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16);
       float* trow0 = tile + r * ACH;
       if (P.units) {
-        // anchor-aligned work units (see decode_levels_tma_kernel): per anchor its objectness / class channels in
-        // groups of usz <= 8, numbered first, then the 4 box channels of every anchor
-        const int ns = ch - 4, grp = (ns + 7) / 8, usz = (ns + grp - 1) / grp, nsig = P.A * grp, nunit = nsig + P.A;
+#pragma unroll 1
         for (int u = jq; u < nunit; u += P.wq) {
-          if (u >= nsig) {
-            const int c0 = (u - nsig) * ch;
+          const uint32_t ue = utab[u];
+          const int c0 = (int)(ue & 0xffffu), cnt = (int)(ue >> 16);
+          if (cnt == 0) {
             uint32_t v[4];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(tacc + (uint32_t)c0) : "memory");
@@ -543,8 +560,6 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
             }
             decode_box4(raw, gx, gy, P.stride, trow0 + c0);
           } else {
-            const int a = u / grp, j = u - a * grp;
-            const int k = 4 + j * usz, cnt = min(usz, ch - k), c0 = a * ch + k;
             uint32_t v[8];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -558,16 +573,7 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
               for (int i = 0; i < 8; ++i)
                 if (i < cnt) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
             }
-            if (cnt == 8) {
-              decode_sig<8>(raw, 8, trow0 + c0);
-            } else if (cnt == 7) {                                 // 1 + 20 classes = 3 x 7
-              float r7[7];
-#pragma unroll
-              for (int i = 0; i < 7; ++i) r7[i] = raw[i];
-              decode_sig<7>(r7, 7, trow0 + c0);
-            } else {
-              decode_sig<8>(raw, cnt, trow0 + c0);
-            }
+            decode_sig_n(raw, cnt, trow0 + c0);
           }
         }
       } else {
@@ -729,7 +735,8 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   // anchor); with 8-column blocks: fewer warps when that does not lengthen the longest block list.
   int buf_cols = 32;
   while (buf_cols < N) buf_cols <<= 1;
-  P.units = (ACH + 7 <= buf_cols) ? 1 : 0;          // a unit's 8-column read may run 7 columns past the last channel
+  // a unit's 8-column read may run 7 columns past the last channel; the kernel's unit table holds 64 entries
+  P.units = (ACH + 7 <= buf_cols && A * ((5 + C - 4 + 7) / 8) + A <= 64) ? 1 : 0;
   int best = 1;
   if (P.units) {
     const int nsig = A * ((5 + C - 4 + 7) / 8), nunit = nsig + A;
