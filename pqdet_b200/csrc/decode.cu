@@ -389,8 +389,11 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       if (u >= nsig) {
         e = (uint32_t)((u - nsig) * ch);
       } else {
-        const int a = u / grp, j = u - a * grp, k = 4 + j * usz;
-        e = (uint32_t)(a * ch + k) | ((uint32_t)min(usz, ch - k) << 16);
+        // balanced: the first `big` groups of an anchor hold usz channels, the others usz - 1 (81 = 4 x 8 + 7 x 7)
+        const int big = ns - grp * (usz - 1);
+        const int a = u / grp, j = u - a * grp;
+        const int k = 4 + (j < big ? j * usz : big * usz + (j - big) * (usz - 1));
+        e = (uint32_t)(a * ch + k) | ((uint32_t)(j < big ? usz : usz - 1) << 16);
       }
       utab[u] = e;
     }

@@ -332,6 +332,8 @@ struct HeadConvWsParams {
   int wq;              // epilogue warps per TMEM lane quadrant
   int tile_bufs;       // 1 or 2 staging tiles for the output
   int all_bulk;        // every output tile is full and 16-byte aligned: all of them leave as bulk stores
+  int slice;           // 1: the staging tiles hold ONE anchor's rows of a tile (A * (5+C) * 512 bytes would not fit beside
+                       // the resident weights: COCO's 255 channels); the epilogue then works anchor by anchor
   int units;           // 1: anchor-aligned work units in the epilogue (needs ACH + 7 <= buf_cols), 0: 8-column blocks
   int buf_cols;        // TMEM column stride between the two accumulators
   int tiles_per_img, ntiles;
@@ -347,7 +349,7 @@ struct HeadConvWsParams {
 };
 
 // Body of the persistent kernel: this CTA is number `cta` of the `ncta` that share the level described by P.
-template <bool WANT_RAW, bool HITS = false>
+template <bool WANT_RAW, bool HITS = false, bool SLICE = false>
 __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, const CUtensorMap* tmap_x, const int cta,
                                                   const int ncta) {
   extern __shared__ __align__(1024) unsigned char hsm_ws[];
@@ -364,7 +366,8 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
   const uint32_t sX = base;
   const uint32_t sW = base + (uint32_t)S * stage_bytes;
   float* tile0 = reinterpret_cast<float*>(aligned + (size_t)S * stage_bytes + (size_t)P.Cin * N * 4);
-  const int tile_stride = kHcM * ACH + 4;                   // + 16 bytes: a tile is written at the output's 16-byte phase
+  // + 16 bytes: a tile is written at the output's 16-byte phase; slice mode: one anchor's rows (128 x (5+C))
+  const int tile_stride = (P.slice ? kHcM * ch : kHcM * ACH) + 4;
   float* sbias = tile0 + P.tile_bufs * tile_stride;         // N + 8 floats, zero beyond ACH or without a bias
   const int n_epi = 4 * P.wq * 32;
 
@@ -481,20 +484,24 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
     // anchor-aligned work units (see decode_levels_tma_kernel): per anchor its objectness / class channels in groups
     // of usz <= 8, numbered first, then the 4 box channels of every anchor; the same for every tile, so the table is
     // worked out once (no division in the tile loop)
+    // (balanced: the first `big` groups of an anchor hold usz channels, the others usz - 1; 81 = 4 x 8 + 7 x 7)
     const int ns = ch - 4, grp = (ns + 7) / 8, usz = (ns + grp - 1) / grp, nsig = P.A * grp, nunit = nsig + P.A;
+    const int big = ns - grp * (usz - 1);
     if (P.units && !HITS) {
       for (int u = etid; u < nunit; u += 4 * P.wq * 32) {
         uint32_t e;
         if (u >= nsig) {
           e = (uint32_t)((u - nsig) * ch);
         } else {
-          const int a = u / grp, j = u - a * grp, k = 4 + j * usz;
-          e = (uint32_t)(a * ch + k) | ((uint32_t)min(usz, ch - k) << 16);
+          const int a = u / grp, j = u - a * grp;
+          const int k = 4 + (j < big ? j * usz : big * usz + (j - big) * (usz - 1));
+          e = (uint32_t)(a * ch + k) | ((uint32_t)(j < big ? usz : usz - 1) << 16);
         }
         utab[u] = e;
       }
       epi_bar_sync(4 * P.wq * 32);
     }
+    uint32_t sl = 0;                                        // slice mode: running slice count (staging buffer = sl & 1)
     // per-tile bookkeeping without divisions: (image, tile within image) advance by ncta with carries
     int b = cta / P.tiles_per_img, ti = cta - b * P.tiles_per_img;
     const int step_b = ncta / P.tiles_per_img, step_t = ncta - step_b * P.tiles_per_img;
@@ -541,41 +548,69 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
       epi_bar_sync(n_epi);
       const uint32_t tacc = tmem_base + buf * (uint32_t)P.buf_cols + ((uint32_t)(q * 32) << 16);
       float* trow0 = tile + r * ACH;
-      if (P.units) {
+      // one work unit of this thread's cell: TMEM -> + bias -> (raw planes) -> decode into the staging row at trow
+      auto do_unit = [&](const uint32_t ue, float* __restrict__ trow) {
+        const int c0 = (int)(ue & 0xffffu), cnt = (int)(ue >> 16);
+        if (cnt == 0) {
+          uint32_t v[4];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(tacc + (uint32_t)c0) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float raw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
+          if (WANT_RAW && in_level) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
+          }
+          decode_box4(raw, gx, gy, P.stride, trow + c0);
+        } else {
+          uint32_t v[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(tacc + (uint32_t)c0) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float raw[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
+          if (WANT_RAW && in_level) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i < cnt) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
+          }
+          decode_sig_n(raw, cnt, trow + c0);
+        }
+      };
+      if (SLICE) {
+        // Anchor by anchor through two small staging tiles: decode anchor a's channels of the 128 cells, barrier, copy
+        // its rows out (runs of 5+C floats, A*(5+C) apart) - the copy of slice i and the decode of slice i+1 need no
+        // barrier between them, the other buffer is rewritten only after the next barrier.
+        const int ewarp = (warp - 4), nwarp_e = 4 * P.wq;
+        for (int a = 0; a < P.A; ++a, ++sl) {
+          float* stile = tile0 + ((sl & 1u) ? tile_stride : 0);
+          float* trow_a = stile + r * ch - a * ch;            // so that trow_a + c0 is channel (c0 - a*ch) of row r
 #pragma unroll 1
-        for (int u = jq; u < nunit; u += P.wq) {
-          const uint32_t ue = utab[u];
-          const int c0 = (int)(ue & 0xffffu), cnt = (int)(ue >> 16);
-          if (cnt == 0) {
-            uint32_t v[4];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(tacc + (uint32_t)c0) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float raw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
-            if (WANT_RAW && in_level) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
+          for (int i = jq; i <= grp; i += P.wq) do_unit(utab[i < grp ? a * grp + i : nsig + a], trow_a);
+          if (a == P.A - 1) {
+            // this warp no longer needs the accumulator: the MMA warp may start the tile after next in it
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          epi_bar_sync(n_epi);
+          if (P.out_dec) {
+            for (int rr = ewarp; rr < ncell; rr += nwarp_e) {
+              const float* srow = stile + rr * ch;
+              float* drow = dst + ((size_t)rr * P.A + a) * ch;
+              for (int k = lane; k < ch; k += 32) drow[k] = srow[k];
             }
-            decode_box4(raw, gx, gy, P.stride, trow0 + c0);
-          } else {
-            uint32_t v[8];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                         : "r"(tacc + (uint32_t)c0) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float raw[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) raw[i] = PQ_ADD(__uint_as_float(v[i]), sbias[c0 + i]);
-            if (WANT_RAW && in_level) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (i < cnt) P.out_raw[raw_base + (size_t)(c0 + i) * P.HW] = raw[i];
-            }
-            decode_sig_n(raw, cnt, trow0 + c0);
           }
         }
+        continue;
+      }
+      if (P.units) {
+#pragma unroll 1
+        for (int u = jq; u < nunit; u += P.wq) do_unit(utab[u], trow0);
       } else {
         int k0 = k_first;
         for (int blk = jq; blk < nblk; blk += P.wq) {
@@ -637,10 +672,10 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
 }
 
 
-template <bool WANT_RAW>
+template <bool WANT_RAW, bool SLICE = false>
 __global__ void __launch_bounds__(768, 1)
 head_conv_decode_ws_kernel(const __grid_constant__ HeadConvWsParams P, const __grid_constant__ CUtensorMap tmap_x) {
-  head_conv_ws_body<WANT_RAW>(P, &tmap_x, (int)blockIdx.x, (int)gridDim.x);
+  head_conv_ws_body<WANT_RAW, false, SLICE>(P, &tmap_x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 __global__ void __launch_bounds__(768, 1)
@@ -690,7 +725,8 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   if (!enc) return 0;
   HeadConvWsParams P;
   memset(&P, 0, sizeof(P));
-  const size_t w_bytes = (size_t)Cin * N * 4, tile_bytes = (size_t)(kHcM * ACH + 4) * 4, bias_bytes = (size_t)(N + 8) * 4;
+  const size_t w_bytes = (size_t)Cin * N * 4, bias_bytes = (size_t)(N + 8) * 4;
+  size_t tile_bytes = (size_t)(kHcM * ACH + 4) * 4;
   DeviceLimits lim;
   if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
   const int max_smem = lim.max_smem_optin, sms = lim.sms;
@@ -724,7 +760,14 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
       P.tile_bufs = 2;
       if (!plan(2, 8, &P.KC, &P.stages)) {
         P.tile_bufs = 1;
-        if (!plan(1, 8, &P.KC, &P.stages)) return 0;
+        if (!plan(1, 8, &P.KC, &P.stages)) {
+          // the whole tile does not fit beside the resident weights (COCO: 255 channels = 130 KB): two staging tiles
+          // of ONE anchor's rows each, the epilogue works anchor by anchor
+          tile_bytes = (size_t)(kHcM * (5 + C) + 4) * 4;
+          P.tile_bufs = 2;
+          P.slice = 1;
+          if (!plan(2, 48, &P.KC, &P.stages) && !plan(2, 8, &P.KC, &P.stages)) return 0;
+        }
       }
     }
   }
@@ -735,8 +778,14 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   // anchor); with 8-column blocks: fewer warps when that does not lengthen the longest block list.
   int buf_cols = 32;
   while (buf_cols < N) buf_cols <<= 1;
-  // a unit's 8-column read may run 7 columns past the last channel; the kernel's unit table holds 64 entries
-  P.units = (ACH + 7 <= buf_cols && A * ((5 + C - 4 + 7) / 8) + A <= 64) ? 1 : 0;
+  // anchor-aligned units (balanced: sizes usz and usz - 1): the 8-column read of the last one may run past the last
+  // channel but must stay inside the accumulator buffer; the kernel's unit table holds 64 entries
+  {
+    const int ns = C + 1, grp = (ns + 7) / 8, usz = (ns + grp - 1) / grp, big = ns - grp * (usz - 1);
+    const int last_cnt = big == grp ? usz : usz - 1;
+    P.units = (ACH - last_cnt + 8 <= buf_cols && A * grp + A <= 64) ? 1 : 0;
+  }
+  if (P.slice && !P.units) return 0;
   int best = 1;
   if (P.units) {
     const int nsig = A * ((5 + C - 4 + 7) / 8), nunit = nsig + A;
@@ -799,19 +848,16 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
                                    device, &P, &tmap, &smem, &sms);
   if (rc != 1) return rc;
   const int grid = P.ntiles < sms ? P.ntiles : sms;
-  static int smem_set[2][64];                 // the attribute sticks per device: raise it only when needed
-  const int which = out_raw ? 1 : 0;
+  static int smem_set[4][64];                 // the attribute sticks per device: raise it only when needed
+  const int which = (out_raw ? 1 : 0) + (P.slice ? 2 : 0);
+  void (*kern)(const HeadConvWsParams, const CUtensorMap) =
+      which == 0 ? head_conv_decode_ws_kernel<false, false> : which == 1 ? head_conv_decode_ws_kernel<true, false>
+      : which == 2 ? head_conv_decode_ws_kernel<false, true> : head_conv_decode_ws_kernel<true, true>;
   if (device < 0 || device >= 64 || (int)smem > smem_set[which][device]) {
-    if (out_raw)
-      PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (device >= 0 && device < 64) smem_set[which][device] = (int)smem;
   }
-  if (out_raw)
-    head_conv_decode_ws_kernel<true><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
-  else
-    head_conv_decode_ws_kernel<false><<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
+  kern<<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
   PQ_LAUNCH_CHECK();
   return 1;
 }
@@ -954,7 +1000,7 @@ extern "C" int pqdet_head_conv_decode_levels(int n_levels, const float* const* x
     const int rc = plan_head_conv_ws(x[l], weight[l], bias ? bias[l] : nullptr, out_decoded, nullptr, B, Cin[l], H[l], W[l], A,
                                      C, stride[l], rows_total, row_off, device, &LP.P[l], &maps.m[l], &sm_l, &sms);
     if (rc < 0) return rc;
-    if (rc == 0) return PQDET_ERR_UNSUPPORTED;
+    if (rc == 0 || LP.P[l].slice) return PQDET_ERR_UNSUPPORTED;      // (sliced epilogue: per-level launches)
     smem = sm_l > smem ? sm_l : smem;
     const int th = (4 + 4 * LP.P[l].wq) * 32;
     if (threads && th != threads) return PQDET_ERR_UNSUPPORTED;

@@ -519,7 +519,7 @@ def test_features_to_detections_falls_back_on_unaligned_levels_and_dense_images(
         assert torch.equal(got[b], want[b])
 
 
-@pytest.mark.parametrize("C,cins", [(10, (352, 176, 80)), (80, (64, 48, 32))])
+@pytest.mark.parametrize("C,cins", [(10, (352, 176, 80)), (80, (64, 48, 32)), (80, (352, 176, 80))])
 def test_head_conv_608_levels_persistent_vs_general(C, cins, monkeypatch):
     """608 x 608 inputs (BASELINE configs C / D): 38 x 38 and 76 x 76 levels now take the persistent kernel (partial
     last tile through TMA zero fill, rows of the concatenated prediction not 16-byte aligned -> cooperative stores);
