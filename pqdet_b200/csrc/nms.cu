@@ -1067,6 +1067,11 @@ gen_select_kernel(const __grid_constant__ GenParams G) {
       const float* r0 = L.raw + (size_t)(b * P.A + a) * P.ch * L.HW + cell;
       const float x = r0[(size_t)4 * L.HW];
       if (x > P.logit_lo) {
+        // the box channels are requested before the objectness is evaluated: one round trip instead of two for the
+        // rows that pass (this path serves dense scenes; the prefilter already dropped the rows far below thr)
+        float rb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rb[k] = r0[(size_t)k * L.HW];
         conf = sigmoidf_(x);
         if (conf > G.thr_f) {
           live = true;
@@ -1075,8 +1080,7 @@ gen_select_kernel(const __grid_constant__ GenParams G) {
             const Affine af = image_affine(P, b);
             const int cy = cell / L.W, cx = cell - cy * L.W;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              box[k] = recover_coord(k, decode_coord(k, r0[(size_t)k * L.HW], cx, cy, L.stride), af);
+            for (int k = 0; k < 4; ++k) box[k] = recover_coord(k, decode_coord(k, rb[k], cx, cy, L.stride), af);
           }
         }
       }
@@ -1093,7 +1097,38 @@ gen_select_kernel(const __grid_constant__ GenParams G) {
     return G.from_heads ? PQ_MUL(sigmoidf_(cls0[(size_t)c * HW]), conf) : scores[c];
   };
   uint64_t m0 = 0, m1 = 0;          // classes of this row with score > thr
-  if (live) {
+  float sc16[16];                   // scores of classes 0..15 (static indexing only; the rest is re-evaluated on use)
+#pragma unroll
+  for (int u = 0; u < 16; ++u) sc16[u] = 0.0f;
+  if (G.from_heads) {
+    // warp-uniform loop over batches of 8 classes: the 8 logits of a batch are requested together (one round trip per
+    // batch instead of one per class), and the per-class counts go through a ballot (one shared atomic per warp and
+    // class instead of one per candidate)
+    if (__any_sync(PQ_FULL, live)) {
+      const int lane = lane_id();
+#pragma unroll 2
+      for (int c0 = 0; c0 < C; c0 += 8) {
+        float z[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) z[u] = (live && c0 + u < C) ? cls0[(size_t)(c0 + u) * HW] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + u;
+          if (c < C) {                                      // warp-uniform
+            const float sc = PQ_MUL(sigmoidf_(z[u]), conf); // == score_of(c)
+            const bool pass = live && sc > G.thr_f;
+            const unsigned bm = __ballot_sync(PQ_FULL, pass);
+            if (pass) {
+              if (c < 64) m0 |= 1ull << c; else m1 |= 1ull << (c - 64);
+            }
+            if (c0 == 0) sc16[u] = sc;
+            else if (c0 == 8) sc16[8 + u] = sc;
+            if (lane == 0 && bm) atomicAdd(&s_cnt[c], (unsigned)__popc(bm));
+          }
+        }
+      }
+    }
+  } else if (live) {
     for (int c = 0; c < C; ++c) {
       if (score_of(c) > G.thr_f) {
         if (c < 64) m0 |= 1ull << c; else m1 |= 1ull << (c - 64);
@@ -1132,6 +1167,17 @@ gen_select_kernel(const __grid_constant__ GenParams G) {
     if (!any) return;
     uint64_t slot = (uint64_t)s_stage_base + before + inc - mine;
     uint64_t* stage = G.kkeys + (size_t)ii * (size_t)G.stage_quota;
+    if (G.from_heads) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {                          // classes 0..15: scores kept in registers
+        if ((m0 >> u) & 1ull) {
+          if (slot < (uint64_t)G.stage_quota)
+            stage[slot] = ((uint64_t)(~float_to_ordered(sc16[u])) << 32) | ((uint64_t)u << kHitBits) | (uint32_t)row;
+          ++slot;
+        }
+      }
+      m0 &= ~0xffffull;
+    }
     for (int h = 0; h < 2; ++h) {
       uint64_t m = h ? m1 : m0;
       while (m) {
