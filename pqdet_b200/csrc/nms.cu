@@ -991,6 +991,8 @@ struct GenParams {
   int64_t* img_off;          // [n_images]      start of the image's kept-key region in `kkeys`
   uint32_t* img_cap;         // [n_images]      its capacity (pow2 >= M)
   uint32_t* kept_count;      // [n_images]
+  uint32_t* run_off;         // [n_images][C]   where the bucket's kept keys start in the image's kept region ...
+  uint32_t* run_len;         // [n_images][C]   ... and how many there are (they are in score order)
   uint64_t* keys;            // [cand_capacity] bucketed candidate keys (~score | row)
   uint64_t* kkeys;           // [cand_capacity] kept keys per image
   uint32_t* klist;           // [cand_capacity] kept positions per bucket
@@ -1523,7 +1525,11 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
                              [&](int q, uint32_t pos, const float4&) { kl[q] = pos; }, s_dead, s_rows, &s_k);
   }
   // append kept keys (score desc, row asc, class asc order key) to the image's kept region
-  if (tid == 0) s_dst = atomicAdd(&G.kept_count[ii], (uint32_t)k);
+  if (tid == 0) {
+    s_dst = atomicAdd(&G.kept_count[ii], (uint32_t)k);
+    G.run_off[(size_t)ii * C + c] = s_dst;
+    G.run_len[(size_t)ii * C + c] = (uint32_t)k;
+  }
   __syncthreads();
   uint64_t* kk = G.kkeys + G.img_off[ii] + s_dst;
   for (int q = tid; q < k; q += kSegThreads) {
@@ -1552,6 +1558,52 @@ gen_finalize_kernel(const __grid_constant__ GenParams G, const __grid_constant__
     return;
   }
   uint64_t* gk = G.kkeys + G.img_off[ii];
+  const float4* rbox0 = G.from_heads ? G.rbox + (size_t)ii * G.N : nullptr;
+  const float* bb0 = G.from_heads ? nullptr : G.bboxes + (size_t)b * G.N * (4 + C);
+  if (K <= (uint32_t)kFinSmemKeys) {
+    // The kept keys of a bucket were appended in score order: the image's region is C sorted runs.  Every key finds
+    // its place by counting, run by run (binary search), how many keys of the other classes come before it - no
+    // sort, no barrier but the one after staging; the detection is written straight to its rank.
+    __shared__ uint32_t s_roff[PQDET_MAX_CLASSES + 2], s_rlen[PQDET_MAX_CLASSES + 2];
+    for (int i = tid; i < (int)K; i += kFinThreads) skeys[i] = gk[i];
+    for (int q = tid; q < C; q += kFinThreads) {
+      s_roff[q] = G.run_off[(size_t)ii * C + q];
+      s_rlen[q] = G.run_len[(size_t)ii * C + q];
+    }
+    __syncthreads();
+    for (int j = tid; j < (int)K; j += kFinThreads) {
+      const uint64_t mine = skeys[j];
+      const int c = (int)(mine & 127u);
+      uint32_t rank = (uint32_t)j - s_roff[c];
+      for (int q = 0; q < C; ++q) {
+        const uint32_t len = s_rlen[q];
+        if (q == c || len == 0) continue;
+        const uint64_t* run = skeys + s_roff[q];
+        uint32_t lo = 0, hi = len;                           // first position whose key is > mine (keys are distinct)
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (run[mid] < mine) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < (uint32_t)O.max_det) {
+        const float score = ordered_to_float(~(uint32_t)(mine >> 32));
+        const uint32_t row = (uint32_t)mine >> 7;
+        float4 bx;
+        if (rbox0) bx = rbox0[row];
+        else {
+          const float* r = bb0 + (size_t)row * (4 + C);
+          bx = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        write_det(O, ob, (int)rank, bx, score, c, row, C);
+      }
+    }
+    if (tid == 0) {
+      O.counts[ob] = (int32_t)K;
+      if ((int)K > O.max_det) O.status[ob] = PQDET_ST_DET_TRUNCATED;
+    }
+    return;
+  }
   const int Pn = next_pow2((int)K);
   uint64_t* keys = gk;
   if (Pn <= kFinSmemKeys) {
@@ -1842,7 +1894,8 @@ extern "C" int pqdet_nms_fused(const float* bboxes, int B, int64_t N, int C, dou
 
 namespace pq {
 struct GenLayout {
-  size_t cls_count, cls_fill, seg_off, seg_cap, max_ord, stage_fill, img_off, img_cap, kept_count, needed_ok, keys,
+  size_t cls_count, cls_fill, seg_off, seg_cap, max_ord, stage_fill, run_off, run_len, img_off, img_cap, kept_count,
+      needed_ok, keys,
       kkeys, klist, rbox, total;
 };
 static GenLayout gen_layout(int n_images, int64_t N, int C, int64_t cap, int from_heads) {
@@ -1855,6 +1908,8 @@ static GenLayout gen_layout(int n_images, int64_t N, int C, int64_t cap, int fro
   L.kept_count = take((size_t)n_images * 4);
   L.max_ord = take((size_t)n_images * 4);
   L.stage_fill = take((size_t)n_images * 4);
+  L.run_off = take(nc * 4);
+  L.run_len = take(nc * 4);
   L.needed_ok = take(16);
   L.seg_off = take(nc * 8);
   L.seg_cap = take(nc * 4);
@@ -1918,6 +1973,8 @@ extern "C" int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes
   G.kept_count = (uint32_t*)(ws + L.kept_count);
   G.max_ord = (uint32_t*)(ws + L.max_ord);
   G.stage_fill = (uint32_t*)(ws + L.stage_fill);
+  G.run_off = (uint32_t*)(ws + L.run_off);
+  G.run_len = (uint32_t*)(ws + L.run_len);
   G.needed = needed ? needed : (int64_t*)(ws + L.needed_ok);
   G.ok = (int32_t*)(ws + L.needed_ok + 8);
   G.seg_off = (int64_t*)(ws + L.seg_off);
@@ -1930,7 +1987,7 @@ extern "C" int pqdet_nms_general(const pqdet_heads_t* heads, const float* bboxes
   G.rbox = (float4*)(ws + L.rbox);
   G.cand_capacity = cand_capacity;
   DetOut O{det, det_idx, max_det, counts, ncand, status};
-  // the counters are the first four (contiguous) regions of the layout
+  // the counters (and the run table) are the first contiguous regions of the layout
   PQ_CUDA(cudaMemsetAsync(ws, 0, L.seg_off, st));
   dim3 sel_grid((unsigned)((G.N + 255) / 256), n_images);
   // PQDET_GEN_SELECT=twopass: count, plan, re-evaluate + scatter (round 1); default: one read of the heads
