@@ -1383,10 +1383,35 @@ __device__ __forceinline__ int bucket_greedy(uint32_t n, float iou_f, double iou
     if (valid) me = box(p);
     bool dead = !valid;
     const int k0 = *s_k;
-    for (int q = warp; q < k0; q += kSegWarps) {          // A
-      const float4 a = kget(q);
-      const float Sa = box_area(a.x, a.y, a.z, a.w);
-      if (!dead && nms_suppresses<ROUND>(a.x, a.y, a.z, a.w, Sa, me.x, me.y, me.z, me.w, iou_f, iou_d)) dead = true;
+    // A: four kept boxes per iteration - their loads and intersection chains are independent (the walk is bound by
+    // dependent-issue latency, not by the pair count), and the division is only reached by a pair that intersects
+    {
+      int q = warp;
+      for (; q + 3 * kSegWarps < k0; q += 4 * kSegWarps) {
+        float4 a[4];
+        float I[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = kget(q + u * kSegWarps);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float w = fmaxf(PQ_SUB(fminf(a[u].z, me.z), fmaxf(a[u].x, me.x)), 0.0f);
+          const float h = fmaxf(PQ_SUB(fminf(a[u].w, me.w), fmaxf(a[u].y, me.y)), 0.0f);
+          I[u] = PQ_MUL(w, h);
+        }
+        if ((I[0] > 0.0f) | (I[1] > 0.0f) | (I[2] > 0.0f) | (I[3] > 0.0f)) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (I[u] > 0.0f && !dead &&
+                nms_suppresses<ROUND>(a[u].x, a[u].y, a[u].z, a[u].w, box_area(a[u].x, a[u].y, a[u].z, a[u].w), me.x, me.y,
+                                      me.z, me.w, iou_f, iou_d))
+              dead = true;
+        }
+      }
+      for (; q < k0; q += kSegWarps) {
+        const float4 a = kget(q);
+        const float Sa = box_area(a.x, a.y, a.z, a.w);
+        if (!dead && nms_suppresses<ROUND>(a.x, a.y, a.z, a.w, Sa, me.x, me.y, me.z, me.w, iou_f, iou_d)) dead = true;
+      }
     }
     const unsigned dm = __ballot_sync(PQ_FULL, dead);
     if (lane == 0) s_dead[warp] = dm;
