@@ -338,21 +338,26 @@ struct DecodeTmaMaps {
   CUtensorMap m[PQDET_MAX_LEVELS];
 };
 
+// CELLS = cells per tile: 128 (four 32-cell quarters, up to 5 compute warps each) or, where four 128-cell tiles of
+// A*(5+C) channels do not fit in shared memory (COCO: 255 channels), 32 (one quarter, up to 20 compute warps sharing
+// the units of its cells).
+template <int CELLS>
 __global__ void __launch_bounds__(768, 1)
 decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid_constant__ DecodeTmaMaps maps) {
+  constexpr int NQ = CELLS / 32;
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ __align__(8) uint64_t full_bar[kDtmMaxStages], empty_bar[kDtmMaxStages];
   __shared__ uint32_t utab[kDtmMaxUnits];
   const int tid = threadIdx.x, lane = lane_id(), warp = warp_id();
   const int ch = P.ch, ACH = P.A * ch, S = P.stages;
-  const uint32_t stage_bytes = (uint32_t)ACH * kDtmCells * 4u;
+  const uint32_t stage_bytes = (uint32_t)ACH * CELLS * 4u;
   // dynamic smem: [S input stages: ACH x 128 floats][2 staging tiles: 128 x ACH floats]
   float* tile0 = reinterpret_cast<float*>(dsm + (size_t)S * stage_bytes);
-  const int n_cmp = 4 * P.wq * 32;
+  const int n_cmp = NQ * P.wq * 32;
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 4 * P.wq);
+      mbar_init(&empty_bar[s], NQ * P.wq);
     }
     mbar_init_fence();
   }
@@ -364,7 +369,7 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       const int b = g / P.tiles_img, t = g - b * P.tiles_img;
       int l = 0;
       while (l + 1 < P.n_levels && t >= P.tile_off[l + 1]) ++l;
-      const int cell0 = (t - P.tile_off[l]) * kDtmCells;
+      const int cell0 = (t - P.tile_off[l]) * CELLS;
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(&full_bar[s], stage_bytes);
@@ -375,7 +380,7 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
     }
   } else if (warp >= 4) {
     // ---- compute: warp%4 = which 32 cells of the tile, the wq warps of a quarter take the 8-channel blocks round robin
-    const int q = warp & 3, jq = (warp - 4) >> 2;
+    const int q = (warp - 4) % NQ, jq = (warp - 4) / NQ;
     const int ctid = tid - 128;
     const int r = q * 32 + lane;
     // work units of one cell row: per anchor its 1 + C objectness / class channels in `grp` groups of `usz` <= 8
@@ -405,9 +410,9 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
     for (int g = blockIdx.x; g < P.ntiles; g += gridDim.x, ++tl) {
       int l = 0;
       while (l + 1 < P.n_levels && t >= P.tile_off[l + 1]) ++l;
-      const int cell0 = (t - P.tile_off[l]) * kDtmCells;
+      const int cell0 = (t - P.tile_off[l]) * CELLS;
       const int cell = cell0 + r;
-      const int ncell = min(kDtmCells, P.HW[l] - cell0);     // < 128 on a level's last tile (TMA zero-fills the rest)
+      const int ncell = min(CELLS, P.HW[l] - cell0);     // < 128 on a level's last tile (TMA zero-fills the rest)
       const int Wd = P.Wd[l];
       const int cy = P.magic_w[l] ? (int)__umulhi((uint32_t)cell, P.magic_w[l]) : cell, cx = cell - cy * Wd;
       const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
@@ -417,7 +422,7 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
       // 3 floats at either end leaves as one bulk store even when this image's rows are not 16-byte aligned in the
       // prediction (608 x 608: 22743 rows per image; a level behind a 19 x 19 level)
       const int mis = (int)((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);
-      float* tile = tile0 + (size_t)(tl & 1u) * (kDtmCells * ACH + 4) + mis;
+      float* tile = tile0 + (size_t)(tl & 1u) * (CELLS * ACH + 4) + mis;
       // the bulk store that last used this staging tile must have read it before it is overwritten
       if (ctid == 0) tma_store_wait_read<1>();
       epi_bar_sync(n_cmp);
@@ -430,14 +435,14 @@ decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid
         for (int u = jq; u < nunit; u += P.wq) {
           const uint32_t e = utab[u];
           const int c0 = (int)(e & 0xffffu), cnt = (int)(e >> 16);
-          const float* sp = src + c0 * kDtmCells;
+          const float* sp = src + c0 * CELLS;
           if (cnt == 0) {
             float raw[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) raw[k] = sp[k * kDtmCells];
+            for (int k = 0; k < 4; ++k) raw[k] = sp[k * CELLS];
             decode_box4(raw, gx, gy, stride, trow0 + c0);
           } else {
-            decode_sig_n_strided(sp, kDtmCells, cnt, trow0 + c0);
+            decode_sig_n_strided(sp, CELLS, cnt, trow0 + c0);
           }
         }
       }
@@ -489,6 +494,14 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   using namespace pq;
   const int ch = 5 + C, ACH = A * ch;
   if (ACH > 256 || A * ((ch - 4 + 7) / 8) + A > kDtmMaxUnits) return 0;
+  DeviceLimits lim;
+  if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
+  const int max_smem = lim.max_smem_optin, sms = lim.sms;
+  const size_t room = (size_t)max_smem - 1024 - 32;                 // static barriers, 16 bytes of phase room per staging tile
+  // cells per tile: 128 where two input stages + two staging tiles of that size fit, else 32 (255 channels)
+  int cells = 128;
+  if (room < 4 * (size_t)cells * ACH * 4 || getenv("PQDET_DECODE_CELLS32")) cells = 32;
+  if (room < 4 * (size_t)cells * ACH * 4) return 0;
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (((size_t)rows * ch * 4) & 15) == 0;
   PqEncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return 0;
@@ -505,9 +518,9 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
     P.Wd[l] = W[l]; P.HW[l] = HW; P.stride[l] = stride[l]; P.row_off[l] = row_off; P.tile_off[l] = tiles;
     P.bulk[l] = (out_aligned && (((size_t)row_off * ch * 4) & 15) == 0) ? 1 : 0;
     P.magic_w[l] = W[l] == 1 ? 0u : (uint32_t)((0x100000000ull + (uint64_t)W[l] - 1) / (uint64_t)W[l]);
-    tiles += (HW + kDtmCells - 1) / kDtmCells;
+    tiles += (HW + cells - 1) / cells;
     cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)B * ACH}, strides[1] = {(cuuint64_t)HW * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kDtmCells, (cuuint32_t)ACH}, estr[2] = {1u, 1u};
+    cuuint32_t box[2] = {(cuuint32_t)cells, (cuuint32_t)ACH}, estr[2] = {1u, 1u};
     if (enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(raw[l]), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -517,12 +530,7 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   if ((int64_t)B * tiles > 0x7fffffff) return 0;
   P.out = out; P.A = A; P.ch = ch; P.n_levels = n_levels;
   P.tiles_img = tiles; P.ntiles = B * tiles; P.rows_total = rows;
-  DeviceLimits lim;
-  if (!device_limits(device, &lim)) return PQDET_ERR_CUDA;
-  const int max_smem = lim.max_smem_optin, sms = lim.sms;
-  const size_t tile_bytes = (size_t)kDtmCells * ACH * 4;
-  const size_t room = (size_t)max_smem - 1024 - 32;                 // static barriers, 16 bytes of phase room per staging tile
-  if (room < 4 * tile_bytes) return 0;                              // 2 input stages + 2 staging tiles at least
+  const size_t tile_bytes = (size_t)cells * ACH * 4;
   size_t st = room / tile_bytes - 2;
   if (st > (size_t)kDtmMaxStages) st = kDtmMaxStages;
   if (const char* e = getenv("PQDET_DECODE_STAGES")) {                // A/B switch: cap the input ring
@@ -534,7 +542,8 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   // (cost model: a group of objectness / class channels ~ 2.5 x the 4 box channels of an anchor)
   const int nsig = A * ((ch - 4 + 7) / 8), nunit = nsig + A;
   int wq = 1, best_load = 1 << 30;
-  for (int w = 1; w <= 5 && w <= nunit; ++w) {
+  const int nq = cells / 32;
+  for (int w = 1; w <= 20 / nq && w <= nunit; ++w) {
     int worst = 0;
     for (int j = 0; j < w; ++j) {
       int load = 0;
@@ -545,13 +554,16 @@ int try_decode_levels_tma(int n_levels, const float* const* raw, const int* H, c
   }
   P.wq = wq;
   const size_t smem = (st + 2) * tile_bytes + 32;
-  static int smem_set[64];                    // the attribute sticks per device: raise it only when needed
-  if (device < 0 || device >= 64 || (int)smem > smem_set[device]) {
-    PQ_CUDA(cudaFuncSetAttribute(decode_levels_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (device >= 0 && device < 64) smem_set[device] = (int)smem;
+  static int smem_set[2][64];                 // the attribute sticks per device: raise it only when needed
+  const int which = cells == 128 ? 0 : 1;
+  void (*kern)(const DecodeTmaParams, const DecodeTmaMaps) =
+      which == 0 ? decode_levels_tma_kernel<128> : decode_levels_tma_kernel<32>;
+  if (device < 0 || device >= 64 || (int)smem > smem_set[which][device]) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (device >= 0 && device < 64) smem_set[which][device] = (int)smem;
   }
   const int grid = P.ntiles < sms ? P.ntiles : sms;
-  decode_levels_tma_kernel<<<grid, (4 + 4 * wq) * 32, smem, stream>>>(P, maps);
+  kern<<<grid, (4 + nq * wq) * 32, smem, stream>>>(P, maps);
   PQ_LAUNCH_CHECK();
   return 1;
 }
