@@ -112,7 +112,7 @@ struct DecodeLevels {
 
 __global__ void __launch_bounds__(kDecodeThreads)
 decode_levels_kernel(const __grid_constant__ DecodeLevels L, float* __restrict__ out, int A, int ch,
-                     int64_t rows_total) {
+                     int64_t rows_total, int behind_primary) {
   extern __shared__ __align__(16) float tile[];
   int l = 0;
 #pragma unroll
@@ -120,6 +120,10 @@ decode_levels_kernel(const __grid_constant__ DecodeLevels L, float* __restrict__
     if (i < L.n_levels && (int)blockIdx.x >= L.tile_off[i]) l = i;
   decode_tile(L.raw[l], out, A, ch, L.H[l], L.W[l], L.stride[l], rows_total, L.row_off[l],
               (int)blockIdx.x - L.tile_off[l], blockIdx.y, tile);
+  // Launched as a programmatic dependent of the TMA pipeline (disjoint row ranges, no data dependency): one CTA
+  // stays until that grid has completed, so that THIS grid - the last one of the call in stream order - does not
+  // complete before it and whatever the caller enqueues next sees all rows.
+  if (behind_primary && blockIdx.x == 0 && blockIdx.y == 0) cudaGridDependencySynchronize();
 }
 
 // grad_raw[b][c][cell] = grad_out[b][cell][a][k] * d out/d raw:
@@ -345,6 +349,9 @@ template <int CELLS>
 __global__ void __launch_bounds__(768, 1)
 decode_levels_tma_kernel(const __grid_constant__ DecodeTmaParams P, const __grid_constant__ DecodeTmaMaps maps) {
   constexpr int NQ = CELLS / 32;
+  // a level this pipeline cannot take (19 x 19) is decoded by decode_levels_kernel launched right behind it as a
+  // programmatic dependent: its small CTAs run beside the persistent ones instead of after them
+  cudaTriggerProgrammaticLaunchCompletion();
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ __align__(8) uint64_t full_bar[kDtmMaxStages], empty_bar[kDtmMaxStages];
   __shared__ uint32_t utab[kDtmMaxUnits];
@@ -649,7 +656,24 @@ extern "C" int pqdet_decode_levels(int n_levels, const float* const* raw, const 
   if (smem > 48 * 1024)
     PQ_CUDA(cudaFuncSetAttribute(decode_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tiles, B);
-  decode_levels_kernel<<<grid, kDecodeThreads, smem, (cudaStream_t)stream>>>(L, out, A, ch, rows);
+  bool behind = false;
+  for (int l = 0; l < n_levels; ++l) behind |= on_tma[l];
+  if (behind && !getenv("PQDET_DECODE_NO_PDL")) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kDecodeThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PQ_CUDA(cudaLaunchKernelEx(&cfg, decode_levels_kernel, L, out, A, ch, rows, 1));
+  } else {
+    decode_levels_kernel<<<grid, kDecodeThreads, smem, (cudaStream_t)stream>>>(L, out, A, ch, rows, 0);
+  }
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
