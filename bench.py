@@ -1154,7 +1154,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d_pulled, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps, "host_input_bytes_per_step": h2d, "identical_to_resident_run": e2e_same,
                 "staged_full_copy_value": staged_val, "host_sets_rotated": N_HOST,
-                "note": "fused.decode_nms_host / pqdet_decode_nms_host: heads in pinned host memory, detections in "
+                "note": "fused.decode_nms_host / pqdet_decode_nms_host (capacity class large: 256-thread CTAs keep more PCIe reads in flight): heads in pinned host memory, detections in "
                         "pinned host memory, stream synchronised every step; the kernel reads host memory in place "
                         "over PCIe (objectness planes + channels of the rows above threshold = h2d_bytes_per_step, "
                         "of host_input_bytes_per_step) and writes counts + rows back; staged_full_copy_value = "

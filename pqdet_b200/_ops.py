@@ -322,7 +322,7 @@ def alloc_host_outputs(B: int, max_det: int, want_index: bool, device):
 
 
 def decode_nms_host(heads_t, keep_alive, max_det: int, want_index: bool, device, out=None,
-                    capacity: str = "compact"):
+                    capacity: str = "large"):
     """Host buffers in, host buffers out (pqdet_decode_nms_host).  -> det, idx, meta (pinned host), work (device).
     Asynchronous on the current stream of `device`: synchronise before reading the outputs."""
     device = torch.device(device)

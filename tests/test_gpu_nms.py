@@ -251,12 +251,14 @@ def test_host_buffer_path_equals_device_path(profile, C, size, kind):
     dev = fused.decode_nms([h.cuda() for h in heads], synth.FPN_STRIDES, C, (size, size), orig.cuda(), kind, 0.1, 0.45,
                            return_index=True)
     pinned = [h.pin_memory() for h in heads]
-    host = fused.decode_nms_host(pinned, synth.FPN_STRIDES, C, (size, size), orig, kind, 0.1, 0.45, return_index=True)
-    rows = host.to_numpy_list()
-    for b in range(B):
-        assert np.array_equal(rows[b], dev[b].cpu().numpy()), (profile, b)
-        assert np.array_equal(host.idx[b, :int(host.counts[b])].numpy(), dev.indices(b).cpu().numpy().astype(np.int32))
-    assert int(host.counts.sum()) > 0
+    for capacity in ("large", "compact"):                      # "large" is the default of the host path
+        host = fused.decode_nms_host(pinned, synth.FPN_STRIDES, C, (size, size), orig, kind, 0.1, 0.45, return_index=True,
+                                     capacity=capacity)
+        rows = host.to_numpy_list()
+        for b in range(B):
+            assert np.array_equal(rows[b], dev[b].cpu().numpy()), (profile, capacity, b)
+            assert np.array_equal(host.idx[b, :int(host.counts[b])].numpy(), dev.indices(b).cpu().numpy().astype(np.int32))
+        assert int(host.counts.sum()) > 0
 
 
 def test_host_buffer_path_rejects_pageable_memory():
