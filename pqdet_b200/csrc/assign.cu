@@ -37,17 +37,27 @@ __device__ __forceinline__ size_t owner_slot(const AssignParams& P, int b, int s
 // background: zeros, mixw channel (last) = 1.0
 __global__ void __launch_bounds__(256)
 assign_fill_kernel(float* __restrict__ dst, int64_t total, int LW) {
+  // the owner pass that follows has no dependency on this fill: it is launched as a programmatic dependent and runs
+  // beside it (its last CTA waits for this grid, see assign_kernel)
+  cudaTriggerProgrammaticLaunchCompletion();
   const int64_t n4 = total >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const int64_t e = i << 2;
-    const int r = (int)(e % LW);
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // position inside a label row, advanced by (4 * stride) mod LW per iteration: one division per thread instead of
+  // four per store (the fill was issue bound on them before it was HBM bound)
+  int r = (int)((i0 << 2) % LW);
+  const int step = (int)((stride << 2) % LW);
+  for (int64_t i = i0; i < n4; i += stride) {
+    // element 4i + u is the mixw channel of its row iff r + u == LW - 1 (r < LW, u <= 3 and LW >= 7: no second wrap)
+    const int t = LW - 1 - r;
     float4 v;
-    v.x = (r == LW - 1) ? 1.0f : 0.0f;
-    v.y = ((r + 1) % LW == LW - 1) ? 1.0f : 0.0f;
-    v.z = ((r + 2) % LW == LW - 1) ? 1.0f : 0.0f;
-    v.w = ((r + 3) % LW == LW - 1) ? 1.0f : 0.0f;
+    v.x = (t == 0) ? 1.0f : 0.0f;
+    v.y = (t == 1) ? 1.0f : 0.0f;
+    v.z = (t == 2) ? 1.0f : 0.0f;
+    v.w = (t == 3) ? 1.0f : 0.0f;
     reinterpret_cast<float4*>(dst)[i] = v;
+    r += step;
+    if (r >= LW) r -= LW;
   }
   for (int64_t e = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
     dst[e] = ((int)(e % LW) == LW - 1) ? 1.0f : 0.0f;
@@ -56,7 +66,7 @@ assign_fill_kernel(float* __restrict__ dst, int64_t total, int LW) {
 // One CTA per image.  PASS 0: owner map + GT lists.  PASS 1: owners write their label rows.
 template <int PASS>
 __global__ void __launch_bounds__(256)
-assign_kernel(const __grid_constant__ AssignParams P) {
+assign_kernel(const __grid_constant__ AssignParams P, int behind_fill) {
   __shared__ int s_warp[3][8];
   __shared__ int s_base[3];
   const int b = blockIdx.x;
@@ -129,6 +139,9 @@ assign_kernel(const __grid_constant__ AssignParams P) {
   if (PASS == 0) {
     __syncthreads();
     if (tid < 3) P.list_len[b * 3 + tid] = s_base[tid];
+    // launched as a programmatic dependent of assign_fill_kernel: one CTA stays until the fill has completed, so that
+    // the write pass behind this grid (a normal launch: it waits for THIS grid) also finds the background in place
+    if (behind_fill && b == 0) cudaGridDependencySynchronize();
   }
 }
 
@@ -204,9 +217,24 @@ extern "C" int pqdet_assign_labels(const float* gt, const int32_t* gt_count, int
     for (int s = 0; s < 3; ++s)
       if (fill(labels[s], ltot[s]) != PQDET_OK) return PQDET_ERR_CUDA;
   }
-  assign_kernel<0><<<B, 256, 0, st>>>(P);
+  if (one_label_buf && !getenv("PQDET_ASSIGN_NO_PDL")) {
+    // (one fill launch directly in front: the owner pass may start while it streams)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(B);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PQ_CUDA(cudaLaunchKernelEx(&cfg, assign_kernel<0>, P, 1));
+  } else {
+    assign_kernel<0><<<B, 256, 0, st>>>(P, 0);
+  }
   PQ_LAUNCH_CHECK();
-  assign_kernel<1><<<B, 256, 0, st>>>(P);
+  assign_kernel<1><<<B, 256, 0, st>>>(P, 0);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
@@ -257,7 +285,7 @@ extern "C" int pqdet_assign_sparse(const float* gt, const int32_t* gt_count, int
   } else {
     for (int s = 0; s < 3; ++s) PQ_CUDA(cudaMemsetAsync(lists[s], 0, list_floats * sizeof(float), st));
   }
-  assign_kernel<0><<<B, 256, 0, st>>>(P);
+  assign_kernel<0><<<B, 256, 0, st>>>(P, 0);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }
