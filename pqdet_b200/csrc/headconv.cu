@@ -332,6 +332,10 @@ struct HeadConvWsParams {
   int wq;              // epilogue warps per TMEM lane quadrant
   int tile_bufs;       // 1 or 2 staging tiles for the output
   int all_bulk;        // every output tile is full and 16-byte aligned: all of them leave as bulk stores
+  // Anchor split (weights of all anchors too large to stay resident: COCO at Cin 176): this launch computes ONE anchor
+  // (A = 1, weights / bias of that anchor) of a head with A_out anchors; its rows are A_out rows apart in the
+  // prediction, its raw planes at plane a_off * (5+C) of the raw head.  Otherwise A_out = A, a_off = 0.
+  int A_out, a_off;
   int slice;           // 1: the staging tiles hold ONE anchor's rows of a tile (A * (5+C) * 512 bytes would not fit beside
                        // the resident weights: COCO's 255 channels); the epilogue then works anchor by anchor
   int units;           // 1: anchor-aligned work units in the epilogue (needs ACH + 7 <= buf_cols), 0: 8-column blocks
@@ -513,8 +517,8 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
       const bool in_level = r < ncell;
       const int cy = P.magic_w ? (int)__umulhi((uint32_t)cell, P.magic_w) : cell, cx = cell - cy * P.Wd;
       const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
-      float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch;
-      const size_t raw_base = (size_t)b * ACH * P.HW + cell;
+      float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A_out + P.a_off) * ch;
+      const size_t raw_base = ((size_t)b * P.A_out + P.a_off) * ch * P.HW + cell;   // (A_out == A: b * ACH * HW + cell)
       ti += step_t; b += step_b;
       if (ti >= P.tiles_per_img) { ti -= P.tiles_per_img; ++b; }
       mbar_wait(&acc_full[buf], (tl >> 1) & 1u);
@@ -601,7 +605,7 @@ __device__ __forceinline__ void head_conv_ws_body(const HeadConvWsParams& P, con
           if (P.out_dec) {
             for (int rr = ewarp; rr < ncell; rr += nwarp_e) {
               const float* srow = stile + rr * ch;
-              float* drow = dst + ((size_t)rr * P.A + a) * ch;
+              float* drow = dst + ((size_t)rr * P.A_out + a) * ch;
               for (int k = lane; k < ch; k += 32) drow[k] = srow[k];
             }
           }
@@ -702,6 +706,18 @@ head_conv_decode_ws_levels_kernel(const __grid_constant__ HeadConvLevelsParams L
   head_conv_ws_body<false>(LP.P[l], &maps.m[l], (int)blockIdx.x - LP.cta_lo[l], LP.cta_lo[l + 1] - LP.cta_lo[l]);
 }
 
+// Anchor split in one launch: the CTAs are dealt to the anchors (cta_lo), every CTA keeps its anchor's slice of the
+// weights resident and runs the sliced epilogue on that anchor's rows of every tile it takes.
+template <bool WANT_RAW>
+__global__ void __launch_bounds__(768, 1)
+head_conv_decode_ws_anchors_kernel(const __grid_constant__ HeadConvLevelsParams LP,
+                                   const __grid_constant__ HeadConvLevelsMaps maps) {
+  int l = 0;
+  while (l + 1 < LP.n_levels && (int)blockIdx.x >= LP.cta_lo[l + 1]) ++l;
+  head_conv_ws_body<WANT_RAW, false, true>(LP.P[l], &maps.m[l], (int)blockIdx.x - LP.cta_lo[l],
+                                           LP.cta_lo[l + 1] - LP.cta_lo[l]);
+}
+
 }  // namespace pq
 
 namespace {
@@ -710,7 +726,8 @@ namespace {
 // general kernel must run), < 0 = error.
 int plan_head_conv_ws(const float* x, const float* weight, const float* bias, float* out_decoded, float* out_raw,
                       int B, int Cin, int H, int W, int A, int C, float stride, int64_t rows_total, int64_t row_off,
-                      int device, pq::HeadConvWsParams* Pout, CUtensorMap* tmap_out, size_t* smem_out, int* sms_out) {
+                      int device, pq::HeadConvWsParams* Pout, CUtensorMap* tmap_out, size_t* smem_out, int* sms_out,
+                      int a_out = 0, int a_off = 0) {
   using namespace pq;
   const int HW = H * W, ACH = A * (5 + C), N = (ACH + 15) / 16 * 16;
   // the planes must be addressable by a tensor map (plane stride a multiple of 16 bytes); the last tile of a level
@@ -753,8 +770,15 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   };
   // preference: large stages (>= 48 channels keep the MMA warp ahead of HBM) with two staging tiles, large stages
   // with one, then whatever fits
+  P.A_out = a_out > 0 ? a_out : A;
+  P.a_off = a_off;
   P.tile_bufs = 2;
-  if (!plan(2, 48, &P.KC, &P.stages)) {
+  if (a_out > 0) {
+    // one anchor of several: its rows are not contiguous in the prediction -> the sliced epilogue's row-wise copy
+    tile_bytes = (size_t)(kHcM * (5 + C) + 4) * 4;
+    P.slice = 1;
+    if (!plan(2, 48, &P.KC, &P.stages) && !plan(2, 8, &P.KC, &P.stages)) return 0;
+  } else if (!plan(2, 48, &P.KC, &P.stages)) {
     P.tile_bufs = 1;
     if (!plan(1, 48, &P.KC, &P.stages)) {
       P.tile_bufs = 2;
@@ -835,6 +859,24 @@ int plan_head_conv_ws(const float* x, const float* weight, const float* bias, fl
   return 1;
 }
 
+int launch_head_conv_ws(const pq::HeadConvWsParams& P, const CUtensorMap& tmap, size_t smem, int sms, bool want_raw,
+                        int device, cudaStream_t stream) {
+  using namespace pq;
+  const int grid = P.ntiles < sms ? P.ntiles : sms;
+  static int smem_set[4][64];                 // the attribute sticks per device: raise it only when needed
+  const int which = (want_raw ? 1 : 0) + (P.slice ? 2 : 0);
+  void (*kern)(const HeadConvWsParams, const CUtensorMap) =
+      which == 0 ? head_conv_decode_ws_kernel<false, false> : which == 1 ? head_conv_decode_ws_kernel<true, false>
+      : which == 2 ? head_conv_decode_ws_kernel<false, true> : head_conv_decode_ws_kernel<true, true>;
+  if (device < 0 || device >= 64 || (int)smem > smem_set[which][device]) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (device >= 0 && device < 64) smem_set[which][device] = (int)smem;
+  }
+  kern<<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
+  PQ_LAUNCH_CHECK();
+  return 1;
+}
+
 // Launches the persistent kernel for one level when the shape qualifies; 1 = launched, 0 = general kernel, < 0 = error.
 int try_head_conv_ws(const float* x, const float* weight, const float* bias, float* out_decoded, float* out_raw,
                      int B, int Cin, int H, int W, int A, int C, float stride, int64_t rows_total, int64_t row_off,
@@ -846,18 +888,42 @@ int try_head_conv_ws(const float* x, const float* weight, const float* bias, flo
   int sms = 0;
   const int rc = plan_head_conv_ws(x, weight, bias, out_decoded, out_raw, B, Cin, H, W, A, C, stride, rows_total, row_off,
                                    device, &P, &tmap, &smem, &sms);
-  if (rc != 1) return rc;
-  const int grid = P.ntiles < sms ? P.ntiles : sms;
-  static int smem_set[4][64];                 // the attribute sticks per device: raise it only when needed
-  const int which = (out_raw ? 1 : 0) + (P.slice ? 2 : 0);
-  void (*kern)(const HeadConvWsParams, const CUtensorMap) =
-      which == 0 ? head_conv_decode_ws_kernel<false, false> : which == 1 ? head_conv_decode_ws_kernel<true, false>
-      : which == 2 ? head_conv_decode_ws_kernel<false, true> : head_conv_decode_ws_kernel<true, true>;
-  if (device < 0 || device >= 64 || (int)smem > smem_set[which][device]) {
-    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (device >= 0 && device < 64) smem_set[which][device] = (int)smem;
+  if (rc < 0) return rc;
+  if (rc == 1) return launch_head_conv_ws(P, tmap, smem, sms, out_raw != nullptr, device, stream);
+  // The weights of all anchors do not fit beside the pipeline (COCO at Cin 176: 180 KB): one launch per anchor with
+  // that anchor's slice of the weights resident; the features are read A times (mostly from L2), the rows of an anchor
+  // leave through the sliced epilogue's row-wise copy.
+  if (A < 2 || getenv("PQDET_HEADCONV_NO_SPLIT")) return 0;
+  const int ch = 5 + C;
+  if (A > PQDET_MAX_LEVELS) return 0;
+  HeadConvLevelsParams LP;
+  HeadConvLevelsMaps maps;
+  memset(&LP, 0, sizeof(LP));
+  memset(&maps, 0, sizeof(maps));
+  size_t smem_a = 0;
+  for (int a = 0; a < A; ++a) {
+    size_t sm1 = 0;
+    const int ra = plan_head_conv_ws(x, weight + (size_t)a * ch * Cin, bias ? bias + (size_t)a * ch : nullptr, out_decoded,
+                                     out_raw, B, Cin, H, W, 1, C, stride, rows_total, row_off, device, &LP.P[a],
+                                     &maps.m[a], &sm1, &sms, A, a);
+    if (ra != 1) return ra;                                 // nothing launched yet: the general kernel takes the level
+    smem_a = sm1 > smem_a ? sm1 : smem_a;
   }
-  kern<<<grid, (4 + 4 * P.wq) * 32, smem, stream>>>(P, tmap);
+  // the anchors cost the same: equal shares of the SMs (the first ones take the remainder)
+  const int ctas = LP.P[0].ntiles * A < sms ? LP.P[0].ntiles * A : sms;
+  if (ctas < A) return 0;
+  LP.n_levels = A;
+  for (int a = 0; a < A; ++a) LP.cta_lo[a + 1] = LP.cta_lo[a] + ctas / A + (a < ctas % A ? 1 : 0);
+  for (int a = A; a < PQDET_MAX_LEVELS; ++a) LP.cta_lo[a + 1] = LP.cta_lo[A];
+  static int smem_set[2][64];
+  const int which = out_raw ? 1 : 0;
+  void (*kern)(const HeadConvLevelsParams, const HeadConvLevelsMaps) =
+      out_raw ? head_conv_decode_ws_anchors_kernel<true> : head_conv_decode_ws_anchors_kernel<false>;
+  if (device < 0 || device >= 64 || (int)smem_a > smem_set[which][device]) {
+    PQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    if (device >= 0 && device < 64) smem_set[which][device] = (int)smem_a;
+  }
+  kern<<<LP.cta_lo[A], (4 + 4 * LP.P[0].wq) * 32, smem_a, stream>>>(LP, maps);
   PQ_LAUNCH_CHECK();
   return 1;
 }

@@ -47,6 +47,16 @@ for _ in range(reps):
     e.record()
     torch.cuda.synchronize()
     ts.append(s.elapsed_time(e) * 1e3)
+from pqdet_b200.graphs import GraphedLossStep  # noqa: E402
+g = GraphedLossStep(head, [r.requires_grad_(True) for r in raws], target)
+tg = []
+for _ in range(reps):
+    flush.zero_()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); g.replay(); e.record(); torch.cuda.synchronize()
+    tg.append(s.elapsed_time(e) * 1e3)
+print("%s config %s %s: CUDA-graph replay median %.1f us min %.1f us" % (
+    os.path.basename(os.environ.get("PQDET_B200_LIB", "in-tree")), which, form, float(np.median(tg)), float(np.min(tg))))
 print("%s config %s %s: loss step median %.1f us min %.1f us, loss %.6f" % (
     os.path.basename(os.environ.get("PQDET_B200_LIB", "in-tree")), which, form, float(np.median(ts)), float(np.min(ts)),
     float(out["loss"])))
