@@ -143,9 +143,13 @@ def test_head_conv_decode_tensor_cores(B, Cin, H, W, C, stride):
 
 @pytest.mark.parametrize("B,Cin,H,W,C", [(3, 352, 16, 16, 20), (7, 176, 32, 32, 20), (40, 80, 64, 64, 20), (2, 48, 16, 16, 10),
                                          (150, 80, 16, 16, 40), (3, 80, 16, 16, 80), (5, 8, 32, 16, 1), (2, 1024, 16, 8, 20),
-                                         (4, 64, 16, 16, 5), (3, 32, 16, 16, 0)])
+                                         (4, 64, 16, 16, 5), (3, 32, 16, 16, 0),
+                                         # 255 channels: anchor-sliced epilogue (weights fit) and CTAs split between the
+                                         # anchors (Cin 176 / 352: they do not), partial last tiles, one image, W != H
+                                         (1, 176, 38, 38, 80), (2, 80, 24, 40, 80), (3, 176, 20, 28, 80), (2, 352, 12, 20, 80),
+                                         (5, 176, 76, 76, 80)])
 def test_head_conv_persistent_kernel_equals_general_kernel(B, Cin, H, W, C, monkeypatch):
-    """H*W a multiple of 128 takes the persistent warp-specialised kernel (TMA ring, resident weights, two TMEM
+    """H*W a multiple of 4 takes the persistent warp-specialised kernel (TMA ring, resident weights, two TMEM
     accumulators); PQDET_HEADCONV_GENERAL forces the general kernel.  Same K order of the same tf32 MMAs: identical
     raw heads and decoded rows; more tiles than SMs (40 x 32) exercises the ring / accumulator phases."""
     from pqdet_b200 import _ops
