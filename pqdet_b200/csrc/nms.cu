@@ -1360,7 +1360,10 @@ gen_plan_kernel(const __grid_constant__ GenParams G, const __grid_constant__ Det
 
 // Two shared-memory tiers for the (image, class) buckets: up to 2048 candidates with 256 threads
 // (56 KB, 4 CTAs/SM) and up to 8192 with 512 threads (224 KB, 1 CTA/SM); anything larger runs on global arrays.
-constexpr int kSegSmallKeys = 2048, kSegSmallThreads = 256;
+#ifndef PQ_SEG_THREADS
+#define PQ_SEG_THREADS 256
+#endif
+constexpr int kSegSmallKeys = 2048, kSegSmallThreads = PQ_SEG_THREADS;
 constexpr int kSegBigKeys = 8192, kSegBigThreads = 512;
 
 // Greedy NMS over a sorted bucket of n candidates by one CTA.  box(pos) = trick-shifted box of sorted
@@ -1519,7 +1522,7 @@ gen_bucket_nms_kernel(const __grid_constant__ GenParams G) {
   int k;
   if (in_smem) {
     // keys -> registers (and global), barrier, then the boxes take over the region
-    constexpr int R = kSegSmemKeys / kSegThreads;
+    constexpr int R = (kSegSmemKeys + kSegThreads - 1) / kSegThreads;
     uint32_t rows[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
