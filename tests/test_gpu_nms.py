@@ -194,6 +194,16 @@ def test_fused_full_size_properties():
         assert torch.equal(a, half[b // 512][b % 512])
         s = a[:, 4]
         assert bool((s[:-1] >= s[1:]).all()) and bool((s > 0.1).all())
+        # idempotence: no two kept boxes of one class overlap above the threshold (NMS of the output keeps all of it)
+        bx, cl = a[:, :4], a[:, 5]
+        lt = torch.maximum(bx[:, None, :2], bx[None, :, :2])
+        rb = torch.minimum(bx[:, None, 2:], bx[None, :, 2:])
+        wh = (rb - lt).clamp(min=0)
+        inter = wh[..., 0] * wh[..., 1]
+        area = (bx[:, 2] - bx[:, 0]) * (bx[:, 3] - bx[:, 1])
+        iou = inter / (area[:, None] + area[None, :] - inter)
+        same = (cl[:, None] == cl[None, :]) & ~torch.eye(len(a), dtype=torch.bool, device=a.device)
+        assert float(torch.where(same, iou, torch.zeros_like(iou)).max()) <= 0.45 + 1e-6
     counts = full.counts.to(torch.float32)
     assert 60 < float(counts.mean()) < 200
     from pqdet_b200.interpreter import DetectionHead
