@@ -268,25 +268,27 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
           : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (r < ncell) {
+        // two blocks of 8 columns, each with its exp / reciprocal chains interleaved (decode_block8: bit-identical to
+        // the scalar functions); ST == ACH or ACH + 1, a block may run into the padding columns behind ACH, which
+        // decode_block8 does not store
         int k = c0 % ch;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = c0 + i;
-          if (c < ACH) {
-            float raw = __uint_as_float(v[i]);
-            if (P.bias) raw = PQ_ADD(raw, __ldg(P.bias + c));
-            if (P.out_raw) P.out_raw[((size_t)b * ACH + c) * HW + cell] = raw;
-            float o;
-            if (k < 4) {
-              const float e = expf(raw);
-              const float g = (k & 1) ? gy : gx;
-              o = PQ_MUL((k < 2) ? PQ_SUB(g, e) : PQ_ADD(g, e), P.stride);      // decode_coord
-            } else {
-              o = __frcp_rn(PQ_ADD(1.0f, expf(-raw)));                          // sigmoidf_
+        for (int h = 0; h < 2; ++h) {
+          const int cb = c0 + 8 * h;
+          if (cb < ACH) {
+            float raw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = cb + i;
+              raw[i] = __uint_as_float(v[8 * h + i]);
+              if (P.bias && c < ACH) raw[i] = PQ_ADD(raw[i], __ldg(P.bias + c));
+              if (P.out_raw && c < ACH) P.out_raw[((size_t)b * ACH + c) * HW + cell] = raw[i];
             }
-            tile[r * ST + c] = o;
+            decode_block8(raw, k, cb, ACH, ch, gx, gy, P.stride, tile + r * ST + cb);
           }
-          if (++k == ch) k = 0;
+          k += 8;
+          if (k >= ch) k -= ch;
+          if (k >= ch) k -= ch;
         }
       }
     }
