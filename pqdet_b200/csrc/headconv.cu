@@ -41,6 +41,7 @@ struct HeadConvParams {
   int B, Cin, H, W, A, C;
   int N;               // A*(5+C) rounded up to a multiple of 16
   int tmem_cols;       // power of two >= max(N, 32)
+  int col_group;       // 0: the whole decoded tile is staged at once; else columns per epilogue pass (multiple of 32)
   float stride;
   int64_t rows_total, row_off;
   // HITS mode (see HeadConvWsParams)
@@ -256,46 +257,66 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
     const int cell = cell0 + r;
     const int cy = cell / P.W, cx = cell - cy * P.W;
     const float gx = (float)cx + 0.5f, gy = (float)cy + 0.5f;
-    const int nblk = N / 16, blk_lo = half ? (nblk + 1) / 2 : 0, blk_hi = half ? nblk : (nblk + 1) / 2;
-    for (int blk = blk_lo; blk < blk_hi; ++blk) {
-      const int c0 = blk * 16;
-      uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (r < ncell) {
-        // two blocks of 8 columns, each with its exp / reciprocal chains interleaved (decode_block8: bit-identical to
-        // the scalar functions); ST == ACH or ACH + 1, a block may run into the padding columns behind ACH, which
-        // decode_block8 does not store
-        int k = c0 % ch;
+    float* dst = P.out_dec ? P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch : nullptr;
+    // The decoded tile is staged either whole (it then leaves as one contiguous run) or, where 128 x A(5+C) floats
+    // would need more shared memory than the operand stages (255 channels: 130 KB, one CTA per SM), in passes of
+    // col_group columns: decode a column group, barrier, copy its segment of every row out, barrier.
+    const int GC = P.col_group ? P.col_group : N;
+    const int STg = P.col_group ? (GC | 1) : ST;
+    for (int g0 = 0; g0 < N; g0 += GC) {
+      const int gb = g0 / 16, ge = min(N, g0 + GC) / 16;            // 16-column blocks of this pass
+      const int nb = ge - gb, blk_lo = gb + (half ? (nb + 1) / 2 : 0), blk_hi = half ? ge : gb + (nb + 1) / 2;
+      for (int blk = blk_lo; blk < blk_hi; ++blk) {
+        const int c0 = blk * 16;
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (r < ncell) {
+          // two blocks of 8 columns, each with its exp / reciprocal chains interleaved (decode_block8: bit-identical to
+          // the scalar functions); a block may run into the padding columns behind ACH, which decode_block8 does not
+          // store
+          int k = c0 % ch;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cb = c0 + 8 * h;
-          if (cb < ACH) {
-            float raw[8];
+          for (int h = 0; h < 2; ++h) {
+            const int cb = c0 + 8 * h;
+            if (cb < ACH) {
+              float raw[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = cb + i;
-              raw[i] = __uint_as_float(v[8 * h + i]);
-              if (P.bias && c < ACH) raw[i] = PQ_ADD(raw[i], __ldg(P.bias + c));
-              if (P.out_raw && c < ACH) P.out_raw[((size_t)b * ACH + c) * HW + cell] = raw[i];
+              for (int i = 0; i < 8; ++i) {
+                const int c = cb + i;
+                raw[i] = __uint_as_float(v[8 * h + i]);
+                if (P.bias && c < ACH) raw[i] = PQ_ADD(raw[i], __ldg(P.bias + c));
+                if (P.out_raw && c < ACH) P.out_raw[((size_t)b * ACH + c) * HW + cell] = raw[i];
+              }
+              decode_block8(raw, k, cb, ACH, ch, gx, gy, P.stride, tile + r * STg + (cb - g0));
             }
-            decode_block8(raw, k, cb, ACH, ch, gx, gy, P.stride, tile + r * ST + cb);
+            k += 8;
+            if (k >= ch) k -= ch;
+            if (k >= ch) k -= ch;
           }
-          k += 8;
-          if (k >= ch) k -= ch;
-          if (k >= ch) k -= ch;
         }
       }
+      if (!P.col_group) break;                              // staged whole: stored below
+      __syncthreads();
+      if (dst) {
+        const int gc = min(GC, ACH - g0);                   // columns of this pass that exist
+        for (int rr = warp; rr < ncell; rr += kHcThreads / 32) {
+          const float* trow = tile + rr * STg;
+          float* drow = dst + (size_t)rr * ACH + g0;
+          for (int c = lane; c < gc; c += 32) drow[c] = trow[c];
+        }
+      }
+      __syncthreads();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (P.out_dec) {
+  if (P.out_dec && !(P.col_group && !HITS)) {
     float* dst = P.out_dec + ((size_t)b * P.rows_total + P.row_off + (size_t)cell0 * P.A) * ch;
     const int n = ncell * ACH;
     if (ST == ACH && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((n & 3) == 0)) {
@@ -1015,7 +1036,10 @@ extern "C" int pqdet_head_conv_decode(const float* x, const float* weight, const
   }
   const size_t stages = 2 * ((size_t)(kHcKC / 4) * kHcM * 16 + (size_t)(kHcKC / 4) * P.N * 16);
   const size_t tile_bytes = (size_t)kHcM * (ACH | 1) * sizeof(float);
-  const size_t smem = stages > tile_bytes ? stages : tile_bytes;
+  // a decoded tile larger than the operand stages (255 channels: 130 KB against 96 KB) is staged in passes of 64
+  // columns instead, so that shared memory - and with it the CTAs per SM - is set by the stages alone
+  P.col_group = (tile_bytes > stages && !getenv("PQDET_HEADCONV_WHOLE_TILE")) ? 64 : 0;
+  const size_t smem = (P.col_group || stages > tile_bytes) ? stages : tile_bytes;
   if (smem > 200 * 1024) return PQDET_ERR_UNSUPPORTED;
   PQ_CUDA(cudaFuncSetAttribute(head_conv_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((H * W + kHcM - 1) / kHcM, B);
