@@ -170,33 +170,41 @@ head_conv_decode_kernel(const __grid_constant__ HeadConvParams P) {
     const int kc0 = i * kHcKC, st = i & 1;
     const uint32_t sA = smem_u32(hsm + (size_t)st * stage_bytes);
     const uint32_t sB = smem_u32(hsm + (size_t)st * stage_bytes + a_bytes);
-    for (int u = tid; u < (kHcKC / 4) * kHcM; u += kHcThreads) {
-      const int j = u >> 7, m = u & (kHcM - 1);            // unit = 4 consecutive channels of one cell
-      const int k = kc0 + 4 * j, cell = cell0 + m;
-      const float* p = xb + (size_t)k * HW + cell;         // consecutive threads -> consecutive cells: coalesced
-      const uint32_t d = sA + (uint32_t)(j * kHcM + m) * 16u;
+    // (the staging loops are what this kernel issues most: kept to pointer increments - a thread's cell is the same
+    // in every iteration of the X loop (256 threads, 128 cells), and the W loop walks n inside j, no division)
+    {
+      const int m = tid & (kHcM - 1), cell = cell0 + m;
+      const bool in = cell < HW;
+      const bool whole = kc0 + kHcKC <= P.Cin;               // no zero-filled channel tail in this chunk
+      const float* p = xb + (size_t)(kc0 + 4 * (tid >> 7)) * HW + cell;   // consecutive threads -> consecutive cells
+      uint32_t d = sA + (uint32_t)((tid >> 7) * kHcM + m) * 16u;
+      const size_t pstep = (size_t)(4 * (kHcThreads >> 7)) * HW;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool ok = (cell < HW) && (k + e < P.Cin);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
-                     ::"r"(d + 4u * e), "l"(ok ? p + (size_t)e * HW : xb), "r"(ok ? 4u : 0u) : "memory");
-      }
-    }
-    for (int u = tid; u < (kHcKC / 4) * N; u += kHcThreads) {
-      const int j = u / N, n = u - j * N;
-      const int k = kc0 + 4 * j;
-      const float* p = P.w + (size_t)n * P.Cin + k;
-      const uint32_t d = sB + (uint32_t)(j * N + n) * 16u;
-      if (vecB) {
-        const bool ok = (n < ACH) && (k < P.Cin);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;"
-                     ::"r"(d), "l"(ok ? p : P.w), "r"(ok ? 16u : 0u) : "memory");
-      } else {
+      for (int j = tid >> 7; j < kHcKC / 4; j += kHcThreads >> 7, p += pstep, d += (uint32_t)((kHcThreads >> 7) * kHcM) * 16u) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const bool ok = (n < ACH) && (k + e < P.Cin);
+          const bool ok = in && (whole || kc0 + 4 * j + e < P.Cin);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
-                       ::"r"(d + 4u * e), "l"(ok ? p + e : P.w), "r"(ok ? 4u : 0u) : "memory");
+                       ::"r"(d + 4u * e), "l"(ok ? p + (size_t)e * HW : xb), "r"(ok ? 4u : 0u) : "memory");
+        }
+      }
+    }
+    for (int j = 0; j < kHcKC / 4; ++j) {
+      const int k = kc0 + 4 * j;
+      for (int n = tid; n < N; n += kHcThreads) {
+        const float* p = P.w + (size_t)n * P.Cin + k;
+        const uint32_t d = sB + (uint32_t)(j * N + n) * 16u;
+        if (vecB) {
+          const bool ok = (n < ACH) && (k < P.Cin);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;"
+                       ::"r"(d), "l"(ok ? p : P.w), "r"(ok ? 16u : 0u) : "memory");
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool ok = (n < ACH) && (k + e < P.Cin);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                         ::"r"(d + 4u * e), "l"(ok ? p + e : P.w), "r"(ok ? 4u : 0u) : "memory");
+          }
         }
       }
     }
