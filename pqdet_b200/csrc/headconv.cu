@@ -29,7 +29,10 @@
 namespace pq {
 
 constexpr int kHcM = 128;       // cells per CTA = UMMA M
-constexpr int kHcKC = 32;       // input channels per smem stage
+#ifndef PQ_HC_KC
+#define PQ_HC_KC 32
+#endif
+constexpr int kHcKC = PQ_HC_KC;  // input channels per smem stage of the general kernel
 constexpr int kHcThreads = 256;
 
 struct HeadConvParams {
