@@ -1124,7 +1124,12 @@ def run_ours(args):
     ms_step = total_ms / args.steps
     k_mean = kept_mean / B
     alg_bytes = raw_bytes(C_VOC, SIZE) * B + 24.0 * kept_mean
-    kern_ms = float(np.mean(per_step))
+    # average duration of a launch over the timed region (CUDA events around the K back-to-back launches, max over
+    # ranks): consecutive launches overlap - a launch starts while the previous one drains its slowest images
+    # (programmatic dependent launch, outputs written behind the dependency point) - so this is lower than the
+    # duration of a launch bracketed by its own events (stats.kernel_ms_isolated, which breaks the overlap)
+    kern_ms = ms_step
+    kern_ms_isolated = float(np.mean(per_step))
     achieved_alg = alg_bytes / (kern_ms * 1e-3) / 1e9
     # what the kernel MUST move: every objectness plane, one 32-byte sector per (row above the objectness threshold,
     # box/class channel) -- the channels of a row sit in different planes --, and the result rows + 3 words per image
@@ -1143,11 +1148,15 @@ def run_ours(args):
                      "bytes_breakdown": {"objectness_planes": plane_bytes,
                                          "hit_row_sectors": n_hit_mean * (4 + C_VOC) * 32,
                                          "output": 3 * 4 * B + 24.0 * kept_mean},
+                     "frac_isolated": must_move / (kern_ms_isolated * 1e-3) / 1e9 / peak,
                      "frac_algorithmic": achieved_alg / peak, "achieved_algorithmic": achieved_alg,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "achieved_dram": (traffic / (kern_ms * 1e-3) / 1e9) if traffic else None,
                      "note": "frac = bytes the kernel must move (objectness planes in full + one 32-byte sector per "
-                             "(row with conf > thr, box/class channel) + output rows) / mean kernel time / peak. "
+                             "(row with conf > thr, box/class channel) + output rows) / average launch duration "
+                             "over the timed region (= ms_per_step: the K launches are queued back to back and overlap "
+                             "head to tail; frac_isolated uses the duration of a launch bracketed by its own events) "
+                             "/ peak. "
                              "frac_algorithmic uses SURVEY 8d's R*B + 24*K, which the exact conf <= thr early-out "
                              "never reads in full, so it exceeds 1 and is NOT a roofline fraction; traffic / "
                              "achieved_dram = measured ncu DRAM bytes of the committed capture"},
@@ -1165,7 +1174,8 @@ def run_ours(args):
         "stats": {"kept_per_image": k_mean, "candidates_per_image": float(ncand.float().mean()),
                   "max_candidates": int(ncand.max()), "overflow_images": overflow,
                   "rows_above_objectness_threshold_per_image": n_hit_mean / B, "input_sets_rotated": N_SETS,
-                  "kernel_ms_mean": kern_ms, "kernel_ms_min": float(np.min(per_step))},
+                  "kernel_ms_mean": kern_ms, "kernel_ms_isolated": kern_ms_isolated,
+                  "kernel_ms_isolated_min": float(np.min(per_step))},
         "legs": legs,
     }
     del hsets, dev_in

@@ -109,6 +109,12 @@ int pqdet_recover(const float* pred, float* out, int B, int64_t N, int C, int af
  *                        call on the same stream, because the last CTA to leave re-arms them - so a
  *                        steady-state loop enqueues nothing but the kernel
  * capacity_class         PQDET_CAP_* (above)
+ * Stream semantics: ordinary stream order for everything the caller can observe.  Internally, when every CTA owns one
+ * image (B <= one resident wave) the kernel is launched as a programmatic dependent of whatever precedes it on the
+ * stream and may START while the previous pqdet_decode_nms launch is draining; it reads only `heads` (and orig_hw)
+ * until that launch has completed, and writes its outputs afterwards - the same output buffers may be reused from
+ * call to call.  Kernels of other libraries in front of it are waited for as usual.  (PQDET_FUSED_NO_PDL=1 in the
+ * environment disables the overlap.)
  * heads->score_threshold must be >= 0 (scores are products of sigmoids; the keys order non-negative floats):
  *                        negative thresholds return PQDET_ERR_UNSUPPORTED - use pqdet_nms_general */
 typedef struct {

@@ -490,10 +490,25 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
 #ifdef PQ_PHASE_TIMING
   long long pq_t0 = clock64();
 #endif
+  // Programmatic dependent launch (launch_fused sets the attribute when every CTA owns exactly one image): this grid may
+  // start while the previous one on the stream is still draining its slowest images.  Everything up to the output
+  // stage reads only the caller's inputs and writes shared memory; the outputs (possibly the very buffers the
+  // previous launch is still writing) are touched only behind cudaGridDependencySynchronize(), i.e. after that grid
+  // has completed.  Without the attribute both calls return at once.
+  cudaTriggerProgrammaticLaunchCompletion();
+  const bool static_sched = ((int)gridDim.x == P.B);        // one image per CTA: no scheduler words (shared by launches)
+  bool first = true;
   for (;;) {
-    if (tid == 0) S.b = atomicAdd(work, 1);
-    __syncthreads();
-    const int b = S.b;
+    int b;
+    if (static_sched) {
+      if (!first) break;
+      first = false;
+      b = (int)blockIdx.x;
+    } else {
+      if (tid == 0) S.b = atomicAdd(work, 1);
+      __syncthreads();
+      b = S.b;
+    }
     if (b >= P.B) break;
     PQ_PHASE(0);
     if (SRC == 0 && tid < P.n_levels) S.lvbase[tid] = P.lv[tid].raw + ((size_t)b * A * ch + 4) * P.lv[tid].HW;
@@ -586,6 +601,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     PQ_PHASE(2);
     const int H = S.H;
     if (H > CAPH || (SRC == 2 && H > P.rec_cap)) {
+      cudaGridDependencySynchronize();
       if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = -1; }
       __syncthreads();
       continue;
@@ -801,6 +817,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     PQ_PHASE(4);
     const int M = S.M;
     if (M > CAPM || M == 0) {
+      cudaGridDependencySynchronize();
       if (tid == 0) {
         O.status[b] = M ? PQDET_ST_CAND_OVERFLOW : PQDET_ST_OK;
         set_count(O, b, 0);
@@ -882,6 +899,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     // ---- 7. kept keys -> (score desc, row, class) order -> output -------------------------------
     const int K = S.K;
     PQ_PHASE(8);
+    cudaGridDependencySynchronize();                       // the previous launch has completed: outputs may be written
     if (K > Smem::kOutCap) {                               // more kept detections than the output list holds
       if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = M; }
       __syncthreads();
@@ -957,7 +975,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
   }
   // re-arm the scheduler for the next launch on this stream: the last CTA to leave zeroes both words
   // (work[0] = next image, work[1] = CTAs that have finished), so steady-state calls need no memset
-  if (tid == 0) {
+  if (tid == 0 && !static_sched) {
     __threadfence();
     if (atomicAdd(work + 1, 1) == (int)gridDim.x - 1) {
       work[0] = 0;
@@ -1745,7 +1763,24 @@ static int launch_fused(const HeadsDev& P, const DetOut& O, int32_t* work_counte
     }
     int grid = per_sm_grid;
     if (grid > P.B) grid = P.B;
-    kern<<<grid, threads, smem, st>>>(P, O, work_counter);
+    if (grid == P.B && src == 0 && !getenv("PQDET_FUSED_NO_PDL")) {
+      // every CTA owns one image and the kernel reads nothing but the caller's heads before its dependency point: it
+      // may overlap the tail of the previous launch on this stream (see the kernel)
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      PQ_CUDA(cudaLaunchKernelEx(&cfg, kern, P, O, work_counter));
+    } else {
+      kern<<<grid, threads, smem, st>>>(P, O, work_counter);
+    }
     PQ_LAUNCH_CHECK();
     return PQDET_OK;
   };

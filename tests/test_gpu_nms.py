@@ -215,6 +215,37 @@ def test_fused_full_size_properties():
         assert_same_detections(full[b].cpu().numpy(), want, what="full-size img %d" % b)
 
 
+def test_fused_back_to_back_launches_share_output_buffers():
+    """Consecutive launches on one stream overlap (programmatic dependent launch: a launch may start while the previous
+    one drains) yet write the SAME output buffers: every launch must leave exactly its own results, whatever the
+    order in which the two grids' CTAs finish.  Alternating a light and a heavy input makes the earlier launch the
+    slower one."""
+    from pqdet_b200 import _ops, synth
+    C, size, B = 20, 512, 592
+    dev = torch.device("cuda")
+    orig = torch.tensor([float(size), float(size)], device=dev)
+    sets = []
+    for seed, thr in ((1, 0.1), (2, 0.02)):                     # the second set keeps many more candidates: slower images
+        hs = synth.make_heads(B, C, size, "sparse", seed=seed, device=dev)
+        sets.append((hs,) + _ops.make_heads(hs, synth.FPN_STRIDES, C, (size, size), orig, "voc", thr, 0.45, "auto_cuda", "tv_cuda"))
+    want = []
+    for _, h, keep in sets:
+        det, idx, meta = _ops.decode_nms_fused(h, keep, 2048, True)
+        torch.cuda.synchronize()
+        want.append((det.clone(), idx.clone(), meta.clone()))
+    out = _ops.alloc_fused_outputs(B, 2048, True, dev)
+    for order in ((1, 0), (0, 1), (1, 1, 0), (0, 0, 1), (1, 0, 1, 0)):
+        for which in order:
+            _ops.decode_nms_fused(sets[which][1], sets[which][2], 2048, True, out=out)
+        torch.cuda.synchronize()
+        last = order[-1]
+        cnt = out[2][:B]
+        assert torch.equal(out[2][:3 * B], want[last][2][:3 * B]), order
+        for b in range(0, B, 7):
+            k = int(cnt[b])
+            assert torch.equal(out[0][b, :k], want[last][0][b, :k]) and torch.equal(out[1][b, :k], want[last][1][b, :k]), (order, b)
+
+
 @pytest.mark.parametrize("size,C", [(320, 20), (352, 1), (416, 20), (480, 3), (544, 80), (576, 20)])
 def test_fused_multi_scale_input_sizes(size, C):
     """The reference trains/evaluates at 320..608 (config.py:67): grids such as 11x11, 13x13, 19x19 exercise the
