@@ -103,11 +103,14 @@ def _fused_vs_chain(B, C, size, profile, kind, thr, iou, sem, seed, orig=None, s
                             hints=hints, **kw)
     # the general path for every image must give the same rows (strategy='general', and what 'auto' switches to
     # after a mostly-overflowing call)
-    for strat in ("general", "auto"):
+    # (small batches start on the large capacity class; both classes are asked for explicitly as well)
+    for strat in ("general", "auto", "compact", "large"):
         alt = fused.decode_nms(dheads, strides, C, (size, size), cuda(orig), kind, thr, iou, return_index=True,
                                strategy=strat, hints=hints, **kw)
         if strat == "auto" and len(dets._spill) * 2 > B:
             assert alt.general_first and alt.images_via_general_path == B      # the hint routed the batch
+        if strat in ("compact", "large"):
+            assert alt.capacity == strat
         for b in range(B):
             assert torch.equal(alt[b], dets[b]) and torch.equal(alt.indices(b), dets.indices(b)), (strat, b)
     # decoded boxes themselves: within 1e-5 of the oracle's decode
