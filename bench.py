@@ -484,8 +484,9 @@ def bench_other_configs(device, peak):
         hh, kk = _ops.make_heads(hA, STRIDES, C_VOC, (SIZE, SIZE), oA, "voc", THR, IOU, "auto_cpu", "tv_cpu")
         bufA = _ops.alloc_fused_outputs(1, 2048, False, device)
         for _ in range(5):
-            _ops.decode_nms_fused(hh, kk, 2048, False, out=bufA)
-        tA = time_steps(lambda: _ops.decode_nms_fused(hh, kk, 2048, False, out=bufA), 20)
+            _ops.decode_nms_fused(hh, kk, 2048, False, out=bufA, capacity="large")
+        # (the class fused.decode_nms picks for a batch this small: 256 threads on the one image)
+        tA = time_steps(lambda: _ops.decode_nms_fused(hh, kk, 2048, False, out=bufA, capacity="large"), 20)
         hc = [t.cpu() for t in hA]
         torch.set_num_threads(cpu_path.host_cores())
         cpu_path.eval_chain(hc, STRIDES, C_VOC, (SIZE, SIZE), oA.cpu().reshape(1, 2), "voc", THR, IOU)
