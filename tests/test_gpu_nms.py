@@ -249,6 +249,46 @@ def test_fused_back_to_back_launches_share_output_buffers():
             assert torch.equal(out[0][b, :k], want[last][0][b, :k]) and torch.equal(out[1][b, :k], want[last][1][b, :k]), (order, b)
 
 
+def test_fused_launches_in_a_cuda_graph():
+    """The overlapping launches (programmatic dependent launch) captured in one CUDA graph and replayed: same results."""
+    from pqdet_b200 import _ops, synth
+    B, C, size = 256, 20, 512
+    dev = torch.device("cuda")
+    orig = torch.tensor([float(size), float(size)], device=dev)
+    sets = []
+    for seed in (1, 2):
+        hs = synth.make_heads(B, C, size, "sparse", seed=seed, device=dev)
+        sets.append((hs,) + _ops.make_heads(hs, synth.FPN_STRIDES, C, (size, size), orig, "voc", 0.1, 0.45, "auto_cuda", "tv_cuda"))
+    det, _, meta = _ops.decode_nms_fused(sets[1][1], sets[1][2], 2048, False)
+    torch.cuda.synchronize()
+    want_det, want_meta = det.clone(), meta.clone()
+    out, out2 = _ops.alloc_fused_outputs(B, 2048, False, dev), _ops.alloc_fused_outputs(B, 2048, False, dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                               # warm-up on the capture stream arms the scheduler words
+        for _ in range(2):
+            _ops.decode_nms_fused(sets[0][1], sets[0][2], 2048, False, out=out)
+            _ops.decode_nms_fused(sets[1][1], sets[1][2], 2048, False, out=out2)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        _ops.decode_nms_fused(sets[0][1], sets[0][2], 2048, False, out=out)
+        _ops.decode_nms_fused(sets[1][1], sets[1][2], 2048, False, out=out2)
+        _ops.decode_nms_fused(sets[1][1], sets[1][2], 2048, False, out=out)      # overwrites the first launch's rows
+    for o in (out, out2):
+        o[0].zero_()
+        o[2][:3 * B].zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for o in (out, out2):
+        assert torch.equal(o[2][:3 * B], want_meta[:3 * B])
+        for b in range(0, B, 5):
+            k = int(want_meta[b])
+            assert torch.equal(o[0][b, :k], want_det[b, :k]), b
+
+
 @pytest.mark.parametrize("size,C", [(320, 20), (352, 1), (416, 20), (480, 3), (544, 80), (576, 20)])
 def test_fused_multi_scale_input_sizes(size, C):
     """The reference trains/evaluates at 320..608 (config.py:67): grids such as 11x11, 13x13, 19x19 exercise the
