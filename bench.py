@@ -941,8 +941,10 @@ def collective_legs(device, rank, world, steps, warmup, peak):
                 peer = {"us_per_step": us_peer, "value": world * Bv / (us_peer * 1e-6), "unit": "images/s",
                         "identical_to_nccl_gather": same,
                         "what": "pqdet_decode_nms_gather: kept rows + counts stored into every rank's gathered buffers "
-                                "through NVLink peer memory from inside the kernel, then a symmetric-memory barrier; no "
-                                "collective in the step"}
+                                "through NVLink peer memory from inside the kernel, which also bumps an arrival counter "
+                                "per image on every peer; a one-warp wait kernel (pqdet_peer_wait) on the receiving side "
+                                "instead of a barrier, so consecutive steps keep overlapping; no collective in the step",
+                        "wait_errors": int(pg.err)}
             except Exception as e:
                 peer = {"error": repr(e)[:200]}
         legs["E_eval_gather"] = {

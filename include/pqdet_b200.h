@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PQDET_VERSION 110          /* 0.1.1: capacity_class on the fused entry points */
+#define PQDET_VERSION 111          /* 0.1.1: capacity_class on the fused entry points; 111: arrival counters */
 #define PQDET_MAX_LEVELS 4
 #define PQDET_MAX_CLASSES 126      /* class id is a 7-bit field of the 64-bit sort keys (class:7 | ~score:32 | row:25);
                                       more classes (or >= 2^25 rows per image) return PQDET_ERR_UNSUPPORTED */
@@ -144,11 +144,19 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
  * fills block `rank` of every buffer (counts clamped to gather_cap, rows beyond it dropped; gather_cap must be
  * even: an image's rows are staged on chip and leave as coalesced 16-byte stores).  The buffers are complete
  * on a rank once every rank's call has finished - a device-side barrier (symmetric-memory signal pads) after the
- * launch, no data-path collective.  det / counts / ncand / status are the usual local outputs. */
+ * launch, no data-path collective.  det / counts / ncand / status are the usual local outputs.
+ * peer_arrived (nullable): peer_arrived[p] = the address, in rank p's buffer, of the 32-bit arrival counter that
+ * belongs to THIS rank (zero at start, never reset).  The kernel then adds 1 to it on every peer for every image whose
+ * rows and count it has stored there (release, system scope), and pqdet_peer_wait on the receiving side replaces the
+ * barrier: arrived[0..n) = this rank's counters (one per source rank), expected = images per rank x calls so far
+ * (modulo 2^32).  The wait is a one-warp kernel launched as a programmatic dependent, so consecutive
+ * pqdet_decode_nms_gather calls still overlap; *err_flag (nullable, device) is set to 1 + source rank if a counter
+ * does not arrive within about a second. */
 int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, int max_det, int32_t* counts, int32_t* ncand,
-                            int32_t* status, float* const* peer_det, int32_t* const* peer_counts, int n_peers,
-                            int rank, int gather_cap, int32_t* work_counter, int counter_armed, int capacity_class,
-                            int device, void* stream);
+                            int32_t* status, float* const* peer_det, int32_t* const* peer_counts,
+                            uint32_t* const* peer_arrived, int n_peers, int rank, int gather_cap,
+                            int32_t* work_counter, int counter_armed, int capacity_class, int device, void* stream);
+int pqdet_peer_wait(const uint32_t* arrived, int n, uint32_t expected, int32_t* err_flag, int device, void* stream);
 
 /* The training path's per-step loss exchange over the same peer memory (model/loss.py:105-108 + trainer.py:233:
  * the mean of the replicas' losses): pqdet_peer_publish stores src[0..n) * scale into row `rank` of every rank's

@@ -65,8 +65,9 @@ SIGNATURES = {
     "pqdet_decode_nms_host": (c_int, [POINTER(HeadsT), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int, c_int, c_int, c_void_p]),
     "pqdet_decode_nms_gather": (c_int, [POINTER(HeadsT), c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                        POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_void_p, c_int,
-                                        c_int, c_int, c_void_p]),
+                                        POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int,
+                                        c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pqdet_peer_wait": (c_int, [c_void_p, c_int, ctypes.c_uint32, c_void_p, c_int, c_void_p]),
     "pqdet_peer_publish": (c_int, [c_void_p, c_int, c_float, POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
     "pqdet_peer_sum_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pqdet_head_conv_hits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_double,

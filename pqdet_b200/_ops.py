@@ -718,9 +718,10 @@ def records_nms(heads_t, keep_alive, rec: torch.Tensor, rec_count: torch.Tensor,
 
 
 def decode_nms_gather(heads_t, keep_alive, max_det: int, out, det_ptrs: Sequence[int], cnt_ptrs: Sequence[int], rank: int,
-                      gather_cap: int, capacity: str = "compact"):
+                      gather_cap: int, capacity: str = "compact", arr_ptrs: Optional[Sequence[int]] = None):
     """pqdet_decode_nms_gather: the fused kernel that also stores its rows / counts into every rank's gathered buffers
-    (peer memory).  out = buffers of alloc_fused_outputs (reused across calls).  -> det, meta."""
+    (peer memory).  out = buffers of alloc_fused_outputs (reused across calls).  arr_ptrs: this rank's arrival counter
+    in every rank's buffer (the kernel then signals per image; peer_wait on the receiving side).  -> det, meta."""
     raws, _ = keep_alive
     device = raws[0].device
     B = heads_t.B
@@ -732,8 +733,18 @@ def decode_nms_gather(heads_t, keep_alive, max_det: int, out, det_ptrs: Sequence
     n = len(det_ptrs)
     VP = ctypes.c_void_p * n
     _lib.check(_lib.load().pqdet_decode_nms_gather(ctypes.byref(heads_t), _ptr(det), int(max_det), _ptr(counts),
-                                                   _ptr(ncand), _ptr(status), VP(*det_ptrs), VP(*cnt_ptrs), n, int(rank),
+                                                   _ptr(ncand), _ptr(status), VP(*det_ptrs), VP(*cnt_ptrs),
+                                                   VP(*arr_ptrs) if arr_ptrs is not None else None, n, int(rank),
                                                    int(gather_cap), _ptr(work), armed, _lib.CAPACITY[capacity],
                                                    _dev(raws[0]), _stream(device)), "pqdet_decode_nms_gather")
     _FUSED_ARMED.add(key)
     return det, meta
+
+
+def peer_wait(arrived: torch.Tensor, n: int, expected: int, err_flag: Optional[torch.Tensor] = None) -> None:
+    """pqdet_peer_wait: block the stream (one warp, programmatic dependent) until the n arrival counters in `arrived`
+    (uint32 bit patterns in an int32 CUDA tensor) have reached `expected` modulo 2^32."""
+    device = arrived.device
+    _lib.check(_lib.load().pqdet_peer_wait(_ptr(arrived), int(n), int(expected) & 0xffffffff,
+                                           _ptr(err_flag) if err_flag is not None else None, _dev(arrived),
+                                           _stream(device)), "pqdet_peer_wait")

@@ -81,12 +81,25 @@ struct DetOut {
   float* peer_det[8];
   int32_t* peer_cnt[8];
   int n_peers, gather_cap, img_off;
+  // optional: peer_arr[p] = the arrival counter of THIS rank in rank p's buffer: +1 per image whose rows and count have
+  // been stored there (release at system scope); a rank's gathered block is complete when the counter of its source
+  // has advanced by B (pqdet_peer_wait) - no barrier kernel between consecutive launches
+  uint32_t* peer_arr[8];
 };
 
 // the image's kept count, locally and - in gather mode - in every rank's gathered counts
 __device__ __forceinline__ void set_count(const DetOut& O, int b, int k) {
   O.counts[b] = k;
   for (int p = 0; p < O.n_peers; ++p) O.peer_cnt[p][O.img_off + b] = min(k, O.gather_cap);
+}
+
+// gather mode with arrival counters: called by ONE thread after the image's peer stores (its own, and - ordered by the
+// __threadfence_system + __syncthreads in front of it - those of the CTA's other threads)
+__device__ __forceinline__ void signal_peers(const DetOut& O) {
+  if (O.n_peers == 0 || O.peer_arr[0] == nullptr) return;
+  __threadfence_system();
+  for (int p = 0; p < O.n_peers; ++p)
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(O.peer_arr[p]) : "memory");
 }
 
 __device__ __forceinline__ bool use_trick(int mode, int64_t M) {
@@ -602,7 +615,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     const int H = S.H;
     if (H > CAPH || (SRC == 2 && H > P.rec_cap)) {
       cudaGridDependencySynchronize();
-      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = -1; }
+      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = -1; signal_peers(O); }
       __syncthreads();
       continue;
     }
@@ -822,6 +835,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         O.status[b] = M ? PQDET_ST_CAND_OVERFLOW : PQDET_ST_OK;
         set_count(O, b, 0);
         O.ncand[b] = M;
+        signal_peers(O);
       }
       __syncthreads();
       continue;
@@ -901,7 +915,7 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
     PQ_PHASE(8);
     cudaGridDependencySynchronize();                       // the previous launch has completed: outputs may be written
     if (K > Smem::kOutCap) {                               // more kept detections than the output list holds
-      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = M; }
+      if (tid == 0) { O.status[b] = PQDET_ST_CAND_OVERFLOW; set_count(O, b, 0); O.ncand[b] = M; signal_peers(O); }
       __syncthreads();
       continue;
     }
@@ -965,10 +979,15 @@ decode_nms_fused_kernel(const __grid_constant__ HeadsDev P, const __grid_constan
         }
       }
     }
+    if (O.n_peers && O.peer_arr[0]) {                      // every thread's peer stores before the arrival signal
+      __threadfence_system();
+      __syncthreads();
+    }
     if (tid == 0) {
       set_count(O, b, K);
       O.ncand[b] = M;
       O.status[b] = (K > O.max_det) ? PQDET_ST_DET_TRUNCATED : PQDET_ST_OK;
+      signal_peers(O);
     }
     __syncthreads();
     PQ_PHASE(9);
@@ -1843,11 +1862,54 @@ static int device_alias(T** p, int allow_null) {
 }
 }  // namespace pq
 
+namespace pq {
+// The receiving side of the arrival counters: thread t waits until source rank t's counter in THIS rank's buffer has
+// reached `expected` (wrap-safe), i.e. until that rank's rows and counts of the step have landed here.  Launched as
+// a programmatic dependent right behind the fused kernel and triggering at once, so that the NEXT fused launch may
+// start behind it while this one still waits; that launch writes nothing before this grid has completed.
+__global__ void __launch_bounds__(32)
+peer_wait_kernel(const uint32_t* __restrict__ arrived, int n, uint32_t expected, int32_t* __restrict__ err) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  const int t = threadIdx.x;
+  if (t >= n) return;
+  const uint32_t* a = arrived + t;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    if ((int32_t)(v - expected) >= 0) break;
+    if (spin > (1u << 25)) {                              // ~ a second: a peer is gone; do not hang the device
+      if (err) *err = 1 + t;
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+}  // namespace pq
+
+extern "C" int pqdet_peer_wait(const uint32_t* arrived, int n, uint32_t expected, int32_t* err_flag, int device,
+                               void* stream) {
+  if (!arrived || n < 1 || n > 8) return PQDET_ERR_INVALID_ARG;
+  PQ_ENTER(device);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(32);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PQ_CUDA(cudaLaunchKernelEx(&cfg, pq::peer_wait_kernel, arrived, n, expected, err_flag));
+  PQ_LAUNCH_CHECK();
+  return PQDET_OK;
+}
+
 extern "C" int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, int max_det, int32_t* counts,
                                        int32_t* ncand, int32_t* status, float* const* peer_det,
-                                       int32_t* const* peer_counts, int n_peers, int rank, int gather_cap,
-                                       int32_t* work_counter, int counter_armed, int capacity_class, int device,
-                                       void* stream) {
+                                       int32_t* const* peer_counts, uint32_t* const* peer_arrived, int n_peers,
+                                       int rank, int gather_cap, int32_t* work_counter, int counter_armed,
+                                       int capacity_class, int device, void* stream) {
   using namespace pq;
   HeadsDev P;
   memset(&P, 0, sizeof(P));
@@ -1864,6 +1926,8 @@ extern "C" int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, i
     if (!peer_det[p] || !peer_counts[p]) return PQDET_ERR_INVALID_ARG;
     O.peer_det[p] = peer_det[p];
     O.peer_cnt[p] = peer_counts[p];
+    if (peer_arrived && !peer_arrived[p]) return PQDET_ERR_INVALID_ARG;
+    O.peer_arr[p] = peer_arrived ? peer_arrived[p] : nullptr;
   }
   O.n_peers = n_peers; O.gather_cap = gather_cap; O.img_off = rank * P.B;
   return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 0, capacity_class, device, (cudaStream_t)stream);

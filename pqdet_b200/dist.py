@@ -139,24 +139,38 @@ class PeerGather:
 
     Raises RuntimeError where symmetric memory is unavailable (callers fall back to gather_detections_fixed)."""
 
-    def __init__(self, B: int, k_cap: int, device, group=None):
+    def __init__(self, B: int, k_cap: int, device, group=None, sync: str = "signal"):
+        """sync = 'signal': the kernel bumps an arrival counter on every peer per image and a one-warp wait kernel on
+        the receiving side replaces the barrier (consecutive steps keep overlapping); 'barrier': a symmetric-memory
+        barrier after every launch."""
         import torch.distributed._symmetric_memory as symm
+        if sync not in ("signal", "barrier"):
+            raise ValueError("sync must be 'signal' or 'barrier'")
+        self.sync = sync
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if self.world > 8:
             raise RuntimeError("PeerGather maps at most 8 peers (one node)")
         self.B, self.k_cap, self.device = B, k_cap, torch.device(device)
         n_det = self.world * B * k_cap * 6
-        # one symmetric allocation: [gathered rows | gathered counts (int32 bit patterns)]
-        self.buf = symm.empty(n_det + self.world * B, dtype=torch.float32, device=self.device)
+        # one symmetric allocation: [gathered rows | gathered counts (int32 bit patterns) | arrival counters (8)]
+        n_cnt = self.world * B
+        self.buf = symm.empty(n_det + n_cnt + 8, dtype=torch.float32, device=self.device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         self.all_det = self.buf[:n_det].view(self.world, B, k_cap, 6)
-        self.all_counts = self.buf[n_det:].view(torch.int32).view(self.world, B)
+        self.all_counts = self.buf[n_det:n_det + n_cnt].view(torch.int32).view(self.world, B)
+        self.arrived = self.buf[n_det + n_cnt:].view(torch.int32)      # [source rank]: images of that rank landed here
         self.all_counts.zero_()
+        self.arrived.zero_()
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self._det_ptrs = ptrs
         self._cnt_ptrs = [p + n_det * 4 for p in ptrs]
+        # this rank's counter inside every rank's buffer
+        self._arr_ptrs = [p + (n_det + n_cnt + self.rank) * 4 for p in ptrs]
+        self.err = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._steps = 0
         self._out = None
+        torch.cuda.synchronize(self.device)
         self.hdl.barrier()
 
     def decode_nms(self, heads_t, keep_alive, max_det: int = 2048, capacity: str = "compact"):
@@ -165,9 +179,16 @@ class PeerGather:
         from . import _ops
         if self._out is None:
             self._out = _ops.alloc_fused_outputs(self.B, max_det, False, self.device)
+        if self.sync == "barrier":
+            det, meta = _ops.decode_nms_gather(heads_t, keep_alive, max_det, self._out, self._det_ptrs, self._cnt_ptrs,
+                                               self.rank, self.k_cap, capacity)
+            self.hdl.barrier()                                # every rank's rows have landed everywhere
+            return self.all_det, self.all_counts, det, meta
         det, meta = _ops.decode_nms_gather(heads_t, keep_alive, max_det, self._out, self._det_ptrs, self._cnt_ptrs,
-                                           self.rank, self.k_cap, capacity)
-        self.hdl.barrier()                                    # every rank's rows have landed everywhere
+                                           self.rank, self.k_cap, capacity, arr_ptrs=self._arr_ptrs)
+        self._steps += 1
+        # every source rank has delivered B images per step (equal shards: B is the same on every rank)
+        _ops.peer_wait(self.arrived, self.world, self._steps * self.B, self.err)
         return self.all_det, self.all_counts, det, meta
 
 

@@ -48,15 +48,18 @@ def main():
         sub = [h[lo2:hi2].to(dev) for h in heads]
         hs, keep = _ops.make_heads(sub, synth.FPN_STRIDES, C, (size, size), orig[lo2:hi2].to(dev), "voc", 0.1, 0.45,
                                    "auto_cuda", "tv_cuda")
-        pg = pqd.PeerGather(Bs, 512, dev)
-        for _ in range(3):                                   # repeated calls reuse the buffers
-            all_det, all_cnt, _, _ = pg.decode_nms(hs, keep)
-        torch.cuda.synchronize()
-        for r in range(world):
-            for j in range(Bs):
-                k = int(all_cnt[r, j])
-                assert torch.equal(all_det[r, j, :k], full[r * Bs + j]), "peer gather rank %d image %d" % (r, j)
-        peer = "peer-memory gather ok"
+        for sync in ("signal", "barrier"):                   # arrival counters + wait kernel | barrier per step
+            pg = pqd.PeerGather(Bs, 512, dev, sync=sync)
+            for _ in range(3):                               # repeated calls reuse the buffers
+                all_det, all_cnt, _, _ = pg.decode_nms(hs, keep)
+            torch.cuda.synchronize()
+            assert int(pg.err) == 0, "peer wait timed out on source rank %d" % (int(pg.err) - 1)
+            for r in range(world):
+                for j in range(Bs):
+                    k = int(all_cnt[r, j])
+                    assert torch.equal(all_det[r, j, :k], full[r * Bs + j]), "peer gather (%s) rank %d image %d" % (sync, r, j)
+            dist.barrier()
+        peer = "peer-memory gather ok (signal and barrier forms)"
     except RuntimeError as e:
         peer = "peer-memory gather unavailable: %s" % (str(e).splitlines()[0][:120],)
     # training: local loss over the shard, reduced, vs the whole batch on one GPU

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(_lib.lib_path())
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.pqdet_version() == 110
+    assert lib.pqdet_version() == 111
     assert lib.pqdet_strerror(0) == b"ok" and b"unsupported" in lib.pqdet_strerror(-3)
 
 
