@@ -146,8 +146,9 @@ int pqdet_decode_nms(const pqdet_heads_t* heads, float* det, int32_t* det_idx, i
  * on a rank once every rank's call has finished - a device-side barrier (symmetric-memory signal pads) after the
  * launch, no data-path collective.  det / counts / ncand / status are the usual local outputs.
  * peer_arrived (nullable): peer_arrived[p] = the address, in rank p's buffer, of the 32-bit arrival counter that
- * belongs to THIS rank (zero at start, never reset).  The kernel then adds 1 to it on every peer for every image whose
- * rows and count it has stored there (release, system scope), and pqdet_peer_wait on the receiving side replaces the
+ * belongs to THIS rank (zero at start, never reset; work_counter is then int32[3]).  The launch then adds its image
+ * count to it on every peer once all its rows and counts are stored there (release, system scope; one remote add per
+ * peer and launch), and pqdet_peer_wait on the receiving side replaces the
  * barrier: arrived[0..n) = this rank's counters (one per source rank), expected = images per rank x calls so far
  * (modulo 2^32).  The wait is a one-warp kernel launched as a programmatic dependent, so consecutive
  * pqdet_decode_nms_gather calls still overlap; *err_flag (nullable, device) is set to 1 + source rank if a counter

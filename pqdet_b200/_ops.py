@@ -226,10 +226,11 @@ def make_heads(raws: Sequence[torch.Tensor], strides: Sequence[float], num_class
 
 
 def alloc_fused_outputs(B: int, max_det: int, want_index: bool, device):
-    """Output buffers of the fused kernel.  meta = [counts(B), ncand(B), status(B), scheduler words(2)]."""
+    """Output buffers of the fused kernel.  meta = [counts(B), ncand(B), status(B), scheduler words(2), images done(1),
+    pad(1)]."""
     det = torch.empty((B, max_det, 6), dtype=torch.float32, device=device)
     idx = torch.empty((B, max_det), dtype=torch.int32, device=device) if want_index else None
-    meta = torch.zeros((3 * B + 2,), dtype=torch.int32, device=device)
+    meta = torch.zeros((3 * B + 4,), dtype=torch.int32, device=device)
     return det, idx, meta
 
 

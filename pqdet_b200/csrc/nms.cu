@@ -85,6 +85,8 @@ struct DetOut {
   // been stored there (release at system scope); a rank's gathered block is complete when the counter of its source
   // has advanced by B (pqdet_peer_wait) - no barrier kernel between consecutive launches
   uint32_t* peer_arr[8];
+  int32_t* img_done;     // with peer_arr: images of this launch whose outputs are stored (local word, zero between launches)
+  int n_images;          // with peer_arr: images of this launch (the last one to finish sends the signals)
 };
 
 // the image's kept count, locally and - in gather mode - in every rank's gathered counts
@@ -95,11 +97,18 @@ __device__ __forceinline__ void set_count(const DetOut& O, int b, int k) {
 
 // gather mode with arrival counters: called by ONE thread after the image's peer stores (its own, and - ordered by the
 // __threadfence_system + __syncthreads in front of it - those of the CTA's other threads)
+// One signal per launch and peer, not per image: 8 ranks x 1024 images on one counter serialise at the receiver
+// (measured: 155 against 112 us per step at 8 GPUs).  Every image is counted in a LOCAL word behind a system-scope
+// fence; the CTA that counts the last one adds the launch's image count to this rank's counter on every peer
+// (fences are cumulative: the other CTAs' peer stores are ordered before that release).
 __device__ __forceinline__ void signal_peers(const DetOut& O) {
   if (O.n_peers == 0 || O.peer_arr[0] == nullptr) return;
   __threadfence_system();
+  if (atomicAdd(O.img_done, 1) != O.n_images - 1) return;
+  *O.img_done = 0;                                          // the next launch counts only after this grid has completed
+  __threadfence_system();
   for (int p = 0; p < O.n_peers; ++p)
-    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(O.peer_arr[p]) : "memory");
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(O.peer_arr[p]), "r"((uint32_t)O.n_images) : "memory");
 }
 
 __device__ __forceinline__ bool use_trick(int mode, int64_t M) {
@@ -1929,7 +1938,10 @@ extern "C" int pqdet_decode_nms_gather(const pqdet_heads_t* heads, float* det, i
     if (peer_arrived && !peer_arrived[p]) return PQDET_ERR_INVALID_ARG;
     O.peer_arr[p] = peer_arrived ? peer_arrived[p] : nullptr;
   }
+  O.img_done = work_counter + 2;                            // (int32[3] with peer_arrived)
+  O.n_images = P.B;
   O.n_peers = n_peers; O.gather_cap = gather_cap; O.img_off = rank * P.B;
+  if (peer_arrived && !counter_armed) PQ_CUDA(cudaMemsetAsync(work_counter + 2, 0, sizeof(int32_t), (cudaStream_t)stream));
   return launch_fused(P, O, work_counter, counter_armed, heads->iou_round, 0, capacity_class, device, (cudaStream_t)stream);
 }
 
