@@ -161,10 +161,12 @@ int pqdet_peer_wait(const uint32_t* arrived, int n, uint32_t expected, int32_t* 
 
 /* The training path's per-step loss exchange over the same peer memory (model/loss.py:105-108 + trainer.py:233:
  * the mean of the replicas' losses): pqdet_peer_publish stores src[0..n) * scale into row `rank` of every rank's
- * symmetric buffer (peer_bufs[p] = rank p's (world, row_stride) buffer as mapped here); after a device-side barrier
- * pqdet_peer_sum_rows adds the rows in rank order into out[0..n).  n <= 1024. */
-int pqdet_peer_publish(const float* src, int n, float scale, float* const* peer_bufs, int n_peers, int rank,
-                       int row_stride, int device, void* stream);
+ * symmetric buffer (peer_bufs[p] = rank p's (world, row_stride) buffer as mapped here); after a device-side barrier -
+ * or, with peer_arrived (nullable; as for pqdet_decode_nms_gather: +1 per call on this rank's arrival counter in every
+ * rank's buffer) after pqdet_peer_wait(arrived, n_peers, calls so far) - pqdet_peer_sum_rows adds the rows in rank
+ * order into out[0..n).  n <= 1024. */
+int pqdet_peer_publish(const float* src, int n, float scale, float* const* peer_bufs, uint32_t* const* peer_arrived,
+                       int n_peers, int rank, int row_stride, int device, void* stream);
 int pqdet_peer_sum_rows(const float* rows, int n, int n_rows, int row_stride, float* out, int device, void* stream);
 
 /* ---- 8f-2 (second half): the eval path starting at the INPUT of the head convolutions, with nothing of size

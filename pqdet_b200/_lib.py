@@ -68,7 +68,8 @@ SIGNATURES = {
                                         POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int,
                                         c_void_p, c_int, c_int, c_int, c_void_p]),
     "pqdet_peer_wait": (c_int, [c_void_p, c_int, ctypes.c_uint32, c_void_p, c_int, c_void_p]),
-    "pqdet_peer_publish": (c_int, [c_void_p, c_int, c_float, POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
+    "pqdet_peer_publish": (c_int, [c_void_p, c_int, c_float, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int,
+                                   c_int, c_void_p]),
     "pqdet_peer_sum_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pqdet_head_conv_hits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
                                      c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -11,12 +11,25 @@ struct PeerPtrs {
   float* p[8];
 };
 
-__global__ void peer_publish_kernel(const float* __restrict__ src, int n, float scale, PeerPtrs peers, int n_peers,
-                                    int rank, int row_stride) {
+struct PeerArr {
+  uint32_t* p[8];       // this rank's arrival counter in every rank's buffer, or all null
+};
+
+__global__ void peer_publish_kernel(const float* __restrict__ src, int n, float scale, PeerPtrs peers, PeerArr arr,
+                                    int n_peers, int rank, int row_stride) {
   const int i = threadIdx.x;
-  if (i >= n) return;
-  const float v = PQ_MUL(src[i], scale);
-  for (int p = 0; p < n_peers; ++p) peers.p[p][(size_t)rank * row_stride + i] = v;
+  if (i < n) {
+    const float v = PQ_MUL(src[i], scale);
+    for (int p = 0; p < n_peers; ++p) peers.p[p][(size_t)rank * row_stride + i] = v;
+  }
+  if (arr.p[0]) {
+    // arrival signal instead of a barrier kernel: every thread's peer stores, then one release-add per peer
+    // (pqdet_peer_wait on the receiving side)
+    __threadfence_system();
+    __syncthreads();
+    if (i == 0)
+      for (int p = 0; p < n_peers; ++p) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(arr.p[p]) : "memory");
+  }
 }
 
 __global__ void peer_sum_rows_kernel(const float* __restrict__ rows, int n, int n_rows, int row_stride,
@@ -30,8 +43,9 @@ __global__ void peer_sum_rows_kernel(const float* __restrict__ rows, int n, int 
 
 }  // namespace pq
 
-extern "C" int pqdet_peer_publish(const float* src, int n, float scale, float* const* peer_bufs, int n_peers, int rank,
-                                  int row_stride, int device, void* stream) {
+extern "C" int pqdet_peer_publish(const float* src, int n, float scale, float* const* peer_bufs,
+                                  uint32_t* const* peer_arrived, int n_peers, int rank, int row_stride, int device,
+                                  void* stream) {
   if (!src || !peer_bufs || n < 1 || n > 1024 || n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers ||
       row_stride < n)
     return PQDET_ERR_INVALID_ARG;
@@ -39,8 +53,14 @@ extern "C" int pqdet_peer_publish(const float* src, int n, float scale, float* c
   for (int p = 0; p < 8; ++p) pp.p[p] = p < n_peers ? peer_bufs[p] : nullptr;
   for (int p = 0; p < n_peers; ++p)
     if (!pp.p[p]) return PQDET_ERR_INVALID_ARG;
+  pq::PeerArr pa;
+  for (int p = 0; p < 8; ++p) pa.p[p] = (peer_arrived && p < n_peers) ? peer_arrived[p] : nullptr;
+  if (peer_arrived)
+    for (int p = 0; p < n_peers; ++p)
+      if (!pa.p[p]) return PQDET_ERR_INVALID_ARG;
   PQ_ENTER(device);
-  pq::peer_publish_kernel<<<1, (n + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(src, n, scale, pp, n_peers, rank, row_stride);
+  pq::peer_publish_kernel<<<1, (n + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(src, n, scale, pp, pa, n_peers, rank,
+                                                                             row_stride);
   PQ_LAUNCH_CHECK();
   return PQDET_OK;
 }

@@ -200,8 +200,10 @@ class PeerReduce:
 
     ROW = 64
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, sync: str = "signal"):
         import torch.distributed._symmetric_memory as symm
+        if sync not in ("signal", "barrier"):
+            raise ValueError("sync must be 'signal' or 'barrier'")
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if self.world > 8:
@@ -210,11 +212,19 @@ class PeerReduce:
         # two row sets used alternately: a fast rank's step k+1 never touches rows a slow rank still sums for step k,
         # and by the time it reaches step k+2 it has passed step k+1's barrier, which the slow rank only enters after
         # its step-k sum (stream order) - one barrier per step suffices
-        self.buf = symm.empty(2 * self.world * self.ROW, dtype=torch.float32, device=self.device)
+        # [row set 0 | row set 1 | arrival counters (8)]: a publish adds 1 to this rank's counter in every rank's buffer,
+        # pqdet_peer_wait on the receiving side replaces the barrier kernel (sync='barrier' keeps it)
+        n_rows = 2 * self.world * self.ROW
+        self.buf = symm.empty(n_rows + 8, dtype=torch.float32, device=self.device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         self.buf.zero_()
         self._ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.arrived = self.buf[n_rows:].view(torch.int32)
+        self._arr_ptrs = [p + (n_rows + self.rank) * 4 for p in self._ptrs]
+        self.err = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self.sync = sync
         self._step = 0
+        torch.cuda.synchronize(self.device)
         self.hdl.barrier()
 
     def reduce_losses(self, losses: dict, local_batch: int, global_batch: int) -> dict:
@@ -232,10 +242,16 @@ class PeerReduce:
         lib = _lib.load()
         half = (self._step & 1) * self.world * self.ROW * 4          # byte offset of this step's row set
         self._step += 1
+        signal = self.sync == "signal"
         _lib.check(lib.pqdet_peer_publish(ctypes.c_void_p(raw.data_ptr()), n, float(local_batch) / float(global_batch),
-                                          VP(*[p + half for p in self._ptrs]), self.world, self.rank, self.ROW,
+                                          VP(*[p + half for p in self._ptrs]),
+                                          VP(*self._arr_ptrs) if signal else None, self.world, self.rank, self.ROW,
                                           dev_index, st), "pqdet_peer_publish")
-        self.hdl.barrier()
+        if signal:
+            from . import _ops
+            _ops.peer_wait(self.arrived, self.world, self._step, self.err)      # every rank has published this step
+        else:
+            self.hdl.barrier()
         vec = torch.empty((n,), dtype=torch.float32, device=self.device)
         _lib.check(lib.pqdet_peer_sum_rows(ctypes.c_void_p(self.buf.data_ptr() + half), n, self.world, self.ROW,
                                            ctypes.c_void_p(vec.data_ptr()), dev_index, st), "pqdet_peer_sum_rows")

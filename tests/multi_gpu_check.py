@@ -78,14 +78,17 @@ def main():
     for a, b in zip(red["loss_per_branch"], whole["loss_per_branch"]):
         assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
     try:
-        pr = pqd.PeerReduce(dev)
-        for _ in range(3):
-            red2 = pr.reduce_losses(local_out, hi - lo, total)
-        for k in ("loss", "giou_loss", "conf_loss", "class_loss"):
-            assert abs(float(red2[k]) - float(whole[k])) <= 1e-5 * abs(float(whole[k])), (k, float(red2[k]), float(whole[k]))
-        for a, b in zip(red2["loss_per_branch"], whole["loss_per_branch"]):
-            assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
-        peer += ", peer-memory loss reduce ok"
+        for sync in ("signal", "barrier"):                   # arrival counters + wait kernel | barrier per step
+            pr = pqd.PeerReduce(dev, sync=sync)
+            for _ in range(5):
+                red2 = pr.reduce_losses(local_out, hi - lo, total)
+            for k in ("loss", "giou_loss", "conf_loss", "class_loss"):
+                assert abs(float(red2[k]) - float(whole[k])) <= 1e-5 * abs(float(whole[k])), (sync, k, float(red2[k]), float(whole[k]))
+            for a, b in zip(red2["loss_per_branch"], whole["loss_per_branch"]):
+                assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
+            assert int(pr.err) == 0, "peer wait timed out on source rank %d" % (int(pr.err) - 1)
+            dist.barrier()
+        peer += ", peer-memory loss reduce ok (signal and barrier forms)"
     except RuntimeError as e:
         peer += ", peer-memory loss reduce unavailable: %s" % (str(e).splitlines()[0][:120],)
     dist.barrier()
