@@ -870,10 +870,8 @@ def collective_legs(device, rank, world, steps, warmup, peak):
                 peer_red = {"us_per_step": us_peer, "value": world * B / (us_peer * 1e-6), "unit": "images/s",
                             "global_loss": float(last["p"]["loss"]),
                             "rel_diff_to_nccl": abs(float(last["p"]["loss"]) - float(last["o"]["loss"])) / abs(float(last["o"]["loss"])),
-                            "what": "pqdet_peer_publish into every rank's symmetric buffer (+1 on this rank's arrival "
-                                    "counter on every peer) + pqdet_peer_wait + pqdet_peer_sum_rows: no collective and "
-                                    "no barrier kernel in the step",
-                            "wait_errors": int(pr.err)}
+                            "what": "pqdet_peer_publish into every rank's symmetric buffer + signal-pad barriers + "
+                                    "pqdet_peer_sum_rows: no collective in the step"}
             except Exception as e:
                 peer_red = {"error": repr(e)[:200]}
         alg = (2 * raw_bytes(C, size) + 4 * 3 * cells(size)) * B

@@ -200,7 +200,10 @@ class PeerReduce:
 
     ROW = 64
 
-    def __init__(self, device, group=None, sync: str = "signal"):
+    def __init__(self, device, group=None, sync: str = "barrier"):
+        """sync = 'barrier' (default): a symmetric-memory barrier between publish and sum; 'signal': arrival counters
+        and pqdet_peer_wait as in PeerGather (same results; its step time was not reproducible between boxes, see
+        DESIGN section 7, so it is not the default here)."""
         import torch.distributed._symmetric_memory as symm
         if sync not in ("signal", "barrier"):
             raise ValueError("sync must be 'signal' or 'barrier'")
