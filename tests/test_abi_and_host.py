@@ -120,3 +120,29 @@ def test_build_center_grid_matches_reference_orientation():
     assert tuple(g.shape) == (2, 3, 1, 2)
     assert g[..., 0, 0].tolist() == [[0.5, 1.5, 2.5], [0.5, 1.5, 2.5]]       # x along W
     assert g[..., 0, 1].tolist() == [[0.5, 0.5, 0.5], [1.5, 1.5, 1.5]]       # y along H
+
+
+def test_route_hints_record_the_capacity_a_workload_needs():
+    """fused._next_route: what a complete run's candidate counts say about the next call (the hint stored in a
+    caller-held StrategyHints): compact lists while every image fits them, the large lists while every image fits
+    those and the mean stays at half of them, the bucketed general path beyond."""
+    from pqdet_b200 import _lib, fused
+    (h_c, m_c), (h_l, m_l) = _lib.CAPACITY_LIMITS["compact"], _lib.CAPACITY_LIMITS["large"]
+    assert (h_c, m_c, h_l, m_l) == (512, 1280, 1024, 2048)
+    assert fused._next_route(0, 0.0) == "compact"
+    assert fused._next_route(m_c, 600.0) == "compact"
+    assert fused._next_route(m_c + 1, 600.0) == "large"
+    assert fused._next_route(m_l, m_l / 2) == "large"
+    assert fused._next_route(m_l, m_l / 2 + 1) == "general"
+    assert fused._next_route(m_l + 1, 10.0) == "general"
+    hints = fused.StrategyHints()
+    assert isinstance(hints, dict) and len(hints) == 0
+
+
+def test_peer_wait_validates_its_arguments(lib):
+    """pqdet_peer_wait (the receiving side of the arrival counters): argument checks before any CUDA call."""
+    import ctypes
+    assert lib.pqdet_peer_wait(None, 2, 0, None, 0, None) == -1            # PQDET_ERR_INVALID_ARG
+    buf = (ctypes.c_uint32 * 8)()
+    assert lib.pqdet_peer_wait(ctypes.cast(buf, ctypes.c_void_p), 0, 0, None, 0, None) == -1
+    assert lib.pqdet_peer_wait(ctypes.cast(buf, ctypes.c_void_p), 9, 0, None, 0, None) == -1
